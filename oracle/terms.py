@@ -1,0 +1,414 @@
+"""Oracle restatement of the reference's term catalog on the hot path
+(SURVEY.md 8a rows a11, a13, a16-a19).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Citations: /root/reference.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional
+
+import numpy as np
+
+from . import pfutil
+from .pf import DerivedField, LaplacianN, as_frequency
+
+
+# ==========================================================================
+# pf/squareGradientTerm.go
+# ==========================================================================
+class SquaredGradient:
+    """pf/squareGradientTerm.go:14-68: Factor * sum_d FFT((IFFT(i 2pi f_d u^)/N)^2);
+    only the +0.5 Nyquist is zeroed (:48).  The reference uses gosfft here; the
+    DFT is the same, so the oracle uses its own FFTWWrapper."""
+
+    def __init__(self, field: str, domain_size, workers: int = 1):
+        if len(domain_size) not in (2, 3):
+            raise ValueError("squaregradient: Domain size has to be of length 2 or 3")
+        self.Field = field
+        self.Factor = 1.0
+        self.FT = pfutil.NewFFTW(domain_size, workers)
+
+    def Construct(self, bricks):
+        def fn(freq, t, field: np.ndarray):
+            n = field.shape[0]
+            field[:] = 0.0
+            f = as_frequency(freq).table(n)
+            dim = f.shape[1]
+            idx = np.arange(n)
+            for d in range(dim):
+                fd = f[:, d].copy()
+                fd[np.abs(fd - 0.5) < 1e-10] = 0.0
+                work = np.asarray(bricks[self.Field].Get(idx)) * (1j * (2.0 * math.pi * fd))
+                work = np.ascontiguousarray(work, dtype=np.complex128)
+                self.FT.IFFT(work)
+                work = pfutil.go_cpow(work / complex(float(n), 0.0), 2.0)
+                work = np.ascontiguousarray(work)
+                self.FT.FFT(work)
+                field += work * complex(self.Factor, 0.0)
+
+        return fn
+
+    def OnStepFinished(self, t, bricks):
+        pass
+
+
+def NewSquareGradient(field: str, domain_size, workers: int = 1) -> SquaredGradient:
+    return SquaredGradient(field, domain_size, workers)
+
+
+# ==========================================================================
+# pf/vandeven.go
+# ==========================================================================
+class Vandeven:
+    """pf/vandeven.go:8-40: 1000-point trapezoid table + linear interpolation."""
+
+    def __init__(self, order: int):
+        data = np.zeros(1000, dtype=np.float64)
+        data[0] = 1.0
+        prefactor = math.gamma(float(2 * order)) / (math.gamma(float(order)) * math.gamma(float(order)))
+        dx = 1.0 / 999.0
+        for i in range(1, 1000):
+            x = float(i) * dx
+            i2 = math.pow(x * (1 - x), float(order - 1))
+            x1 = x - dx
+            i1 = math.pow(x1 * (1.0 - x1), float(order - 1))
+            data[i] = data[i - 1] - prefactor * 0.5 * (i1 + i2) * dx
+        self.Data = data
+
+    def Eval(self, x: float) -> float:
+        n = float(len(self.Data) - 1)
+        idx = int(x * n)
+        if idx >= len(self.Data) - 1:
+            return float(self.Data[-1])
+        dx = 1.0 / n
+        dy = self.Data[idx + 1] - self.Data[idx]
+        x0 = float(idx) * dx
+        return float(self.Data[idx] + (x - x0) * dy / dx)
+
+    def eval_array(self, x: np.ndarray) -> np.ndarray:
+        n = float(len(self.Data) - 1)
+        idx = (x * n).astype(np.int64)  # Go int() truncates toward zero; x >= 0
+        last = idx >= len(self.Data) - 1
+        idc = np.where(last, 0, idx)
+        dx = 1.0 / n
+        dy = self.Data[idc + 1] - self.Data[idc]
+        x0 = idc.astype(np.float64) * dx
+        val = self.Data[idc] + (x - x0) * dy / dx
+        return np.where(last, self.Data[-1], val)
+
+
+def NewVandeven(order: int) -> Vandeven:
+    return Vandeven(order)
+
+
+# ==========================================================================
+# pf/spectralViscosity.go
+# ==========================================================================
+def interpolant(f: float, peak_position: float) -> float:
+    """pf/spectralViscosity.go:31-40 (2x^2 - 3x^3 as written; pinned by
+    spectralViscosity_test.go:10-35)."""
+    frac = 1.0 / 3.0
+    if f < frac * peak_position:
+        return 0.0
+    if f > peak_position:
+        return 1.0
+    x = 1.5 * (f - frac * peak_position) / peak_position
+    return 2.0 * x * x - 3.0 * x * x * x
+
+
+def interpolant_array(f: np.ndarray, peak_position: float) -> np.ndarray:
+    frac = 1.0 / 3.0
+    x = 1.5 * (f - frac * peak_position) / peak_position
+    mid = 2.0 * x * x - 3.0 * x * x * x
+    return np.where(f < frac * peak_position, 0.0, np.where(f > peak_position, 1.0, mid))
+
+
+class SpectralViscosity:
+    """pf/spectralViscosity.go:23-56: implicit term -Eps*Q(|f|)*|f|^Power."""
+
+    def __init__(self, Eps: float, DissipationThreshold: float, Power: int):
+        self.Eps = Eps
+        self.DissipationThreshold = DissipationThreshold
+        self.Power = Power
+
+    def Construct(self, bricks):
+        def fn(freq, t, field: np.ndarray):
+            f = as_frequency(freq).table(field.shape[0])
+            f_rad = np.sqrt(np.sum(f * f, axis=1))
+            value = interpolant_array(f_rad, self.DissipationThreshold)
+            field[:] = -self.Eps * value * np.power(f_rad, float(self.Power))
+
+        return fn
+
+    def OnStepFinished(self, t, bricks):
+        pass
+
+
+# ==========================================================================
+# pf/noise.go
+# ==========================================================================
+class WhiteNoise:
+    """pf/noise.go:11-23.  The Go math/rand stream cannot be reproduced
+    (unseeded global source), so the normal draws come from an injectable
+    ``normal(n) -> array`` callable; parity tests share one pre-generated array."""
+
+    def __init__(self, Strength: float, normal: Optional[Callable[[int], np.ndarray]] = None):
+        self.Strength = Strength
+        self.normal = normal or (lambda n: np.random.default_rng().standard_normal(n))
+
+    def Generate(self, i, bricks):
+        std = math.sqrt(2.0 * self.Strength)
+        n = i.shape[0] if isinstance(i, np.ndarray) else 1
+        return (self.normal(n) * std).astype(np.complex128)
+
+
+class ConservativeNoise:
+    """pf/noise.go:25-100: sum_c 2i sin(pi f_c) xi^_c, modes with ||f_c|-1/2| <= 1e-6
+    skipped (:70)."""
+
+    def __init__(self, strength: float, dim: int, unique_prefix: int = 0,
+                 normal: Optional[Callable[[int], np.ndarray]] = None):
+        self.UniquePrefix = unique_prefix
+        self.Strength = strength
+        self.Dim = dim
+        self.normal = normal or (lambda n: np.random.default_rng().standard_normal(n))
+
+    def GetCurrentName(self, comp: int) -> str:
+        return f"{self.UniquePrefix}_current_{comp}"
+
+    def CurrentFieldsAreRegistered(self, bricks) -> bool:
+        return all(self.GetCurrentName(c) in bricks for c in range(self.Dim))
+
+    def Construct(self, bricks):
+        if not self.CurrentFieldsAreRegistered(bricks):
+            raise RuntimeError("ConservativeCurrent: Current fields are not register.")
+
+        def fn(freq, t, field: np.ndarray):
+            n = field.shape[0]
+            field[:] = 0.0
+            f = as_frequency(freq).table(n)
+            idx = np.arange(n)
+            for comp in range(self.Dim):
+                fc = f[:, comp]
+                keep = np.abs(np.abs(fc) - 0.5) > 1e-6
+                contrib = (1j * 2.0 * np.sin(math.pi * fc)) * np.asarray(bricks[self.GetCurrentName(comp)].Get(idx))
+                field += np.where(keep, contrib, 0.0)
+
+        return fn
+
+    def OnStepFinished(self, t, bricks):
+        pass
+
+    def RequiredDerivedFields(self, num_nodes: int) -> List[DerivedField]:
+        out = []
+        for i in range(self.Dim):
+            def calc(data, self=self):
+                std = math.sqrt(2.0 * self.Strength)
+                data[:] = self.normal(data.shape[0]) * std
+
+            out.append(DerivedField(np.zeros(num_nodes, dtype=np.complex128), self.GetCurrentName(i), calc))
+        return out
+
+
+# ==========================================================================
+# pf/volumeConserving.go
+# ==========================================================================
+class VolumeConservingLP:
+    """pf/volumeConserving.go:3-61."""
+
+    def __init__(self, field_name: str, indicator: str, dt: float, num_nodes: int):
+        self.Multiplier = 0.0
+        self.Indicator = indicator
+        self.Field = field_name
+        self.CurrentIntegral = 0.0
+        self.Dt = dt
+        self.NumNodes = num_nodes
+        self.IsFirstUpdate = True
+
+    def Construct(self, bricks):
+        def fn(freq, t, field: np.ndarray):
+            if self.Indicator not in bricks:
+                raise RuntimeError("VolumeConservingLP: Indicator is not a derived field")
+            idx = np.arange(field.shape[0])
+            field[:] = np.asarray(bricks[self.Indicator].Get(idx)) * complex(self.Multiplier, 0.0)
+
+        return fn
+
+    def OnStepFinished(self, t, bricks):
+        idx = np.arange(self.NumNodes)
+        # sequential left-to-right sum in the reference; pairwise here (diff ~1e-16 rel)
+        field_integral = float(np.sum(np.asarray(bricks[self.Field].Get(idx)).real))
+        indicator_integral = float(np.real(bricks[self.Indicator].Get(0)))
+        if self.IsFirstUpdate:
+            self.CurrentIntegral = field_integral
+            self.IsFirstUpdate = False
+        else:
+            delta = field_integral - self.CurrentIntegral
+            self.CurrentIntegral = field_integral
+            self.Multiplier = self.Multiplier - delta / (self.Dt * indicator_integral)
+
+
+def NewVolumeConservingLP(field_name, indicator, dt, num_nodes) -> VolumeConservingLP:
+    return VolumeConservingLP(field_name, indicator, dt, num_nodes)
+
+
+# ==========================================================================
+# pfc/pairCorrelation.go, pfc/ideal.go, pf/pairCorrelationTerm.go
+# ==========================================================================
+class Peak:
+    def __init__(self, PlaneDensity: float, Location: float, Width: float, NumPlanes: int):
+        self.PlaneDensity = PlaneDensity
+        self.Location = Location
+        self.Width = Width
+        self.NumPlanes = NumPlanes
+
+
+class ReciprocalSpacePairCorrelation:
+    """pfc/pairCorrelation.go:18-37."""
+
+    def __init__(self, EffTemp: float, Peaks: List[Peak]):
+        self.EffTemp = EffTemp
+        self.Peaks = Peaks
+
+    def eval_array(self, k: np.ndarray) -> np.ndarray:
+        result = np.zeros_like(k)
+        for p in self.Peaks:
+            pref = np.exp(-self.EffTemp * self.EffTemp * k * k / (2.0 * p.PlaneDensity * float(p.NumPlanes)))
+            value = pref * np.exp(-0.5 * np.power((k - p.Location) / p.Width, 2))
+            result = np.where(value > result, value, result)
+        return result
+
+    def Eval(self, k: float) -> float:
+        return float(self.eval_array(np.array([k], dtype=np.float64))[0])
+
+
+def SquareLattice2D(width: float, a: float) -> List[Peak]:
+    a2 = a / math.sqrt(2.0)
+    return [Peak(1.0, 2.0 * math.pi / a, width, 4), Peak(1.0 / math.sqrt(2.0), 2.0 * math.pi / a2, width, 4)]
+
+
+def TriangularLattice2D(width: float, a: float) -> List[Peak]:
+    return [Peak(2.0, 2.0 * math.pi / a, width, 3)]
+
+
+class IdealMix:
+    """pfc/ideal.go:17-50."""
+
+    def __init__(self, C3: float, C4: float):
+        self.C3 = C3
+        self.C4 = C4
+
+    def QuadraticPrefactor(self):
+        return 0.5
+
+    def ThirdOrderPrefactor(self):
+        return -self.C3 / 6.0
+
+    def FourthOrderPrefactor(self):
+        return self.C4 / 12.0
+
+    def Eval(self, n):
+        return self.QuadraticPrefactor() * n * n + self.ThirdOrderPrefactor() * n * n * n + self.FourthOrderPrefactor() * n * n * n * n
+
+    def Deriv(self, n):
+        return 2.0 * self.QuadraticPrefactor() * n + 3.0 * self.ThirdOrderPrefactor() * n * n + 4.0 * self.FourthOrderPrefactor() * n * n * n
+
+
+class PairCorrlationTerm:
+    """pf/pairCorrelationTerm.go:22-84 (implicit): -Prefactor*C2(2pi|f|) [* (-k^2)]."""
+
+    def __init__(self, PairCorrFunc, Field: str, Prefactor: float, Laplacian: bool):
+        self.PairCorrFunc = PairCorrFunc
+        self.Field = Field
+        self.Prefactor = Prefactor
+        self.Laplacian = Laplacian
+
+    def _multiplier(self, freq, n):
+        f = as_frequency(freq).table(n)
+        f_rad = np.sqrt(np.sum(f * f, axis=1))
+        return self.Prefactor * self.PairCorrFunc.eval_array(2.0 * math.pi * f_rad)
+
+    def Construct(self, bricks):
+        def fn(freq, t, out: np.ndarray):
+            out[:] = -self._multiplier(freq, out.shape[0])
+            if self.Laplacian:
+                LaplacianN(1).Eval(freq, out)
+
+        return fn
+
+    def OnStepFinished(self, t, bricks):
+        pass
+
+    def GetEnergy(self, bricks, ft, domain_size) -> float:
+        n = pfutil.prod_int(domain_size)
+        b = np.asarray(bricks[self.Field].Get(np.arange(n)))
+        field = np.array(b, dtype=np.complex128)
+        ft.FFT(field)
+        field *= self._multiplier(ft.Freq, n)
+        ft.IFFT(field)
+        pfutil.div_real_scalar(field, float(n))
+        return -0.5 * float(np.sum((field * b).real))
+
+
+class ExplicitPairCorrelationTerm(PairCorrlationTerm):
+    """pf/pairCorrelationTerm.go:89-110."""
+
+    def Construct(self, bricks):
+        def fn(freq, t, out: np.ndarray):
+            n = out.shape[0]
+            out[:] = -self._multiplier(freq, n) * np.asarray(bricks[self.Field].Get(np.arange(n)))
+            if self.Laplacian:
+                LaplacianN(1).Eval(freq, out)
+
+        return fn
+
+
+class IdealMixtureTerm:
+    """pf/pairCorrelationTerm.go:116-193 (mixed term)."""
+
+    def __init__(self, IdealMix_: IdealMix, Field: str, Prefactor: float, Laplacian: bool):
+        self.IdealMix = IdealMix_
+        self.Field = Field
+        self.Prefactor = Prefactor
+        self.Laplacian = Laplacian
+
+    def Eval(self, i, bricks):
+        value = np.real(bricks[self.Field].Get(i))
+        return (self.Prefactor * self.IdealMix.Deriv(value)) + 0j
+
+    def ConstructLinear(self, bricks):
+        def fn(freq, t, field: np.ndarray):
+            field[:] = complex(self.Prefactor, 0.0)
+            if self.Laplacian:
+                LaplacianN(1).Eval(freq, field)
+
+        return fn
+
+    def nonLinearDerivedFieldName(self) -> str:
+        return f"ideal_mixture_{self.Field}_nonlin"
+
+    def DerivedField(self, num_nodes: int, bricks) -> DerivedField:
+        def calc(out: np.ndarray):
+            v = np.real(bricks[self.Field].Get(np.arange(out.shape[0])))
+            out[:] = 3.0 * self.IdealMix.ThirdOrderPrefactor() * v * v + 4.0 * self.IdealMix.FourthOrderPrefactor() * v * v * v
+
+        return DerivedField(np.zeros(num_nodes, dtype=np.complex128), self.nonLinearDerivedFieldName(), calc)
+
+    def ConstructNonLinear(self, bricks):
+        def fn(freq, t, field: np.ndarray):
+            name = self.nonLinearDerivedFieldName()
+            if name not in bricks:
+                raise RuntimeError(f"Missing derived field {name}.")
+            field[:] = bricks[name].Get(np.arange(field.shape[0]))
+            if self.Laplacian:
+                LaplacianN(1).Eval(freq, field)
+
+        return fn
+
+    def OnStepFinished(self, t, bricks):
+        pass
+
+    def GetEnergy(self, bricks, nodes: int) -> float:
+        v = np.real(bricks[self.Field].Get(np.arange(nodes)))
+        return float(np.sum(self.Prefactor * self.IdealMix.Eval(v)))
