@@ -1,0 +1,211 @@
+// Register/shared-memory Stockham FFT engine for one line of N complex128 points.
+//
+// Replaces the FFTW plan execution behind FFTWWrapper.FFT/IFFT
+// (/root/reference/pfutil/fftWrap.go:19-20,28,36).  Forward sign -1, unnormalised;
+// the inverse is obtained by swapping re/im on the way in and out
+// (IDFT(x) = swap(DFT(swap(x)))), so one set of butterflies and twiddles serves both.
+//
+// Decomposition N = R0*R1*R2 (each radix <= 16), decimation in frequency,
+// autosort (natural order in, natural order out):
+//   stage s (radix R, L = product of earlier radices, T = N/E threads per line):
+//     butterfly b = t + T*i  (i < E/R) takes positions b + n*N/R, n < R
+//     -> DFT_R -> times W_N^{k * (b - b mod L)} -> position (b mod L) + L*k + L*R*(b div L)
+//   thread t always holds positions {t + T*m : m < E} in register slot m, both before
+//   the first stage and after the last, for every radix.  That invariant is what lets
+//   an inverse pass, a pointwise real-space function and the following forward pass
+//   along the same axis run back to back in registers (fused kernels in step_kernels.cuh).
+#pragma once
+#include "cplx.cuh"
+
+namespace gopf {
+
+#define GOPF_SQRT1_2 0.70710678118654752440
+#define GOPF_C1_16 0.92387953251128675613  // cos(pi/8)
+#define GOPF_S1_16 0.38268343236508977173  // sin(pi/8)
+
+__device__ __forceinline__ cplx cmulc(cplx a, double c, double s) {  // a * (c + i s)
+    return mk(fma(a.x, c, -a.y * s), fma(a.x, s, a.y * c));
+}
+
+// ---- forward DFT of R points held in registers, natural order in and out -------------
+template <int R>
+struct Dft;
+
+template <>
+struct Dft<1> {
+    static __device__ __forceinline__ void run(cplx (&a)[1]) {}
+};
+template <>
+struct Dft<2> {
+    static __device__ __forceinline__ void run(cplx (&a)[2]) {
+        cplx t = a[0];
+        a[0] = t + a[1];
+        a[1] = t - a[1];
+    }
+};
+__device__ __forceinline__ void dft4(cplx& a0, cplx& a1, cplx& a2, cplx& a3) {
+    cplx t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3, t3 = mul_mi(a1 - a3);
+    a0 = t0 + t2;
+    a2 = t0 - t2;
+    a1 = t1 + t3;
+    a3 = t1 - t3;
+}
+template <>
+struct Dft<4> {
+    static __device__ __forceinline__ void run(cplx (&a)[4]) { dft4(a[0], a[1], a[2], a[3]); }
+};
+template <>
+struct Dft<8> {
+    static __device__ __forceinline__ void run(cplx (&a)[8]) {
+        dft4(a[0], a[2], a[4], a[6]);  // E_k in a[2k]
+        dft4(a[1], a[3], a[5], a[7]);  // O_k in a[2k+1]
+        cplx o0 = a[1];
+        cplx o1 = mk((a[3].x + a[3].y) * GOPF_SQRT1_2, (a[3].y - a[3].x) * GOPF_SQRT1_2);
+        cplx o2 = mul_mi(a[5]);
+        cplx o3 = mk((a[7].y - a[7].x) * GOPF_SQRT1_2, (-a[7].x - a[7].y) * GOPF_SQRT1_2);
+        cplx e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6];
+        a[0] = e0 + o0;
+        a[4] = e0 - o0;
+        a[1] = e1 + o1;
+        a[5] = e1 - o1;
+        a[2] = e2 + o2;
+        a[6] = e2 - o2;
+        a[3] = e3 + o3;
+        a[7] = e3 - o3;
+    }
+};
+template <>
+struct Dft<16> {
+    static __device__ __forceinline__ void run(cplx (&a)[16]) {
+        // step 1: y[n2][k1] = DFT4 over n1 of x[4*n1 + n2]; kept in a[4*k1 + n2]
+        dft4(a[0], a[4], a[8], a[12]);
+        dft4(a[1], a[5], a[9], a[13]);
+        dft4(a[2], a[6], a[10], a[14]);
+        dft4(a[3], a[7], a[11], a[15]);
+        // step 2: times W16^{n2*k1}
+        a[5] = cmulc(a[5], GOPF_C1_16, -GOPF_S1_16);                                   // 1
+        a[6] = mk((a[6].x + a[6].y) * GOPF_SQRT1_2, (a[6].y - a[6].x) * GOPF_SQRT1_2);  // 2
+        a[7] = cmulc(a[7], GOPF_S1_16, -GOPF_C1_16);                                   // 3
+        a[9] = mk((a[9].x + a[9].y) * GOPF_SQRT1_2, (a[9].y - a[9].x) * GOPF_SQRT1_2);  // 2
+        a[10] = mul_mi(a[10]);                                                         // 4
+        a[11] = mk((a[11].y - a[11].x) * GOPF_SQRT1_2, (-a[11].x - a[11].y) * GOPF_SQRT1_2);  // 6
+        a[13] = cmulc(a[13], GOPF_S1_16, -GOPF_C1_16);                                 // 3
+        a[14] = mk((a[14].y - a[14].x) * GOPF_SQRT1_2, (-a[14].x - a[14].y) * GOPF_SQRT1_2);  // 6
+        a[15] = cmulc(a[15], -GOPF_C1_16, GOPF_S1_16);                                 // 9
+        // step 3: X[k1 + 4*k2] = DFT4 over n2 of y[n2][k1]; result k2 lands in a[4*k1 + k2]
+        dft4(a[0], a[1], a[2], a[3]);
+        dft4(a[4], a[5], a[6], a[7]);
+        dft4(a[8], a[9], a[10], a[11]);
+        dft4(a[12], a[13], a[14], a[15]);
+        // transpose 4x4 so that X[k] sits in a[k]
+        cplx t;
+#define GOPF_SWAP(i, j) t = a[i]; a[i] = a[j]; a[j] = t;
+        GOPF_SWAP(1, 4) GOPF_SWAP(2, 8) GOPF_SWAP(3, 12) GOPF_SWAP(6, 9) GOPF_SWAP(7, 13) GOPF_SWAP(11, 14)
+#undef GOPF_SWAP
+    }
+};
+
+// ---- per-length plans ------------------------------------------------------------
+template <int N>
+struct PlanFor;
+#define GOPF_PLAN(N_, E_, NS_, R0_, R1_, R2_)                         \
+    template <>                                                       \
+    struct PlanFor<N_> {                                              \
+        enum { E = E_, NS = NS_, R0 = R0_, R1 = R1_, R2 = R2_, T = N_ / E_ }; \
+    };
+GOPF_PLAN(2, 2, 1, 2, 1, 1)
+GOPF_PLAN(4, 4, 1, 4, 1, 1)
+GOPF_PLAN(8, 8, 1, 8, 1, 1)
+GOPF_PLAN(16, 16, 1, 16, 1, 1)
+GOPF_PLAN(32, 8, 2, 8, 4, 1)
+GOPF_PLAN(64, 8, 2, 8, 8, 1)
+GOPF_PLAN(128, 16, 2, 16, 8, 1)
+GOPF_PLAN(256, 16, 2, 16, 16, 1)
+GOPF_PLAN(512, 8, 3, 8, 8, 8)
+GOPF_PLAN(1024, 16, 3, 16, 4, 16)
+GOPF_PLAN(2048, 16, 3, 16, 8, 16)
+GOPF_PLAN(4096, 16, 3, 16, 16, 16)
+#undef GOPF_PLAN
+
+template <int N, int S>
+struct StageInfo {
+    typedef PlanFor<N> P;
+    enum {
+        R = (S == 0 ? P::R0 : (S == 1 ? P::R1 : P::R2)),
+        L = (S == 0 ? 1 : (S == 1 ? P::R0 : P::R0 * P::R1)),
+        LAST = (S == P::NS - 1)
+    };
+};
+
+// ---- shared-memory layouts -------------------------------------------------------
+// Strided-axis tiles: TX adjacent lines, line index fastest.  Any group of 8 threads
+// with equal position and consecutive line index touches one 128-B row: conflict free
+// for every stage without padding.
+template <int TX>
+struct LayoutInterleaved {
+    static __device__ __forceinline__ int at(int pos, int l) { return pos * TX + l; }
+    static constexpr int elems(int n, int lines) { return n * lines; }
+};
+// Contiguous-axis lines: position fastest, one pad cell per 16 so that the radix-16
+// scatter (stride 16 cells = 256 B) spreads over all bank groups.
+template <int N>
+struct LayoutPadded {
+    enum { LS = N + N / 16 };
+    static __device__ __forceinline__ int at(int pos, int l) { return l * LS + pos + (pos >> 4); }
+    static constexpr int elems(int n, int lines) { return (n + n / 16) * lines; }
+};
+
+struct SyncCta {
+    static __device__ __forceinline__ void run() { __syncthreads(); }
+};
+struct SyncWarp {
+    static __device__ __forceinline__ void run() { __syncwarp(); }
+};
+
+// ---- one stage -------------------------------------------------------------------
+template <int N, int S, class Layout, class Sync>
+__device__ __forceinline__ void fft_stage(cplx (&v)[PlanFor<N>::E], int t, int l, cplx* sm,
+                                          const cplx* __restrict__ tw) {
+    typedef PlanFor<N> P;
+    typedef StageInfo<N, S> SI;
+    constexpr int E = P::E, T = P::T, R = SI::R, L = SI::L, Q = E / R;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        cplx a[R];
+#pragma unroll
+        for (int n = 0; n < R; ++n) a[n] = v[i + n * Q];
+        Dft<R>::run(a);
+        if (SI::LAST) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[i + k * Q] = a[k];
+        } else {
+            const int b = t + T * i;
+            const int bl = b & (L - 1);
+            const int bh = b - bl;  // (b div L) * L
+#pragma unroll
+            for (int k = 1; k < R; ++k) a[k] = a[k] * ld_tab(tw + k * bh);
+            const int base = bl + (bh * R);
+#pragma unroll
+            for (int k = 0; k < R; ++k) sm[Layout::at(base + L * k, l)] = a[k];
+        }
+    }
+    if (!SI::LAST) {
+        Sync::run();
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = sm[Layout::at(t + T * m, l)];
+        Sync::run();
+    }
+}
+
+// Forward DFT of one line.  v[m] <-> position t + T*m on entry and on exit.
+// sm: the CTA's exchange buffer (unused when NS == 1).  tw: W_N^j = exp(-2 pi i j / N).
+template <int N, class Layout, class Sync>
+__device__ __forceinline__ void line_fft(cplx (&v)[PlanFor<N>::E], int t, int l, cplx* sm,
+                                         const cplx* __restrict__ tw) {
+    typedef PlanFor<N> P;
+    fft_stage<N, 0, Layout, Sync>(v, t, l, sm, tw);
+    if (P::NS > 1) fft_stage<N, (P::NS > 1 ? 1 : 0), Layout, Sync>(v, t, l, sm, tw);
+    if (P::NS > 2) fft_stage<N, (P::NS > 2 ? 2 : 0), Layout, Sync>(v, t, l, sm, tw);
+}
+
+}  // namespace gopf

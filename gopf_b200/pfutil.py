@@ -1,0 +1,97 @@
+"""Mirror of the reference's ``pfutil`` hot-path surface over the C ABI.
+
+``FFTWWrapper`` keeps the reference's exported names (pfutil/fftWrap.go:8-95):
+``NewFFTW(n)``, ``Dimensions``, ``FFT``, ``IFFT``, ``Freq``, ``ConjugateNode``.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from ._lib import check, int_array, lib
+
+
+def ProdInt(a) -> int:
+    res = 1
+    for v in a:
+        res *= int(v)
+    return res
+
+
+def NodeIdx(domain_size, idx) -> int:
+    """pfutil.NodeIdx (pfutil/indexPositionConversion.go:14-22)."""
+    if len(domain_size) != len(idx):
+        raise ValueError("util: Domain size and idx has to be of length 2 or 3")
+    out = ctypes.c_int64(0)
+    check(lib().gopf_node_idx(len(domain_size), int_array(domain_size), int_array(idx), ctypes.byref(out)))
+    return out.value
+
+
+def Pos(domain_size, node_num: int):
+    """pfutil.Pos (pfutil/indexPositionConversion.go:37-44)."""
+    out = (ctypes.c_int * 3)()
+    check(lib().gopf_pos(len(domain_size), int_array(domain_size), ctypes.c_int64(node_num), out))
+    return [out[i] for i in range(len(domain_size))]
+
+
+def _c128_ptr(a: np.ndarray):
+    if a.dtype != np.complex128 or not a.flags.c_contiguous:
+        raise TypeError("expected a C-contiguous complex128 array ([]complex128)")
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+class FFTWWrapper:
+    """pfutil.FFTWWrapper over ``gopf_fft_plan`` (transform-level API)."""
+
+    def __init__(self, n, device: int = -1):
+        self.Dimensions = [int(v) for v in n]
+        self._h = ctypes.c_void_p()
+        check(lib().gopf_fft_plan_create(len(self.Dimensions), int_array(self.Dimensions), device,
+                                         ctypes.byref(self._h)))
+
+    def FFT(self, data: np.ndarray) -> np.ndarray:
+        check(lib().gopf_fft_exec(self._h, _c128_ptr(data), -1))
+        return data
+
+    def IFFT(self, data: np.ndarray) -> np.ndarray:
+        check(lib().gopf_fft_exec(self._h, _c128_ptr(data), 1))
+        return data
+
+    def exec_device(self, dev_ptr: int, sign: int, stream: int = 0):
+        check(lib().gopf_fft_exec_device(self._h, ctypes.c_void_p(dev_ptr), sign, ctypes.c_void_p(stream)))
+
+    def Freq(self, i: int):
+        out = (ctypes.c_double * 3)()
+        check(lib().gopf_freq(len(self.Dimensions), int_array(self.Dimensions), ctypes.c_int64(i), out))
+        return [out[k] for k in range(len(self.Dimensions))]
+
+    def freq_device(self, nodes) -> np.ndarray:
+        nodes = np.ascontiguousarray(nodes, dtype=np.int64)
+        out = np.empty((nodes.shape[0], len(self.Dimensions)), dtype=np.float64)
+        check(lib().gopf_fft_freq_device(self._h, nodes.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                         ctypes.c_int64(nodes.shape[0]),
+                                         out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        return out
+
+    def ConjugateNode(self, i: int) -> int:
+        out = ctypes.c_int64(0)
+        check(lib().gopf_conjugate_node(len(self.Dimensions), int_array(self.Dimensions), ctypes.c_int64(i),
+                                        ctypes.byref(out)))
+        return out.value
+
+    def close(self):
+        if self._h:
+            lib().gopf_fft_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def NewFFTW(n, device: int = -1) -> FFTWWrapper:
+    """pfutil.NewFFTW (pfutil/fftWrap.go:16-23)."""
+    return FFTWWrapper(n, device)
