@@ -1,0 +1,453 @@
+// C ABI, part 2: pf.Model / pf.Solver.  Contract: include/gopf_cuda.h.
+#include <cmath>
+#include <cstring>
+
+#include "../../include/gopf_cuda.h"
+#include "solver.h"
+
+using namespace gopf;
+
+struct gopf_model {
+    Model m;
+    int live_solvers = 0;
+};
+
+struct gopf_solver {
+    Solver* s;
+    gopf_model* owner;
+    std::vector<KernelTimer> prof;
+};
+
+static const char* need(const char* p, const char* what) {
+    if (!p) throw Error(std::string(what) + " is NULL");
+    return p;
+}
+
+static void copy_name(const std::string& s, char* buf, int len) {
+    if (!buf || len <= 0) throw Error("name buffer is NULL/empty");
+    std::strncpy(buf, s.c_str(), (size_t)len - 1);
+    buf[len - 1] = '\0';
+}
+
+extern "C" {
+
+int gopf_model_create(gopf_model** out) {
+    GOPF_API_BEGIN
+    if (!out) throw Error("gopf_model_create: out is NULL");
+    *out = new gopf_model;
+    GOPF_API_END
+}
+
+int gopf_model_add_field(gopf_model* m, const char* name, int64_t n_nodes, double* host) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    if (n_nodes <= 0) throw Error("model: Inconsistent length of data");
+    m->m.add_field(need(name, "name"), (size_t)n_nodes, host);
+    GOPF_API_END
+}
+
+int gopf_model_add_scalar(gopf_model* m, const char* name, double re, double im) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    m->m.add_scalar(need(name, "name"), re, im);
+    GOPF_API_END
+}
+
+int gopf_model_add_equation(gopf_model* m, const char* eq) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    m->m.add_equation(need(eq, "equation"));
+    GOPF_API_END
+}
+
+int gopf_model_register_function(gopf_model* m, const char* name, const char* expr) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    m->m.register_function(need(name, "name"), need(expr, "expression"));
+    GOPF_API_END
+}
+
+int gopf_model_register_white_noise(gopf_model* m, const char* name, double strength, uint64_t seed) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    m->m.register_white_noise(need(name, "name"), strength, seed);
+    GOPF_API_END
+}
+
+int gopf_model_register_table_field(gopf_model* m, const char* name, const double* values, int64_t n_steps) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    m->m.register_table_field(need(name, "name"), values, n_steps);
+    GOPF_API_END
+}
+
+int gopf_model_register_spectral_viscosity(gopf_model* m, const char* name, double eps, double threshold, int power) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    UserTerm u;
+    u.name = need(name, "name");
+    u.cls = UserTermClass::Implicit;
+    u.kind = UserTermKind::SpectralViscosity;
+    u.sv.eps = eps;
+    u.sv.threshold = threshold;
+    u.sv.power = power;
+    u.sv.pad = 0;
+    m->m.register_user_term(u);
+    GOPF_API_END
+}
+
+int gopf_model_register_pair_correlation(gopf_model* m, const char* name, int explicit_term, const char* field,
+                                         double prefactor, int laplacian, double eff_temp, int n_peaks,
+                                         const double* plane_density, const double* location, const double* width,
+                                         const int* num_planes) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    if (n_peaks < 0 || n_peaks > GOPF_MAX_PEAKS) throw Error(strf("pair correlation: at most %d peaks", GOPF_MAX_PEAKS));
+    if (n_peaks > 0 && (!plane_density || !location || !width || !num_planes)) throw Error("pair correlation: NULL peak array");
+    UserTerm u;
+    u.name = need(name, "name");
+    u.cls = explicit_term ? UserTermClass::Explicit : UserTermClass::Implicit;
+    u.kind = explicit_term ? UserTermKind::ExplicitPairCorrelation : UserTermKind::PairCorrelation;
+    u.field = field ? field : "";
+    u.prefactor = prefactor;
+    u.laplacian = laplacian != 0;
+    std::memset(&u.pc, 0, sizeof(u.pc));
+    u.pc.prefactor = prefactor;
+    u.pc.eff_temp = eff_temp;
+    u.pc.n_peaks = n_peaks;
+    for (int i = 0; i < n_peaks; ++i) {
+        u.pc.plane_density[i] = plane_density[i];
+        u.pc.location[i] = location[i];
+        u.pc.width[i] = width[i];
+        u.pc.num_planes[i] = (double)num_planes[i];
+    }
+    m->m.register_user_term(u);
+    GOPF_API_END
+}
+
+int gopf_model_register_ideal_mixture(gopf_model* m, const char* name, const char* field, double c3, double c4,
+                                      double prefactor, int laplacian, int register_derived) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    UserTerm u;
+    u.name = need(name, "name");
+    u.cls = UserTermClass::Mixed;
+    u.kind = UserTermKind::IdealMixture;
+    u.field = need(field, "field");
+    u.prefactor = prefactor;
+    u.laplacian = laplacian != 0;
+    m->m.register_user_term(u);
+    if (register_derived) {
+        // IdealMixtureTerm.DerivedField (pairCorrelationTerm.go:144-156): 3*c3'*v*v + 4*c4'*v*v*v,
+        // c3' = -C3/6, c4' = C4/12 (pfc/ideal.go:42-50)
+        const std::string dn = "ideal_mixture_" + u.field + "_nonlin";
+        if (!m->m.is_field_name(dn)) {
+            const std::string v = "re(" + u.field + ")";
+            const std::string e = strf("3.0*(%.17g)*", -c3 / 6.0) + v + "*" + v + strf("+4.0*(%.17g)*", c4 / 12.0) + v +
+                                  "*" + v + "*" + v;
+            m->m.register_function(dn, e);
+        }
+    }
+    GOPF_API_END
+}
+
+static void add_cons_noise_term(gopf_model* m, const char* name, int dim, uint32_t unique_prefix) {
+    if (dim < 1 || dim > 3) throw Error("ConservativeNoise: Dim must be 1..3");
+    UserTerm u;
+    u.name = need(name, "name");
+    u.cls = UserTermClass::Explicit;
+    u.kind = UserTermKind::ConservativeNoise;
+    u.dim = dim;
+    for (int c = 0; c < dim; ++c) u.current_names.push_back(strf("%u_current_%d", unique_prefix, c));  // noise.go:44-46
+    m->m.register_user_term(u);
+}
+
+int gopf_model_register_conservative_noise(gopf_model* m, const char* name, double strength, int dim,
+                                           uint32_t unique_prefix, uint64_t seed) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    add_cons_noise_term(m, name, dim, unique_prefix);
+    for (int c = 0; c < dim; ++c) {  // RequiredDerivedFields (noise.go:85-100)
+        const std::string dn = strf("%u_current_%d", unique_prefix, c);
+        if (!m->m.is_field_name(dn)) {
+            // names start with digits; bypass the reserved-prefix check exactly like the reference (no check there)
+            m->m.register_white_noise(dn, strength, seed + 0x9E3779B97F4A7C15ull * (uint64_t)(c + 1));
+        }
+    }
+    GOPF_API_END
+}
+
+int gopf_model_register_conservative_noise_term(gopf_model* m, const char* name, int dim, uint32_t unique_prefix) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    add_cons_noise_term(m, name, dim, unique_prefix);
+    GOPF_API_END
+}
+
+int gopf_model_register_volume_conserving_lp(gopf_model* m, const char* name, const char* field,
+                                             const char* indicator, double dt) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    UserTerm u;
+    u.name = need(name, "name");
+    u.cls = UserTermClass::Explicit;
+    u.kind = UserTermKind::VolumeConservingLP;
+    u.field = need(field, "field");
+    u.indicator = need(indicator, "indicator");
+    u.dt = dt;
+    m->m.register_user_term(u);
+    GOPF_API_END
+}
+
+int gopf_model_register_squared_gradient(gopf_model* m, const char* name, const char* field, double factor) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    UserTerm u;
+    u.name = need(name, "name");
+    u.cls = UserTermClass::Explicit;
+    u.kind = UserTermKind::SquaredGradient;
+    u.field = need(field, "field");
+    u.prefactor = factor;
+    m->m.register_user_term(u);
+    GOPF_API_END
+}
+
+int gopf_model_init(gopf_model* m) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    m->m.init();
+    GOPF_API_END
+}
+
+int gopf_model_num_fields(gopf_model* m, int* n) {
+    GOPF_API_BEGIN
+    if (!m || !n) throw Error("NULL argument");
+    *n = (int)m->m.fields.size();
+    GOPF_API_END
+}
+
+int gopf_model_num_derived_fields(gopf_model* m, int* n) {
+    GOPF_API_BEGIN
+    if (!m || !n) throw Error("NULL argument");
+    *n = (int)m->m.derived.size();
+    GOPF_API_END
+}
+
+int gopf_model_derived_field_name(gopf_model* m, int index, char* buf, int buf_len) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    if (index < 0 || index >= (int)m->m.derived.size()) throw Error("derived field index out of range");
+    copy_name(m->m.derived[index].name, buf, buf_len);
+    GOPF_API_END
+}
+
+int gopf_model_num_terms(gopf_model* m, int eq, int* n_terms, int* n_denum) {
+    GOPF_API_BEGIN
+    if (!m || !n_terms || !n_denum) throw Error("NULL argument");
+    if (!m->m.initialised) throw Error("Model not initialized");
+    if (eq < 0 || eq >= (int)m->m.compiled.size()) throw Error("equation index out of range");
+    *n_terms = (int)m->m.compiled[eq].rhs.size();
+    *n_denum = (int)m->m.compiled[eq].den.size();
+    GOPF_API_END
+}
+
+int gopf_model_eq_number(gopf_model* m, const char* field_name, int* eq) {
+    GOPF_API_BEGIN
+    if (!m || !eq) throw Error("NULL argument");
+    *eq = m->m.eq_number(need(field_name, "field_name"));
+    GOPF_API_END
+}
+
+int gopf_model_destroy(gopf_model* m) {
+    GOPF_API_BEGIN
+    if (m) {
+        if (m->live_solvers > 0) throw Error("gopf_model_destroy: destroy the model's solvers first");
+        delete m;
+    }
+    GOPF_API_END
+}
+
+// pf/vandeven.go:13-27
+int gopf_vandeven_table(int order, double* out, int n) {
+    GOPF_API_BEGIN
+    if (!out || n != 1000) throw Error("gopf_vandeven_table: the reference table has exactly 1000 points");
+    if (order < 1) throw Error("gopf_vandeven_table: order must be >= 1");
+    out[0] = 1.0;
+    const double prefactor = std::tgamma((double)(2 * order)) / (std::tgamma((double)order) * std::tgamma((double)order));
+    const double dx = 1.0 / 999.0;
+    for (int i = 1; i < 1000; ++i) {
+        const double x = (double)i * dx;
+        const double i2 = std::pow(x * (1 - x), (double)(order - 1));
+        const double x1 = x - dx;
+        const double i1 = std::pow(x1 * (1.0 - x1), (double)(order - 1));
+        out[i] = out[i - 1] - prefactor * 0.5 * (i1 + i2) * dx;
+    }
+    GOPF_API_END
+}
+
+int gopf_solver_create(gopf_model* m, int rank, const int* domain_size, double dt, int device, gopf_solver** out) {
+    GOPF_API_BEGIN
+    if (!m || !domain_size || !out) throw Error("gopf_solver_create: NULL argument");
+    *out = nullptr;
+    Solver* s = new Solver(&m->m, rank, domain_size, dt, device);
+    gopf_solver* h = new gopf_solver;
+    h->s = s;
+    h->owner = m;
+    m->live_solvers++;
+    *out = h;
+    GOPF_API_END
+}
+
+int gopf_solver_set_stepper(gopf_solver* s, const char* name) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->set_stepper(need(name, "name"));
+    GOPF_API_END
+}
+
+int gopf_solver_set_filter(gopf_solver* s, const double* table, int n) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->set_filter(table, n);
+    GOPF_API_END
+}
+
+int gopf_solver_set_stream(gopf_solver* s, void* stream) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->set_stream(reinterpret_cast<cudaStream_t>(stream));
+    GOPF_API_END
+}
+
+int gopf_solver_propagate(gopf_solver* s, int nsteps) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->propagate(nsteps);
+    GOPF_API_END
+}
+
+int gopf_solver_upload(gopf_solver* s) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->upload();
+    GOPF_API_END
+}
+
+int gopf_solver_step(gopf_solver* s, int nsteps) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->step(nsteps);
+    GOPF_API_END
+}
+
+int gopf_solver_download(gopf_solver* s) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->download();
+    GOPF_API_END
+}
+
+int gopf_solver_synchronize(gopf_solver* s) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->synchronize();
+    GOPF_API_END
+}
+
+int gopf_solver_get_time(gopf_solver* s, double* t) {
+    GOPF_API_BEGIN
+    if (!s || !t) throw Error("NULL argument");
+    *t = s->s->get_time();
+    GOPF_API_END
+}
+
+int gopf_solver_is_fused(gopf_solver* s, int* fused) {
+    GOPF_API_BEGIN
+    if (!s || !fused) throw Error("NULL argument");
+    *fused = s->s->fused() ? 1 : 0;
+    GOPF_API_END
+}
+
+int gopf_solver_force_generic(gopf_solver* s, int on) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->force_generic(on != 0);
+    GOPF_API_END
+}
+
+int gopf_solver_kernel_launches(gopf_solver* s, int64_t* n, int reset) {
+    GOPF_API_BEGIN
+    if (!s || !n) throw Error("NULL argument");
+    *n = s->s->kernel_launches();
+    if (reset) s->s->reset_launch_count();
+    GOPF_API_END
+}
+
+int gopf_solver_get_spectrum(gopf_solver* s, int index, double* host) {
+    GOPF_API_BEGIN
+    if (!s || !host) throw Error("NULL argument");
+    if (index < 0 || index >= GOPF_MAX_SPECTRA || !s->s->spectrum(index)) throw Error("spectrum not resident on the device");
+    s->s->synchronize();
+    GOPF_CUDA(cudaMemcpy(host, s->s->spectrum(index), sizeof(cplx) * s->s->plan().N, cudaMemcpyDeviceToHost));
+    GOPF_API_END
+}
+
+int gopf_solver_lp_multiplier(gopf_solver* s, int slot, double* value) {
+    GOPF_API_BEGIN
+    if (!s || !value) throw Error("NULL argument");
+    *value = s->s->lp_multiplier(slot);
+    GOPF_API_END
+}
+
+int gopf_solver_profile_begin(gopf_solver* s) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->set_profiling(true);
+    GOPF_API_END
+}
+
+int gopf_solver_profile_end(gopf_solver* s, int* n_kernels) {
+    GOPF_API_BEGIN
+    if (!s || !n_kernels) throw Error("NULL argument");
+    s->prof = s->s->collect_profile();
+    s->s->set_profiling(false);
+    *n_kernels = (int)s->prof.size();
+    GOPF_API_END
+}
+
+int gopf_solver_profile_get(gopf_solver* s, int i, char* name, int name_len, double* total_ms, int64_t* launches,
+                            double* bytes_per_launch) {
+    GOPF_API_BEGIN
+    if (!s || !total_ms || !launches || !bytes_per_launch) throw Error("NULL argument");
+    if (i < 0 || i >= (int)s->prof.size()) throw Error("profile index out of range");
+    copy_name(s->prof[i].name, name, name_len);
+    *total_ms = s->prof[i].total_ms;
+    *launches = s->prof[i].launches;
+    *bytes_per_launch = s->prof[i].bytes_per_launch;
+    GOPF_API_END
+}
+
+int gopf_solver_destroy(gopf_solver* s) {
+    GOPF_API_BEGIN
+    if (s) {
+        delete s->s;
+        if (s->owner) s->owner->live_solvers--;
+        delete s;
+    }
+    GOPF_API_END
+}
+
+int gopf_host_alloc(int64_t bytes, void** out) {
+    GOPF_API_BEGIN
+    if (!out || bytes <= 0) throw Error("gopf_host_alloc: bad argument");
+    GOPF_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    GOPF_API_END
+}
+
+int gopf_host_free(void* p) {
+    GOPF_API_BEGIN
+    if (p) GOPF_CUDA(cudaFreeHost(p));
+    GOPF_API_END
+}
+
+}  // extern "C"

@@ -1,12 +1,14 @@
 // Axis-pass kernels: one HBM read + one HBM write of every 16-byte cell per pass
-// (B_T = 32*rank bytes per cell per transform).  Pointwise work is
-// attached through load/store functors so it costs no extra HBM traffic.
+// (B_T = 32*rank bytes per cell per transform).  Pointwise work rides
+// on the load (PassIO::load_kind) or the store (scale) so it costs no extra HBM
+// traffic.
 //
 // Array view for a pass along `axis` of a row-major [n0][n1][n2] array:
 //   [A][N][B], element (a, j, b) at (a*N + j)*B + b, N = n[axis],
 //   B = product of faster extents (inner stride), A = product of slower extents.
 #pragma once
 #include "fft_engine.cuh"
+#include "step_program.h"
 
 namespace gopf {
 
@@ -26,23 +28,111 @@ inline PassGeom make_geom(int n0, int n1, int n2, int axis) {
     return g;
 }
 
-// ---- functors ------------------------------------------------------------------
-struct LoadPlain {
-    const cplx* __restrict__ in;
-    __device__ __forceinline__ void begin(const PassGeom&, long long, long long) {}
-    __device__ __forceinline__ cplx operator()(size_t idx, int) const { return in[idx]; }
-};
-struct StorePlain {
-    cplx* __restrict__ out;
-    double scale;
-    __device__ __forceinline__ void begin(const PassGeom&, long long, long long) {}
-    __device__ __forceinline__ void operator()(size_t idx, int, cplx v) const { out[idx] = mk(v.x * scale, v.y * scale); }
+// Reference k-table geometry.  Freq() decomposes the node number with
+// Dimensions[1] / Dimensions[0] (pfutil/fftWrap.go:42-54), which matches the FFTW
+// row-major layout for every 2-D shape and for cubic 3-D shapes only.
+struct FreqGeom {
+    int rank;
+    int d0, d1, d2;  // reference Dimensions[0..2] (d2 = 1 for rank 2)
 };
 
+// Literal restatement of FFTWWrapper.Freq for node i (pfutil/fftWrap.go:57-74).
+__host__ __device__ inline void ref_freq(const FreqGeom& g, long long i, double* res) {
+    long long c = i % g.d1;
+    long long r = (i / g.d1) % g.d0;
+    res[1] = (double)c / (double)g.d1;
+    res[0] = (double)r / (double)g.d0;
+    if (g.rank > 2) {
+        long long d = i / ((long long)g.d0 * g.d1);
+        res[2] = (double)d / (double)g.d2;
+    }
+    for (int k = 0; k < g.rank; ++k)
+        if (res[k] > 0.5) res[k] -= 1.0;
+}
+
+struct RealPtrs {
+    const cplx* r[GOPF_MAX_FIELDS];  // real-space fields (complex-carrying, like the reference)
+};
+
+// What a pass reads and writes.  One POD for every use keeps the number of kernel
+// instantiations at (lengths x tile widths) instead of multiplying it by functor types.
+enum LoadKind {
+    LK_PLAIN = 0,     // in[idx]
+    LK_DERIVED = 1,   // derived-field value from the real-space fields (model.go:237-241)
+    LK_GRADIENT = 2,  // i 2 pi f_comp * in[idx], +0.5 Nyquist zeroed (squareGradientTerm.go:45-50)
+    LK_SUM_SQUARES = 3  // sum_d g_d[idx]^2 (squareGradientTerm.go:53-62, summed before the transform)
+};
+
+struct PassIO {
+    const cplx* in;
+    cplx* out;
+    double scale;  // applied on store (1/N on the last inverse pass, sliceOperations.go:34-40)
+    int inv;       // 0: forward (sign -1), 1: inverse (sign +1)
+    int load_kind;
+    // LK_DERIVED
+    DevDerived D;
+    RealPtrs R;
+    unsigned long long step;
+    // LK_GRADIENT
+    FreqGeom fg;
+    int comp;
+    // LK_SUM_SQUARES
+    int dim;
+    const cplx* g[3];
+};
+
+inline PassIO plain_io(const cplx* in, cplx* out, bool inverse, double scale) {
+    PassIO io;
+    io.in = in;
+    io.out = out;
+    io.scale = scale;
+    io.inv = inverse ? 1 : 0;
+    io.load_kind = LK_PLAIN;
+    io.step = 0;
+    io.comp = 0;
+    io.dim = 0;
+    io.D.kind = 0;
+    io.D.n_factors = 0;
+    io.D.n_ops = 0;
+    return io;
+}
+
+__device__ __forceinline__ cplx pass_load(const PassIO& io, size_t idx) {
+    cplx x;
+    if (io.load_kind == LK_PLAIN) {
+        x = io.in[idx];
+    } else if (io.load_kind == LK_DERIVED) {
+        x = eval_derived(io.D, [&](int f) -> cplx { return io.R.r[f][idx]; }, io.step, idx);
+    } else if (io.load_kind == LK_GRADIENT) {
+        double f[3] = {0.0, 0.0, 0.0};
+        ref_freq(io.fg, (long long)idx, f);
+        double fd = f[io.comp];
+        if (fabs(fd - 0.5) < 1e-10) fd = 0.0;
+        const double w = 2.0 * GOPF_PI * fd;
+        const cplx u = io.in[idx];
+        x = mk(-u.y * w, u.x * w);
+    } else {
+        cplx a = io.g[0][idx];
+        x = a * a;
+        a = io.g[1][idx];
+        x += a * a;
+        if (io.dim > 2) {
+            a = io.g[2][idx];
+            x += a * a;
+        }
+    }
+    return io.inv ? cswap(x) : x;
+}
+
+__device__ __forceinline__ void pass_store(const PassIO& io, size_t idx, cplx v) {
+    if (io.inv) v = cswap(v);
+    io.out[idx] = mk(v.x * io.scale, v.y * io.scale);
+}
+
 // ---- strided axis (B > 1): tile = N x TX, TX adjacent lines ---------------------
-template <int N, int TX, bool INV, class Ld, class St>
+template <int N, int TX>
 __global__ void __launch_bounds__(PlanFor<N>::T* TX)
-    k_pass_strided(PassGeom g, Ld ld, St st, const cplx* __restrict__ tw) {
+    k_pass_strided(const PassGeom g, const __grid_constant__ PassIO io, const cplx* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char gopf_smem_raw[];
     cplx* sm = reinterpret_cast<cplx*>(gopf_smem_raw);
     constexpr int E = PlanFor<N>::E, T = PlanFor<N>::T;
@@ -53,21 +143,12 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX)
     const long long a = tile / tilesB;
     const long long b = (tile - a * tilesB) * TX + l;
     const size_t base = (size_t)a * N * g.B + b;
-    ld.begin(g, a, b);
-    st.begin(g, a, b);
     cplx v[E];
 #pragma unroll
-    for (int m = 0; m < E; ++m) {
-        const int j = t + T * m;
-        cplx x = ld(base + (size_t)j * g.B, j);
-        v[m] = INV ? cswap(x) : x;
-    }
+    for (int m = 0; m < E; ++m) v[m] = pass_load(io, base + (size_t)(t + T * m) * g.B);
     line_fft<N, LayoutInterleaved<TX>, SyncCta>(v, t, l, sm, tw);
 #pragma unroll
-    for (int m = 0; m < E; ++m) {
-        const int j = t + T * m;
-        st(base + (size_t)j * g.B, j, INV ? cswap(v[m]) : v[m]);
-    }
+    for (int m = 0; m < E; ++m) pass_store(io, base + (size_t)(t + T * m) * g.B, v[m]);
 }
 
 // ---- contiguous axis (B == 1): LINES lines per CTA, position fastest ------------
@@ -80,9 +161,9 @@ struct ContigCfg {
     };
 };
 
-template <int N, bool INV, class Ld, class St>
+template <int N>
 __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES)
-    k_pass_contig(PassGeom g, Ld ld, St st, const cplx* __restrict__ tw) {
+    k_pass_contig(const PassGeom g, const __grid_constant__ PassIO io, const cplx* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char gopf_smem_raw[];
     cplx* sm = reinterpret_cast<cplx*>(gopf_smem_raw);
     constexpr int E = PlanFor<N>::E, T = PlanFor<N>::T, LINES = ContigCfg<N>::LINES;
@@ -92,136 +173,89 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES)
     const bool live = line < g.A;
     if (!live) line = g.A - 1;
     const size_t base = (size_t)line * N;
-    ld.begin(g, line, 0);
-    st.begin(g, line, 0);
     cplx v[E];
 #pragma unroll
-    for (int m = 0; m < E; ++m) {
-        const int j = p + T * m;
-        cplx x = ld(base + j, j);
-        v[m] = INV ? cswap(x) : x;
-    }
+    for (int m = 0; m < E; ++m) v[m] = pass_load(io, base + p + T * m);
     if (ContigCfg<N>::WARP_SYNC)
         line_fft<N, LayoutPadded<N>, SyncWarp>(v, p, l, sm, tw);
     else
         line_fft<N, LayoutPadded<N>, SyncCta>(v, p, l, sm, tw);
     if (live) {
 #pragma unroll
-        for (int m = 0; m < E; ++m) {
-            const int j = p + T * m;
-            st(base + j, j, INV ? cswap(v[m]) : v[m]);
-        }
+        for (int m = 0; m < E; ++m) pass_store(io, base + p + T * m, v[m]);
     }
 }
 
-// ---- any length (non power of two): O(n^2) DFT per line, out of place -----------
-// Completes the FFTWWrapper contract (FFTW accepts any n); not a performance path.
-template <bool INV>
-__global__ void k_pass_dft_generic(PassGeom g, const cplx* __restrict__ in, cplx* __restrict__ out,
-                                   const cplx* __restrict__ tw, double scale) {
-    const long long total = g.A * g.N * g.B;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long b = i % g.B;
-        const long long k = (i / g.B) % g.N;
-        const long long a = i / (g.B * g.N);
-        const cplx* src = in + (size_t)a * g.N * g.B + b;
-        double sx = 0.0, sy = 0.0;
-        long long e = 0;  // (j*k) mod N
-        for (int j = 0; j < g.N; ++j) {
-            cplx w = tw[e];
-            if (INV) w.y = -w.y;
-            cplx x = src[(size_t)j * g.B];
-            sx += x.x * w.x - x.y * w.y;
-            sy += x.x * w.y + x.y * w.x;
-            e += k;
-            if (e >= g.N) e -= g.N;
-        }
-        out[i] = mk(sx * scale, sy * scale);
-    }
-}
-
-// ---- launch helpers --------------------------------------------------------------
+// ---- launch-side helpers ------------------------------------------------------------
 inline int pick_tx(int N, long long B, int want) {
     int tx = want;
-    while (tx > 1 && ((long long)N * tx * 16 > 128 * 1024)) tx >>= 1;  // keep >= 1 CTA of headroom
+    while (tx > 1 && ((long long)N * tx * 16 > 128 * 1024)) tx >>= 1;
     while (tx > 1 && (B % tx) != 0) tx >>= 1;
     if (tx < 2) tx = (B % 2 == 0) ? 2 : 1;
     return tx;
 }
 
-template <int N, int TX, bool INV, class Ld, class St>
-cudaError_t launch_strided_n_tx(const PassGeom& g, Ld ld, St st, const cplx* tw, cudaStream_t s) {
+template <int N, int TX>
+cudaError_t launch_strided_n_tx(const PassGeom& g, const PassIO& io, const cplx* tw, cudaStream_t s) {
     constexpr int T = PlanFor<N>::T;
     const size_t smem = PlanFor<N>::NS > 1 ? (size_t)N * TX * sizeof(cplx) : 0;
-    auto kern = k_pass_strided<N, TX, INV, Ld, St>;
+    auto kern = k_pass_strided<N, TX>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const long long tiles = g.A * (g.B / TX);
-    kern<<<(unsigned)tiles, T * TX, smem, s>>>(g, ld, st, tw);
+    kern<<<(unsigned)tiles, T * TX, smem, s>>>(g, io, tw);
     return cudaGetLastError();
 }
 
-template <int N, bool INV, class Ld, class St>
-cudaError_t launch_strided_n(const PassGeom& g, int tx, Ld ld, St st, const cplx* tw, cudaStream_t s) {
+template <int N>
+cudaError_t launch_strided_n(const PassGeom& g, int tx, const PassIO& io, const cplx* tw, cudaStream_t s) {
     constexpr size_t line_bytes = (size_t)N * sizeof(cplx);
     switch (tx) {
-        case 2: return launch_strided_n_tx<N, 2, INV>(g, ld, st, tw, s);
+        case 2: return launch_strided_n_tx<N, 2>(g, io, tw, s);
         case 4:
-            if constexpr (line_bytes * 4 <= 200 * 1024) return launch_strided_n_tx<N, 4, INV>(g, ld, st, tw, s);
+            if constexpr (line_bytes * 4 <= 200 * 1024) return launch_strided_n_tx<N, 4>(g, io, tw, s);
             break;
         case 8:
-            if constexpr (line_bytes * 8 <= 200 * 1024) return launch_strided_n_tx<N, 8, INV>(g, ld, st, tw, s);
+            if constexpr (line_bytes * 8 <= 200 * 1024) return launch_strided_n_tx<N, 8>(g, io, tw, s);
             break;
         case 16:
             if constexpr (line_bytes * 16 <= 200 * 1024 && PlanFor<N>::T * 16 <= 1024)
-                return launch_strided_n_tx<N, 16, INV>(g, ld, st, tw, s);
+                return launch_strided_n_tx<N, 16>(g, io, tw, s);
             break;
         default: break;
     }
     return cudaErrorInvalidConfiguration;
 }
 
-template <int N, bool INV, class Ld, class St>
-cudaError_t launch_contig_n(const PassGeom& g, Ld ld, St st, const cplx* tw, cudaStream_t s) {
+template <int N>
+cudaError_t launch_contig_n(const PassGeom& g, const PassIO& io, const cplx* tw, cudaStream_t s) {
     constexpr int T = ContigCfg<N>::T, LINES = ContigCfg<N>::LINES;
     const size_t smem = PlanFor<N>::NS > 1 ? (size_t)LayoutPadded<N>::elems(N, LINES) * sizeof(cplx) : 0;
-    auto kern = k_pass_contig<N, INV, Ld, St>;
+    auto kern = k_pass_contig<N>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const long long blocks = (g.A + LINES - 1) / LINES;
-    kern<<<(unsigned)blocks, T * LINES, smem, s>>>(g, ld, st, tw);
+    kern<<<(unsigned)blocks, T * LINES, smem, s>>>(g, io, tw);
     return cudaGetLastError();
+}
+
+template <int N>
+cudaError_t launch_pass_n(const PassGeom& g, int tx_want, const PassIO& io, const cplx* tw, cudaStream_t s) {
+    if (g.B == 1) return launch_contig_n<N>(g, io, tw, s);
+    const int tx = pick_tx(N, g.B, tx_want);
+    if (tx < 2) return cudaErrorInvalidValue;
+    return launch_strided_n<N>(g, tx, io, tw, s);
 }
 
 inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 inline bool fast_length(int n) { return is_pow2(n) && n >= 2 && n <= 4096; }
 
-#define GOPF_FOR_EACH_N(X) X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
-
-// One pass along g.axis with the given functors (power-of-two length only).
-template <bool INV, class Ld, class St>
-cudaError_t launch_pass(const PassGeom& g, int tx_want, Ld ld, St st, const cplx* tw, cudaStream_t s) {
-    if (g.B == 1) {
-        switch (g.N) {
-#define X(n) case n: return launch_contig_n<n, INV>(g, ld, st, tw, s);
-            GOPF_FOR_EACH_N(X)
-#undef X
-            default: return cudaErrorInvalidValue;
-        }
-    }
-    const int tx = pick_tx(g.N, g.B, tx_want);
-    if (tx < 2) return cudaErrorInvalidValue;
-    switch (g.N) {
-#define X(n) case n: return launch_strided_n<n, INV>(g, tx, ld, st, tw, s);
-        GOPF_FOR_EACH_N(X)
-#undef X
-        default: return cudaErrorInvalidValue;
-    }
-}
+// One pass along g.axis (power-of-two length 2..4096).  Defined in pass_launch.cu; the
+// instantiations are spread over pass_inst_*.cu so they compile in parallel.
+cudaError_t launch_pass(const PassGeom& g, int tx_want, const PassIO& io, const cplx* tw, cudaStream_t s);
 
 }  // namespace gopf

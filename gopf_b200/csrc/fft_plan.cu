@@ -10,6 +10,33 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* get_last_error() { return g_last_error.c_str(); }
 
+// ---- any length (non power of two): O(n^2) DFT per line, out of place -----------
+// Completes the FFTWWrapper contract (FFTW accepts any n); not a performance path.
+template <bool INV>
+__global__ void k_pass_dft_generic(PassGeom g, const cplx* __restrict__ in, cplx* __restrict__ out,
+                                   const cplx* __restrict__ tw, double scale) {
+    const long long total = g.A * g.N * g.B;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i % g.B;
+        const long long k = (i / g.B) % g.N;
+        const long long a = i / (g.B * g.N);
+        const cplx* src = in + (size_t)a * g.N * g.B + b;
+        double sx = 0.0, sy = 0.0;
+        long long e = 0;  // (j*k) mod N
+        for (int j = 0; j < g.N; ++j) {
+            cplx w = tw[e];
+            if (INV) w.y = -w.y;
+            cplx x = src[(size_t)j * g.B];
+            sx += x.x * w.x - x.y * w.y;
+            sy += x.x * w.y + x.y * w.x;
+            e += k;
+            if (e >= g.N) e -= g.N;
+        }
+        out[i] = mk(sx * scale, sy * scale);
+    }
+}
+
 __global__ void k_fill_freq(double* f, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -157,10 +184,7 @@ void FftPlan::exec_device(cplx* data, int sign, cudaStream_t s) {
         if (extent(axis) <= 1) continue;
         if (axis_fast(axis)) {
             const PassGeom g = geom(axis);
-            LoadPlain ld{data};
-            StorePlain st{data, 1.0};
-            cudaError_t e = (sign < 0) ? launch_pass<false>(g, tx_want, ld, st, twiddle(axis), s)
-                                       : launch_pass<true>(g, tx_want, ld, st, twiddle(axis), s);
+            cudaError_t e = launch_pass(g, tx_want, plain_io(data, data, sign > 0, 1.0), twiddle(axis), s);
             if (e != cudaSuccess)
                 throw Error(strf("fft exec: pass along axis %d (n=%d) failed: %s", axis, g.N, cudaGetErrorString(e)));
         } else {

@@ -1,0 +1,20 @@
+// Dispatch of one axis pass to the per-length instantiations (pass_inst_*.cu).
+#include "fft_kernels.cuh"
+
+namespace gopf {
+
+#define GOPF_DECL(n) cudaError_t launch_pass_##n(const PassGeom&, int, const PassIO&, const cplx*, cudaStream_t);
+GOPF_DECL(2) GOPF_DECL(4) GOPF_DECL(8) GOPF_DECL(16) GOPF_DECL(32) GOPF_DECL(64) GOPF_DECL(128) GOPF_DECL(256)
+GOPF_DECL(512) GOPF_DECL(1024) GOPF_DECL(2048) GOPF_DECL(4096)
+#undef GOPF_DECL
+
+cudaError_t launch_pass(const PassGeom& g, int tx_want, const PassIO& io, const cplx* tw, cudaStream_t s) {
+    switch (g.N) {
+#define X(n) case n: return launch_pass_##n(g, tx_want, io, tw, s);
+        X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
+#undef X
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace gopf

@@ -1,0 +1,698 @@
+// Solver implementation (see solver.h).  Citations: /root/reference.
+#include "solver.h"
+
+#include <cstring>
+
+#include "fused_launch.h"
+
+namespace gopf {
+
+// ---- small kernels -------------------------------------------------------------------
+// generic pointwise update over every k (any shape, literal Freq from the node number)
+__global__ void __launch_bounds__(256)
+    k_update_generic(const __grid_constant__ DevKProgram P, SpectraPtrs sp, FreqGeom fg, long long n) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        double f[3] = {0.0, 0.0, 0.0};
+        ref_freq(fg, idx, f);
+        const KPoint kp = make_kpoint(f[0], f[1], f[2]);
+        auto get = [&](int b) -> cplx { return sp.s[b][idx]; };
+        for (int i = 0; i < P.n_fields; ++i) {
+            const cplx d = sp.s[i][idx];
+            sp.s[i][idx] = euler_update(P, i, kp, d, get);  // later equations read the updated value
+        }
+    }
+}
+
+__global__ void k_scale(cplx* a, double s, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        a[i] = mk(a[i].x * s, a[i].y * s);
+}
+
+__global__ void __launch_bounds__(256)
+    k_eval_derived(const __grid_constant__ DevDerived D, RealPtrs R, cplx* out, unsigned long long step, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = eval_derived(D, [&](int f) -> cplx { return R.r[f][i]; }, step, i);
+}
+
+// VolumeConservingLP.OnStepFinished (pf/volumeConserving.go:31-50).  sum_i Re c_i is the
+// DC mode of the updated spectrum, the indicator integral the DC mode of the indicator
+// spectrum.  state = {multiplier, current integral, first-update flag}
+__global__ void k_volume_lp_update(double* state, const cplx* field_spec, const cplx* indicator_spec, double dt) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double field_integral = field_spec[0].x;
+        const double indicator_integral = indicator_spec[0].x;
+        if (state[2] != 0.0) {
+            state[1] = field_integral;
+            state[2] = 0.0;
+        } else {
+            const double delta = field_integral - state[1];
+            state[1] = field_integral;
+            state[0] = state[0] - delta / (dt * indicator_integral);
+        }
+    }
+}
+
+// RK4 pointwise kernels (pf/rk4.go:58-68, 77-84, 87-96, 101-111, 123-126)
+__global__ void __launch_bounds__(256)
+    k_rk4_rhs(const __grid_constant__ DevKProgram P, SpectraPtrs sp, SpectraPtrs kout, FreqGeom fg, long long n) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        double f[3] = {0.0, 0.0, 0.0};
+        ref_freq(fg, idx, f);
+        const KPoint kp = make_kpoint(f[0], f[1], f[2]);
+        auto get = [&](int b) -> cplx { return sp.s[b][idx]; };
+        for (int i = 0; i < P.n_fields; ++i) {
+            const DevEquation& q = P.eq[i];
+            cplx rhs = mk(0.0, 0.0);
+            for (int j = 0; j < q.n_rhs; ++j) rhs += eval_term(P, q.rhs[j], kp, get);
+            kout.s[i][idx] = rhs;
+        }
+    }
+}
+
+// mode 0: final += fdt*k ; field = initial                       (PrepareNextCorrection)
+// mode 1: field = (field + fdt*k) / (1 - fdt*den)                 (correction, first loop)
+// mode 2: final /= (1 - fdt*den); field = final; filter           (end of Step)
+__global__ void __launch_bounds__(256)
+    k_rk4_point(const __grid_constant__ DevKProgram P, int mode, double fdt, SpectraPtrs field, SpectraPtrs initial,
+                SpectraPtrs final_, SpectraPtrs kf, FreqGeom fg, long long n) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        KPoint kp;
+        if (mode != 0) {
+            double f[3] = {0.0, 0.0, 0.0};
+            ref_freq(fg, idx, f);
+            kp = make_kpoint(f[0], f[1], f[2]);
+        }
+        auto get = [&](int b) -> cplx { return field.s[b][idx]; };
+        for (int i = 0; i < P.n_fields; ++i) {
+            if (mode == 0) {
+                const cplx k = kf.s[i][idx];
+                cplx fv = final_.s[i][idx];
+                fv = mk(fv.x + fdt * k.x, fv.y + fdt * k.y);
+                final_.s[i][idx] = fv;
+                field.s[i][idx] = initial.s[i][idx];
+                continue;
+            }
+            const DevEquation& q = P.eq[i];
+            cplx den = mk(0.0, 0.0);
+            for (int j = 0; j < q.n_den; ++j) den += eval_term(P, q.den[j], kp, get);
+            const cplx dn = mk(1.0 - fdt * den.x, -fdt * den.y);
+            if (mode == 1) {
+                const cplx k = kf.s[i][idx];
+                cplx fv = field.s[i][idx];
+                fv = mk(fv.x + fdt * k.x, fv.y + fdt * k.y);
+                field.s[i][idx] = cdiv(fv, dn);
+            } else {
+                cplx fv = cdiv(final_.s[i][idx], dn);
+                final_.s[i][idx] = fv;
+                if (P.filter) {
+                    const double s = filter_eval(P.filter, P.filter_n, kp.frad * 2.0 / GOPF_PI);
+                    fv = mk(fv.x * s, fv.y * s);
+                }
+                field.s[i][idx] = fv;
+            }
+        }
+    }
+}
+
+static unsigned grid_for(long long n) {
+    long long blocks = (n + 255) / 256;
+    const long long cap = 148LL * 16;
+    return (unsigned)(blocks < cap ? blocks : cap);
+}
+
+// ---- construction --------------------------------------------------------------------
+Solver::Solver(Model* m, int rank, const int* n, double dt, int device) : m_(m), dt_(dt) {
+    if (!m) throw Error("solver: model is NULL");
+    if (rank != 2 && rank != 3)
+        throw Error(strf("solver: rank must be 2 or 3 (got %d); FFTWWrapper.Freq indexes res[1] (fftWrap.go:61)", rank));
+    m_->init();  // NewSolver calls m.Init() (solver.go:42)
+    plan_.reset(new FftPlan(rank, n, device));
+    for (const HostField& f : m_->fields)  // solver.go:55-60
+        if (f.n != plan_->N) throw Error("solver: Inconsistent domain size and number of grid points");
+    std::memset(&S_, 0, sizeof(S_));
+    std::memset(&R_, 0, sizeof(R_));
+    for (int i = 0; i < GOPF_MAX_FIELDS; ++i) Rw_[i] = rk_initial_[i] = rk_final_[i] = rk_k_[i] = nullptr;
+    for (int i = 0; i < 3; ++i) sg_tmp_[i] = nullptr;
+    for (int i = 0; i < GOPF_MAX_SPECTRA; ++i) d_table_[i] = nullptr;
+    decide_path();
+}
+
+Solver::~Solver() {
+    cudaSetDevice(plan_->device);
+    for (int i = 0; i < GOPF_MAX_SPECTRA; ++i)
+        if (S_.s[i]) cudaFree(S_.s[i]);
+    for (int i = 0; i < GOPF_MAX_FIELDS; ++i) {
+        if (Rw_[i]) cudaFree(Rw_[i]);
+        if (rk_initial_[i]) cudaFree(rk_initial_[i]);
+        if (rk_final_[i]) cudaFree(rk_final_[i]);
+        if (rk_k_[i]) cudaFree(rk_k_[i]);
+    }
+    for (int i = 0; i < 3; ++i)
+        if (sg_tmp_[i]) cudaFree(sg_tmp_[i]);
+    for (int i = 0; i < GOPF_MAX_SPECTRA; ++i)
+        if (d_table_[i]) cudaFree(d_table_[i]);
+    if (W_) cudaFree(W_);
+    if (d_filter_) cudaFree(d_filter_);
+    if (d_lp_state_) cudaFree(d_lp_state_);
+    for (KernelTimer& t : timers_)
+        for (auto& ev : t.events) {
+            cudaEventDestroy(ev.first);
+            cudaEventDestroy(ev.second);
+        }
+}
+
+void Solver::synchronize() {
+    plan_->use_device();
+    GOPF_CUDA(cudaStreamSynchronize(stream()));
+}
+
+void Solver::set_stepper(const std::string& name) {
+    if (name == "euler") stepper_ = StepperKind::Euler;
+    else if (name == "rk4") stepper_ = StepperKind::RK4;
+    else throw Error("Unknown stepper scheme");  // solver.go:101
+    current_step_ = 0;  // SetStepper builds a fresh stepper struct (solver.go:90-99)
+    decide_path();
+}
+
+void Solver::force_generic(bool on) {
+    allow_fused_ = !on;
+    decide_path();
+}
+
+void Solver::set_filter(const double* table, int n) {
+    plan_->use_device();
+    if (d_filter_) {
+        cudaFree(d_filter_);
+        d_filter_ = nullptr;
+    }
+    filter_n_ = 0;
+    if (table && n > 1) {
+        GOPF_CUDA(cudaMalloc(&d_filter_, sizeof(double) * n));
+        GOPF_CUDA(cudaMemcpy(d_filter_, table, sizeof(double) * n, cudaMemcpyHostToDevice));
+        filter_n_ = n;
+    }
+    prog_dirty_ = true;
+}
+
+// which derived fields are transformed, and whether the single-field fused path applies
+void Solver::decide_path() {
+    fused_ = false;
+    fused_derived_ = -1;
+    w_valid_ = false;
+    const int F = (int)m_->fields.size();
+    int n_used = 0, used = -1;
+    for (size_t d = 0; d < m_->derived.size(); ++d)
+        if (m_->derived[d].used) { n_used++; used = (int)d; }
+    bool ok = allow_fused_ && stepper_ == StepperKind::Euler && F == 1 && n_used == 1 && m_->n_work_spectra == 0 &&
+              plan_->freq_axis_consistent() && m_->compiled.size() == 1;
+    for (int ax = 0; ax < 3 && ok; ++ax) {
+        if (plan_->extent(ax) <= 1) continue;
+        if (!plan_->axis_fast(ax) || !fused_length_supported(plan_->extent(ax))) ok = false;
+    }
+    if (ok && plan_->rank == 2 && (plan_->n1 < 2 || plan_->n2 < 2)) ok = false;
+    if (ok) {
+        // VolumeConservingLP reads the indicator spectrum after the step; keep that on the generic path
+        for (const auto& kv : m_->user_terms)
+            if (kv.second.kind == UserTermKind::VolumeConservingLP || kv.second.kind == UserTermKind::ConservativeNoise)
+                ok = false;
+    }
+    fused_ = ok;
+    fused_derived_ = ok ? used : -1;
+    prog_dirty_ = true;
+}
+
+void Solver::ensure_buffers() {
+    plan_->use_device();
+    const int F = (int)m_->fields.size();
+    const size_t bytes = sizeof(cplx) * plan_->N;
+    for (int i = 0; i < F; ++i)
+        if (!S_.s[i]) GOPF_CUDA(cudaMalloc(&S_.s[i], bytes));
+    if (fused_) {
+        if (!W_) GOPF_CUDA(cudaMalloc(&W_, bytes));
+    } else {
+        bool need_real = m_->n_work_spectra > 0;
+        for (size_t d = 0; d < m_->derived.size(); ++d) {
+            if (!m_->derived[d].used) continue;
+            need_real = true;
+            if (!S_.s[F + d]) GOPF_CUDA(cudaMalloc(&S_.s[F + d], bytes));
+        }
+        for (int w = 0; w < m_->n_work_spectra; ++w) {
+            const int si = F + (int)m_->derived.size() + w;
+            if (!S_.s[si]) GOPF_CUDA(cudaMalloc(&S_.s[si], bytes));
+        }
+        if (m_->n_work_spectra > 0)
+            for (int d = 0; d < plan_->rank; ++d)
+                if (!sg_tmp_[d]) GOPF_CUDA(cudaMalloc(&sg_tmp_[d], bytes));
+        if (need_real)
+            for (int i = 0; i < F; ++i)
+                if (!Rw_[i]) {
+                    GOPF_CUDA(cudaMalloc(&Rw_[i], bytes));
+                    R_.r[i] = Rw_[i];
+                }
+    }
+    if (stepper_ == StepperKind::RK4)
+        for (int i = 0; i < F; ++i) {
+            if (!rk_initial_[i]) GOPF_CUDA(cudaMalloc(&rk_initial_[i], bytes));
+            if (!rk_final_[i]) GOPF_CUDA(cudaMalloc(&rk_final_[i], bytes));
+            if (!rk_k_[i]) GOPF_CUDA(cudaMalloc(&rk_k_[i], bytes));
+        }
+    // prescribed (table) derived fields: upload once, patch the device pointer
+    for (size_t d = 0; d < m_->derived.size(); ++d) {
+        DerivedSpec& ds = m_->derived[d];
+        if (ds.origin != DerivedOrigin::Table || d_table_[d]) continue;
+        GOPF_CUDA(cudaMalloc(&d_table_[d], sizeof(double) * ds.table.size()));
+        GOPF_CUDA(cudaMemcpy(d_table_[d], ds.table.data(), sizeof(double) * ds.table.size(), cudaMemcpyHostToDevice));
+        ds.dev.table = d_table_[d];
+        ds.dev.table_n = (long long)plan_->N;
+    }
+    // download target
+    for (int i = 0; i < F; ++i)
+        if (!Rw_[i]) {
+            GOPF_CUDA(cudaMalloc(&Rw_[i], bytes));
+            R_.r[i] = Rw_[i];
+        }
+    if (!d_lp_state_) {
+        GOPF_CUDA(cudaMalloc(&d_lp_state_, sizeof(double) * 3 * GOPF_MAX_SPECIAL));
+        double init[3 * GOPF_MAX_SPECIAL];
+        for (int i = 0; i < GOPF_MAX_SPECIAL; ++i) {
+            init[3 * i + 0] = 0.0;  // Multiplier
+            init[3 * i + 1] = 0.0;  // CurrentIntegral
+            init[3 * i + 2] = 1.0;  // IsFirstUpdate
+        }
+        GOPF_CUDA(cudaMemcpy(d_lp_state_, init, sizeof(init), cudaMemcpyHostToDevice));
+    }
+}
+
+void Solver::rebuild_program() {
+    if (!prog_dirty_) return;
+    m_->fill_program(&prog_, dt_, plan_->rank);
+    prog_.filter = d_filter_;
+    prog_.filter_n = filter_n_;
+    for (int i = 0; i < GOPF_MAX_SPECIAL; ++i) prog_.lp_multiplier[i] = d_lp_state_ ? d_lp_state_ + 3 * i : nullptr;
+    fused_prog_ = prog_;
+    if (fused_) {
+        // spectra seen by the fused kernel: 0 = the field, 1 = the derived field
+        const int F = (int)m_->fields.size();
+        DevEquation& q = fused_prog_.eq[0];
+        for (int j = 0; j < q.n_rhs; ++j)
+            if (q.rhs[j].brick >= F) q.rhs[j].brick = 1;
+        for (int j = 0; j < q.n_den; ++j)
+            if (q.den[j].brick >= F) q.den[j].brick = 1;
+    }
+    prog_dirty_ = false;
+}
+
+FreqTabs Solver::freq_tabs() const {
+    FreqTabs ft;
+    ft.f0 = plan_->freq_axis(0);
+    ft.f1 = plan_->freq_axis(1);
+    ft.f2 = plan_->freq_axis(2);
+    ft.rank = plan_->rank;
+    return ft;
+}
+
+// ---- profiling -----------------------------------------------------------------------
+void Solver::set_profiling(bool on) {
+    profiling_ = on;
+    if (on) {
+        for (KernelTimer& t : timers_) {
+            for (auto& ev : t.events) {
+                cudaEventDestroy(ev.first);
+                cudaEventDestroy(ev.second);
+            }
+            t.events.clear();
+            t.total_ms = 0.0;
+            t.launches = 0;
+        }
+    }
+}
+
+int Solver::tick(const char* name, double bytes) {
+    launches_++;
+    if (!profiling_) return -1;
+    int id = -1;
+    for (size_t i = 0; i < timers_.size(); ++i)
+        if (timers_[i].name == name) id = (int)i;
+    if (id < 0) {
+        KernelTimer t;
+        t.name = name;
+        timers_.push_back(t);
+        id = (int)timers_.size() - 1;
+    }
+    timers_[id].bytes_per_launch = bytes;
+    cudaEvent_t a, b;
+    GOPF_CUDA(cudaEventCreate(&a));
+    GOPF_CUDA(cudaEventCreate(&b));
+    timers_[id].events.push_back({a, b});
+    GOPF_CUDA(cudaEventRecord(a, stream()));
+    return id;
+}
+
+void Solver::tock(int id) {
+    if (id < 0) return;
+    GOPF_CUDA(cudaEventRecord(timers_[id].events.back().second, stream()));
+}
+
+const std::vector<KernelTimer>& Solver::collect_profile() {
+    synchronize();
+    for (KernelTimer& t : timers_) {
+        for (auto& ev : t.events) {
+            float ms = 0.f;
+            GOPF_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+            t.total_ms += ms;
+            t.launches++;
+            cudaEventDestroy(ev.first);
+            cudaEventDestroy(ev.second);
+        }
+        t.events.clear();
+    }
+    return timers_;
+}
+
+// ---- transforms ----------------------------------------------------------------------
+void Solver::inverse_to_real(const cplx* spec, cplx* out) {
+    cudaStream_t s = stream();
+    const double inv_n = 1.0 / (double)plan_->N;
+    bool all_fast = true;
+    int n_active = 0, last_axis = -1;
+    for (int ax = 0; ax < 3; ++ax)
+        if (plan_->extent(ax) > 1) {
+            n_active++;
+            last_axis = ax;
+            if (!plan_->axis_fast(ax)) all_fast = false;
+        }
+    const double cell = 32.0 * (double)plan_->N;
+    if (!all_fast || n_active == 0) {
+        GOPF_CUDA(cudaMemcpyAsync(out, spec, sizeof(cplx) * plan_->N, cudaMemcpyDeviceToDevice, s));
+        plan_->exec_device(out, +1, s);
+        k_scale<<<grid_for((long long)plan_->N), 256, 0, s>>>(out, inv_n, (long long)plan_->N);
+        GOPF_CUDA(cudaGetLastError());
+        launches_ += 2;
+        return;
+    }
+    bool first = true;
+    for (int ax = 0; ax < 3; ++ax) {
+        if (plan_->extent(ax) <= 1) continue;
+        const PassGeom g = plan_->geom(ax);
+        const PassIO io = plain_io(first ? spec : out, out, true, ax == last_axis ? inv_n : 1.0);
+        const int id = tick("pass_inverse", cell);
+        cudaError_t e = launch_pass(g, plan_->tx_want, io, plan_->twiddle(ax), s);
+        tock(id);
+        if (e != cudaSuccess) throw Error(strf("inverse pass axis %d: %s", ax, cudaGetErrorString(e)));
+        first = false;
+    }
+}
+
+void Solver::forward_in_place(cplx* data) { plan_->exec_device(data, -1, stream()); }
+
+void Solver::forward_derived(int d) {
+    cudaStream_t s = stream();
+    const int F = (int)m_->fields.size();
+    cplx* out = S_.s[F + d];
+    bool all_fast = true;
+    int first_axis = -1;
+    for (int ax = 2; ax >= 0; --ax)
+        if (plan_->extent(ax) > 1) {
+            if (first_axis < 0) first_axis = ax;
+            if (!plan_->axis_fast(ax)) all_fast = false;
+        }
+    const double cell = 32.0 * (double)plan_->N;
+    const unsigned long long step_no = (unsigned long long)steps_taken_;
+    if (!all_fast || first_axis < 0) {
+        k_eval_derived<<<grid_for((long long)plan_->N), 256, 0, s>>>(m_->derived[d].dev, R_, out, step_no,
+                                                                     (long long)plan_->N);
+        GOPF_CUDA(cudaGetLastError());
+        launches_++;
+        plan_->exec_device(out, -1, s);
+        return;
+    }
+    for (int ax = 2; ax >= 0; --ax) {
+        if (plan_->extent(ax) <= 1) continue;
+        const PassGeom g = plan_->geom(ax);
+        PassIO io = plain_io(out, out, false, 1.0);
+        if (ax == first_axis) {
+            io.load_kind = LK_DERIVED;
+            io.D = m_->derived[d].dev;
+            io.R = R_;
+            io.step = step_no;
+        }
+        const int id = tick(ax == first_axis ? "pass_forward_derived" : "pass_forward", cell);
+        cudaError_t e = launch_pass(g, plan_->tx_want, io, plan_->twiddle(ax), s);
+        tock(id);
+        if (e != cudaSuccess) throw Error(strf("derived forward pass axis %d: %s", ax, cudaGetErrorString(e)));
+    }
+}
+
+void Solver::eval_real_fields() {
+    const int F = (int)m_->fields.size();
+    for (int i = 0; i < F; ++i) inverse_to_real(S_.s[i], Rw_[i]);
+}
+
+// SquaredGradient (pf/squareGradientTerm.go:38-65): dim inverse transforms of the gradient
+// components, squares summed in real space, ONE forward transform.
+void Solver::squared_gradient_terms() {
+    if (m_->n_work_spectra == 0) return;
+    cudaStream_t s = stream();
+    const double cell = 32.0 * (double)plan_->N;
+    for (const auto& kv : m_->user_terms) {
+        const UserTerm& u = kv.second;
+        if (u.kind != UserTermKind::SquaredGradient) continue;
+        const int fi = m_->field_index(u.field);
+        if (fi < 0) throw Error("SquaredGradient: unknown field " + u.field);
+        for (size_t e = 0; e < m_->compiled.size(); ++e)
+            for (const DevTerm& t : m_->compiled[e].rhs)
+                if (t.brick == u.work_spectrum && (int)e > fi)
+                    throw Error("SquaredGradient of field '" + u.field +
+                                "' used in a later equation than its own: the reference would read the already "
+                                "updated spectrum (euler.go:27-39); this ordering is not supported on the device");
+        bool all_fast = true;
+        for (int ax = 0; ax < 3; ++ax)
+            if (plan_->extent(ax) > 1 && !plan_->axis_fast(ax)) all_fast = false;
+        if (!all_fast) throw Error("SquaredGradient needs power-of-two extents on the device path");
+        const double inv_n = 1.0 / (double)plan_->N;
+        int last_axis = -1;
+        for (int ax = 0; ax < 3; ++ax)
+            if (plan_->extent(ax) > 1) last_axis = ax;
+        for (int d = 0; d < plan_->rank; ++d) {
+            bool first = true;
+            for (int ax = 0; ax < 3; ++ax) {
+                if (plan_->extent(ax) <= 1) continue;
+                const PassGeom g = plan_->geom(ax);
+                PassIO io = plain_io(first ? S_.s[fi] : sg_tmp_[d], sg_tmp_[d], true, ax == last_axis ? inv_n : 1.0);
+                if (first) {
+                    io.load_kind = LK_GRADIENT;
+                    io.fg = plan_->freq_geom();
+                    io.comp = d;
+                }
+                const int id = tick("pass_inverse_gradient", cell);
+                cudaError_t e = launch_pass(g, plan_->tx_want, io, plan_->twiddle(ax), s);
+                tock(id);
+                if (e != cudaSuccess) throw Error(strf("gradient pass: %s", cudaGetErrorString(e)));
+                first = false;
+            }
+        }
+        cplx* out = S_.s[u.work_spectrum];
+        bool first = true;
+        for (int ax = 2; ax >= 0; --ax) {
+            if (plan_->extent(ax) <= 1) continue;
+            const PassGeom g = plan_->geom(ax);
+            PassIO io = plain_io(out, out, false, 1.0);
+            if (first) {
+                io.load_kind = LK_SUM_SQUARES;
+                io.dim = plan_->rank;
+                io.g[0] = sg_tmp_[0];
+                io.g[1] = sg_tmp_[1];
+                io.g[2] = plan_->rank > 2 ? sg_tmp_[2] : sg_tmp_[1];
+            }
+            const int id = tick("pass_forward_gradsq", cell);
+            cudaError_t e = launch_pass(g, plan_->tx_want, io, plan_->twiddle(ax), s);
+            tock(id);
+            if (e != cudaSuccess) throw Error(strf("gradient-square forward pass: %s", cudaGetErrorString(e)));
+            first = false;
+        }
+    }
+}
+
+void Solver::volume_lp_hooks() {
+    for (const auto& kv : m_->user_terms) {
+        const UserTerm& u = kv.second;
+        if (u.kind != UserTermKind::VolumeConservingLP) continue;
+        const int fi = m_->field_index(u.field);
+        const int ii = m_->spectrum_index(u.indicator);
+        if (fi < 0 || ii < 0) throw Error("VolumeConservingLP: unknown field or indicator");
+        k_volume_lp_update<<<1, 32, 0, stream()>>>(d_lp_state_ + 3 * u.slot, S_.s[fi], S_.s[ii], u.dt);
+        GOPF_CUDA(cudaGetLastError());
+        launches_++;
+    }
+}
+
+double Solver::lp_multiplier(int slot) {
+    if (slot < 0 || slot >= GOPF_MAX_SPECIAL || !d_lp_state_) throw Error("lp_multiplier: bad slot");
+    synchronize();
+    double v = 0.0;
+    GOPF_CUDA(cudaMemcpy(&v, d_lp_state_ + 3 * slot, sizeof(double), cudaMemcpyDeviceToHost));
+    return v;
+}
+
+void Solver::launch_update(const DevKProgram& P) {
+    const long long n = (long long)plan_->N;
+    const int id = tick("k_update", 32.0 * (double)n * P.n_fields);
+    k_update_generic<<<grid_for(n), 256, 0, stream()>>>(P, S_, plan_->freq_geom(), n);
+    tock(id);
+    GOPF_CUDA(cudaGetLastError());
+}
+
+// ---- host synchronisation ------------------------------------------------------------
+void Solver::upload() {
+    ensure_buffers();
+    rebuild_program();
+    cudaStream_t s = stream();
+    const int F = (int)m_->fields.size();
+    for (int i = 0; i < F; ++i) {
+        if (!m_->fields[i].host) throw Error("solver: field '" + m_->fields[i].name + "' has no host array");
+        GOPF_CUDA(cudaMemcpyAsync(S_.s[i], m_->fields[i].host, sizeof(cplx) * plan_->N, cudaMemcpyHostToDevice, s));
+        plan_->exec_device(S_.s[i], -1, s);  // euler.go:19-21
+    }
+    on_device_ = true;
+    w_valid_ = false;
+}
+
+void Solver::download() {
+    if (!on_device_) throw Error("solver: nothing on the device to download");
+    cudaStream_t s = stream();
+    const int F = (int)m_->fields.size();
+    for (int i = 0; i < F; ++i) {
+        inverse_to_real(S_.s[i], Rw_[i]);  // euler.go:42-45
+        GOPF_CUDA(cudaMemcpyAsync(m_->fields[i].host, Rw_[i], sizeof(cplx) * plan_->N, cudaMemcpyDeviceToHost, s));
+    }
+    GOPF_CUDA(cudaStreamSynchronize(s));
+}
+
+// ---- steppers ------------------------------------------------------------------------
+void Solver::euler_step_generic() {
+    bool any_derived = false;
+    for (const DerivedSpec& d : m_->derived) any_derived |= d.used;
+    if (any_derived) {
+        eval_real_fields();                                  // real-space fields for SyncDerivedFields (euler.go:18)
+        for (size_t d = 0; d < m_->derived.size(); ++d)
+            if (m_->derived[d].used) forward_derived((int)d);  // euler.go:22-24
+    }
+    squared_gradient_terms();
+    launch_update(prog_);                                    // euler.go:27-39
+    volume_lp_hooks();                                       // solver.go:74-82
+}
+
+void Solver::euler_step_fused() {
+    cudaStream_t s = stream();
+    const double n = (double)plan_->N;
+    const int slow = plan_->rank == 3 ? 0 : 1;  // slowest active axis
+    const PassGeom gs = plan_->geom(slow);
+    if (!w_valid_) {
+        // first inverse pass of the current spectrum: S -> W
+        const int id = tick("pass_inverse", 32.0 * n);
+        cudaError_t e = launch_pass(gs, plan_->tx_want, plain_io(S_.s[0], W_, true, 1.0), plan_->twiddle(slow), s);
+        tock(id);
+        if (e != cudaSuccess) throw Error(strf("fused: first inverse pass: %s", cudaGetErrorString(e)));
+        w_valid_ = true;
+    }
+    if (plan_->rank == 3) {
+        const PassGeom g1 = plan_->geom(1);
+        const int id = tick("pass_inverse_mid", 32.0 * n);
+        cudaError_t e = launch_pass(g1, plan_->tx_want, plain_io(W_, W_, true, 1.0), plan_->twiddle(1), s);
+        tock(id);
+        if (e != cudaSuccess) throw Error(strf("fused: middle inverse pass: %s", cudaGetErrorString(e)));
+    }
+    {
+        const PassGeom g2 = plan_->geom(2);
+        const int id = tick("fused_real", 32.0 * n);
+        cudaError_t e = launch_fused_real(g2, 0, W_, nullptr, m_->derived[fused_derived_].dev, 1.0 / n,
+                                          (unsigned long long)steps_taken_, plan_->twiddle(2), s);
+        tock(id);
+        if (e != cudaSuccess) throw Error(strf("fused: real-space kernel: %s", cudaGetErrorString(e)));
+    }
+    if (plan_->rank == 3) {
+        const PassGeom g1 = plan_->geom(1);
+        const int id = tick("pass_forward_mid", 32.0 * n);
+        cudaError_t e = launch_pass(g1, plan_->tx_want, plain_io(W_, W_, false, 1.0), plan_->twiddle(1), s);
+        tock(id);
+        if (e != cudaSuccess) throw Error(strf("fused: middle forward pass: %s", cudaGetErrorString(e)));
+    }
+    {
+        const int id = tick("fused_kspace", 64.0 * n);
+        cudaError_t e = launch_fused_kspace(gs, plan_->tx_want, W_, S_.s[0], fused_prog_, freq_tabs(),
+                                            plan_->twiddle(slow), s);
+        tock(id);
+        if (e != cudaSuccess) throw Error(strf("fused: k-space kernel: %s", cudaGetErrorString(e)));
+    }
+}
+
+// pf/rk4.go:29-74
+void Solver::rk4_step() {
+    cudaStream_t s = stream();
+    const int F = (int)m_->fields.size();
+    const long long n = (long long)plan_->N;
+    const FreqGeom fg = plan_->freq_geom();
+    SpectraPtrs init{}, fin{}, kf{};
+    for (int i = 0; i < F; ++i) {
+        init.s[i] = rk_initial_[i];
+        fin.s[i] = rk_final_[i];
+        kf.s[i] = rk_k_[i];
+    }
+    bool any_derived = false;
+    for (const DerivedSpec& d : m_->derived) any_derived |= d.used;
+    auto sync_and_rhs = [&]() {
+        if (any_derived) {
+            eval_real_fields();
+            for (size_t d = 0; d < m_->derived.size(); ++d)
+                if (m_->derived[d].used) forward_derived((int)d);
+        }
+        squared_gradient_terms();
+        k_rk4_rhs<<<grid_for(n), 256, 0, s>>>(prog_, S_, kf, fg, n);
+        GOPF_CUDA(cudaGetLastError());
+        launches_++;
+    };
+    auto point = [&](int mode, double fdt) {
+        k_rk4_point<<<grid_for(n), 256, 0, s>>>(prog_, mode, fdt, S_, init, fin, kf, fg, n);
+        GOPF_CUDA(cudaGetLastError());
+        launches_++;
+    };
+    for (int i = 0; i < F; ++i) {  // rk4.go:36-43
+        GOPF_CUDA(cudaMemcpyAsync(rk_initial_[i], S_.s[i], sizeof(cplx) * n, cudaMemcpyDeviceToDevice, s));
+        GOPF_CUDA(cudaMemcpyAsync(rk_final_[i], S_.s[i], sizeof(cplx) * n, cudaMemcpyDeviceToDevice, s));
+    }
+    sync_and_rhs();                 // firstCorrection
+    point(0, dt_ / 6.0);
+    point(1, 0.5 * dt_);            // correction(0.5)
+    sync_and_rhs();
+    point(0, dt_ / 3.0);
+    point(1, 0.5 * dt_);
+    sync_and_rhs();
+    point(0, dt_ / 3.0);
+    point(1, 1.0 * dt_);            // correction(1.0)
+    sync_and_rhs();
+    point(0, dt_ / 6.0);
+    point(2, dt_);                  // rk4.go:57-68
+}
+
+void Solver::step(int nsteps) {
+    if (!on_device_) throw Error("solver: upload() must run before step()");
+    if (nsteps < 0) throw Error("solver: negative step count");
+    plan_->use_device();
+    ensure_buffers();
+    rebuild_program();
+    for (int i = 0; i < nsteps; ++i) {
+        if (stepper_ == StepperKind::RK4) {
+            rk4_step();  // Step does not advance CurrentStep (rk4.go:130-135)
+        } else {
+            if (fused_) euler_step_fused();
+            else euler_step_generic();
+            current_step_++;  // euler.go:46
+        }
+        steps_taken_++;
+    }
+}
+
+}  // namespace gopf

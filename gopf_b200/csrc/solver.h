@@ -1,0 +1,113 @@
+// Solver: device-resident counterpart of pf.Solver + pf.Euler / pf.RK4
+// (/root/reference/pf/solver.go:29-120, pf/euler.go:16-47, pf/rk4.go:29-127).
+//
+// State between host synchronisations is the k-space spectrum of every field,
+// resident in HBM.  The reference re-transforms c every step (euler.go:19-21);
+// FFT(IFFT(c^)/N) == c^ to rounding, so the persistent spectrum is algebraically
+// the same step with one transform fewer (T_min = 2 for
+// Cahn-Hilliard).
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "fft_plan.h"
+#include "model.h"
+#include "step_kernels.cuh"
+
+namespace gopf {
+
+enum class StepperKind { Euler, RK4 };
+
+struct KernelTimer {  // CUDA-event timing of one kernel class, accumulated over launches
+    std::string name;
+    double bytes_per_launch = 0.0;  // algorithmic HBM bytes
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    double total_ms = 0.0;
+    long long launches = 0;
+};
+
+class Solver {
+public:
+    Solver(Model* m, int rank, const int* n, double dt, int device);
+    ~Solver();
+    Solver(const Solver&) = delete;
+    Solver& operator=(const Solver&) = delete;
+
+    void set_stepper(const std::string& name);   // Solver.SetStepper (solver.go:88-103)
+    void set_filter(const double* table, int n);  // TimeStepper.SetFilter with a tabulated ModalFilter
+    void set_stream(cudaStream_t s) { user_stream_ = s; }
+    void upload();              // host Field.Data -> device spectra
+    void step(int nsteps);      // nsteps x Stepper.Step on device-resident state
+    void download();            // device spectra -> real-space host Field.Data
+    void propagate(int nsteps)  // Solver.Propagate on host buffers (solver.go:70-84)
+    {
+        upload();
+        step(nsteps);
+        download();
+    }
+    double get_time() const { return (double)current_step_ * dt_; }
+    bool fused() const { return fused_; }
+    long long kernel_launches() const { return launches_; }
+    void reset_launch_count() { launches_ = 0; }
+    void set_profiling(bool on);
+    const std::vector<KernelTimer>& collect_profile();
+    cplx* spectrum(int i) { return S_.s[i]; }
+    FftPlan& plan() { return *plan_; }
+    void synchronize();
+    void force_generic(bool on);
+    double lp_multiplier(int slot);
+
+private:
+    Model* m_;
+    double dt_;
+    std::unique_ptr<FftPlan> plan_;
+    StepperKind stepper_ = StepperKind::Euler;
+    long long current_step_ = 0;   // Euler.CurrentStep (RK4.Step never advances it: rk4.go:130-135)
+    long long steps_taken_ = 0;    // counter for the noise stream
+    cudaStream_t user_stream_ = nullptr;
+    bool on_device_ = false;
+    bool fused_ = false, allow_fused_ = true;
+    bool w_valid_ = false;  // fused path: W holds the first inverse pass of the current spectrum
+    int fused_derived_ = -1;
+    long long launches_ = 0;
+
+    SpectraPtrs S_;            // [fields | derived | work] spectra
+    RealPtrs R_;               // real-space fields (generic path)
+    cplx* Rw_[GOPF_MAX_FIELDS];
+    cplx* W_ = nullptr;        // fused work array
+    double* d_filter_ = nullptr;
+    int filter_n_ = 0;
+    double* d_lp_state_ = nullptr;  // per VolumeConservingLP: multiplier, current integral, first flag
+    cplx* rk_initial_[GOPF_MAX_FIELDS];
+    cplx* rk_final_[GOPF_MAX_FIELDS];
+    cplx* rk_k_[GOPF_MAX_FIELDS];
+    cplx* sg_tmp_[3];
+    double* d_table_[GOPF_MAX_SPECTRA];
+    DevKProgram prog_;
+    DevKProgram fused_prog_;
+    bool prog_dirty_ = true;
+
+    bool profiling_ = false;
+    std::vector<KernelTimer> timers_;
+
+    cudaStream_t stream() const { return user_stream_ ? user_stream_ : plan_->stream; }
+    void ensure_buffers();
+    void rebuild_program();
+    void decide_path();
+    void euler_step_generic();
+    void euler_step_fused();
+    void rk4_step();
+    void inverse_to_real(const cplx* spec, cplx* real_out);           // IFFT + /N, out of place
+    void forward_derived(int d);                                       // derived d -> its spectrum
+    void forward_in_place(cplx* data);
+    void eval_real_fields();
+    void squared_gradient_terms();
+    void volume_lp_hooks();
+    void launch_update(const DevKProgram& P);
+    int tick(const char* name, double bytes);
+    void tock(int id);
+    FreqTabs freq_tabs() const;
+};
+
+}  // namespace gopf

@@ -1,0 +1,323 @@
+// Plain-old-data "programs" the host model compiles the reference's closures into,
+// and the device evaluators that run them inside the pass kernels.
+//
+//   DevKProgram  <- RHS{Terms,Denum} of every equation (pf/rhsBuilder.go:19-54,
+//                   125-190), evaluated per k-point in declaration order
+//                   (Gauss-Seidel, pf/euler.go:27-39), plus the semi-implicit divide
+//                   (pf/euler.go:33) and the modal filter (pf/util.go:125-132).
+//   DevDerived   <- DerivedField.Calc: monomials (pf/util.go:38-65), registered
+//                   functions (pf/model.go:400-412) as an RPN over real parts, and
+//                   white noise (pf/noise.go:20-23).
+#pragma once
+#include <stdint.h>
+
+#include "cplx.cuh"
+
+namespace gopf {
+
+#define GOPF_MAX_FIELDS 4
+#define GOPF_MAX_SPECTRA 16
+#define GOPF_MAX_TERMS 8
+#define GOPF_MAX_FACTORS 4
+#define GOPF_MAX_RPN 64
+#define GOPF_MAX_PEAKS 4
+#define GOPF_MAX_SPECIAL 2
+#define GOPF_RPN_STACK 12
+
+enum TermKind {
+    TK_MONOMIAL = 0,       // coef * [brick] * L^lap                       rhsBuilder.go:158-188
+    TK_SPECTRAL_VISC = 1,  // coef * (-eps Q(|f|) |f|^p) * L^lap            spectralViscosity.go:44-54
+    TK_PAIR_CORR = 2,      // coef * (-A C2(2 pi |f|)) [* brick] * L^lap    pairCorrelationTerm.go:37-51,96-110
+    TK_CONS_NOISE = 3,     // coef * sum_c 2i sin(pi f_c) xi_c * L^lap      noise.go:60-78
+    TK_VOLUME_LP = 4       // coef * lambda * [brick] * L^lap               volumeConserving.go:19-29
+};
+
+struct DevTerm {
+    double cre, cim;  // sign * prod scalar^p (Go cmplx.Pow semantics, evaluated on the host)
+    int brick;        // spectrum index or -1
+    int lap;          // total Laplacian power (own LAP^n plus LAP prefixes)
+    int kind;         // TermKind
+    int param;        // index into the matching special-parameter array
+};
+
+struct DevEquation {
+    int n_rhs, n_den;
+    DevTerm rhs[GOPF_MAX_TERMS];
+    DevTerm den[GOPF_MAX_TERMS];
+};
+
+struct SpectralViscParams {
+    double eps, threshold;
+    int power, pad;
+};
+
+struct PairCorrParams {
+    double prefactor, eff_temp;
+    int n_peaks, pad;
+    double plane_density[GOPF_MAX_PEAKS], location[GOPF_MAX_PEAKS], width[GOPF_MAX_PEAKS];
+    double num_planes[GOPF_MAX_PEAKS];
+};
+
+struct ConsNoiseParams {
+    int dim;
+    int brick[3];  // spectrum index of the current component fields
+};
+
+struct DevKProgram {
+    int rank, n_fields;
+    double dt;
+    DevEquation eq[GOPF_MAX_FIELDS];
+    const double* filter;  // modal-filter table on the device (NULL: no filter)
+    int filter_n, pad;
+    SpectralViscParams sv[GOPF_MAX_SPECIAL];
+    PairCorrParams pc[GOPF_MAX_SPECIAL];
+    ConsNoiseParams cn[GOPF_MAX_SPECIAL];
+    const double* lp_multiplier[GOPF_MAX_SPECIAL];  // device scalars (VolumeConservingLP.Multiplier)
+};
+
+// ---- k-point ---------------------------------------------------------------------
+struct KPoint {
+    double f[3];  // reference Freq components [row, col, depth]
+    double frad;  // sqrt(Dot(f, f))
+    double L;     // -(2 pi |f|)^2, the LaplacianN base (pf/diffOp.go:27)
+};
+
+#define GOPF_PI 3.14159265358979323846
+
+__device__ __forceinline__ KPoint make_kpoint(double f0, double f1, double f2) {
+    KPoint kp;
+    kp.f[0] = f0;
+    kp.f[1] = f1;
+    kp.f[2] = f2;
+    kp.frad = sqrt(f0 * f0 + f1 * f1 + f2 * f2);
+    const double k = 2.0 * GOPF_PI * kp.frad;
+    kp.L = -(k * k);
+    return kp;
+}
+
+__device__ __forceinline__ double ipow(double x, int n) {
+    double r = 1.0;
+    for (int i = 0; i < n; ++i) r *= x;
+    return r;
+}
+
+// pf/spectralViscosity.go:31-40
+__device__ __forceinline__ double sv_interpolant(double f, double peak) {
+    const double frac = 1.0 / 3.0;
+    if (f < frac * peak) return 0.0;
+    if (f > peak) return 1.0;
+    const double x = 1.5 * (f - frac * peak) / peak;
+    return 2.0 * x * x - 3.0 * x * x * x;
+}
+
+// pfc/pairCorrelation.go:27-37
+__device__ __forceinline__ double pair_corr_eval(const PairCorrParams& p, double k) {
+    double result = 0.0;
+    for (int i = 0; i < p.n_peaks; ++i) {
+        const double pref = exp(-p.eff_temp * p.eff_temp * k * k / (2.0 * p.plane_density[i] * p.num_planes[i]));
+        const double z = (k - p.location[i]) / p.width[i];
+        const double value = pref * exp(-0.5 * (z * z));
+        if (value > result) result = value;
+    }
+    return result;
+}
+
+// pf/vandeven.go:30-40 applied at x = |f| * 2 / pi (pf/util.go:125-132)
+__device__ __forceinline__ double filter_eval(const double* __restrict__ tab, int n, double x) {
+    const double nn = (double)(n - 1);
+    const int idx = (int)(x * nn);
+    if (idx >= n - 1) return tab[n - 1];
+    const double dx = 1.0 / nn;
+    const double y0 = tab[idx];
+    const double dy = tab[idx + 1] - y0;
+    const double x0 = (double)idx * dx;
+    return y0 + (x - x0) * dy / dx;
+}
+
+// One RHS / denominator term at one k-point.  `get(brick)` returns the current
+// spectrum value of that brick at this k-point.
+template <class Get>
+__device__ __forceinline__ cplx eval_term(const DevKProgram& P, const DevTerm& t, const KPoint& kp, Get get) {
+    cplx val;
+    switch (t.kind) {
+        case TK_SPECTRAL_VISC: {
+            const SpectralViscParams& s = P.sv[t.param];
+            val = mk(-s.eps * sv_interpolant(kp.frad, s.threshold) * ipow(kp.frad, s.power), 0.0);
+            break;
+        }
+        case TK_PAIR_CORR: {
+            const PairCorrParams& p = P.pc[t.param];
+            const double m = -(p.prefactor * pair_corr_eval(p, 2.0 * GOPF_PI * kp.frad));
+            val = mk(m, 0.0);
+            if (t.brick >= 0) val = get(t.brick) * m;
+            break;
+        }
+        case TK_CONS_NOISE: {
+            const ConsNoiseParams& c = P.cn[t.param];
+            val = mk(0.0, 0.0);
+            for (int comp = 0; comp < c.dim; ++comp) {
+                const double f = kp.f[comp];
+                if (fabs(fabs(f) - 0.5) > 1e-6) {
+                    const double s2 = 2.0 * sin(GOPF_PI * f);
+                    const cplx xi = get(c.brick[comp]);
+                    val += mk(-s2 * xi.y, s2 * xi.x);  // (0 + i s2) * xi
+                }
+            }
+            break;
+        }
+        case TK_VOLUME_LP: {
+            const double lam = *P.lp_multiplier[t.param];
+            val = get(t.brick) * lam;
+            break;
+        }
+        default:
+            val = (t.brick >= 0) ? get(t.brick) : mk(1.0, 0.0);
+            break;
+    }
+    val = val * mk(t.cre, t.cim);
+    if (t.lap > 0) val = val * ipow(kp.L, t.lap);
+    return val;
+}
+
+// Semi-implicit Euler update of field `i` at one k-point (pf/euler.go:28-38).
+template <class Get>
+__device__ __forceinline__ cplx euler_update(const DevKProgram& P, int i, const KPoint& kp, cplx d, Get get) {
+    const DevEquation& q = P.eq[i];
+    cplx rhs = mk(0.0, 0.0), den = mk(0.0, 0.0);
+    for (int j = 0; j < q.n_rhs; ++j) rhs += eval_term(P, q.rhs[j], kp, get);
+    for (int j = 0; j < q.n_den; ++j) den += eval_term(P, q.den[j], kp, get);
+    const cplx num = mk(d.x + P.dt * rhs.x, d.y + P.dt * rhs.y);
+    const cplx dn = mk(1.0 - P.dt * den.x, -P.dt * den.y);
+    cplx r = cdiv(num, dn);
+    if (P.filter) {
+        const double s = filter_eval(P.filter, P.filter_n, kp.frad * 2.0 / GOPF_PI);
+        r = mk(r.x * s, r.y * s);
+    }
+    return r;
+}
+
+// ---- derived fields (real space) ---------------------------------------------------
+enum DerivedKind { DK_MONOMIAL = 0, DK_RPN = 1, DK_WHITE_NOISE = 2, DK_TABLE = 3 };
+
+enum RpnOp {
+    OP_CONST = 0,   // push arg
+    OP_FIELD_RE,    // push real(field[(int)arg])
+    OP_FIELD_IM,
+    OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG,
+    OP_POWI,        // x^(int)arg
+    OP_POW,         // pop y, x -> pow(x, y)
+    OP_H,           // 3x^2 - 2x^3        (pf/homoLinElast.go:10-12)
+    OP_DH,          // 6x - 6x^2          (pf/homoLinElast.go:15-17)
+    OP_LANDAU,      // x^2 - 2x^3 + x^4
+    OP_DLANDAU,     // 2x - 6x^2 + 4x^3
+    OP_EXP, OP_LOG, OP_SIN, OP_COS, OP_TANH, OP_SQRT, OP_ABS
+};
+
+struct DevDerived {
+    int kind;
+    int n_factors;
+    int field[GOPF_MAX_FACTORS];
+    double power[GOPF_MAX_FACTORS];
+    int ipower[GOPF_MAX_FACTORS];  // >= 0: integer power, -1: use the polar form
+    int n_ops, pad;
+    unsigned char op[GOPF_MAX_RPN];
+    double arg[GOPF_MAX_RPN];
+    double noise_std;
+    unsigned long long seed;  // white noise: Philox key; counter = (step, node)
+    const double* table;      // DK_TABLE: prescribed real values, row (step mod table_steps)
+    long long table_steps;
+    long long table_n;
+};
+
+// Go cmplx.Pow(x, p) for real p (math/cmplx/pow.go), polar form
+__device__ __forceinline__ cplx go_cpow(cplx x, double p) {
+    if (x.x == 0.0 && x.y == 0.0) {
+        if (p == 0.0) return mk(1.0, 0.0);
+        if (p < 0.0) return mk(1.0 / 0.0, 0.0);
+        return mk(0.0, 0.0);
+    }
+    const double modulus = hypot(x.x, x.y);
+    const double r = pow(modulus, p);
+    const double theta = p * atan2(x.y, x.x);
+    double s, c;
+    sincos(theta, &s, &c);
+    return mk(r * c, r * s);
+}
+
+__device__ __forceinline__ cplx cpow_int(cplx x, int n) {
+    cplx r = mk(1.0, 0.0);
+    for (int i = 0; i < n; ++i) r = r * x;
+    return r;
+}
+
+// Philox-4x32-10 (Salmon et al., SC'11) -> two standard normals by Box-Muller.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k[0] += 0x9E3779B9u;
+    k[1] += 0xBB67AE85u;
+}
+
+__device__ __forceinline__ double philox_normal(unsigned long long seed, unsigned long long step,
+                                                unsigned long long node) {
+    uint32_t c[4] = {(uint32_t)node, (uint32_t)(node >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
+    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c, k);
+    const unsigned long long a = ((unsigned long long)c[0] << 32) | c[1];
+    const unsigned long long b = ((unsigned long long)c[2] << 32) | c[3];
+    const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);  // (0,1)
+    const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+// Value of one derived field at one node.  `fld(j)` returns field j's real-space value.
+template <class Fld>
+__device__ __forceinline__ cplx eval_derived(const DevDerived& D, Fld fld, unsigned long long step,
+                                             unsigned long long node) {
+    if (D.kind == DK_MONOMIAL) {
+        cplx r = mk(1.0, 0.0);
+        for (int j = 0; j < D.n_factors; ++j) {
+            const cplx x = fld(D.field[j]);
+            r = r * (D.ipower[j] >= 0 ? cpow_int(x, D.ipower[j]) : go_cpow(x, D.power[j]));
+        }
+        return r;
+    }
+    if (D.kind == DK_WHITE_NOISE) return mk(philox_normal(D.seed, step, node) * D.noise_std, 0.0);
+    if (D.kind == DK_TABLE) return mk(D.table[(step % (unsigned long long)D.table_steps) * D.table_n + node], 0.0);
+    double st[GOPF_RPN_STACK];
+    int sp = 0;
+    for (int i = 0; i < D.n_ops; ++i) {
+        const double a = D.arg[i];
+        switch (D.op[i]) {
+            case OP_CONST: st[sp++] = a; break;
+            case OP_FIELD_RE: st[sp++] = fld((int)a).x; break;
+            case OP_FIELD_IM: st[sp++] = fld((int)a).y; break;
+            case OP_ADD: sp--; st[sp - 1] += st[sp]; break;
+            case OP_SUB: sp--; st[sp - 1] -= st[sp]; break;
+            case OP_MUL: sp--; st[sp - 1] *= st[sp]; break;
+            case OP_DIV: sp--; st[sp - 1] /= st[sp]; break;
+            case OP_NEG: st[sp - 1] = -st[sp - 1]; break;
+            case OP_POWI: st[sp - 1] = ipow(st[sp - 1], (int)a); break;
+            case OP_POW: sp--; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
+            case OP_H: { const double x = st[sp - 1]; st[sp - 1] = 3.0 * x * x - 2.0 * x * x * x; break; }
+            case OP_DH: { const double x = st[sp - 1]; st[sp - 1] = 6.0 * x - 6.0 * x * x; break; }
+            case OP_LANDAU: { const double x = st[sp - 1]; st[sp - 1] = x * x - 2.0 * x * x * x + x * x * x * x; break; }
+            case OP_DLANDAU: { const double x = st[sp - 1]; st[sp - 1] = 2.0 * x - 6.0 * x * x + 4.0 * x * x * x; break; }
+            case OP_EXP: st[sp - 1] = exp(st[sp - 1]); break;
+            case OP_LOG: st[sp - 1] = log(st[sp - 1]); break;
+            case OP_SIN: st[sp - 1] = sin(st[sp - 1]); break;
+            case OP_COS: st[sp - 1] = cos(st[sp - 1]); break;
+            case OP_TANH: st[sp - 1] = tanh(st[sp - 1]); break;
+            case OP_SQRT: st[sp - 1] = sqrt(st[sp - 1]); break;
+            case OP_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+            default: break;
+        }
+    }
+    return mk(sp > 0 ? st[sp - 1] : 0.0, 0.0);
+}
+
+}  // namespace gopf

@@ -1,0 +1,537 @@
+"""Mirror of the reference's ``pf`` hot-path surface over the C ABI
+(include/gopf_cuda.h).  Same names and argument meaning as the Go package so the
+parity tests read like the reference's own tests:
+
+    model = pf.NewModel()
+    conc = pf.NewField("conc", N, None)
+    model.AddScalar(pf.NewScalar("gamma", 2.0)); model.AddField(conc)
+    model.AddEquation("dconc/dt = LAP conc^3 + m1*LAP conc + m1*gamma*LAP^2 conc")
+    solver = pf.NewSolver(model, [nx, ny], dt)
+    solver.Solve(10, 10)          # conc.Data holds the result, as in Go
+
+Differences forced by "no Go closures on the device" (hard parts):
+``RegisterFunction`` takes an expression string, and user terms come from the
+catalog below (the reference's own PureTerm/MixedTerm implementations).  Failures
+raise ``GopfError`` where the reference panics.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, List, Optional
+
+import numpy as np
+
+from ._lib import GopfError, check, int_array, lib
+
+
+def _s(x: str) -> bytes:
+    return x.encode("utf-8")
+
+
+def pinned_empty(n: int) -> np.ndarray:
+    """complex128 array of n cells in page-locked host memory (gopf_host_alloc)."""
+    p = ctypes.c_void_p()
+    check(lib().gopf_host_alloc(ctypes.c_int64(16 * n), ctypes.byref(p)))
+    buf = (ctypes.c_double * (2 * n)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.complex128, count=n)
+    return arr, _PinnedOwner(p)
+
+
+class _PinnedOwner:
+    def __init__(self, p):
+        self.p = p
+
+    def __del__(self):
+        try:
+            lib().gopf_host_free(self.p)
+        except Exception:
+            pass
+
+
+class Field:
+    """pf.Field (pf/model.go:16-57): Data is the host []complex128."""
+
+    def __init__(self, name: str, N: int, data: Optional[np.ndarray] = None, pinned: bool = False):
+        if data is None:
+            if pinned:
+                self.Data, self._pin = pinned_empty(N)  # _pin keeps the allocation alive
+                self.Data[:] = 0
+            else:
+                self.Data = np.zeros(N, dtype=np.complex128)
+        else:
+            if data.shape[0] != N:
+                raise GopfError("model: Inconsistent length of data")
+            if data.dtype != np.complex128 or not data.flags.c_contiguous:
+                raise TypeError("Field data must be a C-contiguous complex128 array")
+            self.Data = data
+        self.Name = name
+
+    def Get(self, i):
+        return self.Data[i]
+
+
+def NewField(name: str, N: int, data: Optional[np.ndarray] = None, pinned: bool = False) -> Field:
+    return Field(name, N, data, pinned)
+
+
+class Scalar:
+    """pf.Scalar (pf/model.go:86-111)."""
+
+    def __init__(self, Name: str, Value: complex):
+        self.Name = Name
+        self.Value = complex(Value)
+
+
+def NewScalar(name: str, value: complex) -> Scalar:
+    return Scalar(name, value)
+
+
+# ---- term catalog (device-expressible PureTerm / MixedTerm implementations) ----------
+class SpectralViscosity:
+    """pf.SpectralViscosity (pf/spectralViscosity.go:23-56)."""
+
+    def __init__(self, Eps: float, DissipationThreshold: float, Power: int):
+        self.Eps, self.DissipationThreshold, self.Power = Eps, DissipationThreshold, Power
+
+    def _register(self, m: "Model", name: str, cls: str):
+        if cls != "implicit":
+            raise GopfError("SpectralViscosity is an implicit term")
+        check(lib().gopf_model_register_spectral_viscosity(m._h, _s(name), ctypes.c_double(self.Eps),
+                                                            ctypes.c_double(self.DissipationThreshold), int(self.Power)))
+
+
+class Peak:
+    """pfc.Peak (pfc/pairCorrelation.go:8-13)."""
+
+    def __init__(self, PlaneDensity: float, Location: float, Width: float, NumPlanes: int):
+        self.PlaneDensity, self.Location, self.Width, self.NumPlanes = PlaneDensity, Location, Width, NumPlanes
+
+
+class ReciprocalSpacePairCorrelation:
+    """pfc.ReciprocalSpacePairCorrelation (pfc/pairCorrelation.go:18-25)."""
+
+    def __init__(self, EffTemp: float, Peaks: List[Peak]):
+        self.EffTemp, self.Peaks = EffTemp, Peaks
+
+
+class PairCorrlationTerm:
+    """pf.PairCorrlationTerm (pf/pairCorrelationTerm.go:22-51), implicit."""
+
+    explicit = False
+
+    def __init__(self, PairCorrFunc: ReciprocalSpacePairCorrelation, Field: str, Prefactor: float, Laplacian: bool = False):
+        self.PairCorrFunc, self.Field, self.Prefactor, self.Laplacian = PairCorrFunc, Field, Prefactor, Laplacian
+
+    def _register(self, m: "Model", name: str, cls: str):
+        want = "explicit" if self.explicit else "implicit"
+        if cls != want:
+            raise GopfError(f"{type(self).__name__} is an {want} term")
+        pk = self.PairCorrFunc.Peaks
+        dbl = lambda vals: (ctypes.c_double * len(vals))(*vals)
+        check(lib().gopf_model_register_pair_correlation(
+            m._h, _s(name), 1 if self.explicit else 0, _s(self.Field), ctypes.c_double(self.Prefactor),
+            1 if self.Laplacian else 0, ctypes.c_double(self.PairCorrFunc.EffTemp), len(pk),
+            dbl([p.PlaneDensity for p in pk]), dbl([p.Location for p in pk]), dbl([p.Width for p in pk]),
+            int_array([p.NumPlanes for p in pk])))
+
+
+class ExplicitPairCorrelationTerm(PairCorrlationTerm):
+    """pf.ExplicitPairCorrelationTerm (pf/pairCorrelationTerm.go:89-110)."""
+
+    explicit = True
+
+
+class IdealMix:
+    """pfc.IdealMix (pfc/ideal.go:17-50)."""
+
+    def __init__(self, C3: float, C4: float):
+        self.C3, self.C4 = C3, C4
+
+
+class IdealMixtureTerm:
+    """pf.IdealMixtureTerm (pf/pairCorrelationTerm.go:116-193), mixed term."""
+
+    def __init__(self, IdealMix_: IdealMix, Field: str, Prefactor: float, Laplacian: bool = False):
+        self.IdealMix, self.Field, self.Prefactor, self.Laplacian = IdealMix_, Field, Prefactor, Laplacian
+
+    def DerivedField(self, num_nodes: int = 0, bricks=None):
+        """Token for RegisterMixedTerm's dFields / RegisterDerivedField."""
+        return ("ideal_mixture_derived", self)
+
+    def eval_expression(self) -> str:
+        """IdealMixtureTerm.Eval as a RegisterFunction expression: Prefactor * IdealMix.Deriv(re(field))."""
+        v = f"re({self.Field})"
+        c3, c4 = -self.IdealMix.C3 / 6.0, self.IdealMix.C4 / 12.0
+        return f"({self.Prefactor!r})*(2.0*0.5*{v}+3.0*({c3!r})*{v}*{v}+4.0*({c4!r})*{v}*{v}*{v})"
+
+    def _register(self, m: "Model", name: str, cls: str, with_derived: bool = False):
+        if cls != "mixed":
+            raise GopfError("IdealMixtureTerm is a mixed term")
+        check(lib().gopf_model_register_ideal_mixture(
+            m._h, _s(name), _s(self.Field), ctypes.c_double(self.IdealMix.C3), ctypes.c_double(self.IdealMix.C4),
+            ctypes.c_double(self.Prefactor), 1 if self.Laplacian else 0, 1 if with_derived else 0))
+
+
+class WhiteNoise:
+    """pf.WhiteNoise (pf/noise.go:11-23); pass ``noise.Generate`` to RegisterFunction."""
+
+    def __init__(self, Strength: float, seed: int = 0):
+        self.Strength, self.seed = Strength, seed
+
+    @property
+    def Generate(self):
+        return ("white_noise", self)
+
+
+class ConservativeNoise:
+    """pf.ConservativeNoise (pf/noise.go:25-100)."""
+
+    def __init__(self, strength: float, dim: int, unique_prefix: int = 0, seed: int = 0):
+        self.Strength, self.Dim, self.UniquePrefix, self.seed = strength, dim, unique_prefix, seed
+
+    def GetCurrentName(self, comp: int) -> str:
+        return f"{self.UniquePrefix}_current_{comp}"
+
+    def RequiredDerivedFields(self, num_nodes: int = 0):
+        return ("cons_noise_derived", self)
+
+    def _register(self, m: "Model", name: str, cls: str, with_derived: bool = False):
+        if cls != "explicit":
+            raise GopfError("ConservativeNoise is an explicit term")
+        if with_derived:
+            check(lib().gopf_model_register_conservative_noise(
+                m._h, _s(name), ctypes.c_double(self.Strength), int(self.Dim), ctypes.c_uint32(self.UniquePrefix),
+                ctypes.c_uint64(self.seed)))
+        else:
+            check(lib().gopf_model_register_conservative_noise_term(m._h, _s(name), int(self.Dim),
+                                                                    ctypes.c_uint32(self.UniquePrefix)))
+
+
+def NewConservativeNoise(strength: float, dim: int, unique_prefix: int = 0, seed: int = 0) -> ConservativeNoise:
+    return ConservativeNoise(strength, dim, unique_prefix, seed)
+
+
+class VolumeConservingLP:
+    """pf.VolumeConservingLP (pf/volumeConserving.go:3-61)."""
+
+    def __init__(self, fieldName: str, indicator: str, dt: float, numNodes: int):
+        self.Field, self.Indicator, self.Dt, self.NumNodes = fieldName, indicator, dt, numNodes
+
+    def _register(self, m: "Model", name: str, cls: str):
+        if cls != "explicit":
+            raise GopfError("VolumeConservingLP is registered as an explicit term")
+        check(lib().gopf_model_register_volume_conserving_lp(m._h, _s(name), _s(self.Field), _s(self.Indicator),
+                                                              ctypes.c_double(self.Dt)))
+
+
+def NewVolumeConservingLP(fieldName: str, indicator: str, dt: float, numNodes: int) -> VolumeConservingLP:
+    return VolumeConservingLP(fieldName, indicator, dt, numNodes)
+
+
+class SquaredGradient:
+    """pf.SquaredGradient (pf/squareGradientTerm.go:14-68)."""
+
+    def __init__(self, field: str, domainSize):
+        if len(domainSize) not in (2, 3):
+            raise GopfError("squaregradient: Domain size has to be of length 2 or 3")
+        self.Field, self.Factor = field, 1.0
+
+    def _register(self, m: "Model", name: str, cls: str):
+        if cls != "explicit":
+            raise GopfError("SquaredGradient is an explicit term")
+        check(lib().gopf_model_register_squared_gradient(m._h, _s(name), _s(self.Field), ctypes.c_double(self.Factor)))
+
+
+def NewSquareGradient(field: str, domainSize) -> SquaredGradient:
+    return SquaredGradient(field, domainSize)
+
+
+class Vandeven:
+    """pf.Vandeven (pf/vandeven.go:8-40): Data is the 1000-point table."""
+
+    def __init__(self, order: int):
+        self.Data = np.zeros(1000, dtype=np.float64)
+        check(lib().gopf_vandeven_table(int(order), self.Data.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 1000))
+
+
+def NewVandeven(order: int) -> Vandeven:
+    return Vandeven(order)
+
+
+class TableFilter:
+    """Any ModalFilter (pf/util.go:120-122) sampled on a uniform table over [0, 1]."""
+
+    def __init__(self, data):
+        self.Data = np.ascontiguousarray(data, dtype=np.float64)
+
+
+# ---- Model ------------------------------------------------------------------------------
+class _TermCounts:
+    def __init__(self, n_terms, n_denum):
+        self.Terms = [None] * n_terms
+        self.Denum = [None] * n_denum
+
+
+class Model:
+    """pf.Model (pf/model.go:119-484) over ``gopf_model``."""
+
+    def __init__(self):
+        self._h = ctypes.c_void_p()
+        check(lib().gopf_model_create(ctypes.byref(self._h)))
+        self.Fields: List[Field] = []
+        self.Bricks = {}
+        self.Equations: List[str] = []
+        self._solvers = []
+
+    def AddField(self, f: Field):
+        check(lib().gopf_model_add_field(self._h, _s(f.Name), ctypes.c_int64(f.Data.shape[0]),
+                                         f.Data.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        self.Fields.append(f)
+        self.Bricks[f.Name] = f
+
+    def AddScalar(self, s: Scalar):
+        check(lib().gopf_model_add_scalar(self._h, _s(s.Name), ctypes.c_double(s.Value.real), ctypes.c_double(s.Value.imag)))
+        self.Bricks[s.Name] = s
+
+    def AddEquation(self, eq: str):
+        check(lib().gopf_model_add_equation(self._h, _s(eq)))
+        self.Equations.append(eq.replace(" ", ""))
+
+    def RegisterFunction(self, name: str, F):
+        """F: expression string, or WhiteNoise(...).Generate."""
+        if isinstance(F, tuple) and F[0] == "white_noise":
+            check(lib().gopf_model_register_white_noise(self._h, _s(name), ctypes.c_double(F[1].Strength),
+                                                        ctypes.c_uint64(F[1].seed)))
+        elif isinstance(F, str):
+            check(lib().gopf_model_register_function(self._h, _s(name), _s(F)))
+        else:
+            raise GopfError("RegisterFunction: arbitrary closures cannot run on the device; pass an expression "
+                            "string (see include/gopf_cuda.h) or WhiteNoise(...).Generate")
+
+    def RegisterTableField(self, name: str, values: np.ndarray):
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        if values.ndim != 2:
+            raise GopfError("table field: values must be [n_steps][n_nodes]")
+        check(lib().gopf_model_register_table_field(self._h, _s(name), values.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                    ctypes.c_int64(values.shape[0])))
+
+    def RegisterDerivedField(self, d):
+        if isinstance(d, tuple) and d[0] == "ideal_mixture_derived":
+            term = d[1]
+            v = f"re({term.Field})"
+            c3, c4 = -term.IdealMix.C3 / 6.0, term.IdealMix.C4 / 12.0
+            expr = f"3.0*({c3!r})*{v}*{v}+4.0*({c4!r})*{v}*{v}*{v}"  # pairCorrelationTerm.go:144-156
+            check(lib().gopf_model_register_function(self._h, _s(f"ideal_mixture_{term.Field}_nonlin"), _s(expr)))
+        else:
+            raise GopfError("RegisterDerivedField: only catalog derived fields are device-expressible")
+
+    @staticmethod
+    def _wants_derived(dfields, tag):
+        if dfields is None:
+            return False
+        items = dfields if isinstance(dfields, list) else [dfields]
+        return any(isinstance(x, tuple) and x[0] == tag for x in items)
+
+    def RegisterImplicitTerm(self, name: str, t, dFields=None):
+        t._register(self, name, "implicit")
+
+    def RegisterExplicitTerm(self, name: str, t, dFields=None):
+        if isinstance(t, ConservativeNoise):
+            t._register(self, name, "explicit", self._wants_derived(dFields, "cons_noise_derived"))
+        else:
+            t._register(self, name, "explicit")
+
+    def RegisterMixedTerm(self, name: str, t, dFields=None):
+        t._register(self, name, "mixed", self._wants_derived(dFields, "ideal_mixture_derived"))
+
+    def Init(self):
+        check(lib().gopf_model_init(self._h))
+
+    @property
+    def DerivedFieldNames(self) -> List[str]:
+        n = ctypes.c_int(0)
+        check(lib().gopf_model_num_derived_fields(self._h, ctypes.byref(n)))
+        out = []
+        for i in range(n.value):
+            buf = ctypes.create_string_buffer(256)
+            check(lib().gopf_model_derived_field_name(self._h, i, buf, 256))
+            out.append(buf.value.decode())
+        return out
+
+    def AllFieldNames(self) -> List[str]:
+        return [f.Name for f in self.Fields] + self.DerivedFieldNames
+
+    @property
+    def RHS(self):
+        out = []
+        for i in range(len(self.Equations)):
+            a, b = ctypes.c_int(0), ctypes.c_int(0)
+            check(lib().gopf_model_num_terms(self._h, i, ctypes.byref(a), ctypes.byref(b)))
+            out.append(_TermCounts(a.value, b.value))
+        return out
+
+    def EqNumber(self, fieldName: str) -> int:
+        e = ctypes.c_int(0)
+        check(lib().gopf_model_eq_number(self._h, _s(fieldName), ctypes.byref(e)))
+        return e.value
+
+    def NumNodes(self) -> int:
+        if not self.Fields:
+            raise GopfError("Model: No fields added")
+        return self.Fields[0].Data.shape[0]
+
+    def close(self):
+        for s in list(self._solvers):
+            s.close()
+        if self._h:
+            lib().gopf_model_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def NewModel() -> Model:
+    return Model()
+
+
+# ---- steppers / solver ------------------------------------------------------------------
+class _Stepper:
+    """pf.TimeStepper view (pf/solver.go:15-19) of the solver's device stepper."""
+
+    def __init__(self, solver: "Solver", name: str):
+        self._solver, self.name = solver, name
+        self.Dt = solver.Dt
+
+    def SetFilter(self, filt):
+        self._solver._set_filter(filt)
+
+    def GetTime(self) -> float:
+        t = ctypes.c_double(0.0)
+        check(lib().gopf_solver_get_time(self._solver._h, ctypes.byref(t)))
+        return t.value
+
+    def Step(self, m=None):
+        self._solver.Propagate(1)
+
+
+class Solver:
+    """pf.Solver (pf/solver.go:29-134) over ``gopf_solver``."""
+
+    def __init__(self, m: Model, domainSize, dt: float, device: int = -1):
+        self.Model, self.Dt = m, dt
+        self.Callbacks: List[Callable] = []
+        self.Monitors: list = []
+        self.StartEpoch = 0
+        self._h = ctypes.c_void_p()
+        check(lib().gopf_solver_create(m._h, len(domainSize), int_array(domainSize), ctypes.c_double(dt), device,
+                                       ctypes.byref(self._h)))
+        m._solvers.append(self)
+        self.Stepper = _Stepper(self, "euler")
+
+    # -- reference API
+    def AddCallback(self, cb):
+        self.Callbacks.append(cb)
+
+    def AddMonitor(self, mon):
+        self.Monitors.append(mon)
+
+    def SetStepper(self, name: str):
+        check(lib().gopf_solver_set_stepper(self._h, _s(name)))
+        self.Stepper = _Stepper(self, name)
+
+    def Propagate(self, nsteps: int):
+        """Solver.Propagate on the host Field.Data arrays (upload, steps, download)."""
+        check(lib().gopf_solver_propagate(self._h, int(nsteps)))
+
+    def Solve(self, nepochs: int, nsteps: int):
+        for i in range(nepochs):
+            self.Propagate(nsteps)
+            for cb in self.Callbacks:
+                cb(self, i + self.StartEpoch)
+            for mon in self.Monitors:
+                mon.Add(self.Model.Bricks)
+
+    # -- device-resident control
+    def Upload(self):
+        check(lib().gopf_solver_upload(self._h))
+
+    def StepDevice(self, nsteps: int):
+        check(lib().gopf_solver_step(self._h, int(nsteps)))
+
+    def Download(self):
+        check(lib().gopf_solver_download(self._h))
+
+    def Synchronize(self):
+        check(lib().gopf_solver_synchronize(self._h))
+
+    def SetStream(self, stream: int):
+        check(lib().gopf_solver_set_stream(self._h, ctypes.c_void_p(stream)))
+
+    def _set_filter(self, filt):
+        if filt is None:
+            check(lib().gopf_solver_set_filter(self._h, None, 0))
+            return
+        data = np.ascontiguousarray(filt.Data, dtype=np.float64)
+        check(lib().gopf_solver_set_filter(self._h, data.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), data.shape[0]))
+
+    @property
+    def IsFused(self) -> bool:
+        f = ctypes.c_int(0)
+        check(lib().gopf_solver_is_fused(self._h, ctypes.byref(f)))
+        return bool(f.value)
+
+    def ForceGeneric(self, on: bool = True):
+        check(lib().gopf_solver_force_generic(self._h, 1 if on else 0))
+
+    def KernelLaunches(self, reset: bool = False) -> int:
+        n = ctypes.c_int64(0)
+        check(lib().gopf_solver_kernel_launches(self._h, ctypes.byref(n), 1 if reset else 0))
+        return n.value
+
+    def GetSpectrum(self, index: int) -> np.ndarray:
+        out = np.empty(self.Model.NumNodes(), dtype=np.complex128)
+        check(lib().gopf_solver_get_spectrum(self._h, index, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        return out
+
+    def LPMultiplier(self, slot: int = 0) -> float:
+        v = ctypes.c_double(0.0)
+        check(lib().gopf_solver_lp_multiplier(self._h, slot, ctypes.byref(v)))
+        return v.value
+
+    def ProfileBegin(self):
+        check(lib().gopf_solver_profile_begin(self._h))
+
+    def ProfileEnd(self):
+        n = ctypes.c_int(0)
+        check(lib().gopf_solver_profile_end(self._h, ctypes.byref(n)))
+        out = []
+        for i in range(n.value):
+            name = ctypes.create_string_buffer(64)
+            ms, launches, nbytes = ctypes.c_double(0), ctypes.c_int64(0), ctypes.c_double(0)
+            check(lib().gopf_solver_profile_get(self._h, i, name, 64, ctypes.byref(ms), ctypes.byref(launches),
+                                                ctypes.byref(nbytes)))
+            out.append({"kernel": name.value.decode(), "total_ms": ms.value, "launches": launches.value,
+                        "bytes_per_launch": nbytes.value})
+        return out
+
+    def close(self):
+        if self._h:
+            lib().gopf_solver_destroy(self._h)
+            self._h = ctypes.c_void_p()
+            if self in self.Model._solvers:
+                self.Model._solvers.remove(self)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def NewSolver(m: Model, domainSize, dt: float, device: int = -1) -> Solver:
+    """pf.NewSolver (pf/solver.go:40-62)."""
+    return Solver(m, domainSize, dt, device)

@@ -66,6 +66,111 @@ int gopf_fft_exec_device(gopf_fft_plan* plan, void* dev_inout_c128, int sign, vo
 int gopf_fft_freq_device(gopf_fft_plan* plan, const int64_t* nodes, int64_t count, double* out);
 int gopf_fft_plan_destroy(gopf_fft_plan* plan);
 
+/* ---- step level: pf.Model ---------------------------------------------------
+ * The model records what the Go API calls describe and compiles it, at
+ * gopf_model_init / gopf_solver_create, into device programs.  Arbitrary Go
+ * closures cannot run on the device: functions are given as expressions, terms
+ * come from the reference's catalog.  Anything else fails here, loudly. */
+/* pf.NewModel (pf/model.go:130-138) */
+int gopf_model_create(gopf_model** out);
+/* pf.NewField + Model.AddField (pf/model.go:44-57, 141-144).  host_c128 is the
+ * caller-owned Field.Data backing array of n_nodes complex128; it is read by
+ * gopf_solver_upload/propagate and written by gopf_solver_download/propagate,
+ * never retained past the model's lifetime and never freed. */
+int gopf_model_add_field(gopf_model* m, const char* name, int64_t n_nodes, double* host_c128);
+/* pf.NewScalar + Model.AddScalar (pf/model.go:95-101, 147-149) */
+int gopf_model_add_scalar(gopf_model* m, const char* name, double re, double im);
+/* Model.AddEquation (pf/model.go:157-162), e.g. "dconc/dt = LAP conc^3 + m1*LAP conc" */
+int gopf_model_add_equation(gopf_model* m, const char* equation);
+/* Model.RegisterFunction (pf/model.go:400-412) with the GenericFunction given as a
+ * real-valued expression over real parts of fields and scalars:
+ * + - * / ^ ( ), H dH Landau dLandau exp log sin cos tanh sqrt abs re() im() */
+int gopf_model_register_function(gopf_model* m, const char* name, const char* expression);
+/* RegisterFunction(name, WhiteNoise{Strength}.Generate) (pf/noise.go:11-23): N(0, 2*Strength)
+ * per node per step from a counter-based Philox stream (seed, step, node) */
+int gopf_model_register_white_noise(gopf_model* m, const char* name, double strength, uint64_t seed);
+/* RegisterDerivedField with prescribed real values: values[n_steps][n_nodes], step s reads
+ * row s mod n_steps.  Lets a parity test inject one noise array into oracle and device. */
+int gopf_model_register_table_field(gopf_model* m, const char* name, const double* values, int64_t n_steps);
+/* RegisterImplicitTerm(name, &SpectralViscosity{Eps, DissipationThreshold, Power}) (pf/spectralViscosity.go:23-54) */
+int gopf_model_register_spectral_viscosity(gopf_model* m, const char* name, double eps, double threshold, int power);
+/* RegisterImplicitTerm(name, &PairCorrlationTerm{...}) / RegisterExplicitTerm(name,
+ * &ExplicitPairCorrelationTerm{...}) (pf/pairCorrelationTerm.go:22-51, 89-110; pfc/pairCorrelation.go:8-37) */
+int gopf_model_register_pair_correlation(gopf_model* m, const char* name, int explicit_term, const char* field,
+                                         double prefactor, int laplacian, double eff_temp, int n_peaks,
+                                         const double* plane_density, const double* location, const double* width,
+                                         const int* num_planes);
+/* RegisterMixedTerm(name, &IdealMixtureTerm{IdealMix{C3,C4}, Field, Prefactor, Laplacian}, dfields)
+ * (pf/pairCorrelationTerm.go:116-178); register_derived != 0 also registers
+ * IdealMixtureTerm.DerivedField (ideal_mixture_<field>_nonlin) */
+int gopf_model_register_ideal_mixture(gopf_model* m, const char* name, const char* field, double c3, double c4,
+                                      double prefactor, int laplacian, int register_derived);
+/* RegisterExplicitTerm(name, &ConservativeNoise{UniquePrefix, Strength, Dim}, RequiredDerivedFields(N))
+ * (pf/noise.go:25-100) */
+int gopf_model_register_conservative_noise(gopf_model* m, const char* name, double strength, int dim,
+                                           uint32_t unique_prefix, uint64_t seed);
+/* same term over caller-registered current fields named "<unique_prefix>_current_<c>" */
+int gopf_model_register_conservative_noise_term(gopf_model* m, const char* name, int dim, uint32_t unique_prefix);
+/* RegisterExplicitTerm(name, &VolumeConservingLP{Field, Indicator, Dt}) (pf/volumeConserving.go:3-61) */
+int gopf_model_register_volume_conserving_lp(gopf_model* m, const char* name, const char* field,
+                                             const char* indicator, double dt);
+/* RegisterExplicitTerm(name, &SquaredGradient{Field, Factor}) (pf/squareGradientTerm.go:14-68) */
+int gopf_model_register_squared_gradient(gopf_model* m, const char* name, const char* field, double factor);
+/* Model.Init (pf/model.go:244-260): parse + classify every term */
+int gopf_model_init(gopf_model* m);
+int gopf_model_num_fields(gopf_model* m, int* n);
+int gopf_model_num_derived_fields(gopf_model* m, int* n);
+int gopf_model_derived_field_name(gopf_model* m, int index, char* buf, int buf_len);
+/* len(m.RHS[eq].Terms), len(m.RHS[eq].Denum) after Init (pf/rhsBuilder.go:19-22) */
+int gopf_model_num_terms(gopf_model* m, int eq, int* n_terms, int* n_denum);
+/* Model.EqNumber (pf/model.go:441-455) */
+int gopf_model_eq_number(gopf_model* m, const char* field_name, int* eq);
+int gopf_model_destroy(gopf_model* m);
+
+/* pf.NewVandeven(order).Data (pf/vandeven.go:13-27): fills out[1000] */
+int gopf_vandeven_table(int order, double* out, int n);
+
+/* ---- step level: pf.Solver / pf.TimeStepper ------------------------------------ */
+/* pf.NewSolver(m, domainSize, dt) (pf/solver.go:40-62): Init()s the model, plans the
+ * transforms, default stepper Euler.  device < 0: current device. */
+int gopf_solver_create(gopf_model* m, int rank, const int* domain_size, double dt, int device, gopf_solver** out);
+/* Solver.SetStepper("euler" | "rk4") (pf/solver.go:88-103) */
+int gopf_solver_set_stepper(gopf_solver* s, const char* name);
+/* TimeStepper.SetFilter for a tabulated ModalFilter (pf/util.go:120-132, pf/vandeven.go:30-40);
+ * table == NULL removes the filter */
+int gopf_solver_set_filter(gopf_solver* s, const double* table, int n);
+/* run on the caller's cudaStream_t instead of the solver's own stream */
+int gopf_solver_set_stream(gopf_solver* s, void* stream);
+/* Solver.Propagate(nsteps) (pf/solver.go:70-84) on the host Field.Data arrays:
+ * upload, nsteps x Stepper.Step (+ OnStepFinished hooks), download */
+int gopf_solver_propagate(gopf_solver* s, int nsteps);
+/* the same three phases separately, for device-resident stepping between callbacks */
+int gopf_solver_upload(gopf_solver* s);
+int gopf_solver_step(gopf_solver* s, int nsteps);
+int gopf_solver_download(gopf_solver* s);
+int gopf_solver_synchronize(gopf_solver* s);
+/* TimeStepper.GetTime (pf/euler.go:50-52, pf/rk4.go:143-145) */
+int gopf_solver_get_time(gopf_solver* s, double* t);
+/* 1 when the single-field fused kernels are in use, 0 for the general path */
+int gopf_solver_is_fused(gopf_solver* s, int* fused);
+int gopf_solver_force_generic(gopf_solver* s, int on);
+/* kernels launched by this solver since creation / since the last reset */
+int gopf_solver_kernel_launches(gopf_solver* s, int64_t* n, int reset);
+/* k-space spectrum of field / derived field `index` -> host (debug / tests) */
+int gopf_solver_get_spectrum(gopf_solver* s, int index, double* host_c128);
+/* VolumeConservingLP.Multiplier of the slot-th registered term */
+int gopf_solver_lp_multiplier(gopf_solver* s, int slot, double* value);
+/* per-kernel CUDA-event timing over the following gopf_solver_step calls */
+int gopf_solver_profile_begin(gopf_solver* s);
+int gopf_solver_profile_end(gopf_solver* s, int* n_kernels);
+int gopf_solver_profile_get(gopf_solver* s, int i, char* name, int name_len, double* total_ms, int64_t* launches,
+                            double* bytes_per_launch);
+int gopf_solver_destroy(gopf_solver* s);
+
+/* page-locked host memory for Field.Data (NewField adopts a caller slice, pf/model.go:44-57) */
+int gopf_host_alloc(int64_t bytes, void** out);
+int gopf_host_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif
