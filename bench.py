@@ -186,7 +186,8 @@ def run_single_gpu(args):
     model.AddField(conc)
     model.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
     solver = gpf.NewSolver(model, dims, synthetic.CAHN_HILLIARD_DT, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # a real stream: the legacy default stream (handle 0) cannot be handed over
+    torch.cuda.set_stream(stream)
     solver.SetStream(stream.cuda_stream)
     assert solver.IsFused, "Cahn-Hilliard must take the fused single-field path"
 

@@ -23,6 +23,10 @@ namespace gopf {
 #define GOPF_C1_16 0.92387953251128675613  // cos(pi/8)
 #define GOPF_S1_16 0.38268343236508977173  // sin(pi/8)
 
+// __launch_bounds__ second argument: aim for 512 resident threads per SM (<= 128 registers
+// per thread), the occupancy at which 16 independent 128-bit loads per thread cover HBM latency.
+#define GOPF_MINB(threads) ((threads) >= 512 ? 1 : ((512 / (threads)) > 8 ? 8 : (512 / (threads))))
+
 __device__ __forceinline__ cplx cmulc(cplx a, double c, double s) {  // a * (c + i s)
     return mk(fma(a.x, c, -a.y * s), fma(a.x, s, a.y * c));
 }

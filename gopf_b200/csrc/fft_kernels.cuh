@@ -97,11 +97,11 @@ inline PassIO plain_io(const cplx* in, cplx* out, bool inverse, double scale) {
     return io;
 }
 
-__device__ __forceinline__ cplx pass_load(const PassIO& io, size_t idx) {
+// Non-plain loads are kept out of line so the interpreter they contain cannot push the
+// thread's register-resident line into local memory.
+static __device__ __noinline__ cplx pass_load_slow(const PassIO& io, size_t idx) {
     cplx x;
-    if (io.load_kind == LK_PLAIN) {
-        x = io.in[idx];
-    } else if (io.load_kind == LK_DERIVED) {
+    if (io.load_kind == LK_DERIVED) {
         x = eval_derived(io.D, [&](int f) -> cplx { return io.R.r[f][idx]; }, io.step, idx);
     } else if (io.load_kind == LK_GRADIENT) {
         double f[3] = {0.0, 0.0, 0.0};
@@ -121,17 +121,43 @@ __device__ __forceinline__ cplx pass_load(const PassIO& io, size_t idx) {
             x += a * a;
         }
     }
-    return io.inv ? cswap(x) : x;
+    return x;
 }
 
-__device__ __forceinline__ void pass_store(const PassIO& io, size_t idx, cplx v) {
-    if (io.inv) v = cswap(v);
-    io.out[idx] = mk(v.x * io.scale, v.y * io.scale);
+// Loads the E cells of one thread.  `at(m)` maps slot m to its array index.  The plain case
+// issues all E independent 128-bit loads back to back before any is consumed.
+template <int E, class At>
+__device__ __forceinline__ void pass_load_line(const PassIO& io, cplx (&v)[E], At at) {
+    if (io.load_kind == LK_PLAIN) {
+        const cplx* __restrict__ in = io.in;
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = in[at(m)];
+    } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = pass_load_slow(io, at(m));
+    }
+    if (io.inv) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+    }
+}
+
+template <int E, class At>
+__device__ __forceinline__ void pass_store_line(const PassIO& io, cplx (&v)[E], At at) {
+    cplx* __restrict__ out = io.out;
+    const double sc = io.scale;
+    if (io.inv) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) out[at(m)] = mk(v[m].y * sc, v[m].x * sc);
+    } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) out[at(m)] = mk(v[m].x * sc, v[m].y * sc);
+    }
 }
 
 // ---- strided axis (B > 1): tile = N x TX, TX adjacent lines ---------------------
 template <int N, int TX>
-__global__ void __launch_bounds__(PlanFor<N>::T* TX)
+__global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB(PlanFor<N>::T* TX))
     k_pass_strided(const PassGeom g, const __grid_constant__ PassIO io, const cplx* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char gopf_smem_raw[];
     cplx* sm = reinterpret_cast<cplx*>(gopf_smem_raw);
@@ -144,11 +170,11 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX)
     const long long b = (tile - a * tilesB) * TX + l;
     const size_t base = (size_t)a * N * g.B + b;
     cplx v[E];
-#pragma unroll
-    for (int m = 0; m < E; ++m) v[m] = pass_load(io, base + (size_t)(t + T * m) * g.B);
+    const size_t strideB = (size_t)g.B;
+    auto at = [&](int m) -> size_t { return base + (size_t)(t + T * m) * strideB; };
+    pass_load_line<E>(io, v, at);
     line_fft<N, LayoutInterleaved<TX>, SyncCta>(v, t, l, sm, tw);
-#pragma unroll
-    for (int m = 0; m < E; ++m) pass_store(io, base + (size_t)(t + T * m) * g.B, v[m]);
+    pass_store_line<E>(io, v, at);
 }
 
 // ---- contiguous axis (B == 1): LINES lines per CTA, position fastest ------------
@@ -162,7 +188,7 @@ struct ContigCfg {
 };
 
 template <int N>
-__global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES)
+__global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MINB(ContigCfg<N>::T* ContigCfg<N>::LINES))
     k_pass_contig(const PassGeom g, const __grid_constant__ PassIO io, const cplx* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char gopf_smem_raw[];
     cplx* sm = reinterpret_cast<cplx*>(gopf_smem_raw);
@@ -174,16 +200,13 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES)
     if (!live) line = g.A - 1;
     const size_t base = (size_t)line * N;
     cplx v[E];
-#pragma unroll
-    for (int m = 0; m < E; ++m) v[m] = pass_load(io, base + p + T * m);
+    auto at = [&](int m) -> size_t { return base + p + T * m; };
+    pass_load_line<E>(io, v, at);
     if (ContigCfg<N>::WARP_SYNC)
         line_fft<N, LayoutPadded<N>, SyncWarp>(v, p, l, sm, tw);
     else
         line_fft<N, LayoutPadded<N>, SyncCta>(v, p, l, sm, tw);
-    if (live) {
-#pragma unroll
-        for (int m = 0; m < E; ++m) pass_store(io, base + p + T * m, v[m]);
-    }
+    if (live) pass_store_line<E>(io, v, at);
 }
 
 // ---- launch-side helpers ------------------------------------------------------------

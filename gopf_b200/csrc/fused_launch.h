@@ -22,7 +22,8 @@ template <int N, int TX>
 cudaError_t fused_kspace_n_tx(const PassGeom& g, cplx* W, cplx* S, const DevKProgram& P, const FreqTabs& ft,
                               const cplx* tw, cudaStream_t s) {
     constexpr int T = PlanFor<N>::T;
-    const size_t smem = PlanFor<N>::NS > 1 ? (size_t)N * TX * sizeof(cplx) : 0;
+    // exchange buffer (multi-stage lengths only) + the prefetched spectrum tile
+    const size_t smem = (size_t)N * TX * sizeof(cplx) * (PlanFor<N>::NS > 1 ? 2 : 1);
     auto kern = k_fused_kspace<N, TX, true, true>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -37,17 +38,18 @@ template <int N>
 cudaError_t fused_kspace_n(const PassGeom& g, int tx_want, cplx* W, cplx* S, const DevKProgram& P, const FreqTabs& ft,
                            const cplx* tw, cudaStream_t s) {
     constexpr size_t line_bytes = (size_t)N * sizeof(cplx);
-    const int tx = pick_tx(N, g.B, tx_want);
+    int tx = pick_tx(N, g.B, tx_want);
+    while (tx > 2 && line_bytes * tx * 2 > 128 * 1024) tx >>= 1;  // two tiles per CTA
     switch (tx) {
         case 2: return fused_kspace_n_tx<N, 2>(g, W, S, P, ft, tw, s);
         case 4:
-            if constexpr (line_bytes * 4 <= 200 * 1024) return fused_kspace_n_tx<N, 4>(g, W, S, P, ft, tw, s);
+            if constexpr (line_bytes * 4 * 2 <= 200 * 1024) return fused_kspace_n_tx<N, 4>(g, W, S, P, ft, tw, s);
             break;
         case 8:
-            if constexpr (line_bytes * 8 <= 200 * 1024) return fused_kspace_n_tx<N, 8>(g, W, S, P, ft, tw, s);
+            if constexpr (line_bytes * 8 * 2 <= 200 * 1024) return fused_kspace_n_tx<N, 8>(g, W, S, P, ft, tw, s);
             break;
         case 16:
-            if constexpr (line_bytes * 16 <= 200 * 1024 && PlanFor<N>::T * 16 <= 1024)
+            if constexpr (line_bytes * 16 * 2 <= 200 * 1024 && PlanFor<N>::T * 16 <= 1024)
                 return fused_kspace_n_tx<N, 16>(g, W, S, P, ft, tw, s);
             break;
         default: break;

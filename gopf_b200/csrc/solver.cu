@@ -1,6 +1,7 @@
 // Solver implementation (see solver.h).  Citations: /root/reference.
 #include "solver.h"
 
+#include <cmath>
 #include <cstring>
 
 #include "fused_launch.h"
@@ -116,6 +117,11 @@ __global__ void __launch_bounds__(256)
         }
     }
 }
+
+// Go's cmplx.Pow leaves an O(1e-16) imaginary residue on negative real scalars (m1 = -1
+// becomes -1 + 1.2e-16i).  The fused fast form works with real polynomial
+// coefficients and drops a residue below 4 ulp of the real part; the general path keeps it.
+static bool negligible_imag(const DevTerm& t) { return std::fabs(t.cim) <= 1e-15 * std::fabs(t.cre); }
 
 static unsigned grid_for(long long n) {
     long long blocks = (n + 255) / 256;
@@ -301,6 +307,33 @@ void Solver::rebuild_program() {
             if (q.rhs[j].brick >= F) q.rhs[j].brick = 1;
         for (int j = 0; j < q.n_den; ++j)
             if (q.den[j].brick >= F) q.den[j].brick = 1;
+        // real-polynomial fast form: every term a monomial with a real coefficient
+        DevKProgram& P = fused_prog_;
+        bool fast = true;
+        for (int i = 0; i <= GOPF_MAX_POLY; ++i) P.p_nl[i] = P.p_self[i] = P.q[i] = 0.0;
+        P.deg_nl = 0;
+        P.deg_self = -1;
+        P.deg_q = 0;
+        for (int j = 0; j < q.n_rhs && fast; ++j) {
+            const DevTerm& t = q.rhs[j];
+            if (t.kind != TK_MONOMIAL || !negligible_imag(t) || t.lap > GOPF_MAX_POLY || t.brick < 0) { fast = false; break; }
+            if (t.brick == 1) {
+                P.p_nl[t.lap] += t.cre;
+                if (t.lap > P.deg_nl) P.deg_nl = t.lap;
+            } else {
+                P.p_self[t.lap] += t.cre;
+                if (t.lap > P.deg_self) P.deg_self = t.lap;
+            }
+        }
+        for (int j = 0; j < q.n_den && fast; ++j) {
+            const DevTerm& t = q.den[j];
+            if (t.kind != TK_MONOMIAL || !negligible_imag(t) || t.lap > GOPF_MAX_POLY || t.brick >= 0) { fast = false; break; }
+            P.q[t.lap] += t.cre;
+            if (t.lap > P.deg_q) P.deg_q = t.lap;
+        }
+        // FastUpdate (step_program.h) holds degree-4 polynomials and neither a self term nor a filter
+        if (P.deg_nl > 4 || P.deg_q > 4 || P.deg_self >= 0 || P.filter != nullptr) fast = false;
+        P.fast = fast ? 1 : 0;
     }
     prog_dirty_ = false;
 }

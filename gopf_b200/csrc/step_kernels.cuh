@@ -43,7 +43,7 @@ __device__ __forceinline__ KPoint kpoint_at(const FreqTabs& ft, int i0, int i1, 
 // MODE 0: inverse + /N + g + forward (steady state)
 // MODE 1: inverse + /N, store real field only (download / generic path helper)
 template <int N, int MODE>
-__global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES)
+__global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MINB(ContigCfg<N>::T* ContigCfg<N>::LINES))
     k_fused_real(PassGeom g, cplx* __restrict__ W, cplx* __restrict__ real_out, const __grid_constant__ DevDerived D,
                  double inv_n, unsigned long long step, const cplx* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char gopf_smem_raw[];
@@ -74,10 +74,7 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES)
         for (int m = 0; m < E; ++m) real_out[base + p + T * m] = v[m];
     }
 #pragma unroll
-    for (int m = 0; m < E; ++m) {
-        const cplx c = v[m];
-        v[m] = eval_derived(D, [&](int) -> cplx { return c; }, step, base + p + T * m);
-    }
+    for (int m = 0; m < E; ++m) v[m] = eval_derived_single(D, v[m], step, base + p + T * m);
     line_fft<N, LayoutPadded<N>, Sync>(v, p, l, sm, tw);
     if (live) {
 #pragma unroll
@@ -90,7 +87,7 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES)
 //         apply the Euler update to S.  Without DO_FWD, S is used as is.
 // DO_INV: start the next inverse transform from the (new) S and leave it in W.
 template <int N, int TX, bool DO_FWD, bool DO_INV>
-__global__ void __launch_bounds__(PlanFor<N>::T* TX)
+__global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB(PlanFor<N>::T* TX))
     k_fused_kspace(PassGeom g, cplx* __restrict__ W, cplx* __restrict__ S, const __grid_constant__ DevKProgram P,
                    FreqTabs ft, const cplx* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char gopf_smem_raw[];
@@ -103,33 +100,72 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX)
     const long long a = tile / tilesB;
     const long long b = (tile - a * tilesB) * TX + l;
     const size_t base = (size_t)a * N * g.B + b;
-    // fixed FFTW coordinates of this thread's line
-    int c0 = 0, c1 = 0, c2 = 0;
-    if (g.axis == 0) { c1 = (int)(b / g.n2); c2 = (int)(b % g.n2); }
-    else { c0 = (int)a; c2 = (int)b; }  // axis 1
+    // Reference Freq components [row, col, depth] = FFTW axes [1, 2, 0] (fftWrap.go:42-74).
+    // Two of them are fixed along this thread's line, the third runs with j.
+    double fa, fb;          // the two fixed components
+    const double* fline;    // table of the running component
+    if (g.axis == 0) {
+        fa = ft.f1[(int)(b / g.n2)];
+        fb = ft.f2[(int)(b % g.n2)];
+        fline = ft.f0;
+    } else {  // axis 1
+        fa = ft.f2[(int)b];
+        fb = ft.rank > 2 ? ft.f0[(int)a] : 0.0;
+        fline = ft.f1;
+    }
+    const size_t strideB = (size_t)g.B;
+    // The spectrum tile is needed only after the forward transform: start it towards shared
+    // memory now (cp.async, no registers held) so its HBM latency hides behind the W loads
+    // and the first FFT.  Each thread later reads back exactly the cells it copied, so
+    // cp.async.wait_group is the only synchronisation needed.
+    cplx* sS = sm + (PlanFor<N>::NS > 1 ? N * TX : 0);
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(sS + LayoutInterleaved<TX>::at(t + T * m, l));
+        const cplx* src = S + base + (size_t)(t + T * m) * strideB;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
     cplx v[E];
     if (DO_FWD) {
 #pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = W[base + (size_t)(t + T * m) * g.B];
+        for (int m = 0; m < E; ++m) v[m] = W[base + (size_t)(t + T * m) * strideB];
         line_fft<N, LayoutInterleaved<TX>, SyncCta>(v, t, l, sm, tw);
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (DO_FWD) {
+        if (P.fast) {
+            FastUpdate fu;
+            fu.init(P);
+            const double s2 = fa * fa + fb * fb;
 #pragma unroll
-    for (int m = 0; m < E; ++m) {
-        const int j = t + T * m;
-        const size_t idx = base + (size_t)j * g.B;
-        cplx cur = S[idx];
-        if (DO_FWD) {
-            const KPoint kp = (g.axis == 0) ? kpoint_at(ft, j, c1, c2) : kpoint_at(ft, c0, j, c2);
-            const cplx nl = v[m];
-            cur = euler_update(P, 0, kp, cur, [&](int bidx) -> cplx { return bidx == 0 ? cur : nl; });
-            S[idx] = cur;
+            for (int m = 0; m < E; ++m) {
+                const int j = t + T * m;
+                const double fl = fline[j];
+                const cplx cur = fu.apply(fma(fl, fl, s2), sS[LayoutInterleaved<TX>::at(j, l)], v[m]);
+                S[base + (size_t)j * strideB] = cur;
+                v[m] = cswap(cur);
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int j = t + T * m;
+                const double fl = fline[j];
+                const cplx old = sS[LayoutInterleaved<TX>::at(j, l)];
+                const cplx cur = (g.axis == 0) ? euler_update_single_slow(P, fa, fb, fl, old, v[m])  // row, col, depth
+                                               : euler_update_single_slow(P, fl, fa, fb, old, v[m]);
+                S[base + (size_t)j * strideB] = cur;
+                v[m] = cswap(cur);
+            }
         }
-        v[m] = cswap(cur);
+    } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = cswap(sS[LayoutInterleaved<TX>::at(t + T * m, l)]);
     }
     if (DO_INV) {
         line_fft<N, LayoutInterleaved<TX>, SyncCta>(v, t, l, sm, tw);
 #pragma unroll
-        for (int m = 0; m < E; ++m) W[base + (size_t)(t + T * m) * g.B] = cswap(v[m]);
+        for (int m = 0; m < E; ++m) W[base + (size_t)(t + T * m) * strideB] = cswap(v[m]);
     }
 }
 
