@@ -97,9 +97,8 @@ inline PassIO plain_io(const cplx* in, cplx* out, bool inverse, double scale) {
     return io;
 }
 
-// Non-plain loads are kept out of line so the interpreter they contain cannot push the
-// thread's register-resident line into local memory.
-static __device__ __noinline__ cplx pass_load_slow(const PassIO& io, size_t idx) {
+// Non-plain loads (run from a rolled loop, see pass_load_line).
+__device__ __forceinline__ cplx pass_load_slow(const PassIO& io, size_t idx) {
     cplx x;
     if (io.load_kind == LK_DERIVED) {
         x = eval_derived(io.D, [&](int f) -> cplx { return io.R.r[f][idx]; }, io.step, idx);
@@ -126,15 +125,21 @@ static __device__ __noinline__ cplx pass_load_slow(const PassIO& io, size_t idx)
 
 // Loads the E cells of one thread.  `at(m)` maps slot m to its array index.  The plain case
 // issues all E independent 128-bit loads back to back before any is consumed.
-template <int E, class At>
-__device__ __forceinline__ void pass_load_line(const PassIO& io, cplx (&v)[E], At at) {
+// Every other load kind evaluates its interpreter in a ROLLED loop whose results are staged
+// in the thread's own shared-memory cells (`sat(m)`), so the interpreter is instantiated once
+// and the register-resident line never spills.
+template <int E, class At, class SAt>
+__device__ __forceinline__ void pass_load_line(const PassIO& io, cplx (&v)[E], At at, cplx* sm, SAt sat) {
     if (io.load_kind == LK_PLAIN) {
         const cplx* __restrict__ in = io.in;
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = in[at(m)];
     } else {
+#pragma unroll 1
+        for (int m = 0; m < E; ++m) sm[sat(m)] = pass_load_slow(io, at(m));
 #pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = pass_load_slow(io, at(m));
+        for (int m = 0; m < E; ++m) v[m] = sm[sat(m)];
+        __syncthreads();  // before any thread's first exchange write can land on these cells
     }
     if (io.inv) {
 #pragma unroll
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB(PlanFor<N>::T* TX
     cplx v[E];
     const size_t strideB = (size_t)g.B;
     auto at = [&](int m) -> size_t { return base + (size_t)(t + T * m) * strideB; };
-    pass_load_line<E>(io, v, at);
+    pass_load_line<E>(io, v, at, sm, [&](int m) -> int { return LayoutInterleaved<TX>::at(t + T * m, l); });
     line_fft<N, LayoutInterleaved<TX>, SyncCta>(v, t, l, sm, tw);
     pass_store_line<E>(io, v, at);
 }
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
     const size_t base = (size_t)line * N;
     cplx v[E];
     auto at = [&](int m) -> size_t { return base + p + T * m; };
-    pass_load_line<E>(io, v, at);
+    pass_load_line<E>(io, v, at, sm, [&](int m) -> int { return LayoutPadded<N>::at(p + T * m, l); });
     if (ContigCfg<N>::WARP_SYNC)
         line_fft<N, LayoutPadded<N>, SyncWarp>(v, p, l, sm, tw);
     else
@@ -221,7 +226,7 @@ inline int pick_tx(int N, long long B, int want) {
 template <int N, int TX>
 cudaError_t launch_strided_n_tx(const PassGeom& g, const PassIO& io, const cplx* tw, cudaStream_t s) {
     constexpr int T = PlanFor<N>::T;
-    const size_t smem = PlanFor<N>::NS > 1 ? (size_t)N * TX * sizeof(cplx) : 0;
+    const size_t smem = (size_t)N * TX * sizeof(cplx);
     auto kern = k_pass_strided<N, TX>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -255,7 +260,7 @@ cudaError_t launch_strided_n(const PassGeom& g, int tx, const PassIO& io, const 
 template <int N>
 cudaError_t launch_contig_n(const PassGeom& g, const PassIO& io, const cplx* tw, cudaStream_t s) {
     constexpr int T = ContigCfg<N>::T, LINES = ContigCfg<N>::LINES;
-    const size_t smem = PlanFor<N>::NS > 1 ? (size_t)LayoutPadded<N>::elems(N, LINES) * sizeof(cplx) : 0;
+    const size_t smem = (size_t)LayoutPadded<N>::elems(N, LINES) * sizeof(cplx);
     auto kern = k_pass_contig<N>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -23,8 +23,8 @@ cudaError_t fused_kspace_n_tx(const PassGeom& g, cplx* W, cplx* S, const DevKPro
                               const cplx* tw, cudaStream_t s) {
     constexpr int T = PlanFor<N>::T;
     // exchange buffer (multi-stage lengths only) + the prefetched spectrum tile
-    const size_t smem = (size_t)N * TX * sizeof(cplx) * (PlanFor<N>::NS > 1 ? 2 : 1);
-    auto kern = k_fused_kspace<N, TX, true, true>;
+    const size_t smem = (size_t)N * TX * sizeof(cplx) * 2;
+    auto kern = k_fused_kspace<N, TX>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -61,7 +61,7 @@ template <int N, int MODE>
 cudaError_t fused_real_n_mode(const PassGeom& g, cplx* W, cplx* real_out, const DevDerived& D, double inv_n,
                               unsigned long long step, const cplx* tw, cudaStream_t s) {
     constexpr int T = ContigCfg<N>::T, LINES = ContigCfg<N>::LINES;
-    const size_t smem = PlanFor<N>::NS > 1 ? (size_t)LayoutPadded<N>::elems(N, LINES) * sizeof(cplx) : 0;
+    const size_t smem = (size_t)LayoutPadded<N>::elems(N, LINES) * sizeof(cplx);
     auto kern = k_fused_real<N, MODE>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

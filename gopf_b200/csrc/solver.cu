@@ -334,6 +334,10 @@ void Solver::rebuild_program() {
         // FastUpdate (step_program.h) holds degree-4 polynomials and neither a self term nor a filter
         if (P.deg_nl > 4 || P.deg_q > 4 || P.deg_self >= 0 || P.filter != nullptr) fast = false;
         P.fast = fast ? 1 : 0;
+        for (int i = 0; i < 5; ++i) {
+            P.fa[i] = P.dt * P.p_nl[i];
+            P.fq[i] = (i == 0 ? 1.0 : 0.0) - P.dt * P.q[i];
+        }
     }
     prog_dirty_ = false;
 }

@@ -1,5 +1,4 @@
-// Step-level kernels: the pointwise k-space update, derived-field loaders and the
-// fused pass kernels of the single-field fast path.
+// Fused pass kernels of the single-field fast path.
 //
 // Fused Euler step for one field c with one nonlinear (derived) field g(c)
 // (e.g. Cahn-Hilliard, /root/reference/examples/cahnHilliard/main.go:33), k-space
@@ -27,21 +26,15 @@ struct SpectraPtrs {
 };
 
 struct FreqTabs {
-    const double* f0;  // per normalised FFTW axis 0, 1, 2
+    const double* f0;  // per normalised FFTW axis 0, 1, 2: wrap(idx / n), fftWrap.go:57-74
     const double* f1;
     const double* f2;
     int rank;
 };
 
-// Reference Freq components [row, col, depth] from FFTW coordinates (fftWrap.go:42-74;
-// consistent layouts only: any 2-D shape, cubic 3-D shapes).
-__device__ __forceinline__ KPoint kpoint_at(const FreqTabs& ft, int i0, int i1, int i2) {
-    return make_kpoint(ft.f1[i1], ft.f2[i2], ft.rank > 2 ? ft.f0[i0] : 0.0);
-}
-
 // ---- fused real-space kernel (contiguous axis) ------------------------------------
 // MODE 0: inverse + /N + g + forward (steady state)
-// MODE 1: inverse + /N, store real field only (download / generic path helper)
+// MODE 1: inverse + /N, store real field only
 template <int N, int MODE>
 __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MINB(ContigCfg<N>::T* ContigCfg<N>::LINES))
     k_fused_real(PassGeom g, cplx* __restrict__ W, cplx* __restrict__ real_out, const __grid_constant__ DevDerived D,
@@ -50,6 +43,7 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
     cplx* sm = reinterpret_cast<cplx*>(gopf_smem_raw);
     constexpr int E = PlanFor<N>::E, T = PlanFor<N>::T, LINES = ContigCfg<N>::LINES;
     typedef typename std::conditional<(ContigCfg<N>::WARP_SYNC != 0), SyncWarp, SyncCta>::type Sync;
+    typedef LayoutPadded<N> Lay;
     const int tid = threadIdx.x;
     const int p = tid % T, l = tid / T;
     long long line = (long long)blockIdx.x * LINES + l;
@@ -58,8 +52,10 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
     const size_t base = (size_t)line * N;
     cplx v[E];
 #pragma unroll
-    for (int m = 0; m < E; ++m) v[m] = cswap(W[base + p + T * m]);
-    line_fft<N, LayoutPadded<N>, Sync>(v, p, l, sm, tw);
+    for (int m = 0; m < E; ++m) v[m] = W[base + p + T * m];
+#pragma unroll
+    for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+    line_fft<N, Lay, Sync>(v, p, l, sm, tw);
 #pragma unroll
     for (int m = 0; m < E; ++m) v[m] = mk(v[m].y * inv_n, v[m].x * inv_n);  // swap back, /N
     if (MODE == 1) {
@@ -73,9 +69,25 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
 #pragma unroll
         for (int m = 0; m < E; ++m) real_out[base + p + T * m] = v[m];
     }
+    if (derived_is_fast(D)) {
+        const int pw = D.ipower[0];
 #pragma unroll
-    for (int m = 0; m < E; ++m) v[m] = eval_derived_single(D, v[m], step, base + p + T * m);
-    line_fft<N, LayoutPadded<N>, Sync>(v, p, l, sm, tw);
+        for (int m = 0; m < E; ++m) v[m] = derived_fast(pw, v[m]);
+    } else {
+        // general derived field: cells staged in shared memory, interpreter in a rolled loop
+#pragma unroll
+        for (int m = 0; m < E; ++m) sm[Lay::at(p + T * m, l)] = v[m];
+#pragma unroll 1
+        for (int m = 0; m < E; ++m) {
+            const int pos = Lay::at(p + T * m, l);
+            const cplx c = sm[pos];
+            sm[pos] = eval_derived(D, [&](int) -> cplx { return c; }, step, base + p + T * m);
+        }
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = sm[Lay::at(p + T * m, l)];
+        Sync::run();  // other threads' next exchange writes must not land on cells still being read
+    }
+    line_fft<N, Lay, Sync>(v, p, l, sm, tw);
     if (live) {
 #pragma unroll
         for (int m = 0; m < E; ++m) W[base + p + T * m] = v[m];
@@ -83,16 +95,21 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
 }
 
 // ---- fused k-space kernel (slowest active axis, strided) ---------------------------
-// DO_FWD: W holds the partial forward transform of the derived field; finish it and
-//         apply the Euler update to S.  Without DO_FWD, S is used as is.
-// DO_INV: start the next inverse transform from the (new) S and leave it in W.
-template <int N, int TX, bool DO_FWD, bool DO_INV>
-__global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB(PlanFor<N>::T* TX))
+// W holds the partial forward transform of the derived field: finish it, apply the Euler
+// update to S, start the next inverse transform from the new S and leave it in W.
+// Shared memory: [exchange tile N*TX][spectrum tile N*TX].
+// resident CTAs are bounded by the two shared-memory tiles; do not squeeze registers below that
+#define GOPF_MINB_K(threads, smem) \
+    (GOPF_MINB(threads) < (200 * 1024 / (smem)) ? GOPF_MINB(threads) : ((200 * 1024 / (smem)) < 1 ? 1 : (200 * 1024 / (smem))))
+template <int N, int TX>
+__global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* TX, 2 * N * TX * 16))
     k_fused_kspace(PassGeom g, cplx* __restrict__ W, cplx* __restrict__ S, const __grid_constant__ DevKProgram P,
                    FreqTabs ft, const cplx* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char gopf_smem_raw[];
     cplx* sm = reinterpret_cast<cplx*>(gopf_smem_raw);
+    cplx* sS = sm + N * TX;
     constexpr int E = PlanFor<N>::E, T = PlanFor<N>::T;
+    typedef LayoutInterleaved<TX> Lay;
     const int tid = threadIdx.x;
     const int l = tid % TX, t = tid / TX;
     const long long tilesB = g.B / TX;
@@ -100,10 +117,25 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB(PlanFor<N>::T* TX
     const long long a = tile / tilesB;
     const long long b = (tile - a * tilesB) * TX + l;
     const size_t base = (size_t)a * N * g.B + b;
+    const size_t strideB = (size_t)g.B;
+    // The spectrum tile is needed only after the forward transform: start it towards shared
+    // memory now (cp.async, no registers held) so its HBM latency hides behind the W loads
+    // and the first FFT.  Each thread later reads back exactly the cells it copied, so
+    // cp.async.wait_group is the only synchronisation needed.
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(sS + Lay::at(t + T * m, l));
+        const cplx* src = S + base + (size_t)(t + T * m) * strideB;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    cplx v[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) v[m] = W[base + (size_t)(t + T * m) * strideB];
     // Reference Freq components [row, col, depth] = FFTW axes [1, 2, 0] (fftWrap.go:42-74).
     // Two of them are fixed along this thread's line, the third runs with j.
-    double fa, fb;          // the two fixed components
-    const double* fline;    // table of the running component
+    double fa, fb;        // the two fixed components
+    const double* fline;  // table of the running component
     if (g.axis == 0) {
         fa = ft.f1[(int)(b / g.n2)];
         fb = ft.f2[(int)(b % g.n2)];
@@ -113,60 +145,40 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB(PlanFor<N>::T* TX
         fb = ft.rank > 2 ? ft.f0[(int)a] : 0.0;
         fline = ft.f1;
     }
-    const size_t strideB = (size_t)g.B;
-    // The spectrum tile is needed only after the forward transform: start it towards shared
-    // memory now (cp.async, no registers held) so its HBM latency hides behind the W loads
-    // and the first FFT.  Each thread later reads back exactly the cells it copied, so
-    // cp.async.wait_group is the only synchronisation needed.
-    cplx* sS = sm + (PlanFor<N>::NS > 1 ? N * TX : 0);
-#pragma unroll
-    for (int m = 0; m < E; ++m) {
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(sS + LayoutInterleaved<TX>::at(t + T * m, l));
-        const cplx* src = S + base + (size_t)(t + T * m) * strideB;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    cplx v[E];
-    if (DO_FWD) {
-#pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = W[base + (size_t)(t + T * m) * strideB];
-        line_fft<N, LayoutInterleaved<TX>, SyncCta>(v, t, l, sm, tw);
-    }
+    line_fft<N, Lay, SyncCta>(v, t, l, sm, tw);
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    if (DO_FWD) {
-        if (P.fast) {
-            FastUpdate fu;
-            fu.init(P);
-            const double s2 = fa * fa + fb * fb;
+    if (P.fast) {
+        const double s2 = fa * fa + fb * fb;
 #pragma unroll
-            for (int m = 0; m < E; ++m) {
-                const int j = t + T * m;
-                const double fl = fline[j];
-                const cplx cur = fu.apply(fma(fl, fl, s2), sS[LayoutInterleaved<TX>::at(j, l)], v[m]);
-                S[base + (size_t)j * strideB] = cur;
-                v[m] = cswap(cur);
-            }
-        } else {
-#pragma unroll
-            for (int m = 0; m < E; ++m) {
-                const int j = t + T * m;
-                const double fl = fline[j];
-                const cplx old = sS[LayoutInterleaved<TX>::at(j, l)];
-                const cplx cur = (g.axis == 0) ? euler_update_single_slow(P, fa, fb, fl, old, v[m])  // row, col, depth
-                                               : euler_update_single_slow(P, fl, fa, fb, old, v[m]);
-                S[base + (size_t)j * strideB] = cur;
-                v[m] = cswap(cur);
-            }
+        for (int m = 0; m < E; ++m) {
+            const int j = t + T * m;
+            const double fl = fline[j];
+            const cplx cur = fast_update(P, fma(fl, fl, s2), sS[Lay::at(j, l)], v[m]);
+            S[base + (size_t)j * strideB] = cur;
+            v[m] = cswap(cur);
         }
     } else {
+        // general program: cells staged in shared memory, term interpreter in a rolled loop
 #pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = cswap(sS[LayoutInterleaved<TX>::at(t + T * m, l)]);
-    }
-    if (DO_INV) {
-        line_fft<N, LayoutInterleaved<TX>, SyncCta>(v, t, l, sm, tw);
+        for (int m = 0; m < E; ++m) sm[Lay::at(t + T * m, l)] = v[m];
+#pragma unroll 1
+        for (int m = 0; m < E; ++m) {
+            const int j = t + T * m;
+            const int pos = Lay::at(j, l);
+            const double fl = fline[j];
+            const KPoint kp = (g.axis == 0) ? make_kpoint(fa, fb, fl) : make_kpoint(fl, fa, fb);  // row, col, depth
+            const cplx old = sS[pos], nl = sm[pos];
+            const cplx cur = euler_update(P, 0, kp, old, [&](int bi) -> cplx { return bi == 0 ? old : nl; });
+            S[base + (size_t)j * strideB] = cur;
+            sm[pos] = cswap(cur);
+        }
 #pragma unroll
-        for (int m = 0; m < E; ++m) W[base + (size_t)(t + T * m) * strideB] = cswap(v[m]);
+        for (int m = 0; m < E; ++m) v[m] = sm[Lay::at(t + T * m, l)];
+        __syncthreads();
     }
+    line_fft<N, Lay, SyncCta>(v, t, l, sm, tw);
+#pragma unroll
+    for (int m = 0; m < E; ++m) W[base + (size_t)(t + T * m) * strideB] = cswap(v[m]);
 }
 
 }  // namespace gopf

@@ -79,6 +79,7 @@ struct DevKProgram {
     //   c^ <- (c^ + dt*(p_nl(L)*g^ + p_self(L)*c^)) / (1 - dt*q(L))
     int fast, deg_nl, deg_self, deg_q;
     double p_nl[GOPF_MAX_POLY + 1], p_self[GOPF_MAX_POLY + 1], q[GOPF_MAX_POLY + 1];
+    double fa[5], fq[5];  // fast form folded with dt: fa = dt*p_nl, fq = 1 - dt*q (degree <= 4)
 };
 
 // ---- k-point ---------------------------------------------------------------------
@@ -326,53 +327,39 @@ __device__ __forceinline__ cplx eval_derived(const DevDerived& D, Fld fld, unsig
     return mk(sp > 0 ? st[sp - 1] : 0.0, 0.0);
 }
 
-// ---- single-field entry points used inside the fused kernels -------------------------
-// The general evaluators are kept out of line so the kernels' register-resident line
-// (16 cells per thread) is not spilled around an inlined interpreter; the common cases
-// (integer-power monomial, real-polynomial update) stay inline and branch uniformly.
-static __device__ __noinline__ cplx eval_derived_single_slow(const DevDerived& D, cplx c, unsigned long long step,
-                                                             unsigned long long node) {
-    return eval_derived(D, [&](int) -> cplx { return c; }, step, node);
+// ---- single-field fast forms used inside the fused kernels ----------------------------
+// The fused kernels keep a thread's 16 cells in registers.  The common cases below are
+// branch-free and stay in registers; every other case goes through the general evaluators
+// above in a ROLLED loop over cells staged in shared memory (see step_kernels.cuh), so the
+// interpreter is instantiated once and never forces the register-resident line to spill.
+__device__ __forceinline__ bool derived_is_fast(const DevDerived& D) {
+    return D.kind == DK_MONOMIAL && D.n_factors == 1 && D.ipower[0] >= 0 && D.ipower[0] <= 15;
 }
 
-__device__ __forceinline__ cplx eval_derived_single(const DevDerived& D, cplx c, unsigned long long step,
-                                                    unsigned long long node) {
-    if (D.kind == DK_MONOMIAL && D.n_factors == 1 && D.ipower[0] >= 0) {
-        const int p = D.ipower[0];
-        cplx r = (p & 1) ? c : mk(1.0, 0.0);
-        cplx sq = c;
-        for (int e = p >> 1; e > 0; e >>= 1) {  // square-and-multiply: c^3 = c * (c*c)
-            sq = sq * sq;
-            if (e & 1) r = r * sq;
-        }
-        return r;
+// c^p by square-and-multiply (p <= 15): c^3 = c * (c * c)
+__device__ __forceinline__ cplx derived_fast(int p, cplx c) {
+    cplx r = (p & 1) ? c : mk(1.0, 0.0);
+    cplx sq = c;
+#pragma unroll
+    for (int b = 1; b < 4; ++b) {
+        if ((p >> b) == 0) break;
+        sq = sq * sq;
+        if ((p >> b) & 1) r = r * sq;
     }
-    return eval_derived_single_slow(D, c, step, node);
-}
-
-static __device__ __noinline__ cplx euler_update_single_slow(const DevKProgram& P, double f0, double f1, double f2,
-                                                             cplx cur, cplx nl) {
-    const KPoint kp = make_kpoint(f0, f1, f2);
-    return euler_update(P, 0, kp, cur, [&](int b) -> cplx { return b == 0 ? cur : nl; });
+    return r;
 }
 
 // Fast form of the single-field update (DevKProgram::fast): coefficients of two real
 // degree-4 polynomials in L held in registers, no branches in the per-cell code.
 //   c^ <- (c^ + dt * a(L) * g^) / (1 - dt * q(L)),  L = -(2 pi)^2 (f0^2 + f1^2 + f2^2)
-struct FastUpdate {
-    double a0, a1, a2, a3, a4;  // dt * p_nl
-    double q0, q1, q2, q3, q4;  // 1 - dt * q
-    __device__ __forceinline__ void init(const DevKProgram& P) {
-        a0 = P.dt * P.p_nl[0]; a1 = P.dt * P.p_nl[1]; a2 = P.dt * P.p_nl[2]; a3 = P.dt * P.p_nl[3]; a4 = P.dt * P.p_nl[4];
-        q0 = 1.0 - P.dt * P.q[0]; q1 = -P.dt * P.q[1]; q2 = -P.dt * P.q[2]; q3 = -P.dt * P.q[3]; q4 = -P.dt * P.q[4];
-    }
-    __device__ __forceinline__ cplx apply(double frad2, cplx cur, cplx nl) const {
-        const double L = -(4.0 * GOPF_PI * GOPF_PI) * frad2;
-        const double a = fma(fma(fma(fma(a4, L, a3), L, a2), L, a1), L, a0);
-        const double d = fma(fma(fma(fma(q4, L, q3), L, q2), L, q1), L, q0);
-        const double inv = 1.0 / d;
-        return mk(fma(a, nl.x, cur.x) * inv, fma(a, nl.y, cur.y) * inv);
-    }
-};
+// The coefficients (P.fa = dt*p_nl, P.fq = 1 - dt*q, folded on the host) are read as
+// constant-bank operands of the DFMAs, so they occupy no registers.
+__device__ __forceinline__ cplx fast_update(const DevKProgram& P, double frad2, cplx cur, cplx nl) {
+    const double L = -(4.0 * GOPF_PI * GOPF_PI) * frad2;
+    const double a = fma(fma(fma(fma(P.fa[4], L, P.fa[3]), L, P.fa[2]), L, P.fa[1]), L, P.fa[0]);
+    const double d = fma(fma(fma(fma(P.fq[4], L, P.fq[3]), L, P.fq[2]), L, P.fq[1]), L, P.fq[0]);
+    const double inv = 1.0 / d;
+    return mk(fma(a, nl.x, cur.x) * inv, fma(a, nl.y, cur.y) * inv);
+}
 
 }  // namespace gopf
