@@ -1,0 +1,133 @@
+// C ABI, part 3: slab-sharded step.  Contract: include/gopf_cuda.h.
+#include "../../include/gopf_cuda.h"
+#include "c_api_types.h"
+#include "dist_solver.h"
+
+using namespace gopf;
+
+struct gopf_dist_solver {
+    DistSolver* s;
+    gopf_model* owner;
+};
+
+static cplx* cp(void* p, const char* what) {
+    if (!p) throw Error(std::string(what) + " is NULL");
+    return reinterpret_cast<cplx*>(p);
+}
+static const cplx* ccp(const void* p, const char* what) {
+    if (!p) throw Error(std::string(what) + " is NULL");
+    return reinterpret_cast<const cplx*>(p);
+}
+static DistSolver& ds(gopf_dist_solver* s) {
+    if (!s) throw Error("dist solver is NULL");
+    return *s->s;
+}
+
+extern "C" {
+
+int gopf_dist_solver_create(gopf_model* m, int n, int world, int rank, double dt, int device, gopf_dist_solver** out) {
+    GOPF_API_BEGIN
+    if (!m || !out) throw Error("gopf_dist_solver_create: NULL argument");
+    *out = nullptr;
+    DistSolver* s = new DistSolver(&m->m, n, world, rank, dt, device);
+    gopf_dist_solver* h = new gopf_dist_solver;
+    h->s = s;
+    h->owner = m;
+    m->live_solvers++;
+    *out = h;
+    GOPF_API_END
+}
+
+int gopf_dist_solver_set_stream(gopf_dist_solver* s, void* stream) {
+    GOPF_API_BEGIN
+    ds(s).set_stream(reinterpret_cast<cudaStream_t>(stream));
+    GOPF_API_END
+}
+
+int gopf_dist_solver_local_cells(gopf_dist_solver* s, int64_t* cells) {
+    GOPF_API_BEGIN
+    if (!cells) throw Error("cells is NULL");
+    *cells = (int64_t)ds(s).local_cells();
+    GOPF_API_END
+}
+
+int gopf_dist_forward_local(gopf_dist_solver* s, void* w, void* send) {
+    GOPF_API_BEGIN
+    ds(s).forward_local(cp(w, "w"), cp(send, "send"));
+    GOPF_API_END
+}
+
+int gopf_dist_forward_finish(gopf_dist_solver* s, void* t) {
+    GOPF_API_BEGIN
+    ds(s).forward_finish(cp(t, "t"));
+    GOPF_API_END
+}
+
+int gopf_dist_inverse_start(gopf_dist_solver* s, const void* spectrum, void* t) {
+    GOPF_API_BEGIN
+    ds(s).inverse_start(ccp(spectrum, "spectrum"), cp(t, "t"));
+    GOPF_API_END
+}
+
+int gopf_dist_inverse_mid(gopf_dist_solver* s, const void* recv, void* w) {
+    GOPF_API_BEGIN
+    ds(s).inverse_mid(ccp(recv, "recv"), cp(w, "w"));
+    GOPF_API_END
+}
+
+int gopf_dist_real_step(gopf_dist_solver* s, void* w) {
+    GOPF_API_BEGIN
+    ds(s).real_step(cp(w, "w"));
+    GOPF_API_END
+}
+
+int gopf_dist_forward_mid(gopf_dist_solver* s, const void* w, void* send) {
+    GOPF_API_BEGIN
+    ds(s).forward_mid(ccp(w, "w"), cp(send, "send"));
+    GOPF_API_END
+}
+
+int gopf_dist_kspace_step(gopf_dist_solver* s, void* t, void* spectrum) {
+    GOPF_API_BEGIN
+    ds(s).kspace_step(cp(t, "t"), cp(spectrum, "spectrum"));
+    GOPF_API_END
+}
+
+int gopf_dist_inverse_finish(gopf_dist_solver* s, void* w, void* real_out) {
+    GOPF_API_BEGIN
+    ds(s).inverse_finish(cp(w, "w"), cp(real_out, "real_out"));
+    GOPF_API_END
+}
+
+int gopf_dist_advance(gopf_dist_solver* s) {
+    GOPF_API_BEGIN
+    ds(s).advance();
+    GOPF_API_END
+}
+
+int gopf_dist_solver_get_time(gopf_dist_solver* s, double* t) {
+    GOPF_API_BEGIN
+    if (!t) throw Error("t is NULL");
+    *t = ds(s).get_time();
+    GOPF_API_END
+}
+
+int gopf_dist_solver_kernel_launches(gopf_dist_solver* s, int64_t* n, int reset) {
+    GOPF_API_BEGIN
+    if (!n) throw Error("n is NULL");
+    *n = ds(s).kernel_launches();
+    if (reset) ds(s).reset_launch_count();
+    GOPF_API_END
+}
+
+int gopf_dist_solver_destroy(gopf_dist_solver* s) {
+    GOPF_API_BEGIN
+    if (s) {
+        delete s->s;
+        if (s->owner) s->owner->live_solvers--;
+        delete s;
+    }
+    GOPF_API_END
+}
+
+}  // extern "C"

@@ -3,14 +3,10 @@
 #include <cstring>
 
 #include "../../include/gopf_cuda.h"
+#include "c_api_types.h"
 #include "solver.h"
 
 using namespace gopf;
-
-struct gopf_model {
-    Model m;
-    int live_solvers = 0;
-};
 
 struct gopf_solver {
     Solver* s;

@@ -1,0 +1,72 @@
+// DistSolver: slab-sharded single-field Euler step for cubic 3-D grids, one rank per GPU
+// (SURVEY.md 8e).  The reference has no distributed path; this is the B200-native
+// extension of the same step (pf/euler.go:16-47) to grids that do not fit, or do not run
+// fast enough on, one GPU.
+//
+// Rank p of P owns planes i0 in [p*m, (p+1)*m), m = n/P, of the real-space array
+// (contiguous in the reference's node numbering).  k-space lives TRANSPOSED: rank p owns
+// k1 in [p*m, (p+1)*m) for every k0, k2, laid out [k0][k1_local][k2].  One all-to-all per
+// distributed transform; the exchange itself is done by the caller (torch.distributed /
+// NCCL) between the phases below, on buffers it owns.  Pack and unpack are folded into
+// the passes on either side of the exchange through split row maps (fft_kernels.cuh).
+//
+//   send layout (forward)  [q][i0_local][k1_local(q)][k2]  -> all-to-all -> [k0][k1_local][k2]
+//   [k0][k1_local][k2] = [q][k0_local(q)][k1_local][k2]    -> all-to-all -> [p][i0_local][k1_local(p)][k2]
+#pragma once
+#include <memory>
+
+#include "fft_plan.h"
+#include "fused_launch.h"
+#include "model.h"
+#include "solver.h"
+
+namespace gopf {
+
+class DistSolver {
+public:
+    DistSolver(Model* m, int n, int world, int rank, double dt, int device);
+
+    int n() const { return n_; }
+    int slab() const { return m_; }
+    size_t local_cells() const { return (size_t)m_ * n_ * n_; }
+    void set_stream(cudaStream_t s) { stream_ = s; }
+    long long kernel_launches() const { return launches_; }
+    void reset_launch_count() { launches_ = 0; }
+
+    // ---- phases (all arrays: local_cells() complex128 on this rank's device) --------
+    // upload: real slab W [i0l][i1][i2] -> forward axes 2, 1 -> send layout
+    void forward_local(cplx* W, cplx* send);
+    // after the exchange: forward axis 0 of T = [k0][k1l][k2], in place (T becomes the spectrum)
+    void forward_finish(cplx* T);
+    // first inverse pass of the spectrum: S -> T (axis 0)
+    void inverse_start(const cplx* S, cplx* T);
+    // after the exchange: inverse axis 1, recv (split layout) -> W [i0l][k1][k2]
+    void inverse_mid(const cplx* recv, cplx* W);
+    // last inverse pass, /N, derived function, first forward pass; W in place
+    void real_step(cplx* W);
+    // forward axis 1: W -> send layout
+    void forward_mid(const cplx* W, cplx* send);
+    // after the exchange: finish forward (axis 0) of T, Euler update of S, inverse axis 0 -> T
+    void kspace_step(cplx* T, cplx* S);
+    // download: last inverse pass + /N of W -> real slab
+    void inverse_finish(cplx* W, cplx* real_out);
+    void advance() { steps_taken_++; current_step_++; }
+    double get_time() const { return (double)current_step_ * dt_; }
+
+private:
+    Model* m_model_;
+    int n_, world_, rank_, m_;
+    double dt_;
+    std::unique_ptr<FftPlan> plan_;  // tables and twiddles for length n
+    cudaStream_t stream_ = nullptr;
+    DevKProgram prog_;
+    int derived_ = -1;
+    long long steps_taken_ = 0, current_step_ = 0, launches_ = 0;
+
+    cudaStream_t stream() const { return stream_ ? stream_ : plan_->stream; }
+    PassGeom slab_axis1(bool split_in, bool split_out) const;
+    RowMap split_map() const;
+    void check(cudaError_t e, const char* what);
+};
+
+}  // namespace gopf

@@ -12,12 +12,34 @@
 
 namespace gopf {
 
+// Address of row j of the strided tile (a, b):
+//   a*a_stride + b + (j >> split_log)*split_stride + (j & split_mask)*row_stride
+// Uniform arrays use split_log = 31 (no split).  The slab-sharded transform reads the
+// all-to-all receive buffer / writes the send buffer through a split map, so the
+// pack/unpack of the transpose costs no pass of its own (dist_solver.cu).
+struct RowMap {
+    long long a_stride, row_stride, split_stride;
+    int split_log, split_mask;
+};
+
 struct PassGeom {
     int n0, n1, n2;  // extents in FFTW order (2-D: n0 == 1; 1-D: n0 == n1 == 1)
     int axis;        // 0, 1 or 2
     long long A, B;  // outer count / inner stride for this axis
     int N;           // n[axis]
+    RowMap in, out;  // strided kernels only
+    long long node0; // reference node number of this array's first cell (slab offset when sharded)
 };
+
+inline RowMap uniform_rows(long long a_stride, long long row_stride) {
+    RowMap r;
+    r.a_stride = a_stride;
+    r.row_stride = row_stride;
+    r.split_stride = 0;
+    r.split_log = 31;
+    r.split_mask = 0x7fffffff;
+    return r;
+}
 
 inline PassGeom make_geom(int n0, int n1, int n2, int axis) {
     PassGeom g;
@@ -25,6 +47,8 @@ inline PassGeom make_geom(int n0, int n1, int n2, int axis) {
     if (axis == 2) { g.N = n2; g.B = 1; g.A = (long long)n0 * n1; }
     else if (axis == 1) { g.N = n1; g.B = n2; g.A = n0; }
     else { g.N = n0; g.B = (long long)n1 * n2; g.A = 1; }
+    g.in = g.out = uniform_rows((long long)g.N * g.B, g.B);
+    g.node0 = 0;
     return g;
 }
 
@@ -173,13 +197,20 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB(PlanFor<N>::T* TX
     const long long tile = blockIdx.x;
     const long long a = tile / tilesB;
     const long long b = (tile - a * tilesB) * TX + l;
-    const size_t base = (size_t)a * N * g.B + b;
     cplx v[E];
-    const size_t strideB = (size_t)g.B;
-    auto at = [&](int m) -> size_t { return base + (size_t)(t + T * m) * strideB; };
-    pass_load_line<E>(io, v, at, sm, [&](int m) -> int { return LayoutInterleaved<TX>::at(t + T * m, l); });
+    const size_t ibase = (size_t)a * g.in.a_stride + b, obase = (size_t)a * g.out.a_stride + b;
+    auto at_in = [&](int m) -> size_t {
+        const int j = t + T * m;
+        return ibase + (size_t)(j >> g.in.split_log) * g.in.split_stride + (size_t)(j & g.in.split_mask) * g.in.row_stride;
+    };
+    auto at_out = [&](int m) -> size_t {
+        const int j = t + T * m;
+        return obase + (size_t)(j >> g.out.split_log) * g.out.split_stride +
+               (size_t)(j & g.out.split_mask) * g.out.row_stride;
+    };
+    pass_load_line<E>(io, v, at_in, sm, [&](int m) -> int { return LayoutInterleaved<TX>::at(t + T * m, l); });
     line_fft<N, LayoutInterleaved<TX>, SyncCta>(v, t, l, sm, tw);
-    pass_store_line<E>(io, v, at);
+    pass_store_line<E>(io, v, at_out);
 }
 
 // ---- contiguous axis (B == 1): LINES lines per CTA, position fastest ------------

@@ -299,47 +299,63 @@ void Solver::rebuild_program() {
     prog_.filter_n = filter_n_;
     for (int i = 0; i < GOPF_MAX_SPECIAL; ++i) prog_.lp_multiplier[i] = d_lp_state_ ? d_lp_state_ + 3 * i : nullptr;
     fused_prog_ = prog_;
-    if (fused_) {
-        // spectra seen by the fused kernel: 0 = the field, 1 = the derived field
-        const int F = (int)m_->fields.size();
-        DevEquation& q = fused_prog_.eq[0];
-        for (int j = 0; j < q.n_rhs; ++j)
-            if (q.rhs[j].brick >= F) q.rhs[j].brick = 1;
-        for (int j = 0; j < q.n_den; ++j)
-            if (q.den[j].brick >= F) q.den[j].brick = 1;
-        // real-polynomial fast form: every term a monomial with a real coefficient
-        DevKProgram& P = fused_prog_;
-        bool fast = true;
-        for (int i = 0; i <= GOPF_MAX_POLY; ++i) P.p_nl[i] = P.p_self[i] = P.q[i] = 0.0;
-        P.deg_nl = 0;
-        P.deg_self = -1;
-        P.deg_q = 0;
-        for (int j = 0; j < q.n_rhs && fast; ++j) {
-            const DevTerm& t = q.rhs[j];
-            if (t.kind != TK_MONOMIAL || !negligible_imag(t) || t.lap > GOPF_MAX_POLY || t.brick < 0) { fast = false; break; }
-            if (t.brick == 1) {
-                P.p_nl[t.lap] += t.cre;
-                if (t.lap > P.deg_nl) P.deg_nl = t.lap;
-            } else {
-                P.p_self[t.lap] += t.cre;
-                if (t.lap > P.deg_self) P.deg_self = t.lap;
-            }
-        }
-        for (int j = 0; j < q.n_den && fast; ++j) {
-            const DevTerm& t = q.den[j];
-            if (t.kind != TK_MONOMIAL || !negligible_imag(t) || t.lap > GOPF_MAX_POLY || t.brick >= 0) { fast = false; break; }
-            P.q[t.lap] += t.cre;
-            if (t.lap > P.deg_q) P.deg_q = t.lap;
-        }
-        // FastUpdate (step_program.h) holds degree-4 polynomials and neither a self term nor a filter
-        if (P.deg_nl > 4 || P.deg_q > 4 || P.deg_self >= 0 || P.filter != nullptr) fast = false;
-        P.fast = fast ? 1 : 0;
-        for (int i = 0; i < 5; ++i) {
-            P.fa[i] = P.dt * P.p_nl[i];
-            P.fq[i] = (i == 0 ? 1.0 : 0.0) - P.dt * P.q[i];
+    if (fused_) finalize_single_field_program(&fused_prog_, (int)m_->fields.size());
+    prog_dirty_ = false;
+}
+
+// Program as seen by the fused single-field kernels: spectrum 0 = the field, 1 = the derived
+// field; plus the real-polynomial fast form when every term is a monomial with a real
+// coefficient, degree <= 4, no self term on the explicit side and no filter.
+void finalize_single_field_program(DevKProgram* prog, int n_fields) {
+    DevKProgram& P = *prog;
+    DevEquation& q = P.eq[0];
+    for (int j = 0; j < q.n_rhs; ++j)
+        if (q.rhs[j].brick >= n_fields) q.rhs[j].brick = 1;
+    for (int j = 0; j < q.n_den; ++j)
+        if (q.den[j].brick >= n_fields) q.den[j].brick = 1;
+    bool fast = true;
+    for (int i = 0; i <= GOPF_MAX_POLY; ++i) P.p_nl[i] = P.p_self[i] = P.q[i] = 0.0;
+    P.deg_nl = 0;
+    P.deg_self = -1;
+    P.deg_q = 0;
+    for (int j = 0; j < q.n_rhs && fast; ++j) {
+        const DevTerm& t = q.rhs[j];
+        if (t.kind != TK_MONOMIAL || !negligible_imag(t) || t.lap > GOPF_MAX_POLY || t.brick < 0) { fast = false; break; }
+        if (t.brick == 1) {
+            P.p_nl[t.lap] += t.cre;
+            if (t.lap > P.deg_nl) P.deg_nl = t.lap;
+        } else {
+            P.p_self[t.lap] += t.cre;
+            if (t.lap > P.deg_self) P.deg_self = t.lap;
         }
     }
-    prog_dirty_ = false;
+    for (int j = 0; j < q.n_den && fast; ++j) {
+        const DevTerm& t = q.den[j];
+        if (t.kind != TK_MONOMIAL || !negligible_imag(t) || t.lap > GOPF_MAX_POLY || t.brick >= 0) { fast = false; break; }
+        P.q[t.lap] += t.cre;
+        if (t.lap > P.deg_q) P.deg_q = t.lap;
+    }
+    if (P.deg_nl > 4 || P.deg_q > 4 || P.deg_self >= 0 || P.filter != nullptr) fast = false;
+    P.fast = fast ? 1 : 0;
+    for (int i = 0; i < 5; ++i) {
+        P.fa[i] = P.dt * P.p_nl[i];
+        P.fq[i] = (i == 0 ? 1.0 : 0.0) - P.dt * P.q[i];
+    }
+}
+
+// The single-field fused path applies to: one field, one equation, exactly one derived field
+// in use, no work-spectrum terms, no term with a per-step device hook.  Returns the derived
+// field's index or -1.
+int single_field_derived_index(const Model& m) {
+    if (m.fields.size() != 1 || m.compiled.size() != 1 || m.n_work_spectra != 0) return -1;
+    int n_used = 0, used = -1;
+    for (size_t d = 0; d < m.derived.size(); ++d)
+        if (m.derived[d].used) { n_used++; used = (int)d; }
+    if (n_used != 1) return -1;
+    for (const auto& kv : m.user_terms)
+        if (kv.second.kind == UserTermKind::VolumeConservingLP || kv.second.kind == UserTermKind::ConservativeNoise)
+            return -1;
+    return used;
 }
 
 FreqTabs Solver::freq_tabs() const {
@@ -348,6 +364,7 @@ FreqTabs Solver::freq_tabs() const {
     ft.f1 = plan_->freq_axis(1);
     ft.f2 = plan_->freq_axis(2);
     ft.rank = plan_->rank;
+    ft.off1 = 0;
     return ft;
 }
 

@@ -19,6 +19,10 @@ namespace gopf {
 
 enum class StepperKind { Euler, RK4 };
 
+// shared by Solver and DistSolver (solver.cu)
+void finalize_single_field_program(DevKProgram* prog, int n_fields);
+int single_field_derived_index(const Model& m);
+
 struct KernelTimer {  // CUDA-event timing of one kernel class, accumulated over launches
     std::string name;
     double bytes_per_launch = 0.0;  // algorithmic HBM bytes

@@ -30,6 +30,7 @@ struct FreqTabs {
     const double* f1;
     const double* f2;
     int rank;
+    int off1;  // slab-sharded k-space: this rank's first k1 (0 on a single GPU)
 };
 
 // ---- fused real-space kernel (contiguous axis) ------------------------------------
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
         for (int m = 0; m < E; ++m) {
             const int pos = Lay::at(p + T * m, l);
             const cplx c = sm[pos];
-            sm[pos] = eval_derived(D, [&](int) -> cplx { return c; }, step, base + p + T * m);
+            sm[pos] = eval_derived(D, [&](int) -> cplx { return c; }, step, (unsigned long long)g.node0 + base + p + T * m);
         }
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = sm[Lay::at(p + T * m, l)];
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
     double fa, fb;        // the two fixed components
     const double* fline;  // table of the running component
     if (g.axis == 0) {
-        fa = ft.f1[(int)(b / g.n2)];
+        fa = ft.f1[ft.off1 + (int)(b / g.n2)];
         fb = ft.f2[(int)(b % g.n2)];
         fline = ft.f0;
     } else {  // axis 1

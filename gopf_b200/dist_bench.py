@@ -1,0 +1,145 @@
+"""bench.py arm for N > 1: slab-sharded 3-D Cahn-Hilliard (BASELINE.json configs[2]),
+one rank per GPU under torchrun, NCCL all-to-all between the local phases.
+Strong scaling: the grid is fixed (default 1024^3) as N grows."""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+METRIC = "cell-updates/s"
+
+
+class TimedPhases:
+    """Wraps the phase object and the exchange with CUDA events (profiling region only)."""
+
+    def __init__(self, phases, a2a, torch, stream):
+        self.p, self.a2a, self.torch, self.stream = phases, a2a, torch, stream
+        self.ev = {}
+
+    def _timed(self, name, fn, *args):
+        a, b = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        a.record(self.stream)
+        fn(*args)
+        b.record(self.stream)
+        self.ev.setdefault(name, []).append((a, b))
+
+    def __getattr__(self, name):
+        fn = getattr(self.p, name)
+        if name in ("advance", "get_time", "kernel_launches"):
+            return fn
+        return lambda *args: self._timed(name, fn, *args)
+
+    def all_to_all(self, dst, src):
+        self._timed("all_to_all", self.a2a, dst, src)
+
+    def summary(self):
+        self.torch.cuda.synchronize()
+        return {k: {"launches": len(v), "avg_ms": float(np.mean([a.elapsed_time(b) for a, b in v]))}
+                for k, v in self.ev.items()}
+
+
+def run(args):
+    import torch
+    import torch.distributed as tdist
+
+    from . import dist as gdist
+    from . import pf as gpf
+    from . import synthetic
+    import bench as B  # ClockSampler, measured_hbm_peak
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.grid
+    cells = n ** 3 // world
+    model = gpf.NewModel()
+    conc = gpf.NewField("conc", cells, None, pinned=True)
+    synthetic.cahn_hilliard_initial(cells, 0, offset=rank * cells, out=conc.Data)
+    model.AddScalar(gpf.NewScalar("gamma", synthetic.CAHN_HILLIARD_GAMMA))
+    model.AddScalar(gpf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
+    model.AddField(conc)
+    model.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
+    solver = gdist.ShardedSolver(model, n, synthetic.CAHN_HILLIARD_DT, device=local)
+    stream = solver.stream
+
+    solver.Upload()
+    solver.StepDevice(args.warmup)
+    solver.Synchronize()
+    solver.phases.kernel_launches(reset=True)
+    sampler = B.ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    tdist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    solver.StepDevice(args.steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    tdist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)  # the job's time is the slowest rank's
+    ms = float(ms.item())
+    launches = solver.phases.kernel_launches(reset=True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-phase CUDA events over an identical region
+    timed = TimedPhases(solver.phases, solver.all_to_all, torch, stream)
+    with torch.cuda.stream(stream):
+        solver.a_valid = gdist.run_steps(timed, timed.all_to_all, solver.S, solver.A, solver.B, args.steps, solver.a_valid)
+    phases = timed.summary()
+
+    # end to end: Solver.Propagate on the host slabs (H2D, step, D2H inside the timed region)
+    e2e_steps = max(2, min(args.steps, 3))
+    solver.Propagate(1)
+    tdist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        solver.Propagate(1)
+    tdist.barrier()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    tdist.all_reduce(e2e_dt, op=tdist.ReduceOp.MAX)
+    e2e_dt = float(e2e_dt.item())
+
+    if rank == 0:
+        total = n ** 3
+        value = total * args.steps / (ms * 1e-3)
+        peak, peak_src = B.measured_hbm_peak()
+        comp = {k: v for k, v in phases.items() if k != "all_to_all"}
+        top = max(comp.items(), key=lambda kv: kv[1]["avg_ms"] * kv[1]["launches"])
+        top_bytes = (64.0 if top[0] == "kspace_step" else 32.0) * cells
+        a2a_bytes_out = 16.0 * cells * (world - 1) / world  # per exchange, per GPU, each way
+        a2a = phases.get("all_to_all", {"avg_ms": float("nan"), "launches": 0})
+        line = {
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cahn-hilliard-3d-{n}^3-semi-implicit-euler-slab-sharded", "grid": [n, n, n],
+                       "dt": synthetic.CAHN_HILLIARD_DT, "equation": synthetic.CAHN_HILLIARD_EQUATION,
+                       "parallelism": f"slab{world}", "exchange": "2 NCCL all-to-all per step",
+                       "cache": f"per-GPU arrays of {16 * cells / 2**20:.0f} MiB each exceed the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": total * e2e_steps / e2e_dt, "unit": METRIC, "h2d_bytes_per_step": 16 * total,
+                    "d2h_bytes_per_step": 16 * total, "steps": e2e_steps,
+                    "call": "ShardedSolver.Propagate(1) on pinned host slabs, every rank"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": top[0], "achieved": top_bytes / (top[1]["avg_ms"] * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": top_bytes / (top[1]["avg_ms"] * 1e-3) / 1e9 / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "step_model": {"bytes_per_cell_update": 192.0, "achieved_per_gpu": value * 192.0 / 1e9 / world,
+                                        "frac": value * 192.0 / 1e9 / world / peak},
+                         "phases": phases,
+                         "nvlink": {"bytes_out_per_exchange_per_gpu": a2a_bytes_out, "exchanges_per_step": 2,
+                                    "achieved_gbs_per_direction": a2a_bytes_out / (a2a["avg_ms"] * 1e-3) / 1e9
+                                    if a2a["launches"] else None,
+                                    "reference_gbs": 770.0}},
+        }
+        print(json.dumps(line), flush=True)
+    tdist.barrier()
+    tdist.destroy_process_group()

@@ -167,6 +167,37 @@ int gopf_solver_profile_get(gopf_solver* s, int i, char* name, int name_len, dou
                             double* bytes_per_launch);
 int gopf_solver_destroy(gopf_solver* s);
 
+/* ---- slab-sharded step: one rank per GPU ------------------------------------------
+ * No reference counterpart (gopf is single process); this extends pf.Euler.Step
+ * (pf/euler.go:16-47) to a cubic n^3 grid split into `world` slabs of n/world planes
+ * along the slowest axis.  The library runs the local phases; the caller performs the
+ * all-to-all between them (NCCL through torch.distributed, or ncclSend/ncclRecv from Go)
+ * on device buffers it owns, each n/world * n * n complex128.  Order of one step, with
+ * work buffers A, B and spectrum S (see gopf_b200/dist.py and DESIGN.md):
+ *   [first step only: inverse_start(S -> A)]
+ *   all_to_all(A -> B); inverse_mid(B -> A); real_step(A); forward_mid(A -> B);
+ *   all_to_all(B -> A); kspace_step(A, S); advance()
+ * The model must be the single-field fused form (one field holding this rank's slab,
+ * one equation, one nonlinear derived field). */
+typedef struct gopf_dist_solver gopf_dist_solver;
+int gopf_dist_solver_create(gopf_model* m, int n, int world, int rank, double dt, int device, gopf_dist_solver** out);
+int gopf_dist_solver_set_stream(gopf_dist_solver* s, void* stream);
+int gopf_dist_solver_local_cells(gopf_dist_solver* s, int64_t* cells);
+/* upload side: real slab W -> forward axes 2,1 -> send layout; after the exchange forward axis 0 */
+int gopf_dist_forward_local(gopf_dist_solver* s, void* w_c128, void* send_c128);
+int gopf_dist_forward_finish(gopf_dist_solver* s, void* t_c128);
+int gopf_dist_inverse_start(gopf_dist_solver* s, const void* spectrum_c128, void* t_c128);
+int gopf_dist_inverse_mid(gopf_dist_solver* s, const void* recv_c128, void* w_c128);
+int gopf_dist_real_step(gopf_dist_solver* s, void* w_c128);
+int gopf_dist_forward_mid(gopf_dist_solver* s, const void* w_c128, void* send_c128);
+int gopf_dist_kspace_step(gopf_dist_solver* s, void* t_c128, void* spectrum_c128);
+/* download side: last inverse pass and 1/N, W -> real slab */
+int gopf_dist_inverse_finish(gopf_dist_solver* s, void* w_c128, void* real_out_c128);
+int gopf_dist_advance(gopf_dist_solver* s);
+int gopf_dist_solver_get_time(gopf_dist_solver* s, double* t);
+int gopf_dist_solver_kernel_launches(gopf_dist_solver* s, int64_t* n, int reset);
+int gopf_dist_solver_destroy(gopf_dist_solver* s);
+
 /* page-locked host memory for Field.Data (NewField adopts a caller slice, pf/model.go:44-57) */
 int gopf_host_alloc(int64_t bytes, void** out);
 int gopf_host_free(void* p);
