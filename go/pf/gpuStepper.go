@@ -1,0 +1,179 @@
+// +build cuda
+
+// GPU time stepper for davidkleiven/gopf: implements pf.TimeStepper (pf/solver.go:15-19) by
+// mirroring the host Model into libgopfcuda.so (include/gopf_cuda.h) and stepping on the device.
+// Usage, with the reference's API otherwise unchanged:
+//
+//	solver := pf.NewSolver(&model, domainSize, dt)
+//	solver.Stepper = pf.NewGPUStepper(&model, domainSize, dt, "euler")   // Solver.Stepper is exported
+//	solver.Solve(nepochs, nsteps)
+//
+// Step() uploads Field.Data, advances one step and downloads (API-exact, PCIe-bound);
+// Propagate(n) does the same around n device-resident steps and is what a GPU-aware
+// Solver.Propagate should call once per epoch (host data only needs to be current when callbacks
+// and monitors fire, pf/solver.go:110-117).
+//
+// Registered Go closures cannot run on the device: functions must be given as expressions through
+// RegisterFunctionExpr, user terms must be catalog types (type switch below).  Anything else panics
+// at construction, not in the middle of a run.
+//
+// NOT COMPILED IN THIS REPOSITORY'S CI (no Go toolchain in the image); gopf_b200/pf.py is the
+// binding the tests exercise, call for call.
+package pf
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../gopf_b200/lib -lgopfcuda
+#include <stdlib.h>
+#include "gopf_cuda.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"unsafe"
+)
+
+// GPUStepper is a TimeStepper backed by gopf_solver
+type GPUStepper struct {
+	model  *C.gopf_model
+	solver *C.gopf_solver
+	Dt     float64
+}
+
+func gpuCheck(status C.int) {
+	if status != 0 {
+		panic("gopfcuda: " + C.GoString(C.gopf_last_error()))
+	}
+}
+
+func cstr(s string) *C.char { return C.CString(s) }
+
+// FunctionExprs maps RegisterFunction names to device expressions, e.g.
+// "CHEMICALPOT": "-((0.1*conc*(1-H(phase)) - 0.1*(1-conc)*H(phase))*1.0)"
+type FunctionExprs map[string]string
+
+// NewGPUStepper mirrors m (fields, scalars, equations, catalog terms) into the device library.
+func NewGPUStepper(m *Model, domainSize []int, dt float64, scheme string, exprs FunctionExprs) *GPUStepper {
+	st := &GPUStepper{Dt: dt}
+	gpuCheck(C.gopf_model_create(&st.model))
+	for _, f := range m.Fields {
+		name := cstr(f.Name)
+		gpuCheck(C.gopf_model_add_field(st.model, name, C.int64_t(len(f.Data)), (*C.double)(unsafe.Pointer(&f.Data[0]))))
+		C.free(unsafe.Pointer(name))
+	}
+	for name, b := range m.Bricks {
+		if s, ok := b.(*Scalar); ok {
+			cn := cstr(name)
+			gpuCheck(C.gopf_model_add_scalar(st.model, cn, C.double(real(s.Value)), C.double(imag(s.Value))))
+			C.free(unsafe.Pointer(cn))
+		}
+	}
+	for name, expr := range exprs {
+		cn, ce := cstr(name), cstr(expr)
+		gpuCheck(C.gopf_model_register_function(st.model, cn, ce))
+		C.free(unsafe.Pointer(cn))
+		C.free(unsafe.Pointer(ce))
+	}
+	register := func(name string, t interface{}) {
+		cn := cstr(name)
+		defer C.free(unsafe.Pointer(cn))
+		switch v := t.(type) {
+		case *SpectralViscosity:
+			gpuCheck(C.gopf_model_register_spectral_viscosity(st.model, cn, C.double(v.Eps), C.double(v.DissipationThreshold), C.int(v.Power)))
+		case *VolumeConservingLP:
+			cf, ci := cstr(v.Field), cstr(v.Indicator)
+			gpuCheck(C.gopf_model_register_volume_conserving_lp(st.model, cn, cf, ci, C.double(v.Dt)))
+			C.free(unsafe.Pointer(cf))
+			C.free(unsafe.Pointer(ci))
+		case *SquaredGradient:
+			cf := cstr(v.Field)
+			gpuCheck(C.gopf_model_register_squared_gradient(st.model, cn, cf, C.double(v.Factor)))
+			C.free(unsafe.Pointer(cf))
+		case *PairCorrlationTerm:
+			registerPairCorrelation(st.model, cn, v, 0)
+		case *ExplicitPairCorrelationTerm:
+			registerPairCorrelation(st.model, cn, &v.PairCorrlationTerm, 1)
+		case *IdealMixtureTerm:
+			cf := cstr(v.Field)
+			lap := 0
+			if v.Laplacian {
+				lap = 1
+			}
+			gpuCheck(C.gopf_model_register_ideal_mixture(st.model, cn, cf, C.double(v.IdealMix.C3), C.double(v.IdealMix.C4), C.double(v.Prefactor), C.int(lap), 1))
+			C.free(unsafe.Pointer(cf))
+		case *ConservativeNoise:
+			gpuCheck(C.gopf_model_register_conservative_noise(st.model, cn, C.double(v.Strength), C.int(v.Dim), C.uint32_t(v.UniquePrefix), 0))
+		default:
+			panic(fmt.Sprintf("gopfcuda: term %s (%T) has no device implementation", name, t))
+		}
+	}
+	for name, t := range m.ImplicitTerms {
+		register(name, t)
+	}
+	for name, t := range m.ExplicitTerms {
+		register(name, t)
+	}
+	for name, t := range m.MixedTerms {
+		register(name, t)
+	}
+	for _, eq := range m.Equations {
+		ce := cstr(eq)
+		gpuCheck(C.gopf_model_add_equation(st.model, ce))
+		C.free(unsafe.Pointer(ce))
+	}
+	dims := make([]C.int, len(domainSize))
+	for i, v := range domainSize {
+		dims[i] = C.int(v)
+	}
+	gpuCheck(C.gopf_solver_create(st.model, C.int(len(dims)), &dims[0], C.double(dt), -1, &st.solver))
+	cs := cstr(scheme)
+	gpuCheck(C.gopf_solver_set_stepper(st.solver, cs))
+	C.free(unsafe.Pointer(cs))
+	return st
+}
+
+func registerPairCorrelation(m *C.gopf_model, cn *C.char, v *PairCorrlationTerm, explicit C.int) {
+	n := len(v.PairCorrFunc.Peaks)
+	dens, loc, wid := make([]C.double, n), make([]C.double, n), make([]C.double, n)
+	planes := make([]C.int, n)
+	for i, p := range v.PairCorrFunc.Peaks {
+		dens[i], loc[i], wid[i], planes[i] = C.double(p.PlaneDensity), C.double(p.Location), C.double(p.Width), C.int(p.NumPlanes)
+	}
+	cf := cstr(v.Field)
+	lap := 0
+	if v.Laplacian {
+		lap = 1
+	}
+	gpuCheck(C.gopf_model_register_pair_correlation(m, cn, explicit, cf, C.double(v.Prefactor), C.int(lap),
+		C.double(v.PairCorrFunc.EffTemp), C.int(n), &dens[0], &loc[0], &wid[0], &planes[0]))
+	C.free(unsafe.Pointer(cf))
+}
+
+// Step performs one step on the host Field.Data arrays (pf.TimeStepper)
+func (st *GPUStepper) Step(m *Model) { gpuCheck(C.gopf_solver_propagate(st.solver, 1)) }
+
+// Propagate performs nsteps device-resident steps between one upload and one download
+func (st *GPUStepper) Propagate(nsteps int, m *Model) { gpuCheck(C.gopf_solver_propagate(st.solver, C.int(nsteps))) }
+
+// SetFilter sets a tabulated modal filter (pf.TimeStepper); only *Vandeven carries a table
+func (st *GPUStepper) SetFilter(filter ModalFilter) {
+	if v, ok := filter.(*Vandeven); ok {
+		gpuCheck(C.gopf_solver_set_filter(st.solver, (*C.double)(unsafe.Pointer(&v.Data[0])), C.int(len(v.Data))))
+		return
+	}
+	panic("gopfcuda: only tabulated filters (pf.Vandeven) run on the device")
+}
+
+// GetTime returns the current time (pf.TimeStepper)
+func (st *GPUStepper) GetTime() float64 {
+	var t C.double
+	gpuCheck(C.gopf_solver_get_time(st.solver, &t))
+	return float64(t)
+}
+
+// Close releases the device resources
+func (st *GPUStepper) Close() {
+	C.gopf_solver_destroy(st.solver)
+	C.gopf_model_destroy(st.model)
+}
