@@ -109,6 +109,23 @@ int gopf_fft_exec_device(gopf_fft_plan* plan, void* dev, int sign, void* stream)
     GOPF_API_END
 }
 
+int gopf_fft_exec_axis_device(gopf_fft_plan* plan, const void* in, void* out, int sign, int axis, int tile_cells,
+                              void* stream) {
+    GOPF_API_BEGIN
+    if (!plan || !in || !out) throw Error("gopf_fft_exec_axis_device: NULL argument");
+    FftPlan& p = *plan->p;
+    if (axis < 0 || axis > 2 || p.extent(axis) <= 1) throw Error("gopf_fft_exec_axis_device: bad axis");
+    if (!p.axis_fast(axis)) throw Error("gopf_fft_exec_axis_device: axis length has no fast kernel");
+    if (sign != -1 && sign != 1) throw Error("gopf_fft_exec_axis_device: sign must be -1 or +1");
+    p.use_device();
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : p.stream;
+    cudaError_t e = launch_pass(p.geom(axis), tile_cells > 0 ? tile_cells : p.tx_want,
+                                plain_io(reinterpret_cast<const cplx*>(in), reinterpret_cast<cplx*>(out), sign > 0, 1.0),
+                                p.twiddle(axis), s);
+    if (e != cudaSuccess) throw Error(strf("axis pass failed: %s", cudaGetErrorString(e)));
+    GOPF_API_END
+}
+
 int gopf_fft_freq_device(gopf_fft_plan* plan, const int64_t* nodes, int64_t count, double* out) {
     GOPF_API_BEGIN
     if (!plan || !nodes || !out) throw Error("gopf_fft_freq_device: NULL argument");

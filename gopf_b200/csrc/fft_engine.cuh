@@ -125,7 +125,7 @@ GOPF_PLAN(32, 8, 2, 8, 4, 1)
 GOPF_PLAN(64, 8, 2, 8, 8, 1)
 GOPF_PLAN(128, 16, 2, 16, 8, 1)
 GOPF_PLAN(256, 16, 2, 16, 16, 1)
-GOPF_PLAN(512, 8, 3, 8, 8, 8)
+GOPF_PLAN(512, 16, 3, 16, 2, 16)
 GOPF_PLAN(1024, 16, 3, 16, 4, 16)
 GOPF_PLAN(2048, 16, 3, 16, 8, 16)
 GOPF_PLAN(4096, 16, 3, 16, 16, 16)

@@ -84,7 +84,9 @@ enum LoadKind {
     LK_PLAIN = 0,     // in[idx]
     LK_DERIVED = 1,   // derived-field value from the real-space fields (model.go:237-241)
     LK_GRADIENT = 2,  // i 2 pi f_comp * in[idx], +0.5 Nyquist zeroed (squareGradientTerm.go:45-50)
-    LK_SUM_SQUARES = 3  // sum_d g_d[idx]^2 (squareGradientTerm.go:53-62, summed before the transform)
+    LK_SUM_SQUARES = 3,  // sum_d g_d[idx]^2 (squareGradientTerm.go:53-62, summed before the transform)
+    LK_ELAST_H = 4,      // H(re phi[idx]), phi = g[0]                       (homoLinElast.go:53-57)
+    LK_ELAST_R = 5       // H'(phi) * in[idx] - aux * H(phi) * H'(phi)        (homoLinElast.go:64-97, by linearity)
 };
 
 struct PassIO {
@@ -100,9 +102,10 @@ struct PassIO {
     // LK_GRADIENT
     FreqGeom fg;
     int comp;
-    // LK_SUM_SQUARES
+    // LK_SUM_SQUARES, LK_ELAST_*
     int dim;
     const cplx* g[3];
+    double aux;
 };
 
 inline PassIO plain_io(const cplx* in, cplx* out, bool inverse, double scale) {
@@ -134,6 +137,14 @@ __device__ __forceinline__ cplx pass_load_slow(const PassIO& io, size_t idx) {
         const double w = 2.0 * GOPF_PI * fd;
         const cplx u = io.in[idx];
         x = mk(-u.y * w, u.x * w);
+    } else if (io.load_kind == LK_ELAST_H) {
+        const double p = io.g[0][idx].x;
+        x = mk(3.0 * p * p - 2.0 * p * p * p, 0.0);
+    } else if (io.load_kind == LK_ELAST_R) {
+        const double p = io.g[0][idx].x;
+        const double h = 3.0 * p * p - 2.0 * p * p * p, dh = 6.0 * p - 6.0 * p * p;
+        const cplx e = io.in[idx];
+        x = mk(dh * e.x - io.aux * (h * dh), dh * e.y);
     } else {
         cplx a = io.g[0][idx];
         x = a * a;
@@ -247,6 +258,11 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
 
 // ---- launch-side helpers ------------------------------------------------------------
 inline int pick_tx(int N, long long B, int want) {
+    // Lines of >= 512 cells: a 128-B-wide tile would be the only CTA on its SM (registers), with
+    // no other tile's loads in flight behind it; two 64-B-wide tiles per SM measure faster
+    // (scripts/tune_pass.py, B200: N=1024 4.4 vs 4.0 TB/s, N=512 4.6 vs 3.8 TB/s).
+    // Exception: 1024-cell lines at plane-sized row strides keep 128-B segments (3.9 vs 3.6 TB/s).
+    if (N >= 512 && want > 4 && !(N >= 1024 && B >= 16384)) want = 4;
     int tx = want;
     while (tx > 1 && ((long long)N * tx * 16 > 128 * 1024)) tx >>= 1;
     while (tx > 1 && (B % tx) != 0) tx >>= 1;

@@ -485,6 +485,14 @@ CompiledEquation Model::build(const std::string& eq) {
                     apply_prefixes(&d, prefixes);
                     ce.rhs.push_back(d);
                     break;
+                case UserTermKind::HomogeneousModulusLinElast:
+                    // the solver fills the work spectrum with the whole term (homoLinElast.go:47-99)
+                    if (field_index(u.field) < 0) throw Error("HomogeneousModulusLinElast: unknown field " + u.field);
+                    d.kind = TK_MONOMIAL;
+                    d.brick = u.work_spectrum;
+                    apply_prefixes(&d, prefixes);
+                    ce.rhs.push_back(d);
+                    break;
             }
         } else if (is_bilinear(t.SubString, ce.field, all_field_names())) {
             t.SubString = replace_all(t.SubString, ce.field, "");
@@ -517,6 +525,7 @@ void Model::init() {
             case UserTermKind::ConservativeNoise: u.slot = n_cn++; break;
             case UserTermKind::VolumeConservingLP: u.slot = n_lp++; break;
             case UserTermKind::SquaredGradient:
+            case UserTermKind::HomogeneousModulusLinElast:
                 u.work_spectrum = (int)(fields.size() + derived.size()) + n_work_spectra++;
                 break;
             default: break;

@@ -31,7 +31,7 @@ struct DerivedSpec {
 };
 
 enum class UserTermClass { Implicit, Explicit, Mixed };
-enum class UserTermKind { SpectralViscosity, PairCorrelation, ExplicitPairCorrelation, IdealMixture, ConservativeNoise, VolumeConservingLP, SquaredGradient };
+enum class UserTermKind { SpectralViscosity, PairCorrelation, ExplicitPairCorrelation, IdealMixture, ConservativeNoise, VolumeConservingLP, SquaredGradient, HomogeneousModulusLinElast };
 
 struct UserTerm {
     std::string name;
@@ -47,7 +47,9 @@ struct UserTerm {
     std::vector<std::string> current_names;  // ConservativeNoise current fields
     double dt = 0.0;         // VolumeConservingLP.Dt
     int slot = -1;           // index into the DevKProgram special-parameter arrays
-    int work_spectrum = -1;  // SquaredGradient: spectrum index its result is written to
+    int work_spectrum = -1;  // SquaredGradient / elastic term: spectrum index its result is written to
+    double stiffness[81] = {0};  // HomogeneousModulusLinElast.MatProp (elasticity.Rank4.Data, rank4.go:22-24)
+    double misfit[9] = {0};      // HomogeneousModulusLinElast.Misfit, row-major 3x3
 };
 
 struct CompiledEquation {

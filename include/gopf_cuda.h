@@ -61,6 +61,10 @@ int gopf_fft_plan_create(int rank, const int* n, int device, gopf_fft_plan** out
 int gopf_fft_exec(gopf_fft_plan* plan, double* host_inout_c128, int sign);
 /* same on a device-resident array; stream is a cudaStream_t (NULL = plan stream) */
 int gopf_fft_exec_device(gopf_fft_plan* plan, void* dev_inout_c128, int sign, void* stream);
+/* one axis pass only (0 = slowest axis of the normalised 3-axis view), device arrays, out may
+ * equal in; tile_cells = strided-tile width in cells (0: plan default).  Kernel tuning and tests. */
+int gopf_fft_exec_axis_device(gopf_fft_plan* plan, const void* dev_in_c128, void* dev_out_c128, int sign, int axis,
+                              int tile_cells, void* stream);
 /* Freq(i) for `count` node numbers evaluated ON THE DEVICE by the same code the
  * k-space kernels use (bit-exactness check of the device k-table). */
 int gopf_fft_freq_device(gopf_fft_plan* plan, const int64_t* nodes, int64_t count, double* out);

@@ -412,3 +412,81 @@ class IdealMixtureTerm:
     def GetEnergy(self, bricks, nodes: int) -> float:
         v = np.real(bricks[self.Field].Get(np.arange(nodes)))
         return float(np.sum(self.Prefactor * self.IdealMix.Eval(v)))
+
+
+# ==========================================================================
+# pf/homoLinElast.go
+# ==========================================================================
+def Indicator(x):
+    """pf/homoLinElast.go:10-12."""
+    return 3.0 * x * x - 2.0 * x * x * x
+
+
+def IndicatorDeriv(x):
+    """pf/homoLinElast.go:15-17."""
+    return 6.0 * x - 6.0 * x * x
+
+
+class HomogeneousModulusLinElast:
+    """pf/homoLinElast.go:30-150 (Khachaturyan homogeneous-modulus driving force).
+    ``Field`` is the real-space phase field of the PREVIOUS OnStepFinished (zeros before the
+    first one, :145), so the term is identically zero during the first step."""
+
+    def __init__(self, field_name: str, domain_size, mat_prop, misfit, workers: int = 1):
+        from . import elasticity as el
+        self._el = el
+        self.FieldName = field_name
+        self.Dim = len(domain_size)
+        self.N = pfutil.prod_int(domain_size)
+        self.MatProp = mat_prop
+        self.Misfit = np.asarray(misfit, dtype=np.float64)
+        self.EffForce = el.EffectiveForce(mat_prop, self.Misfit)
+        self.Field = np.zeros(self.N, dtype=np.float64)
+        self.Disps = el.Displacements
+        self.FT = pfutil.NewFFTW(domain_size, workers)
+
+    def Freq3(self) -> np.ndarray:
+        return self._el.pad3(self.FT.freq_table())
+
+    def Force(self, indicator: np.ndarray) -> np.ndarray:
+        """:114-127 -- components i < Dim, frequencies padded to 3."""
+        f3 = self.Freq3()
+        res = np.zeros((self.N, 3), dtype=np.complex128)
+        for i in range(self.Dim):
+            res[:, i] = self.EffForce.Get(i, f3, indicator)
+        return res
+
+    def Construct(self, bricks):
+        el = self._el
+
+        def fn(freq, t, field: np.ndarray):
+            field[:] = 0.0
+            work = Indicator(self.Field).astype(np.complex128)
+            self.FT.FFT(work)
+            force = self.Force(work)
+            f3 = self.Freq3()
+            disp = self.Disps(force, f3, self.MatProp)
+            dwork = IndicatorDeriv(self.Field).astype(np.complex128)
+            A = self.MatProp.ContractLast(self.Misfit)
+            for i in range(self.Dim):
+                for j in range(i, self.Dim):
+                    strains = np.ascontiguousarray(el.Strain(disp, f3, i, j))
+                    self.FT.IFFT(strains)
+                    strains /= complex(float(self.N), 0.0)
+                    strains *= dwork
+                    self.FT.FFT(strains)
+                    factor = 1.0 if i == j else 2.0
+                    field += complex(factor * A[i, j], 0.0) * strains
+            e_density = el.EnergyDensity(self.MatProp, self.Misfit)
+            work = (Indicator(self.Field) * IndicatorDeriv(self.Field)).astype(np.complex128)
+            self.FT.FFT(work)
+            field -= complex(2.0 * e_density, 0.0) * work
+
+        return fn
+
+    def OnStepFinished(self, t, bricks):
+        self.Field[:] = np.real(bricks[self.FieldName].Get(np.arange(self.N)))
+
+
+def NewHomogeneousModolus(field_name, domain_size, mat_prop, misfit, workers: int = 1):
+    return HomogeneousModulusLinElast(field_name, domain_size, mat_prop, misfit, workers)
