@@ -90,6 +90,21 @@ func NewGPUStepper(m *Model, domainSize []int, dt float64, scheme string, exprs 
 			cf := cstr(v.Field)
 			gpuCheck(C.gopf_model_register_squared_gradient(st.model, cn, cf, C.double(v.Factor)))
 			C.free(unsafe.Pointer(cf))
+		case *HomogeneousModulusLinElast:
+			// MatProp.Data is the 81-element rank-4 tensor (elasticity/rank4.go:10-24), Misfit a 3x3 mat.Dense
+			cf := cstr(v.FieldName)
+			misfit := make([]C.double, 9)
+			for i := 0; i < 3; i++ {
+				for j := 0; j < 3; j++ {
+					misfit[3*i+j] = C.double(v.Misfit.At(i, j))
+				}
+			}
+			stiff := make([]C.double, 81)
+			for i, x := range v.MatProp.Data {
+				stiff[i] = C.double(x)
+			}
+			gpuCheck(C.gopf_model_register_homogeneous_modulus_lin_elast(st.model, cn, cf, &stiff[0], &misfit[0]))
+			C.free(unsafe.Pointer(cf))
 		case *PairCorrlationTerm:
 			registerPairCorrelation(st.model, cn, v, 0)
 		case *ExplicitPairCorrelationTerm:

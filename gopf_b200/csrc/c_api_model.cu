@@ -208,6 +208,117 @@ int gopf_model_register_squared_gradient(gopf_model* m, const char* name, const 
     GOPF_API_END
 }
 
+int gopf_model_register_homogeneous_modulus_lin_elast(gopf_model* m, const char* name, const char* field,
+                                                      const double* stiffness81, const double* misfit9) {
+    GOPF_API_BEGIN
+    if (!m || !stiffness81 || !misfit9) throw Error("NULL argument");
+    UserTerm u;
+    u.name = need(name, "name");
+    u.cls = UserTermClass::Explicit;
+    u.kind = UserTermKind::HomogeneousModulusLinElast;
+    u.field = need(field, "field");
+    std::memcpy(u.stiffness, stiffness81, sizeof(u.stiffness));
+    std::memcpy(u.misfit, misfit9, sizeof(u.misfit));
+    m->m.register_user_term(u);
+    GOPF_API_END
+}
+
+// ---- elasticity package helpers (host) ---------------------------------------------------
+static inline int r4(int i, int j, int k, int l) { return i * 27 + j * 9 + k * 3 + l; }
+
+// elasticity/rank4.go:113-128 (as written: only C_ijij and C_jiji carry c44)
+int gopf_elasticity_cubic_material(double c11, double c12, double c44, double* out) {
+    GOPF_API_BEGIN
+    if (!out) throw Error("NULL argument");
+    for (int i = 0; i < 81; ++i) out[i] = 0.0;
+    for (int i = 0; i < 3; ++i) out[r4(i, i, i, i)] = c11;
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j) {
+            out[r4(i, i, j, j)] = c12;
+            out[r4(j, j, i, i)] = c12;
+            out[r4(i, j, i, j)] = c44;
+            out[r4(j, i, j, i)] = c44;
+        }
+    GOPF_API_END
+}
+
+// elasticity/rank4.go:78-110
+int gopf_elasticity_isotropic(double bulk_mod, double poisson, double* out) {
+    GOPF_API_BEGIN
+    if (!out) throw Error("NULL argument");
+    const double shear = 3.0 * bulk_mod * (1.0 - 2.0 * poisson) / (2.0 * (1.0 + poisson));
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            for (int k = 0; k < 3; ++k)
+                for (int l = 0; l < 3; ++l) {
+                    double v = 0.0;
+                    if (i == j && k == l) v += bulk_mod - 2.0 * shear / 3.0;
+                    if (i == k && j == l) v += shear;
+                    if (i == l && j == k) v += shear;
+                    out[r4(i, j, k, l)] = v;
+                }
+    GOPF_API_END
+}
+
+// elasticity/rank4.go:39-60
+int gopf_elasticity_rotate(double* c, const double* rot) {
+    GOPF_API_BEGIN
+    if (!c || !rot) throw Error("NULL argument");
+    double res[81];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            for (int k = 0; k < 3; ++k)
+                for (int l = 0; l < 3; ++l) {
+                    double s = 0.0;
+                    for (int mm = 0; mm < 3; ++mm)
+                        for (int n = 0; n < 3; ++n)
+                            for (int p = 0; p < 3; ++p)
+                                for (int q = 0; q < 3; ++q)
+                                    s += rot[i * 3 + mm] * rot[j * 3 + n] * rot[k * 3 + p] * rot[l * 3 + q] * c[r4(mm, n, p, q)];
+                    res[r4(i, j, k, l)] = s;
+                }
+    std::memcpy(c, res, sizeof(res));
+    GOPF_API_END
+}
+
+// elasticity/rank4.go:62-75
+int gopf_elasticity_contract_last(const double* c, const double* t, double* out) {
+    GOPF_API_BEGIN
+    if (!c || !t || !out) throw Error("NULL argument");
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 3; ++k)
+                for (int l = 0; l < 3; ++l) s += c[r4(i, j, k, l)] * t[k * 3 + l];
+            out[i * 3 + j] = s;
+        }
+    GOPF_API_END
+}
+
+// elasticity/linearElasticity.go:86-98
+int gopf_elasticity_energy_density(const double* c, const double* e, double* out) {
+    GOPF_API_BEGIN
+    if (!c || !e || !out) throw Error("NULL argument");
+    double res = 0.0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            for (int k = 0; k < 3; ++k)
+                for (int l = 0; l < 3; ++l) res += c[r4(i, j, k, l)] * e[i * 3 + j] * e[k * 3 + l];
+    *out = 0.5 * res;
+    GOPF_API_END
+}
+
+int gopf_elasticity_multiplier(const double* c, const double* misfit, int dim, const double* freq3, int64_t count,
+                               double* out) {
+    GOPF_API_BEGIN
+    if (!c || !misfit || !freq3 || !out) throw Error("NULL argument");
+    if (dim != 2 && dim != 3) throw Error("gopf_elasticity_multiplier: dim must be 2 or 3");
+    ElastParams E;
+    make_elast_params(&E, c, misfit, dim);
+    for (int64_t i = 0; i < count; ++i) out[i] = elastic_multiplier(E, freq3[3 * i], freq3[3 * i + 1], freq3[3 * i + 2]);
+    GOPF_API_END
+}
+
 int gopf_model_init(gopf_model* m) {
     GOPF_API_BEGIN
     if (!m) throw Error("model is NULL");

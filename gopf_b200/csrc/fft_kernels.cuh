@@ -86,7 +86,8 @@ enum LoadKind {
     LK_GRADIENT = 2,  // i 2 pi f_comp * in[idx], +0.5 Nyquist zeroed (squareGradientTerm.go:45-50)
     LK_SUM_SQUARES = 3,  // sum_d g_d[idx]^2 (squareGradientTerm.go:53-62, summed before the transform)
     LK_ELAST_H = 4,      // H(re phi[idx]), phi = g[0]                       (homoLinElast.go:53-57)
-    LK_ELAST_R = 5       // H'(phi) * in[idx] - aux * H(phi) * H'(phi)        (homoLinElast.go:64-97, by linearity)
+    LK_ELAST_R = 5,      // H'(phi) * in[idx] - aux * H(phi) * H'(phi)        (homoLinElast.go:64-97, by linearity)
+    LK_MUL_TABLE = 6     // rtab[idx] * in[idx]: tabulated real k-space multiplier (elastic.cuh M(k))
 };
 
 struct PassIO {
@@ -106,6 +107,8 @@ struct PassIO {
     int dim;
     const cplx* g[3];
     double aux;
+    // LK_MUL_TABLE
+    const double* rtab;
 };
 
 inline PassIO plain_io(const cplx* in, cplx* out, bool inverse, double scale) {
@@ -121,6 +124,8 @@ inline PassIO plain_io(const cplx* in, cplx* out, bool inverse, double scale) {
     io.D.kind = 0;
     io.D.n_factors = 0;
     io.D.n_ops = 0;
+    io.aux = 0.0;
+    io.rtab = nullptr;
     return io;
 }
 
@@ -145,6 +150,10 @@ __device__ __forceinline__ cplx pass_load_slow(const PassIO& io, size_t idx) {
         const double h = 3.0 * p * p - 2.0 * p * p * p, dh = 6.0 * p - 6.0 * p * p;
         const cplx e = io.in[idx];
         x = mk(dh * e.x - io.aux * (h * dh), dh * e.y);
+    } else if (io.load_kind == LK_MUL_TABLE) {
+        const double w = io.rtab[idx];
+        const cplx u = io.in[idx];
+        x = mk(u.x * w, u.y * w);
     } else {
         cplx a = io.g[0][idx];
         x = a * a;

@@ -514,7 +514,7 @@ void Model::init() {
     if (equations.size() > fields.size()) throw Error("model: more equations than fields");
     for (DerivedSpec& d : derived) d.used = false;
     // assign parameter slots / work spectra to the registered user terms
-    int n_sv = 0, n_pc = 0, n_cn = 0, n_lp = 0;
+    int n_sv = 0, n_pc = 0, n_cn = 0, n_lp = 0, n_el = 0;
     n_work_spectra = 0;
     for (auto& kv : user_terms) {
         UserTerm& u = kv.second;
@@ -524,14 +524,18 @@ void Model::init() {
             case UserTermKind::ExplicitPairCorrelation: u.slot = n_pc++; break;
             case UserTermKind::ConservativeNoise: u.slot = n_cn++; break;
             case UserTermKind::VolumeConservingLP: u.slot = n_lp++; break;
-            case UserTermKind::SquaredGradient:
             case UserTermKind::HomogeneousModulusLinElast:
+                u.slot = n_el++;
+                u.work_spectrum = (int)(fields.size() + derived.size()) + n_work_spectra++;
+                break;
+            case UserTermKind::SquaredGradient:
                 u.work_spectrum = (int)(fields.size() + derived.size()) + n_work_spectra++;
                 break;
             default: break;
         }
     }
-    if (n_sv > GOPF_MAX_SPECIAL || n_pc > GOPF_MAX_SPECIAL || n_cn > GOPF_MAX_SPECIAL || n_lp > GOPF_MAX_SPECIAL)
+    if (n_sv > GOPF_MAX_SPECIAL || n_pc > GOPF_MAX_SPECIAL || n_cn > GOPF_MAX_SPECIAL || n_lp > GOPF_MAX_SPECIAL ||
+        n_el > GOPF_MAX_SPECIAL)
         throw Error(strf("model: at most %d terms of each special kind", GOPF_MAX_SPECIAL));
     if (n_spectra() > GOPF_MAX_SPECTRA) throw Error(strf("model: at most %d spectra", GOPF_MAX_SPECTRA));
     compiled.clear();

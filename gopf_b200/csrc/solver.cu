@@ -54,6 +54,17 @@ __global__ void k_volume_lp_update(double* state, const cplx* field_spec, const 
     }
 }
 
+// M(k) of the elastic term for every node (elastic.cuh); time-independent, tabulated once.
+__global__ void __launch_bounds__(256)
+    k_elastic_table(const __grid_constant__ ElastParams E, FreqGeom fg, double* out, long long n) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        double f[3] = {0.0, 0.0, 0.0};  // homoLinElast.go:103-111: padded to 3
+        ref_freq(fg, idx, f);
+        out[idx] = elastic_multiplier(E, f[0], f[1], f[2]);
+    }
+}
+
 // RK4 pointwise kernels (pf/rk4.go:58-68, 77-84, 87-96, 101-111, 123-126)
 __global__ void __launch_bounds__(256)
     k_rk4_rhs(const __grid_constant__ DevKProgram P, SpectraPtrs sp, SpectraPtrs kout, FreqGeom fg, long long n) {
@@ -142,6 +153,10 @@ Solver::Solver(Model* m, int rank, const int* n, double dt, int device) : m_(m),
     std::memset(&R_, 0, sizeof(R_));
     for (int i = 0; i < GOPF_MAX_FIELDS; ++i) Rw_[i] = rk_initial_[i] = rk_final_[i] = rk_k_[i] = nullptr;
     for (int i = 0; i < 3; ++i) sg_tmp_[i] = nullptr;
+    for (int i = 0; i < GOPF_MAX_SPECIAL; ++i) {
+        elast_mtab_[i] = nullptr;
+        elast_phi_[i] = nullptr;
+    }
     for (int i = 0; i < GOPF_MAX_SPECTRA; ++i) d_table_[i] = nullptr;
     decide_path();
 }
@@ -158,6 +173,10 @@ Solver::~Solver() {
     }
     for (int i = 0; i < 3; ++i)
         if (sg_tmp_[i]) cudaFree(sg_tmp_[i]);
+    for (int i = 0; i < GOPF_MAX_SPECIAL; ++i) {
+        if (elast_mtab_[i]) cudaFree(elast_mtab_[i]);
+        if (elast_phi_[i]) cudaFree(elast_phi_[i]);
+    }
     for (int i = 0; i < GOPF_MAX_SPECTRA; ++i)
         if (d_table_[i]) cudaFree(d_table_[i]);
     if (W_) cudaFree(W_);
@@ -249,9 +268,28 @@ void Solver::ensure_buffers() {
             const int si = F + (int)m_->derived.size() + w;
             if (!S_.s[si]) GOPF_CUDA(cudaMalloc(&S_.s[si], bytes));
         }
+        bool any_sg = false;
+        for (const auto& kv : m_->user_terms) any_sg |= kv.second.kind == UserTermKind::SquaredGradient;
         if (m_->n_work_spectra > 0)
-            for (int d = 0; d < plan_->rank; ++d)
+            for (int d = 0; d < (any_sg ? plan_->rank : 1); ++d)
                 if (!sg_tmp_[d]) GOPF_CUDA(cudaMalloc(&sg_tmp_[d], bytes));
+        for (const auto& kv : m_->user_terms) {
+            const UserTerm& u = kv.second;
+            if (u.kind != UserTermKind::HomogeneousModulusLinElast) continue;
+            if (!elast_mtab_[u.slot]) {
+                GOPF_CUDA(cudaMalloc(&elast_mtab_[u.slot], sizeof(double) * plan_->N));
+                ElastParams E;
+                make_elast_params(&E, u.stiffness, u.misfit, plan_->rank);
+                k_elastic_table<<<grid_for((long long)plan_->N), 256, 0, stream()>>>(E, plan_->freq_geom(),
+                                                                                     elast_mtab_[u.slot], (long long)plan_->N);
+                GOPF_CUDA(cudaGetLastError());
+                launches_++;
+            }
+            if (stepper_ == StepperKind::RK4 && !elast_phi_[u.slot]) {
+                GOPF_CUDA(cudaMalloc(&elast_phi_[u.slot], bytes));
+                GOPF_CUDA(cudaMemsetAsync(elast_phi_[u.slot], 0, bytes, stream()));
+            }
+        }
         if (need_real)
             for (int i = 0; i < F; ++i)
                 if (!Rw_[i]) {
@@ -570,6 +608,101 @@ void Solver::squared_gradient_terms() {
     }
 }
 
+bool Solver::has_elastic() const {
+    for (const auto& kv : m_->user_terms)
+        if (kv.second.kind == UserTermKind::HomogeneousModulusLinElast) return true;
+    return false;
+}
+
+// HomogeneousModulusLinElast (pf/homoLinElast.go:47-99) with the dim(dim+1)/2 strain round trips
+// collapsed by linearity (elastic.cuh): forward of H(phi), inverse of M(k) H^, forward of
+// H'(phi) e - 2 E H(phi) H'(phi).  phi is the term's own real-space copy of the field: zeros
+// before the first OnStepFinished (:145), the field at the end of the previous step afterwards.
+void Solver::elastic_terms() {
+    cudaStream_t s = stream();
+    const double cell = 32.0 * (double)plan_->N;
+    for (const auto& kv : m_->user_terms) {
+        const UserTerm& u = kv.second;
+        if (u.kind != UserTermKind::HomogeneousModulusLinElast) continue;
+        const int fi = m_->field_index(u.field);
+        if (fi < 0) throw Error("HomogeneousModulusLinElast: unknown field " + u.field);
+        cplx* out = S_.s[u.work_spectrum];
+        if (!elast_valid_) {  // H(0) = H'(0) = 0: the whole term is zero
+            GOPF_CUDA(cudaMemsetAsync(out, 0, sizeof(cplx) * plan_->N, s));
+            continue;
+        }
+        for (int ax = 0; ax < 3; ++ax)
+            if (plan_->extent(ax) > 1 && !plan_->axis_fast(ax))
+                throw Error("HomogeneousModulusLinElast needs power-of-two extents on the device path");
+        const cplx* phi = stepper_ == StepperKind::RK4 ? elast_phi_[u.slot] : Rw_[fi];
+        ElastParams E;
+        const double e_density = make_elast_params(&E, u.stiffness, u.misfit, plan_->rank);
+        int first_fwd = -1, last_inv = -1;
+        for (int ax = 0; ax < 3; ++ax)
+            if (plan_->extent(ax) > 1) {
+                if (first_fwd < 0 || ax > first_fwd) first_fwd = ax;
+                last_inv = ax;
+            }
+        const double inv_n = 1.0 / (double)plan_->N;
+        // FFT(H(phi)) -> out
+        for (int ax = 2; ax >= 0; --ax) {
+            if (plan_->extent(ax) <= 1) continue;
+            PassIO io = plain_io(out, out, false, 1.0);
+            if (ax == first_fwd) {
+                io.load_kind = LK_ELAST_H;
+                io.g[0] = io.g[1] = io.g[2] = phi;
+            }
+            const int id = tick("pass_forward_elast_h", cell);
+            cudaError_t e = launch_pass(plan_->geom(ax), plan_->tx_want, io, plan_->twiddle(ax), s);
+            tock(id);
+            if (e != cudaSuccess) throw Error(strf("elastic indicator pass: %s", cudaGetErrorString(e)));
+        }
+        // IFFT(M(k) H^)/N -> sg_tmp_[0]
+        bool first = true;
+        for (int ax = 0; ax < 3; ++ax) {
+            if (plan_->extent(ax) <= 1) continue;
+            PassIO io = plain_io(first ? out : sg_tmp_[0], sg_tmp_[0], true, ax == last_inv ? inv_n : 1.0);
+            if (first) {
+                io.load_kind = LK_MUL_TABLE;
+                io.rtab = elast_mtab_[u.slot];
+            }
+            const int id = tick("pass_inverse_elast_strain", cell);
+            cudaError_t e = launch_pass(plan_->geom(ax), plan_->tx_want, io, plan_->twiddle(ax), s);
+            tock(id);
+            if (e != cudaSuccess) throw Error(strf("elastic strain pass: %s", cudaGetErrorString(e)));
+            first = false;
+        }
+        // FFT(H'(phi) e - 2 E H(phi) H'(phi)) -> out
+        for (int ax = 2; ax >= 0; --ax) {
+            if (plan_->extent(ax) <= 1) continue;
+            PassIO io = plain_io(ax == first_fwd ? sg_tmp_[0] : out, out, false, 1.0);
+            if (ax == first_fwd) {
+                io.load_kind = LK_ELAST_R;
+                io.g[0] = io.g[1] = io.g[2] = phi;
+                io.aux = 2.0 * e_density;
+            }
+            const int id = tick("pass_forward_elast_force", cell);
+            cudaError_t e = launch_pass(plan_->geom(ax), plan_->tx_want, io, plan_->twiddle(ax), s);
+            tock(id);
+            if (e != cudaSuccess) throw Error(strf("elastic driving-force pass: %s", cudaGetErrorString(e)));
+        }
+    }
+}
+
+// HomogeneousModulusLinElast.OnStepFinished (pf/homoLinElast.go:130-134).  Under Euler the
+// copy is the real-space field the next step computes anyway; RK4 evaluates the term at
+// intermediate stages against the end-of-step snapshot, so it is taken here.
+void Solver::elastic_hooks() {
+    if (!has_elastic()) return;
+    if (stepper_ == StepperKind::RK4)
+        for (const auto& kv : m_->user_terms) {
+            const UserTerm& u = kv.second;
+            if (u.kind != UserTermKind::HomogeneousModulusLinElast) continue;
+            inverse_to_real(S_.s[m_->field_index(u.field)], elast_phi_[u.slot]);
+        }
+    elast_valid_ = true;
+}
+
 void Solver::volume_lp_hooks() {
     for (const auto& kv : m_->user_terms) {
         const UserTerm& u = kv.second;
@@ -629,14 +762,17 @@ void Solver::download() {
 void Solver::euler_step_generic() {
     bool any_derived = false;
     for (const DerivedSpec& d : m_->derived) any_derived |= d.used;
-    if (any_derived) {
+    const bool elastic = has_elastic();
+    if (any_derived || (elastic && elast_valid_)) {
         eval_real_fields();                                  // real-space fields for SyncDerivedFields (euler.go:18)
         for (size_t d = 0; d < m_->derived.size(); ++d)
             if (m_->derived[d].used) forward_derived((int)d);  // euler.go:22-24
     }
     squared_gradient_terms();
+    if (elastic) elastic_terms();
     launch_update(prog_);                                    // euler.go:27-39
     volume_lp_hooks();                                       // solver.go:74-82
+    elastic_hooks();
 }
 
 void Solver::euler_step_fused() {
@@ -704,6 +840,7 @@ void Solver::rk4_step() {
                 if (m_->derived[d].used) forward_derived((int)d);
         }
         squared_gradient_terms();
+        if (has_elastic()) elastic_terms();
         k_rk4_rhs<<<grid_for(n), 256, 0, s>>>(prog_, S_, kf, fg, n);
         GOPF_CUDA(cudaGetLastError());
         launches_++;
@@ -729,6 +866,7 @@ void Solver::rk4_step() {
     sync_and_rhs();
     point(0, dt_ / 6.0);
     point(2, dt_);                  // rk4.go:57-68
+    elastic_hooks();                // solver.go:74-82 (OnStepFinished after Stepper.Step)
 }
 
 void Solver::step(int nsteps) {

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "fft_plan.h"
+#include "elastic.cuh"
 #include "model.h"
 #include "step_kernels.cuh"
 
@@ -87,6 +88,11 @@ private:
     cplx* rk_final_[GOPF_MAX_FIELDS];
     cplx* rk_k_[GOPF_MAX_FIELDS];
     cplx* sg_tmp_[3];
+    // HomogeneousModulusLinElast (pf/homoLinElast.go): tabulated multiplier M(k) per term slot,
+    // RK4's snapshot of the real-space field, and "OnStepFinished has run at least once"
+    double* elast_mtab_[GOPF_MAX_SPECIAL];
+    cplx* elast_phi_[GOPF_MAX_SPECIAL];
+    bool elast_valid_ = false;
     double* d_table_[GOPF_MAX_SPECTRA];
     DevKProgram prog_;
     DevKProgram fused_prog_;
@@ -107,6 +113,9 @@ private:
     void forward_in_place(cplx* data);
     void eval_real_fields();
     void squared_gradient_terms();
+    void elastic_terms();
+    void elastic_hooks();
+    bool has_elastic() const;
     void volume_lp_hooks();
     void launch_update(const DevKProgram& P);
     int tick(const char* name, double bytes);

@@ -246,6 +246,30 @@ def NewSquareGradient(field: str, domainSize) -> SquaredGradient:
     return SquaredGradient(field, domainSize)
 
 
+class HomogeneousModulusLinElast:
+    """pf.HomogeneousModulusLinElast (pf/homoLinElast.go:30-150).  MatProp is an
+    ``elasticity.Rank4`` (or 81 doubles), Misfit the 3x3 misfit strain."""
+
+    def __init__(self, fieldName: str, domainSize, matProp, misfit):
+        if len(domainSize) not in (2, 3):
+            raise GopfError("HomogeneousModulusLinElast: domain size has to be of length 2 or 3")
+        self.FieldName = fieldName
+        self.Dim = len(domainSize)
+        self.MatProp = np.ascontiguousarray(getattr(matProp, "Data", matProp), dtype=np.float64).reshape(81)
+        self.Misfit = np.ascontiguousarray(misfit, dtype=np.float64).reshape(9)
+
+    def _register(self, m: "Model", name: str, cls: str):
+        if cls != "explicit":
+            raise GopfError("HomogeneousModulusLinElast is an explicit term")
+        pd = ctypes.POINTER(ctypes.c_double)
+        check(lib().gopf_model_register_homogeneous_modulus_lin_elast(
+            m._h, _s(name), _s(self.FieldName), self.MatProp.ctypes.data_as(pd), self.Misfit.ctypes.data_as(pd)))
+
+
+def NewHomogeneousModolus(fieldName: str, domainSize, matProp, misfit) -> HomogeneousModulusLinElast:
+    return HomogeneousModulusLinElast(fieldName, domainSize, matProp, misfit)
+
+
 class Vandeven:
     """pf.Vandeven (pf/vandeven.go:8-40): Data is the 1000-point table."""
 

@@ -1,0 +1,100 @@
+"""Workload definitions of BASELINE.json configs 4 and 5, written once against the ``pf``
+surface so the same builder drives this package (``gopf_b200.pf``) and -- in tests and the CPU
+baseline only -- the oracle restatement.  The caller passes the modules; nothing here imports
+``oracle``.
+
+cfg 4: examples/strain_single_precipitate/main.go:45-127 (two fields, three registered
+functions, VolumeConservingLP, HomogeneousModulusLinElast), extended to 3-D as SURVEY.md 8d
+states.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+PRECIPITATE_DT = 0.1          # main.go:67
+PRECIPITATE_KAPPA = 0.1       # main.go:86
+PRECIPITATE_A = PRECIPITATE_B = PRECIPITATE_W = 0.1  # main.go:93-98
+PRECIPITATE_M = 1.0
+PRECIPITATE_MISFIT = np.array([[0.05, 0.0, 0.0], [0.0, -0.01, 0.0], [0.0, 0.0, 0.0]])  # main.go:109
+PRECIPITATE_CUBIC = (110.0, 60.0, 30.0)  # main.go:110
+
+# Device-expressible forms of ModelFunctions.ChemicalPotential / DerivPhase / SmearingDeriv
+# (main.go:45-64); H, dH, dLandau are main.go:18-32.
+CHEMICALPOT_EXPR = "-((0.1*conc*(1.0-H(phase))-0.1*(1.0-conc)*H(phase))*1.0)"
+DERIV_PHASE_EXPR = "-(-0.5*0.1*conc^2*dH(phase)+0.5*0.1*(1.0-conc)^2*dH(phase)+0.1*dLandau(phase))"
+SMEARING_EXPR = "dH(phase)"
+
+
+def _H(x):
+    return 3.0 * x * x - 2.0 * x * x * x
+
+
+def _dH(x):
+    return 6.0 * x - 6.0 * x * x
+
+
+def _dLandau(x):
+    return 2.0 * x - 6.0 * x * x + 4.0 * x * x * x
+
+
+def precipitate_initial(dims) -> np.ndarray:
+    """Cube (square in 2-D) 3M/8 < r, c[, d] < 5M/8 set to one (main.go:76-84)."""
+    M = dims[0]
+    n = int(np.prod(dims))
+    idx = np.arange(n, dtype=np.int64)
+    c = idx % dims[1]
+    r = (idx // dims[1]) % dims[0]
+    inside = (r > 3 * M // 8) & (r < 5 * M // 8) & (c > 3 * M // 8) & (c < 5 * M // 8)
+    if len(dims) == 3:
+        d = idx // (dims[0] * dims[1])
+        inside &= (d > 3 * M // 8) & (d < 5 * M // 8)
+    return inside.astype(np.complex128)
+
+
+def build_precipitate(pf, terms, elasticity, dims, *, expressions: bool, elastic: bool = True, volume: bool = True,
+                      pinned: bool = False):
+    """Returns (model, conc, phase, solver, volume_term).  ``expressions`` selects the
+    device-expressible RegisterFunction form (this package) or Python closures (the oracle)."""
+    n = int(np.prod(dims))
+    dt = PRECIPITATE_DT
+    init = precipitate_initial(dims)
+    m = pf.NewModel()
+    if pinned:
+        conc = pf.NewField("conc", n, None, pinned=True)
+        phase = pf.NewField("phase", n, None, pinned=True)
+        conc.Data[:] = init
+        phase.Data[:] = init
+    else:
+        conc = pf.NewField("conc", n, init.copy())
+        phase = pf.NewField("phase", n, init.copy())
+    m.AddScalar(pf.NewScalar("kappa", PRECIPITATE_KAPPA))
+    m.AddField(conc)
+    m.AddField(phase)
+    if expressions:
+        m.RegisterFunction("CHEMICALPOT", CHEMICALPOT_EXPR)
+        m.RegisterFunction("DERIV_PHASE_ORDER", DERIV_PHASE_EXPR)
+        m.RegisterFunction("SMEARING_DERIV", SMEARING_EXPR)
+    else:
+        A, B, W, Mm = PRECIPITATE_A, PRECIPITATE_B, PRECIPITATE_W, PRECIPITATE_M
+        cc = lambda i, b: np.real(b["conc"].Get(i))
+        xx = lambda i, b: np.real(b["phase"].Get(i))
+        m.RegisterFunction("CHEMICALPOT", lambda i, b: -((A * cc(i, b) * (1.0 - _H(xx(i, b))) - B * (1.0 - cc(i, b)) * _H(xx(i, b))) * Mm) + 0j)
+        m.RegisterFunction("DERIV_PHASE_ORDER", lambda i, b: -(-0.5 * A * cc(i, b) ** 2 * _dH(xx(i, b)) + 0.5 * B * (1.0 - cc(i, b)) ** 2 * _dH(xx(i, b)) + W * _dLandau(xx(i, b))) + 0j)
+        m.RegisterFunction("SMEARING_DERIV", lambda i, b: _dH(xx(i, b)) + 0j)
+    vol = None
+    eq_phase = "dphase/dt = DERIV_PHASE_ORDER"
+    if volume:
+        vol = terms.NewVolumeConservingLP("phase", "SMEARING_DERIV", dt, n)
+        m.RegisterExplicitTerm("CONSERVE_PREC_VOL", vol, None)
+    if elastic:
+        mat_prop = elasticity.CubicMaterial(*PRECIPITATE_CUBIC)
+        lin = terms.NewHomogeneousModolus("phase", dims, mat_prop, PRECIPITATE_MISFIT.copy())
+        m.RegisterExplicitTerm("LIN_ELAST", lin, None)
+        eq_phase += " + LIN_ELAST"
+    eq_phase += " + kappa*LAP phase"
+    if volume:
+        eq_phase += " + CONSERVE_PREC_VOL"
+    m.AddEquation("dconc/dt = CHEMICALPOT + kappa*LAP conc")
+    m.AddEquation(eq_phase)
+    solver = pf.NewSolver(m, dims, dt)
+    return m, conc, phase, solver, vol

@@ -120,6 +120,25 @@ int gopf_model_register_volume_conserving_lp(gopf_model* m, const char* name, co
                                              const char* indicator, double dt);
 /* RegisterExplicitTerm(name, &SquaredGradient{Field, Factor}) (pf/squareGradientTerm.go:14-68) */
 int gopf_model_register_squared_gradient(gopf_model* m, const char* name, const char* field, double factor);
+/* RegisterExplicitTerm(name, NewHomogeneousModolus(fieldName, domainSize, matProp, misfit))
+ * (pf/homoLinElast.go:30-150).  stiffness81 = elasticity.Rank4.Data (index i*27+j*9+k*3+l,
+ * elasticity/rank4.go:10-24), misfit9 = the 3x3 misfit strain, row-major.  The term's private
+ * real-space copy of the field starts as zeros and is refreshed after every step
+ * (OnStepFinished, :130-134), so the term vanishes during the first step -- replicated. */
+int gopf_model_register_homogeneous_modulus_lin_elast(gopf_model* m, const char* name, const char* field,
+                                                      const double* stiffness81, const double* misfit9);
+/* elasticity.CubicMaterial / Isotropic / Rank4.Rotate / Rank4.ContractLast / EnergyDensity
+ * (elasticity/rank4.go:39-128, linearElasticity.go:86-98): host-side tensor helpers */
+int gopf_elasticity_cubic_material(double c11, double c12, double c44, double* out81);
+int gopf_elasticity_isotropic(double bulk_mod, double poisson, double* out81);
+int gopf_elasticity_rotate(double* inout81, const double* rot9);
+int gopf_elasticity_contract_last(const double* stiffness81, const double* tensor9, double* out9);
+int gopf_elasticity_energy_density(const double* stiffness81, const double* strain9, double* out);
+/* The real multiplier M(k) the device applies between the transforms of the elastic term
+ * (gopf_b200/csrc/elastic.cuh), evaluated on the host for `count` frequency triples
+ * [f_row, f_col, f_depth] -- parity tests against elasticity.Displacements + Strain. */
+int gopf_elasticity_multiplier(const double* stiffness81, const double* misfit9, int dim, const double* freq3,
+                               int64_t count, double* out);
 /* Model.Init (pf/model.go:244-260): parse + classify every term */
 int gopf_model_init(gopf_model* m);
 int gopf_model_num_fields(gopf_model* m, int* n);

@@ -474,3 +474,48 @@ def test_cahn_hilliard_256_cubed_properties():
     s.StepDevice(20)
     s.Download()
     assert rel_l2(f.Data, fused) < 1e-12
+
+
+# ---- cfg 4: examples/strain_single_precipitate with HomogeneousModulusLinElast -----------
+def _precipitate_pair(dims, **kw):
+    from gopf_b200 import elasticity as gel
+    from gopf_b200 import workloads
+    from oracle import elasticity as oel
+    g = workloads.build_precipitate(gpf, gpf, gel, dims, expressions=True, **kw)
+    o = workloads.build_precipitate(opf, oterms, oel, dims, expressions=False, **kw)
+    return g, o
+
+
+@pytest.mark.parametrize("dims", [[64, 64], [32, 32, 32]], ids=lambda d: "x".join(map(str, d)))
+def test_strain_single_precipitate_vs_oracle(dims):
+    # the shipped example (2-D 64^2, main.go:66-127) and its 3-D extension (BASELINE.json cfg 4)
+    (gm, gconc, gphase, gs, gvol), (om, oconc, ophase, osolver, ovol) = _precipitate_pair(dims)
+    assert not gs.IsFused
+    gs.Solve(4, 5)
+    osolver.Solve(4, 5)
+    assert rel_l2(gconc.Data, oconc.Data) <= TOL and rel_l2(gphase.Data, ophase.Data) <= TOL
+    assert abs(gs.LPMultiplier(0) - ovol.Multiplier) <= 1e-9 * max(1.0, abs(ovol.Multiplier))
+
+
+def test_elastic_term_vanishes_in_first_step_then_acts():
+    # HomogeneousModulusLinElast.Field starts as zeros and is refreshed in OnStepFinished only
+    # (pf/homoLinElast.go:130-134,145): step 0 must equal the run without the term, step 1 not
+    dims = [32, 32]
+    (gm, gconc, gphase, gs, _), _ = _precipitate_pair(dims, volume=False)
+    (_, _, gphase0, gs0, _), _ = _precipitate_pair(dims, volume=False, elastic=False)
+    gs.Solve(1, 1)
+    gs0.Solve(1, 1)
+    assert np.array_equal(gphase.Data, gphase0.Data)
+    gs.Solve(1, 1)
+    gs0.Solve(1, 1)
+    assert rel_l2(gphase.Data, gphase0.Data) > 1e-6
+
+
+def test_elastic_term_rk4_vs_oracle():
+    dims = [32, 32]
+    (gm, gconc, gphase, gs, _), (om, oconc, ophase, osolver, _) = _precipitate_pair(dims, volume=False)
+    gs.SetStepper("rk4")
+    osolver.SetStepper("rk4")
+    gs.Solve(2, 3)
+    osolver.Solve(2, 3)
+    assert rel_l2(gconc.Data, oconc.Data) <= TOL and rel_l2(gphase.Data, ophase.Data) <= TOL
