@@ -278,6 +278,10 @@ def main():
     ap.add_argument("--grid", type=int, default=0, help="cubic grid edge (default 256 on 1 GPU, 1024 sharded)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "dma", "nccl"],
+                    help="sharded runs: peer stores fused into the passes, copy-engine copies pipelined under the "
+                         "kernels, or NCCL all-to-all")
+    ap.add_argument("--chunks", type=int, default=4, help="--exchange dma: chunks per exchange")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

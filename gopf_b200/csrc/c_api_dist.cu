@@ -99,6 +99,116 @@ int gopf_dist_inverse_finish(gopf_dist_solver* s, void* w, void* real_out) {
     GOPF_API_END
 }
 
+int gopf_dist_peer_alloc(gopf_dist_solver* s) {
+    GOPF_API_BEGIN
+    ds(s).peer_alloc();
+    GOPF_API_END
+}
+
+int gopf_dist_peer_export(gopf_dist_solver* s, int which, void* handle64) {
+    GOPF_API_BEGIN
+    if (!handle64 || (which != 0 && which != 1)) throw Error("gopf_dist_peer_export: bad argument");
+    ds(s).peer_export(which, handle64);
+    GOPF_API_END
+}
+
+int gopf_dist_peer_import(gopf_dist_solver* s, int which, int rank, const void* handle64) {
+    GOPF_API_BEGIN
+    if (!handle64 || (which != 0 && which != 1)) throw Error("gopf_dist_peer_import: bad argument");
+    ds(s).peer_import(which, rank, handle64);
+    GOPF_API_END
+}
+
+int gopf_dist_peer_local(gopf_dist_solver* s, int which, void** dev_ptr) {
+    GOPF_API_BEGIN
+    if (!dev_ptr || (which != 0 && which != 1)) throw Error("gopf_dist_peer_local: bad argument");
+    *dev_ptr = ds(s).peer_local(which);
+    GOPF_API_END
+}
+
+int gopf_dist_inverse_start_peer(gopf_dist_solver* s, const void* spectrum) {
+    GOPF_API_BEGIN
+    ds(s).inverse_start_peer(ccp(spectrum, "spectrum"));
+    GOPF_API_END
+}
+
+int gopf_dist_forward_mid_peer(gopf_dist_solver* s, const void* w) {
+    GOPF_API_BEGIN
+    ds(s).forward_mid_peer(ccp(w, "w"));
+    GOPF_API_END
+}
+
+int gopf_dist_forward_local_peer(gopf_dist_solver* s, void* w) {
+    GOPF_API_BEGIN
+    ds(s).forward_local_peer(cp(w, "w"));
+    GOPF_API_END
+}
+
+int gopf_dist_forward_finish_peer(gopf_dist_solver* s, void* spectrum) {
+    GOPF_API_BEGIN
+    ds(s).forward_finish_peer(cp(spectrum, "spectrum"));
+    GOPF_API_END
+}
+
+int gopf_dist_kspace_step_peer(gopf_dist_solver* s, void* spectrum) {
+    GOPF_API_BEGIN
+    ds(s).kspace_step_peer(cp(spectrum, "spectrum"));
+    GOPF_API_END
+}
+
+static void range_check(int begin, int count, int limit, const char* what) {
+    if (begin < 0 || count < 1 || begin + count > limit) throw Error(std::string(what) + ": chunk out of range");
+}
+
+int gopf_dist_inverse_mid_planes(gopf_dist_solver* s, const void* recv, void* w, int begin, int count) {
+    GOPF_API_BEGIN
+    range_check(begin, count, ds(s).slab(), "gopf_dist_inverse_mid_planes");
+    ds(s).inverse_mid_planes(ccp(recv, "recv"), cp(w, "w"), begin, count);
+    GOPF_API_END
+}
+
+int gopf_dist_real_step_planes(gopf_dist_solver* s, void* w, int begin, int count) {
+    GOPF_API_BEGIN
+    range_check(begin, count, ds(s).slab(), "gopf_dist_real_step_planes");
+    ds(s).real_step_planes(cp(w, "w"), begin, count);
+    GOPF_API_END
+}
+
+int gopf_dist_forward_mid_planes(gopf_dist_solver* s, const void* w, void* send, int begin, int count) {
+    GOPF_API_BEGIN
+    range_check(begin, count, ds(s).slab(), "gopf_dist_forward_mid_planes");
+    ds(s).forward_mid_planes(ccp(w, "w"), cp(send, "send"), begin, count);
+    GOPF_API_END
+}
+
+int gopf_dist_kspace_step_cols(gopf_dist_solver* s, const void* t_in, void* spectrum, void* t_out, int k1_begin,
+                               int k1_count) {
+    GOPF_API_BEGIN
+    range_check(k1_begin, k1_count, ds(s).slab(), "gopf_dist_kspace_step_cols");
+    ds(s).kspace_step_cols(ccp(t_in, "t_in"), cp(spectrum, "spectrum"), cp(t_out, "t_out"), k1_begin, k1_count);
+    GOPF_API_END
+}
+
+int gopf_dist_exchange_forward(gopf_dist_solver* s, const void* send, int begin, int count) {
+    GOPF_API_BEGIN
+    range_check(begin, count, ds(s).slab(), "gopf_dist_exchange_forward");
+    ds(s).exchange_forward(ccp(send, "send"), begin, count);
+    GOPF_API_END
+}
+
+int gopf_dist_exchange_inverse(gopf_dist_solver* s, const void* t, int k1_begin, int k1_count) {
+    GOPF_API_BEGIN
+    range_check(k1_begin, k1_count, ds(s).slab(), "gopf_dist_exchange_inverse");
+    ds(s).exchange_inverse(ccp(t, "t"), k1_begin, k1_count);
+    GOPF_API_END
+}
+
+int gopf_dist_exchange_join(gopf_dist_solver* s) {
+    GOPF_API_BEGIN
+    ds(s).exchange_join();
+    GOPF_API_END
+}
+
 int gopf_dist_advance(gopf_dist_solver* s) {
     GOPF_API_BEGIN
     ds(s).advance();

@@ -33,6 +33,123 @@ DistSolver::DistSolver(Model* m, int n, int world, int rank, double dt, int devi
     prog_.filter = nullptr;
     prog_.filter_n = 0;
     finalize_single_field_program(&prog_, 1);
+    for (int i = 0; i < GOPF_MAX_PEERS; ++i) X_[i] = Y_[i] = nullptr;
+}
+
+DistSolver::~DistSolver() {
+    cudaSetDevice(plan_->device);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    if (ev_compute_) cudaEventDestroy(ev_compute_);
+    if (ev_copy_) cudaEventDestroy(ev_copy_);
+    for (int q = 0; q < GOPF_MAX_PEERS; ++q) {
+        if (q == rank_) {
+            if (X_[q]) cudaFree(X_[q]);
+            if (Y_[q]) cudaFree(Y_[q]);
+        } else {
+            if (X_[q]) cudaIpcCloseMemHandle(X_[q]);
+            if (Y_[q]) cudaIpcCloseMemHandle(Y_[q]);
+        }
+    }
+}
+
+// ---- peer-store exchange ---------------------------------------------------------------
+void DistSolver::peer_alloc() {
+    if (world_ > GOPF_MAX_PEERS) throw Error(strf("dist solver: peer-store exchange supports up to %d ranks", GOPF_MAX_PEERS));
+    plan_->use_device();
+    const size_t bytes = sizeof(cplx) * local_cells();
+    if (!X_[rank_]) GOPF_CUDA(cudaMalloc(&X_[rank_], bytes));
+    if (!Y_[rank_]) GOPF_CUDA(cudaMalloc(&Y_[rank_], bytes));
+}
+
+void DistSolver::peer_export(int which, void* handle64) const {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cplx* p = which == 0 ? X_[rank_] : Y_[rank_];
+    if (!p) throw Error("dist solver: peer_alloc() first");
+    cudaIpcMemHandle_t h;
+    GOPF_CUDA(cudaIpcGetMemHandle(&h, p));
+    std::memcpy(handle64, &h, sizeof(h));
+}
+
+void DistSolver::peer_import(int which, int rank, const void* handle64) {
+    if (rank < 0 || rank >= world_) throw Error("dist solver: peer rank out of range");
+    if (rank == rank_) return;  // own buffers are used directly
+    plan_->use_device();
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    void* p = nullptr;
+    GOPF_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    (which == 0 ? X_ : Y_)[rank] = reinterpret_cast<cplx*>(p);
+}
+
+bool DistSolver::peer_ready() const {
+    for (int q = 0; q < world_; ++q)
+        if (!X_[q] || !Y_[q]) return false;
+    return true;
+}
+
+// kspace_rows: the producing pass runs along k0 (geom (n, m, n) axis 0, rows of m*n cells) and
+// fills X = [p][i0l][k1l][k2]; otherwise along k1 (geom (m, n, n) axis 1, rows of n cells, one
+// tile row index a = i0l) and fills Y = [k0 = p*m + i0l][k1l][k2].
+PeerOut DistSolver::peer_out(cplx* const* bufs, bool kspace_rows) const {
+    if (!peer_ready()) throw Error("dist solver: peer buffers are not mapped (peer_alloc / peer_import)");
+    PeerOut po{};
+    for (int q = 0; q < world_; ++q) po.base[q] = bufs[q];
+    po.block_off = (long long)rank_ * m_ * m_ * n_;
+    po.log = ilog2(m_);
+    po.mask = m_ - 1;
+    po.n = world_;
+    if (kspace_rows) {
+        po.a_stride = 0;
+        po.row_stride = (long long)m_ * n_;
+    } else {
+        po.a_stride = (long long)m_ * n_;
+        po.row_stride = n_;
+    }
+    return po;
+}
+
+void DistSolver::inverse_start_peer(const cplx* S) {
+    plan_->use_device();
+    PassGeom g = make_geom(n_, m_, n_, 0);
+    g.peer = peer_out(X_, true);
+    check(launch_pass(g, plan_->tx_want, plain_io(S, nullptr, true, 1.0), plan_->twiddle(0), stream()),
+          "inverse axis 0 -> peers");
+}
+
+void DistSolver::forward_mid_peer(const cplx* W) {
+    plan_->use_device();
+    PassGeom g = make_geom(m_, n_, n_, 1);
+    g.peer = peer_out(Y_, false);
+    check(launch_pass(g, plan_->tx_want, plain_io(W, nullptr, false, 1.0), plan_->twiddle(1), stream()),
+          "forward axis 1 -> peers");
+}
+
+void DistSolver::forward_local_peer(cplx* W) {
+    plan_->use_device();
+    check(launch_pass(make_geom(m_, n_, n_, 2), plan_->tx_want, plain_io(W, W, false, 1.0), plan_->twiddle(2), stream()),
+          "forward axis 2");
+    forward_mid_peer(W);
+}
+
+void DistSolver::forward_finish_peer(cplx* S) {
+    plan_->use_device();
+    check(launch_pass(make_geom(n_, m_, n_, 0), plan_->tx_want, plain_io(Y_[rank_], S, false, 1.0), plan_->twiddle(0),
+                      stream()),
+          "forward axis 0");
+}
+
+void DistSolver::kspace_step_peer(cplx* S) {
+    plan_->use_device();
+    FreqTabs ft;
+    ft.f0 = plan_->freq_axis(0);
+    ft.f1 = plan_->freq_axis(1);
+    ft.f2 = plan_->freq_axis(2);
+    ft.rank = 3;
+    ft.off1 = rank_ * m_;
+    PassGeom g = make_geom(n_, m_, n_, 0);
+    g.peer = peer_out(X_, true);
+    check(launch_fused_kspace(g, plan_->tx_want, Y_[rank_], nullptr, S, prog_, ft, plan_->twiddle(0), stream()),
+          "fused k-space kernel -> peers");
 }
 
 void DistSolver::check(cudaError_t e, const char* what) {
@@ -55,6 +172,94 @@ PassGeom DistSolver::slab_axis1(bool split_in, bool split_out) const {
     if (split_in) g.in = split_map();
     if (split_out) g.out = split_map();
     return g;
+}
+
+// ---- chunked phases + copy-engine exchange ------------------------------------------------
+void DistSolver::inverse_mid_planes(const cplx* recv, cplx* W, int begin, int count) {
+    plan_->use_device();
+    PassGeom g = slab_axis1(true, false);
+    g.A = count;
+    check(launch_pass(g, plan_->tx_want,
+                      plain_io(recv + (size_t)begin * m_ * n_, W + (size_t)begin * n_ * n_, true, 1.0), plan_->twiddle(1),
+                      stream()),
+          "inverse axis 1 (planes)");
+}
+
+void DistSolver::real_step_planes(cplx* W, int begin, int count) {
+    plan_->use_device();
+    PassGeom g = make_geom(count, n_, n_, 2);
+    g.node0 = ((long long)rank_ * m_ + begin) * n_ * n_;
+    const double inv_n = 1.0 / ((double)n_ * n_ * n_);
+    check(launch_fused_real(g, 0, W + (size_t)begin * n_ * n_, nullptr, m_model_->derived[derived_].dev, inv_n,
+                            (unsigned long long)steps_taken_, plan_->twiddle(2), stream()),
+          "fused real-space kernel (planes)");
+}
+
+void DistSolver::forward_mid_planes(const cplx* W, cplx* send, int begin, int count) {
+    plan_->use_device();
+    PassGeom g = slab_axis1(false, true);
+    g.A = count;
+    check(launch_pass(g, plan_->tx_want,
+                      plain_io(W + (size_t)begin * n_ * n_, send + (size_t)begin * m_ * n_, false, 1.0), plan_->twiddle(1),
+                      stream()),
+          "forward axis 1 (planes)");
+}
+
+void DistSolver::kspace_step_cols(const cplx* Tin, cplx* S, cplx* Tout, int k1_begin, int k1_count) {
+    plan_->use_device();
+    FreqTabs ft;
+    ft.f0 = plan_->freq_axis(0);
+    ft.f1 = plan_->freq_axis(1);
+    ft.f2 = plan_->freq_axis(2);
+    ft.rank = 3;
+    ft.off1 = rank_ * m_;
+    PassGeom g = make_geom(n_, m_, n_, 0);
+    g.b0 = (long long)k1_begin * n_;
+    g.bcount = (long long)k1_count * n_;
+    check(launch_fused_kspace(g, plan_->tx_want, Tin, Tout, S, prog_, ft, plan_->twiddle(0), stream()),
+          "fused k-space kernel (columns)");
+}
+
+void DistSolver::copy_after_compute() {
+    if (!peer_ready()) throw Error("dist solver: peer buffers are not mapped (peer_alloc / peer_import)");
+    plan_->use_device();
+    if (!copy_stream_) {
+        GOPF_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+        GOPF_CUDA(cudaEventCreateWithFlags(&ev_compute_, cudaEventDisableTiming));
+        GOPF_CUDA(cudaEventCreateWithFlags(&ev_copy_, cudaEventDisableTiming));
+    }
+    GOPF_CUDA(cudaEventRecord(ev_compute_, stream()));
+    GOPF_CUDA(cudaStreamWaitEvent(copy_stream_, ev_compute_, 0));
+}
+
+// send = [q][i0l][k1l(q)][k2]; planes [begin, begin+count) of block q -> Y_q[k0 = p*m + i0l][k1l][k2]
+void DistSolver::exchange_forward(const cplx* send, int begin, int count) {
+    copy_after_compute();
+    const size_t plane = (size_t)m_ * n_, block = (size_t)m_ * plane;
+    for (int d = 0; d < world_; ++d) {
+        const int q = (rank_ + 1 + d) % world_;  // stagger the destinations over the ranks
+        GOPF_CUDA(cudaMemcpyAsync(Y_[q] + ((size_t)rank_ * m_ + begin) * plane, send + q * block + begin * plane,
+                                  sizeof(cplx) * count * plane, cudaMemcpyDefault, copy_stream_));
+    }
+}
+
+// T = [q][k0l][k1l][k2]; columns k1l in [k1_begin, k1_begin+k1_count) of block q -> X_q[p][i0l = k0l][k1l][k2]
+void DistSolver::exchange_inverse(const cplx* T, int k1_begin, int k1_count) {
+    copy_after_compute();
+    const size_t plane = (size_t)m_ * n_, block = (size_t)m_ * plane;
+    for (int d = 0; d < world_; ++d) {
+        const int q = (rank_ + 1 + d) % world_;
+        GOPF_CUDA(cudaMemcpy2DAsync(X_[q] + rank_ * block + (size_t)k1_begin * n_, sizeof(cplx) * plane,
+                                    T + q * block + (size_t)k1_begin * n_, sizeof(cplx) * plane,
+                                    sizeof(cplx) * k1_count * n_, m_, cudaMemcpyDefault, copy_stream_));
+    }
+}
+
+void DistSolver::exchange_join() {
+    if (!copy_stream_) return;
+    plan_->use_device();
+    GOPF_CUDA(cudaEventRecord(ev_copy_, copy_stream_));
+    GOPF_CUDA(cudaStreamWaitEvent(stream(), ev_copy_, 0));
 }
 
 void DistSolver::forward_local(cplx* W, cplx* send) {
@@ -114,7 +319,7 @@ void DistSolver::kspace_step(cplx* T, cplx* S) {
     ft.f2 = plan_->freq_axis(2);
     ft.rank = 3;
     ft.off1 = rank_ * m_;
-    check(launch_fused_kspace(make_geom(n_, m_, n_, 0), plan_->tx_want, T, S, prog_, ft, plan_->twiddle(0), stream()),
+    check(launch_fused_kspace(make_geom(n_, m_, n_, 0), plan_->tx_want, T, T, S, prog_, ft, plan_->twiddle(0), stream()),
           "fused k-space kernel");
 }
 

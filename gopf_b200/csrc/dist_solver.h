@@ -50,6 +50,37 @@ public:
     void kspace_step(cplx* T, cplx* S);
     // download: last inverse pass + /N of W -> real slab
     void inverse_finish(cplx* W, cplx* real_out);
+    // ---- peer-store exchange (B200: NVLink 5 / NVSwitch peer memory) ---------------------
+    // Each rank owns two receive buffers, X ([p][i0l][k1l(p)][k2], input of inverse_mid) and
+    // Y ([k0][k1l][k2], input of kspace_step / forward_finish).  Every rank maps every other
+    // rank's X and Y (CUDA IPC) and the pass that produces exchange data stores each row
+    // directly into its owner's buffer, so pack + send + unpack cost no pass and no separate
+    // collective.  The caller separates a peer-writing phase from the phases that read the
+    // buffers with a cross-rank barrier on the stream (gopf_b200/dist.py).
+    void peer_alloc();                                         // cudaMalloc X, Y
+    void peer_export(int which, void* handle64) const;         // which: 0 = X, 1 = Y
+    void peer_import(int which, int rank, const void* handle64);
+    cplx* peer_local(int which) const { return which == 0 ? X_[rank_] : Y_[rank_]; }
+    bool peer_ready() const;
+    void inverse_start_peer(const cplx* S);   // S -> inverse axis 0 -> peers' X
+    void forward_mid_peer(const cplx* W);     // W -> forward axis 1 -> peers' Y
+    void kspace_step_peer(cplx* S);           // local Y, S -> S; inverse axis 0 of the new S -> peers' X
+    void forward_local_peer(cplx* W);         // upload: forward axis 2 in place, then forward_mid_peer
+    void forward_finish_peer(cplx* S);        // upload: local Y -> forward axis 0 -> S
+    // ---- copy-engine exchange, pipelined by chunks ----------------------------------------
+    // The same X / Y receive buffers, filled by DMA copies (cudaMemcpyAsync to the IPC-mapped
+    // peer pointers) on a second stream while the compute stream works on the next chunk:
+    // planes of the slab are independent through inverse_mid -> real_step -> forward_mid, and
+    // columns (k1l) of the spectrum are independent through kspace_step.  The copy engines
+    // reach the NVLink DMA rate and occupy no SM.
+    void inverse_mid_planes(const cplx* recv, cplx* W, int begin, int count);
+    void real_step_planes(cplx* W, int begin, int count);
+    void forward_mid_planes(const cplx* W, cplx* send, int begin, int count);
+    void kspace_step_cols(const cplx* Tin, cplx* S, cplx* Tout, int k1_begin, int k1_count);
+    void exchange_forward(const cplx* send, int begin, int count);    // send planes -> every rank's Y (after the compute so far)
+    void exchange_inverse(const cplx* T, int k1_begin, int k1_count);  // T columns -> every rank's X
+    void exchange_join();                                              // compute stream waits for the copies issued so far
+    ~DistSolver();
     void advance() { steps_taken_++; current_step_++; }
     double get_time() const { return (double)current_step_ * dt_; }
 
@@ -62,6 +93,12 @@ private:
     DevKProgram prog_;
     int derived_ = -1;
     long long steps_taken_ = 0, current_step_ = 0, launches_ = 0;
+    cplx* X_[GOPF_MAX_PEERS];  // [rank]: mapped receive buffers (own rank: owned allocation)
+    cplx* Y_[GOPF_MAX_PEERS];
+    PeerOut peer_out(cplx* const* bufs, bool kspace_rows) const;
+    cudaStream_t copy_stream_ = nullptr;
+    cudaEvent_t ev_compute_ = nullptr, ev_copy_ = nullptr;
+    void copy_after_compute();
 
     cudaStream_t stream() const { return stream_ ? stream_ : plan_->stream; }
     PassGeom slab_axis1(bool split_in, bool split_out) const;

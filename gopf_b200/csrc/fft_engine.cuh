@@ -212,4 +212,20 @@ __device__ __forceinline__ void line_fft(cplx (&v)[PlanFor<N>::E], int t, int l,
     if (P::NS > 2) fft_stage<N, (P::NS > 2 ? 2 : 0), Layout, Sync>(v, t, l, sm, tw);
 }
 
+// The same transform in two parts, for kernels that want the exchange buffer back early:
+// after line_fft_head every thread has passed the last barrier of the last exchange, so `sm`
+// is free while line_fft_tail (register-only butterflies of the last stage) runs.
+template <int N, class Layout, class Sync>
+__device__ __forceinline__ void line_fft_head(cplx (&v)[PlanFor<N>::E], int t, int l, cplx* sm,
+                                              const cplx* __restrict__ tw) {
+    typedef PlanFor<N> P;
+    if (P::NS > 1) fft_stage<N, 0, Layout, Sync>(v, t, l, sm, tw);
+    if (P::NS > 2) fft_stage<N, (P::NS > 2 ? 1 : 0), Layout, Sync>(v, t, l, sm, tw);
+}
+template <int N, class Layout, class Sync>
+__device__ __forceinline__ void line_fft_tail(cplx (&v)[PlanFor<N>::E], int t, int l, cplx* sm,
+                                              const cplx* __restrict__ tw) {
+    fft_stage<N, PlanFor<N>::NS - 1, Layout, Sync>(v, t, l, sm, tw);
+}
+
 }  // namespace gopf

@@ -22,6 +22,19 @@ struct RowMap {
     int split_log, split_mask;
 };
 
+// Peer-store output of the slab-sharded transform: row j of tile (a, b) belongs to rank
+// q = j >> log and is written straight into rank q's receive buffer over NVLink,
+//   base[q] + block_off + a*a_stride + (j & mask)*row_stride + b,
+// so the transpose exchange is fused into the pass that produces the data (no send buffer, no
+// separate collective).  base[own rank] is the local buffer.  n == 0: ordinary output.
+#define GOPF_MAX_PEERS 8
+struct PeerOut {
+    cplx* base[GOPF_MAX_PEERS];
+    long long block_off, a_stride, row_stride;
+    int log, mask;
+    int n, pad;
+};
+
 struct PassGeom {
     int n0, n1, n2;  // extents in FFTW order (2-D: n0 == 1; 1-D: n0 == n1 == 1)
     int axis;        // 0, 1 or 2
@@ -29,7 +42,13 @@ struct PassGeom {
     int N;           // n[axis]
     RowMap in, out;  // strided kernels only
     long long node0; // reference node number of this array's first cell (slab offset when sharded)
+    PeerOut peer;    // strided kernels only
+    long long b0, bcount;  // fused k-space kernel: columns [b0, b0 + bcount) of B (chunked launches)
 };
+
+__device__ __forceinline__ cplx* peer_row(const PeerOut& p, long long a, int j, long long b) {
+    return p.base[j >> p.log] + (p.block_off + a * p.a_stride + (long long)(j & p.mask) * p.row_stride + b);
+}
 
 inline RowMap uniform_rows(long long a_stride, long long row_stride) {
     RowMap r;
@@ -49,6 +68,9 @@ inline PassGeom make_geom(int n0, int n1, int n2, int axis) {
     else { g.N = n0; g.B = (long long)n1 * n2; g.A = 1; }
     g.in = g.out = uniform_rows((long long)g.N * g.B, g.B);
     g.node0 = 0;
+    g.peer = PeerOut{};
+    g.b0 = 0;
+    g.bcount = g.B;
     return g;
 }
 
@@ -204,10 +226,23 @@ __device__ __forceinline__ void pass_store_line(const PassIO& io, cplx (&v)[E], 
     }
 }
 
+// same with one destination pointer per cell (peer-store output)
+template <int E, class Ptr>
+__device__ __forceinline__ void pass_store_ptr(const PassIO& io, cplx (&v)[E], Ptr ptr) {
+    const double sc = io.scale;
+    if (io.inv) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) *ptr(m) = mk(v[m].y * sc, v[m].x * sc);
+    } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) *ptr(m) = mk(v[m].x * sc, v[m].y * sc);
+    }
+}
+
 // ---- strided axis (B > 1): tile = N x TX, TX adjacent lines ---------------------
-template <int N, int TX>
+template <int N, int TX, bool PEER>
 __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB(PlanFor<N>::T* TX))
-    k_pass_strided(const PassGeom g, const __grid_constant__ PassIO io, const cplx* __restrict__ tw) {
+    k_pass_strided(const __grid_constant__ PassGeom g, const __grid_constant__ PassIO io, const cplx* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char gopf_smem_raw[];
     cplx* sm = reinterpret_cast<cplx*>(gopf_smem_raw);
     constexpr int E = PlanFor<N>::E, T = PlanFor<N>::T;
@@ -230,7 +265,10 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB(PlanFor<N>::T* TX
     };
     pass_load_line<E>(io, v, at_in, sm, [&](int m) -> int { return LayoutInterleaved<TX>::at(t + T * m, l); });
     line_fft<N, LayoutInterleaved<TX>, SyncCta>(v, t, l, sm, tw);
-    pass_store_line<E>(io, v, at_out);
+    if (PEER)
+        pass_store_ptr<E>(io, v, [&](int m) -> cplx* { return peer_row(g.peer, a, t + T * m, b); });
+    else
+        pass_store_line<E>(io, v, at_out);
 }
 
 // ---- contiguous axis (B == 1): LINES lines per CTA, position fastest ------------
@@ -266,7 +304,15 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
 }
 
 // ---- launch-side helpers ------------------------------------------------------------
-inline int pick_tx(int N, long long B, int want) {
+inline int pick_tx(int N, long long B, int want, bool peer = false) {
+    // Peer stores go out over NVLink in row segments of TX cells: 128-B segments reach 717 GB/s,
+    // 64-B ones 438 GB/s (scripts/peer_store_probe.cu), so the peer-writing passes take TX >= 8
+    // even where a narrower tile is the faster local choice.
+    if (peer) {
+        int tx = want > 8 ? want : 8;
+        while (tx > 1 && ((long long)N * tx * 16 > 128 * 1024 || (B % tx) != 0)) tx >>= 1;
+        return tx < 2 ? ((B % 2 == 0) ? 2 : 1) : tx;
+    }
     // Lines of >= 512 cells: a 128-B-wide tile would be the only CTA on its SM (registers), with
     // no other tile's loads in flight behind it; two 64-B-wide tiles per SM measure faster
     // (scripts/tune_pass.py, B200: N=1024 4.4 vs 4.0 TB/s, N=512 4.6 vs 3.8 TB/s).
@@ -283,7 +329,7 @@ template <int N, int TX>
 cudaError_t launch_strided_n_tx(const PassGeom& g, const PassIO& io, const cplx* tw, cudaStream_t s) {
     constexpr int T = PlanFor<N>::T;
     const size_t smem = (size_t)N * TX * sizeof(cplx);
-    auto kern = k_pass_strided<N, TX>;
+    auto kern = g.peer.n > 0 ? k_pass_strided<N, TX, true> : k_pass_strided<N, TX, false>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -330,7 +376,7 @@ cudaError_t launch_contig_n(const PassGeom& g, const PassIO& io, const cplx* tw,
 template <int N>
 cudaError_t launch_pass_n(const PassGeom& g, int tx_want, const PassIO& io, const cplx* tw, cudaStream_t s) {
     if (g.B == 1) return launch_contig_n<N>(g, io, tw, s);
-    const int tx = pick_tx(N, g.B, tx_want);
+    const int tx = pick_tx(N, g.B, tx_want, g.peer.n > 0);
     if (tx < 2) return cudaErrorInvalidValue;
     return launch_strided_n<N>(g, tx, io, tw, s);
 }

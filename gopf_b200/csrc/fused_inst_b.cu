@@ -1,8 +1,8 @@
 // Fused-kernel instantiations (see fused_launch.h); split by length so nvcc runs in parallel.
 #include "fused_launch.h"
 namespace gopf {
-cudaError_t fused_kspace_128(const PassGeom& g, int tx, cplx* W, cplx* S, const DevKProgram& P, const FreqTabs& ft, const cplx* tw, cudaStream_t s) { return fused_kspace_n<128>(g, tx, W, S, P, ft, tw, s); }
+cudaError_t fused_kspace_128(const PassGeom& g, int tx, const cplx* W, cplx* Wout, cplx* S, const DevKProgram& P, const FreqTabs& ft, const cplx* tw, cudaStream_t s) { return fused_kspace_n<128>(g, tx, W, Wout, S, P, ft, tw, s); }
 cudaError_t fused_real_128(const PassGeom& g, int mode, cplx* W, cplx* ro, const DevDerived& D, double inv_n, unsigned long long step, const cplx* tw, cudaStream_t s) { return fused_real_n<128>(g, mode, W, ro, D, inv_n, step, tw, s); }
-cudaError_t fused_kspace_256(const PassGeom& g, int tx, cplx* W, cplx* S, const DevKProgram& P, const FreqTabs& ft, const cplx* tw, cudaStream_t s) { return fused_kspace_n<256>(g, tx, W, S, P, ft, tw, s); }
+cudaError_t fused_kspace_256(const PassGeom& g, int tx, const cplx* W, cplx* Wout, cplx* S, const DevKProgram& P, const FreqTabs& ft, const cplx* tw, cudaStream_t s) { return fused_kspace_n<256>(g, tx, W, Wout, S, P, ft, tw, s); }
 cudaError_t fused_real_256(const PassGeom& g, int mode, cplx* W, cplx* ro, const DevDerived& D, double inv_n, unsigned long long step, const cplx* tw, cudaStream_t s) { return fused_real_n<256>(g, mode, W, ro, D, inv_n, step, tw, s); }
 }  // namespace gopf

@@ -1,13 +1,20 @@
 // Dispatch of the fused single-field kernels to their per-length instantiations.
 #include "fused_launch.h"
 
+#include <cstdlib>
+
 namespace gopf {
+
+int env_int(const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : fallback;
+}
 
 #define GOPF_FUSED_N(X) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
 
 #define X(n)                                                                                                     \
-    cudaError_t fused_kspace_##n(const PassGeom&, int, cplx*, cplx*, const DevKProgram&, const FreqTabs&,        \
-                                 const cplx*, cudaStream_t);                                                     \
+    cudaError_t fused_kspace_##n(const PassGeom&, int, const cplx*, cplx*, cplx*, const DevKProgram&,            \
+                                 const FreqTabs&, const cplx*, cudaStream_t);                                                   \
     cudaError_t fused_real_##n(const PassGeom&, int, cplx*, cplx*, const DevDerived&, double, unsigned long long, \
                                const cplx*, cudaStream_t);
 GOPF_FUSED_N(X)
@@ -22,10 +29,10 @@ bool fused_length_supported(int n) {
     }
 }
 
-cudaError_t launch_fused_kspace(const PassGeom& g, int tx_want, cplx* W, cplx* S, const DevKProgram& P,
+cudaError_t launch_fused_kspace(const PassGeom& g, int tx_want, const cplx* W, cplx* Wout, cplx* S, const DevKProgram& P,
                                 const FreqTabs& ft, const cplx* tw, cudaStream_t s) {
     switch (g.N) {
-#define X(v) case v: return fused_kspace_##v(g, tx_want, W, S, P, ft, tw, s);
+#define X(v) case v: return fused_kspace_##v(g, tx_want, W, Wout, S, P, ft, tw, s);
         GOPF_FUSED_N(X)
 #undef X
         default: return cudaErrorInvalidValue;

@@ -9,7 +9,7 @@ bool fused_length_supported(int n);
 
 // Slowest-axis kernel: finish forward of the derived field in W, Euler update of S,
 // first inverse pass of the new S back into W.
-cudaError_t launch_fused_kspace(const PassGeom& g, int tx_want, cplx* W, cplx* S, const DevKProgram& P,
+cudaError_t launch_fused_kspace(const PassGeom& g, int tx_want, const cplx* W, cplx* Wout, cplx* S, const DevKProgram& P,
                                 const FreqTabs& ft, const cplx* tw, cudaStream_t s);
 
 // Contiguous-axis kernel.  mode 0: inverse, /N, derived function, forward (W in place;
@@ -18,43 +18,74 @@ cudaError_t launch_fused_real(const PassGeom& g, int mode, cplx* W, cplx* real_o
                               unsigned long long step, const cplx* tw, cudaStream_t s);
 
 // ---- templates instantiated by fused_inst_*.cu ------------------------------------------
-template <int N, int TX>
-cudaError_t fused_kspace_n_tx(const PassGeom& g, cplx* W, cplx* S, const DevKProgram& P, const FreqTabs& ft,
-                              const cplx* tw, cudaStream_t s) {
+template <int N, int TX, bool LATE>
+cudaError_t fused_kspace_n_tx(const PassGeom& g, const cplx* W, cplx* Wout, cplx* S, const DevKProgram& P,
+                              const FreqTabs& ft, const cplx* tw, cudaStream_t s) {
     constexpr int T = PlanFor<N>::T;
-    // exchange buffer (multi-stage lengths only) + the prefetched spectrum tile
-    const size_t smem = (size_t)N * TX * sizeof(cplx) * 2;
-    auto kern = k_fused_kspace<N, TX>;
+    // exchange tile, plus (early prefetch only) the spectrum tile
+    const size_t smem = (size_t)N * TX * sizeof(cplx) * (LATE ? 1 : 2);
+    auto kern = g.peer.n > 0 ? k_fused_kspace<N, TX, true, LATE> : k_fused_kspace<N, TX, false, LATE>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const long long tiles = g.A * (g.B / TX);
-    kern<<<(unsigned)tiles, T * TX, smem, s>>>(g, W, S, P, ft, tw);
+    const long long tiles = g.A * (g.bcount / TX);
+    kern<<<(unsigned)tiles, T * TX, smem, s>>>(g, W, Wout, S, P, ft, tw);
     return cudaGetLastError();
 }
 
-template <int N>
-cudaError_t fused_kspace_n(const PassGeom& g, int tx_want, cplx* W, cplx* S, const DevKProgram& P, const FreqTabs& ft,
-                           const cplx* tw, cudaStream_t s) {
-    constexpr size_t line_bytes = (size_t)N * sizeof(cplx);
-    int tx = pick_tx(N, g.B, tx_want);
-    while (tx > 2 && line_bytes * tx * 2 > 128 * 1024) tx >>= 1;  // two tiles per CTA
+int env_int(const char* name, int fallback);  // fused_launch.cu
+
+template <int N, bool LATE>
+cudaError_t fused_kspace_n_late(const PassGeom& g, int tx, const cplx* W, cplx* Wout, cplx* S, const DevKProgram& P,
+                                const FreqTabs& ft, const cplx* tw, cudaStream_t s) {
+    constexpr size_t tile_bytes = (size_t)N * sizeof(cplx) * (LATE ? 1 : 2);
     switch (tx) {
-        case 2: return fused_kspace_n_tx<N, 2>(g, W, S, P, ft, tw, s);
+        case 2: return fused_kspace_n_tx<N, 2, LATE>(g, W, Wout, S, P, ft, tw, s);
         case 4:
-            if constexpr (line_bytes * 4 * 2 <= 200 * 1024) return fused_kspace_n_tx<N, 4>(g, W, S, P, ft, tw, s);
+            if constexpr (tile_bytes * 4 <= 200 * 1024) return fused_kspace_n_tx<N, 4, LATE>(g, W, Wout, S, P, ft, tw, s);
             break;
         case 8:
-            if constexpr (line_bytes * 8 * 2 <= 200 * 1024) return fused_kspace_n_tx<N, 8>(g, W, S, P, ft, tw, s);
+            if constexpr (tile_bytes * 8 <= 200 * 1024) return fused_kspace_n_tx<N, 8, LATE>(g, W, Wout, S, P, ft, tw, s);
             break;
         case 16:
-            if constexpr (line_bytes * 16 * 2 <= 200 * 1024 && PlanFor<N>::T * 16 <= 1024)
-                return fused_kspace_n_tx<N, 16>(g, W, S, P, ft, tw, s);
+            if constexpr (tile_bytes * 16 <= 200 * 1024 && PlanFor<N>::T * 16 <= 1024)
+                return fused_kspace_n_tx<N, 16, LATE>(g, W, Wout, S, P, ft, tw, s);
             break;
         default: break;
     }
     return cudaErrorInvalidConfiguration;
+}
+
+// Tile width and spectrum-staging variant.  Fast-form programs take the single-tile (LATE)
+// kernel with the widest tile that keeps two CTAs per SM (64 KB), and never less than 8 cells:
+// row segments of 128 B or more are what HBM sectors and NVLink packets want (peer stores:
+// 128-B segments 717 GB/s, 64-B 438 GB/s, 32-B 219 GB/s; scripts/peer_store_probe.cu).
+// Measured on B200, fused k-space kernel, early two-tile variant -> LATE (scripts/tune_kspace.py):
+//   256^3: 4082 -> 5258 GB/s (TX 16);  512^3: 2963 -> 4268 GB/s (TX 8);  1024^3: 2780 -> 3787 GB/s (TX 8).
+// General programs keep the two-tile kernel (the interpreter stages cells in the exchange tile).
+// GOPF_KSPACE_LATE / GOPF_KSPACE_TX override the choice (tuning).
+template <int N>
+cudaError_t fused_kspace_n(const PassGeom& g, int tx_want, const cplx* W, cplx* Wout, cplx* S, const DevKProgram& P,
+                           const FreqTabs& ft, const cplx* tw, cudaStream_t s) {
+    constexpr size_t line_bytes = (size_t)N * sizeof(cplx);
+    constexpr int T = PlanFor<N>::T;
+    bool late = P.fast != 0;
+    const int env_late = env_int("GOPF_KSPACE_LATE", -1);
+    if (env_late >= 0) late = P.fast && env_late != 0;
+    int tx;
+    if (late) {
+        tx = 16;
+        while (tx > 8 && line_bytes * tx > 64 * 1024) tx >>= 1;
+        while (tx > 2 && (line_bytes * tx > 128 * 1024 || T * tx > 1024 || (g.bcount % tx) != 0)) tx >>= 1;
+    } else {
+        tx = pick_tx(N, g.bcount, tx_want);
+        while (tx > 2 && line_bytes * tx * 2 > 128 * 1024) tx >>= 1;
+    }
+    const int env_tx = env_int("GOPF_KSPACE_TX", 0);
+    if (env_tx > 0 && (g.bcount % env_tx) == 0) tx = env_tx;
+    return late ? fused_kspace_n_late<N, true>(g, tx, W, Wout, S, P, ft, tw, s)
+                : fused_kspace_n_late<N, false>(g, tx, W, Wout, S, P, ft, tw, s);
 }
 
 template <int N, int MODE>

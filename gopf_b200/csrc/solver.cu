@@ -812,7 +812,7 @@ void Solver::euler_step_fused() {
     }
     {
         const int id = tick("fused_kspace", 64.0 * n);
-        cudaError_t e = launch_fused_kspace(gs, plan_->tx_want, W_, S_.s[0], fused_prog_, freq_tabs(),
+        cudaError_t e = launch_fused_kspace(gs, plan_->tx_want, W_, W_, S_.s[0], fused_prog_, freq_tabs(),
                                             plan_->twiddle(slow), s);
         tock(id);
         if (e != cudaSuccess) throw Error(strf("fused: k-space kernel: %s", cudaGetErrorString(e)));

@@ -102,34 +102,56 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
 // resident CTAs are bounded by the two shared-memory tiles; do not squeeze registers below that
 #define GOPF_MINB_K(threads, smem) \
     (GOPF_MINB(threads) < (200 * 1024 / (smem)) ? GOPF_MINB(threads) : ((200 * 1024 / (smem)) < 1 ? 1 : (200 * 1024 / (smem))))
-template <int N, int TX>
-__global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* TX, 2 * N * TX * 16))
-    k_fused_kspace(PassGeom g, cplx* __restrict__ W, cplx* __restrict__ S, const __grid_constant__ DevKProgram P,
-                   FreqTabs ft, const cplx* __restrict__ tw) {
+// PEER: the inverse pass of the new spectrum is stored straight into the owning ranks'
+// receive buffers (g.peer, fft_kernels.cuh) instead of W.
+// LATE = false: the spectrum tile is prefetched into a second shared-memory tile at kernel start
+//   (its latency hides behind the W loads and the whole forward FFT); 2 tiles of shared memory.
+// LATE = true: the spectrum tile lands in the exchange tile itself once the forward FFT has made
+//   its last exchange (its latency hides behind the last register-only butterfly stage and the
+//   other resident CTAs); 1 tile of shared memory, so long lines keep wide tiles / two CTAs per SM.
+template <int N, int TX, bool PEER, bool LATE>
+__global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* TX, (LATE ? 1 : 2) * N * TX * 16))
+    k_fused_kspace(const __grid_constant__ PassGeom g, const cplx* W, cplx* Wout, cplx* __restrict__ S,
+                   const __grid_constant__ DevKProgram P, FreqTabs ft, const cplx* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char gopf_smem_raw[];
     cplx* sm = reinterpret_cast<cplx*>(gopf_smem_raw);
-    cplx* sS = sm + N * TX;
+    cplx* sS = LATE ? sm : sm + N * TX;
     constexpr int E = PlanFor<N>::E, T = PlanFor<N>::T;
     typedef LayoutInterleaved<TX> Lay;
     const int tid = threadIdx.x;
     const int l = tid % TX, t = tid / TX;
-    const long long tilesB = g.B / TX;
+    const long long tilesB = g.bcount / TX;
     const long long tile = blockIdx.x;
     const long long a = tile / tilesB;
-    const long long b = (tile - a * tilesB) * TX + l;
+    const long long b = g.b0 + (tile - a * tilesB) * TX + l;
     const size_t base = (size_t)a * N * g.B + b;
     const size_t strideB = (size_t)g.B;
-    // The spectrum tile is needed only after the forward transform: start it towards shared
-    // memory now (cp.async, no registers held) so its HBM latency hides behind the W loads
-    // and the first FFT.  Each thread later reads back exactly the cells it copied, so
-    // cp.async.wait_group is the only synchronisation needed.
+    // Each thread later reads back exactly the spectrum cells it copied, so cp.async.wait_group
+    // is the only synchronisation the copy needs.
+    auto prefetch_spectrum = [&]() {
+        if (LATE) {
+            // the line is live in registers here: walk the rows with two running addresses in a
+            // rolled loop instead of materialising E address pairs
+            unsigned dst = (unsigned)__cvta_generic_to_shared(sS + Lay::at(t, l));
+            const cplx* src = S + base + (size_t)t * strideB;
+            const size_t src_step = (size_t)T * strideB;
+#pragma unroll 1
+            for (int m = 0; m < E; ++m) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+                dst += (unsigned)(T * TX * sizeof(cplx));
+                src += src_step;
+            }
+        } else {
 #pragma unroll
-    for (int m = 0; m < E; ++m) {
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(sS + Lay::at(t + T * m, l));
-        const cplx* src = S + base + (size_t)(t + T * m) * strideB;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+            for (int m = 0; m < E; ++m) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(sS + Lay::at(t + T * m, l));
+                const cplx* src = S + base + (size_t)(t + T * m) * strideB;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    if (!LATE) prefetch_spectrum();
     cplx v[E];
 #pragma unroll
     for (int m = 0; m < E; ++m) v[m] = W[base + (size_t)(t + T * m) * strideB];
@@ -146,9 +168,15 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
         fb = ft.rank > 2 ? ft.f0[(int)a] : 0.0;
         fline = ft.f1;
     }
-    line_fft<N, Lay, SyncCta>(v, t, l, sm, tw);
+    if (LATE) {
+        line_fft_head<N, Lay, SyncCta>(v, t, l, sm, tw);
+        prefetch_spectrum();  // the exchange tile is free from here until the next transform's first exchange
+        line_fft_tail<N, Lay, SyncCta>(v, t, l, sm, tw);
+    } else {
+        line_fft<N, Lay, SyncCta>(v, t, l, sm, tw);
+    }
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    if (P.fast) {
+    if (LATE || P.fast) {  // LATE is launched for fast-form programs only (fused_launch.h)
         const double s2 = fa * fa + fb * fb;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
@@ -158,6 +186,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
             S[base + (size_t)j * strideB] = cur;
             v[m] = cswap(cur);
         }
+        if (LATE) __syncthreads();  // spectrum cells were read from the exchange tile
     } else {
         // general program: cells staged in shared memory, term interpreter in a rolled loop
 #pragma unroll
@@ -178,8 +207,13 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
         __syncthreads();
     }
     line_fft<N, Lay, SyncCta>(v, t, l, sm, tw);
+    if (PEER) {
 #pragma unroll
-    for (int m = 0; m < E; ++m) W[base + (size_t)(t + T * m) * strideB] = cswap(v[m]);
+        for (int m = 0; m < E; ++m) *peer_row(g.peer, a, t + T * m, b) = cswap(v[m]);
+    } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) Wout[base + (size_t)(t + T * m) * strideB] = cswap(v[m]);
+    }
 }
 
 }  // namespace gopf

@@ -30,6 +30,106 @@ def run_steps(phases, all_to_all, S, A, B, nsteps: int, a_valid: bool) -> bool:
     return a_valid
 
 
+def run_steps_peer(phases, barrier, S, A, nsteps: int, x_valid: bool) -> bool:
+    """nsteps sharded Euler steps with the exchange fused into the producing passes (peer
+    stores over NVLink).  The receive buffers X and Y live in ``phases``; ``barrier()`` orders
+    every rank's earlier stream work before every rank's later stream work.  ``x_valid`` says X
+    already holds the first inverse pass of S.  Returns the new x_valid."""
+    for _ in range(nsteps):
+        if not x_valid:
+            barrier()                        # nobody is still reading X
+            phases.inverse_start_peer(S)     # S -> inverse axis 0 -> every rank's X
+            barrier()
+        phases.inverse_mid_x(A)              # X -> inverse axis 1 -> A
+        phases.real_step(A)                  # inverse axis 2, /N, g(c), forward axis 2
+        phases.forward_mid_peer(A)           # forward axis 1 -> every rank's Y
+        barrier()
+        phases.kspace_step_peer(S)           # Y: forward axis 0, Euler update of S, inverse axis 0 -> every rank's X
+        barrier()
+        phases.advance()
+        x_valid = True
+    return x_valid
+
+
+def chunks(extent: int, nchunks: int):
+    """[(begin, count)] covering range(extent) in at most nchunks near-equal pieces."""
+    nchunks = max(1, min(nchunks, extent))
+    base, rem = divmod(extent, nchunks)
+    out, b = [], 0
+    for i in range(nchunks):
+        c = base + (1 if i < rem else 0)
+        out.append((b, c))
+        b += c
+    return out
+
+
+def run_steps_dma(phases, barrier, S, A, SEND, nsteps: int, x_valid: bool, slab: int, nchunks: int = 4) -> bool:
+    """nsteps sharded Euler steps with the exchange on the copy engines, pipelined by chunks:
+    the DMA copies of chunk c (second stream, peer-mapped X / Y) run under the kernels of chunk
+    c+1.  ``slab`` = n / world (planes per rank = spectrum columns k1l per rank)."""
+    parts = chunks(slab, nchunks)
+    for _ in range(nsteps):
+        if not x_valid:
+            barrier()
+            phases.inverse_start(S, SEND)            # S -> inverse axis 0 -> SEND [k0][k1l][k2]
+            phases.exchange_inverse(SEND, 0, slab)
+            phases.exchange_join()
+            barrier()
+        for b, c in parts:                           # planes are independent up to the exchange
+            phases.inverse_mid_planes_x(A, b, c)     # X -> inverse axis 1 -> A
+            phases.real_step_planes(A, b, c)
+            phases.forward_mid_planes(A, SEND, b, c)
+            phases.exchange_forward(SEND, b, c)      # -> every rank's Y, under the next chunk's kernels
+        phases.exchange_join()
+        barrier()
+        for b, c in parts:                           # columns are independent in k-space
+            phases.kspace_step_cols_y(S, A, b, c)    # Y, S -> S; inverse axis 0 of the new S -> A
+            phases.exchange_inverse(A, b, c)         # -> every rank's X
+        phases.exchange_join()
+        barrier()
+        phases.advance()
+        x_valid = True
+    return x_valid
+
+
+def upload_dma(phases, barrier, real_slab, S, SEND, slab: int):
+    phases.forward_local(real_slab, SEND)
+    phases.exchange_forward(SEND, 0, slab)
+    phases.exchange_join()
+    barrier()
+    phases.forward_finish_peer(S)
+
+
+def download_dma(phases, barrier, S, A, SEND, real_out, x_valid: bool, slab: int) -> bool:
+    if not x_valid:
+        barrier()
+        phases.inverse_start(S, SEND)
+        phases.exchange_inverse(SEND, 0, slab)
+        phases.exchange_join()
+        barrier()
+    phases.inverse_mid_x(A)
+    phases.inverse_finish(A, real_out)
+    return True
+
+
+def upload_peer(phases, barrier, real_slab, S):
+    """real_slab [i0l][i1][i2] (destroyed) -> S = its share of the spectrum."""
+    phases.forward_local_peer(real_slab)     # forward axes 2, 1 -> every rank's Y
+    barrier()
+    phases.forward_finish_peer(S)            # Y -> forward axis 0 -> S
+
+
+def download_peer(phases, barrier, S, A, real_out, x_valid: bool) -> bool:
+    """S -> real_out = this rank's slab of the real-space field.  X stays valid."""
+    if not x_valid:
+        barrier()
+        phases.inverse_start_peer(S)
+        barrier()
+    phases.inverse_mid_x(A)
+    phases.inverse_finish(A, real_out)
+    return True
+
+
 def upload(phases, all_to_all, real_slab, S, B):
     """real_slab [i0l][i1][i2] (destroyed) -> S = its share of the spectrum."""
     phases.forward_local(real_slab, B)
@@ -88,6 +188,66 @@ class CudaPhases:
     def inverse_finish(self, W, real_out):
         check(lib().gopf_dist_inverse_finish(self._h, self._p(W), self._p(real_out)))
 
+    # ---- peer-store exchange -------------------------------------------------------------
+    def peer_alloc(self):
+        check(lib().gopf_dist_peer_alloc(self._h))
+
+    def peer_export(self, which: int) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        check(lib().gopf_dist_peer_export(self._h, int(which), buf))
+        return buf.raw
+
+    def peer_import(self, which: int, rank: int, handle: bytes):
+        if len(handle) != 64:
+            raise ValueError("CUDA IPC handle must be 64 bytes")
+        check(lib().gopf_dist_peer_import(self._h, int(which), int(rank), ctypes.c_char_p(handle)))
+
+    def peer_local(self, which: int) -> int:
+        p = ctypes.c_void_p()
+        check(lib().gopf_dist_peer_local(self._h, int(which), ctypes.byref(p)))
+        return p.value
+
+    def inverse_start_peer(self, S):
+        check(lib().gopf_dist_inverse_start_peer(self._h, self._p(S)))
+
+    def inverse_mid_x(self, W):
+        check(lib().gopf_dist_inverse_mid(self._h, ctypes.c_void_p(self.peer_local(0)), self._p(W)))
+
+    def forward_mid_peer(self, W):
+        check(lib().gopf_dist_forward_mid_peer(self._h, self._p(W)))
+
+    def forward_local_peer(self, W):
+        check(lib().gopf_dist_forward_local_peer(self._h, self._p(W)))
+
+    def forward_finish_peer(self, S):
+        check(lib().gopf_dist_forward_finish_peer(self._h, self._p(S)))
+
+    def kspace_step_peer(self, S):
+        check(lib().gopf_dist_kspace_step_peer(self._h, self._p(S)))
+
+    # ---- chunked phases + copy-engine exchange ----------------------------------------------
+    def inverse_mid_planes_x(self, W, begin: int, count: int):
+        check(lib().gopf_dist_inverse_mid_planes(self._h, ctypes.c_void_p(self.peer_local(0)), self._p(W), int(begin), int(count)))
+
+    def real_step_planes(self, W, begin: int, count: int):
+        check(lib().gopf_dist_real_step_planes(self._h, self._p(W), int(begin), int(count)))
+
+    def forward_mid_planes(self, W, send, begin: int, count: int):
+        check(lib().gopf_dist_forward_mid_planes(self._h, self._p(W), self._p(send), int(begin), int(count)))
+
+    def kspace_step_cols_y(self, S, Tout, k1_begin: int, k1_count: int):
+        check(lib().gopf_dist_kspace_step_cols(self._h, ctypes.c_void_p(self.peer_local(1)), self._p(S), self._p(Tout),
+                                               int(k1_begin), int(k1_count)))
+
+    def exchange_forward(self, send, begin: int, count: int):
+        check(lib().gopf_dist_exchange_forward(self._h, self._p(send), int(begin), int(count)))
+
+    def exchange_inverse(self, T, k1_begin: int, k1_count: int):
+        check(lib().gopf_dist_exchange_inverse(self._h, self._p(T), int(k1_begin), int(k1_count)))
+
+    def exchange_join(self):
+        check(lib().gopf_dist_exchange_join(self._h))
+
     def advance(self):
         check(lib().gopf_dist_advance(self._h))
 
@@ -117,7 +277,12 @@ class ShardedSolver:
     """pf.Solver for a slab-sharded cubic grid.  ``model`` is a gopf_b200.pf.Model whose single
     field's host ``Data`` holds THIS rank's slab (planes [rank*n/world, (rank+1)*n/world))."""
 
-    def __init__(self, model, n: int, dt: float, device: int, group=None):
+    def __init__(self, model, n: int, dt: float, device: int, group=None, exchange: str = "peer", nchunks: int = 4):
+        """exchange = "peer": the transpose is fused into the producing passes as stores into
+        the peers' receive buffers over NVLink (CUDA IPC mappings), with a tiny NCCL all-reduce
+        as the stream barrier; "dma": the same receive buffers filled by copy-engine copies
+        pipelined under the kernels, ``nchunks`` chunks per exchange; "nccl": pack in the pass,
+        ``all_to_all_single``, unpack in the next pass (the baseline)."""
         import torch
         import torch.distributed as tdist
         self.torch, self.tdist, self.group = torch, tdist, group
@@ -128,13 +293,47 @@ class ShardedSolver:
         self.phases = CudaPhases(model, n, self.world, self.rank, dt, device)
         cells = self.phases.local_cells
         mk = lambda: torch.empty(cells, dtype=torch.complex128, device=self.device)
-        self.S, self.A, self.B = mk(), mk(), mk()
-        self.a_valid = False
+        if exchange not in ("peer", "dma", "nccl"):
+            raise ValueError("exchange must be 'peer', 'dma' or 'nccl'")
+        self.exchange = exchange
+        self.nchunks = nchunks
+        self.slab = n // self.world
+        self.S, self.A = mk(), mk()
+        self.B = mk() if exchange in ("nccl", "dma") else None
+        self.a_valid = False   # nccl: A holds the first inverse pass of S; peer: X does
         self.on_device = False
+        if exchange in ("peer", "dma"):
+            self._map_peers()
         # One real stream for kernels, copies and the collective's stream dependencies.  (The
         # legacy default stream has handle 0, which the C ABI reads as "use the plan's stream".)
         self.stream = torch.cuda.Stream(device=self.device)
         self.phases.set_stream(self.stream.cuda_stream)
+
+    def _map_peers(self):
+        """Allocate this rank's receive buffers and map every other rank's (CUDA IPC handles
+        travel through one all_gather)."""
+        torch, tdist = self.torch, self.tdist
+        self.phases.peer_alloc()
+        mine = self.phases.peer_export(0) + self.phases.peer_export(1)
+        if self.world > 1:
+            send = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+            recv = [torch.empty_like(send) for _ in range(self.world)]
+            tdist.all_gather(recv, send, group=self.group)
+            handles = [bytes(t.cpu().tolist()) for t in recv]
+        else:
+            handles = [mine]
+        for q, h in enumerate(handles):
+            if q != self.rank:
+                self.phases.peer_import(0, q, h[:64])
+                self.phases.peer_import(1, q, h[64:])
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    def barrier(self):
+        """Cross-rank barrier in stream order: the all-reduce cannot complete on any rank
+        before every rank has reached it on its stream, i.e. finished its earlier kernels
+        (whose peer stores are complete at kernel end)."""
+        if self.world > 1:
+            self.tdist.all_reduce(self._flag, group=self.group)
 
     def all_to_all(self, dst, src):
         if self.world == 1:
@@ -146,21 +345,37 @@ class ShardedSolver:
         with self.torch.cuda.stream(self.stream):
             host = self.torch.from_numpy(self.model.Fields[0].Data)
             self.A.copy_(host, non_blocking=True)
-            upload(self.phases, self.all_to_all, self.A, self.S, self.B)
+            if self.exchange == "peer":
+                upload_peer(self.phases, self.barrier, self.A, self.S)
+            elif self.exchange == "dma":
+                upload_dma(self.phases, self.barrier, self.A, self.S, self.B, self.slab)
+            else:
+                upload(self.phases, self.all_to_all, self.A, self.S, self.B)
         self.a_valid = False
         self.on_device = True
 
     def StepDevice(self, nsteps: int):
         with self.torch.cuda.stream(self.stream):
-            self.a_valid = run_steps(self.phases, self.all_to_all, self.S, self.A, self.B, nsteps, self.a_valid)
+            if self.exchange == "peer":
+                self.a_valid = run_steps_peer(self.phases, self.barrier, self.S, self.A, nsteps, self.a_valid)
+            elif self.exchange == "dma":
+                self.a_valid = run_steps_dma(self.phases, self.barrier, self.S, self.A, self.B, nsteps, self.a_valid,
+                                             self.slab, self.nchunks)
+            else:
+                self.a_valid = run_steps(self.phases, self.all_to_all, self.S, self.A, self.B, nsteps, self.a_valid)
 
     def Download(self):
         with self.torch.cuda.stream(self.stream):
-            download(self.phases, self.all_to_all, self.S, self.A, self.B, self.A)  # last pass in place on A
+            if self.exchange == "peer":
+                self.a_valid = download_peer(self.phases, self.barrier, self.S, self.A, self.A, self.a_valid)
+            elif self.exchange == "dma":
+                self.a_valid = download_dma(self.phases, self.barrier, self.S, self.A, self.B, self.A, self.a_valid, self.slab)
+            else:
+                download(self.phases, self.all_to_all, self.S, self.A, self.B, self.A)  # last pass in place on A
+                self.a_valid = False
             host = self.torch.from_numpy(self.model.Fields[0].Data)
             host.copy_(self.A)
         self.stream.synchronize()
-        self.a_valid = False
 
     def Synchronize(self):
         self.stream.synchronize()

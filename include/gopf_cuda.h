@@ -216,6 +216,41 @@ int gopf_dist_forward_mid(gopf_dist_solver* s, const void* w_c128, void* send_c1
 int gopf_dist_kspace_step(gopf_dist_solver* s, void* t_c128, void* spectrum_c128);
 /* download side: last inverse pass and 1/N, W -> real slab */
 int gopf_dist_inverse_finish(gopf_dist_solver* s, void* w_c128, void* real_out_c128);
+/* Peer-store exchange (B200 NVLink 5 / NVSwitch): the transpose is fused into the pass that
+ * produces the data.  Every rank owns receive buffers X (which = 0; read by inverse_mid) and
+ * Y (which = 1; read by kspace_step_peer / forward_finish_peer), exports them as 64-byte CUDA
+ * IPC handles and imports every other rank's; the *_peer phases then store each row straight
+ * into its owner's buffer.  The caller places a cross-rank barrier on the stream between a
+ * peer-writing phase and the phases that read the buffers.  One step:
+ *   [first step only: barrier; inverse_start_peer(S); barrier]
+ *   inverse_mid(X_local -> A); real_step(A); forward_mid_peer(A); barrier;
+ *   kspace_step_peer(S); barrier; advance()                                              */
+int gopf_dist_peer_alloc(gopf_dist_solver* s);
+int gopf_dist_peer_export(gopf_dist_solver* s, int which, void* handle64);
+int gopf_dist_peer_import(gopf_dist_solver* s, int which, int rank, const void* handle64);
+int gopf_dist_peer_local(gopf_dist_solver* s, int which, void** dev_ptr);
+int gopf_dist_inverse_start_peer(gopf_dist_solver* s, const void* spectrum_c128);
+int gopf_dist_forward_mid_peer(gopf_dist_solver* s, const void* w_c128);
+int gopf_dist_forward_local_peer(gopf_dist_solver* s, void* w_c128);
+int gopf_dist_forward_finish_peer(gopf_dist_solver* s, void* spectrum_c128);
+int gopf_dist_kspace_step_peer(gopf_dist_solver* s, void* spectrum_c128);
+/* Copy-engine exchange pipelined by chunks (same X / Y buffers and IPC mappings): planes
+ * [begin, begin+count) of the slab are independent through inverse_mid -> real_step ->
+ * forward_mid, columns k1l in [k1_begin, k1_begin+k1_count) through kspace_step, so the DMA
+ * copies of one chunk (second stream, no SM) run under the kernels of the next.  One step:
+ *   for each plane chunk: inverse_mid_planes(X_local -> A); real_step_planes(A);
+ *                         forward_mid_planes(A -> SEND); exchange_forward(SEND)
+ *   exchange_join; barrier
+ *   for each column chunk: kspace_step_cols(Y_local, S -> T); exchange_inverse(T)
+ *   exchange_join; barrier; advance()                                                     */
+int gopf_dist_inverse_mid_planes(gopf_dist_solver* s, const void* recv_c128, void* w_c128, int begin, int count);
+int gopf_dist_real_step_planes(gopf_dist_solver* s, void* w_c128, int begin, int count);
+int gopf_dist_forward_mid_planes(gopf_dist_solver* s, const void* w_c128, void* send_c128, int begin, int count);
+int gopf_dist_kspace_step_cols(gopf_dist_solver* s, const void* t_in_c128, void* spectrum_c128, void* t_out_c128,
+                               int k1_begin, int k1_count);
+int gopf_dist_exchange_forward(gopf_dist_solver* s, const void* send_c128, int begin, int count);
+int gopf_dist_exchange_inverse(gopf_dist_solver* s, const void* t_c128, int k1_begin, int k1_count);
+int gopf_dist_exchange_join(gopf_dist_solver* s);
 int gopf_dist_advance(gopf_dist_solver* s);
 int gopf_dist_solver_get_time(gopf_dist_solver* s, double* t);
 int gopf_dist_solver_kernel_launches(gopf_dist_solver* s, int64_t* n, int reset);

@@ -36,7 +36,7 @@ def _oracle(n, nsteps):
     return f.Data
 
 
-def _worker(rank, world, port, n, split, out_dir):
+def _worker(rank, world, port, n, split, out_dir, exchange):
     import torch.distributed as tdist
     from gopf_b200 import dist as gdist
     from gopf_b200 import pf as gpf
@@ -52,10 +52,12 @@ def _worker(rank, world, port, n, split, out_dir):
         model.AddScalar(gpf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
         model.AddField(f)
         model.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
-        s = gdist.ShardedSolver(model, n, synthetic.CAHN_HILLIARD_DT, device=rank)
+        s = gdist.ShardedSolver(model, n, synthetic.CAHN_HILLIARD_DT, device=rank, exchange=exchange)
         s.Upload()
-        for k in split:
+        for i, k in enumerate(split):
             s.StepDevice(k)
+            if i == 0 and len(split) > 1:
+                s.Download()  # a host read-back between epochs must not disturb the device state
         s.Download()
         torch.cuda.synchronize()
         assert s.phases.kernel_launches() > 0
@@ -64,12 +66,14 @@ def _worker(rank, world, port, n, split, out_dir):
         tdist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,split", [(1, 32, (4, 3)), (1, 64, (10,)), (2, 32, (4, 3)), (2, 64, (10,))])
-def test_sharded_cuda_matches_oracle(tmp_path, world, n, split):
+@pytest.mark.parametrize("exchange", ["peer", "dma", "nccl"])
+@pytest.mark.parametrize("world,n,split", [(1, 32, (4, 3)), (1, 64, (10,)), (2, 32, (4, 3)), (2, 64, (10,)), (4, 64, (3, 2)),
+                                           (8, 64, (5,))])
+def test_sharded_cuda_matches_oracle(tmp_path, world, n, split, exchange):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world, _free_port(), n, split, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, split, str(tmp_path), exchange), nprocs=world, join=True)
     got = np.concatenate([np.load(tmp_path / f"slab{r}.npy") for r in range(world)])
     ref = _oracle(n, sum(split))
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-10
