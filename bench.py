@@ -32,6 +32,14 @@ BYTES_PER_CELL_UPDATE_3D = 192.0  # SURVEY 8d contract: T_min = 2 transforms x 3
 FALLBACK_HBM_GBS = 6650.0         # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+# capture (profiles/r1b_ncu_full_step.md), keyed by (kernel class, cubic grid edge)
+NCU_TRAFFIC = {("fused_kspace", 256): 536.918784e6 + 482.359040e6,
+               ("fused_real", 256): 268.504832e6 + 209.955840e6,
+               ("pass_inverse_mid", 256): 268.507904e6 + 212.805632e6,
+               ("pass_forward_mid", 256): 268.555008e6 + 211.119872e6}
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -165,6 +173,120 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# SURVEY.md 8d contract bytes per cell-update (T_min x 96 B in 3-D) and the reference's own
+# transform count for context
+WORKLOADS = {
+    "precipitate": {"contract_bytes": 576.0, "ref_bytes": 2016.0, "default_grid": 512,
+                    "name": "strain-single-precipitate-3d-{G}^3-khachaturyan-elasticity-volume-constraint"},
+    "pfc": {"contract_bytes": 192.0, "ref_bytes": 480.0, "default_grid": 512,
+            "name": "pfc-3d-{G}^3-pair-correlation-white-noise-vandeven"},
+}
+
+
+def build_workload(kind, pf, terms, elasticity, dims, pinned, device_noise=True):
+    from gopf_b200 import workloads
+    if kind == "precipitate":
+        m, conc, phase, solver, _ = workloads.build_precipitate(pf, terms, elasticity, dims, expressions=pf.__name__.startswith("gopf_b200"),
+                                                               pinned=pinned)
+        return m, solver
+    if device_noise:
+        m, f, solver = workloads.build_pfc(pf, terms, dims, noise="device", pinned=pinned)
+    else:
+        from oracle import terms as oterms
+        m, f, solver = workloads.build_pfc(pf, terms, dims, noise=oterms.WhiteNoise(workloads.PFC_NOISE_STRENGTH).Generate)
+    return m, solver
+
+
+def run_general_workload(args):
+    """cfg 4 / cfg 5 on one GPU: the general (multi-field, catalog-term) path."""
+    import torch
+    from gopf_b200 import elasticity as gel
+    from gopf_b200 import pf as gpf
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference)")
+    W = WORKLOADS[args.workload]
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    G = args.grid
+    dims = [G, G, G]
+    n = G ** 3
+    model, solver = build_workload(args.workload, gpf, gpf, gel, dims, pinned=True)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    solver.SetStream(stream.cuda_stream)
+    solver.Upload()
+    solver.StepDevice(args.warmup)
+    torch.cuda.synchronize()
+    solver.KernelLaunches(reset=True)
+    sampler = ClockSampler(dev)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    solver.StepDevice(args.steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = solver.KernelLaunches(reset=True)
+    solver.ProfileBegin()
+    solver.StepDevice(args.steps)
+    torch.cuda.synchronize()
+    prof = solver.ProfileEnd()
+    clocks = sampler.stop()
+    value = n * args.steps / (ms * 1e-3)
+    peak, peak_src = measured_hbm_peak()
+    kernels = []
+    for k in prof:
+        if k["launches"] == 0:
+            continue
+        avg_ms = k["total_ms"] / k["launches"]
+        kernels.append({"kernel": k["kernel"], "launches_per_step": k["launches"] / args.steps, "avg_ms": avg_ms,
+                        "algorithmic_bytes": k["bytes_per_launch"], "gbs": k["bytes_per_launch"] / (avg_ms * 1e-3) / 1e9})
+    kernels.sort(key=lambda k: -k["avg_ms"] * k["launches_per_step"])
+    top = kernels[0]
+    moved = sum(k["algorithmic_bytes"] * k["launches_per_step"] for k in kernels) / n
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": top["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": top["algorithmic_bytes"], "avg_launch_ms": top["avg_ms"],
+                "step_model": {"bytes_per_cell_update": W["contract_bytes"], "achieved": value * W["contract_bytes"] / 1e9,
+                               "frac": value * W["contract_bytes"] / 1e9 / peak,
+                               "bytes_per_cell_update_moved_by_this_path": moved,
+                               "bytes_per_cell_update_reference_structure": W["ref_bytes"]},
+                "kernels": kernels}
+    e2e_steps = 3
+    solver.Propagate(1)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        solver.Propagate(1)
+    e2e_dt = time.perf_counter() - t0
+    nf = len(model.Fields)
+    e2e = {"value": n * e2e_steps / e2e_dt, "unit": METRIC, "h2d_bytes_per_step": 16 * n * nf, "d2h_bytes_per_step": 16 * n * nf,
+           "steps": e2e_steps, "call": "gopf_solver_propagate(s, 1) on pinned host Field.Data"}
+    line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": W["name"].format(G=G), "grid": dims, "stepper": "euler",
+                       "cache": f"arrays of {16 * n / 2**20:.0f} MiB each exceed the 126 MB L2 (no flush needed)",
+                       "path": "general multi-field path"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
+    if not args.no_cpu_baseline:
+        # oracle on a bounded sample: the same model at 64^3 (cells/s is size-normalised), single thread
+        from oracle import elasticity as oel
+        from oracle import pf as opf
+        from oracle import terms as oterms
+        sg = 64
+        om, osolver = build_workload(args.workload, opf, oterms, oel, [sg] * 3, pinned=False, device_noise=False)
+        osolver.Propagate(1)
+        t0 = time.perf_counter()
+        osolver.Propagate(3)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": sg ** 3 * 3 / dt, "unit": METRIC, "cores": 1, "kind": "port",
+                                "sample": f"3 steps of the same model at {sg}^3 after 1 warm-up step, oracle port, scipy.fft workers=1"}
+    print(json.dumps(line), flush=True)
+
+
 def run_single_gpu(args):
     import torch
     from gopf_b200 import pf as gpf
@@ -231,7 +353,9 @@ def run_single_gpu(args):
     kernels.sort(key=lambda k: -k["avg_ms"] * k["launches_per_step"])
     top = kernels[0]
     roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": top["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": top["gbs"] / peak, "traffic": NCU_TRAFFIC.get((top["kernel"], G)),
+                "traffic_source": "profiles/r1b_ncu_full_step.md" if (top["kernel"], G) in NCU_TRAFFIC else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": top["algorithmic_bytes"], "avg_launch_ms": top["avg_ms"],
                 "step_model": {"bytes_per_cell_update": BYTES_PER_CELL_UPDATE_3D,
                                "achieved": value * BYTES_PER_CELL_UPDATE_3D / 1e9,
@@ -278,14 +402,27 @@ def main():
     ap.add_argument("--grid", type=int, default=0, help="cubic grid edge (default 256 on 1 GPU, 1024 sharded)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="ch", choices=["ch", "precipitate", "pfc"],
+                    help="ch: Cahn-Hilliard (BASELINE.json configs 1-3, the metric's workload); precipitate: cfg 4; pfc: cfg 5")
     ap.add_argument("--exchange", default="peer", choices=["peer", "dma", "nccl"],
                     help="sharded runs: peer stores fused into the passes, copy-engine copies pipelined under the "
                          "kernels, or NCCL all-to-all")
-    ap.add_argument("--chunks", type=int, default=4, help="--exchange dma: chunks per exchange")
+    ap.add_argument("--chunks", type=int, default=8, help="sharded runs: plane / column chunks the exchange is pipelined in")
+    ap.add_argument("--comm-ctas", type=int, default=48,
+                    help="--exchange peer: SMs given to the NVLink-bound peer-storing pass while it overlaps the next chunk")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload != "ch":
+        if max(args.gpus, world) > 1:
+            raise SystemExit("bench.py: the sharded path covers the Cahn-Hilliard workload; cfg 4 / cfg 5 run on one GPU")
+        if args.grid == 0:
+            args.grid = WORKLOADS[args.workload]["default_grid"]
+        if args.impl == "reference":
+            raise SystemExit("bench.py: --impl reference times the metric's workload (ch)")
+        run_general_workload(args)
+        return
     if args.grid == 0:
         args.grid = 256 if max(args.gpus, world) == 1 else 1024
     if args.impl == "reference":

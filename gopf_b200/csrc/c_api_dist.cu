@@ -203,6 +203,13 @@ int gopf_dist_exchange_inverse(gopf_dist_solver* s, const void* t, int k1_begin,
     GOPF_API_END
 }
 
+int gopf_dist_forward_mid_peer_planes(gopf_dist_solver* s, const void* w, int begin, int count, int max_ctas) {
+    GOPF_API_BEGIN
+    range_check(begin, count, ds(s).slab(), "gopf_dist_forward_mid_peer_planes");
+    ds(s).forward_mid_peer_planes(ccp(w, "w"), begin, count, max_ctas);
+    GOPF_API_END
+}
+
 int gopf_dist_exchange_join(gopf_dist_solver* s) {
     GOPF_API_BEGIN
     ds(s).exchange_join();

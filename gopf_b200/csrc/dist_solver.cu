@@ -224,7 +224,9 @@ void DistSolver::copy_after_compute() {
     if (!peer_ready()) throw Error("dist solver: peer buffers are not mapped (peer_alloc / peer_import)");
     plan_->use_device();
     if (!copy_stream_) {
-        GOPF_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+        int lo = 0, hi = 0;
+        GOPF_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        GOPF_CUDA(cudaStreamCreateWithPriority(&copy_stream_, cudaStreamNonBlocking, hi));
         GOPF_CUDA(cudaEventCreateWithFlags(&ev_compute_, cudaEventDisableTiming));
         GOPF_CUDA(cudaEventCreateWithFlags(&ev_copy_, cudaEventDisableTiming));
     }
@@ -253,6 +255,17 @@ void DistSolver::exchange_inverse(const cplx* T, int k1_begin, int k1_count) {
                                     T + q * block + (size_t)k1_begin * n_, sizeof(cplx) * plane,
                                     sizeof(cplx) * k1_count * n_, m_, cudaMemcpyDefault, copy_stream_));
     }
+}
+
+void DistSolver::forward_mid_peer_planes(const cplx* W, int begin, int count, int max_ctas) {
+    copy_after_compute();
+    PassGeom g = make_geom(count, n_, n_, 1);
+    g.peer = peer_out(Y_, false);
+    g.peer.block_off += (long long)begin * g.peer.a_stride;
+    g.peer.max_ctas = max_ctas;
+    check(launch_pass(g, plan_->tx_want, plain_io(W + (size_t)begin * n_ * n_, nullptr, false, 1.0), plan_->twiddle(1),
+                      copy_stream_),
+          "forward axis 1 -> peers (planes)");
 }
 
 void DistSolver::exchange_join() {

@@ -80,6 +80,10 @@ public:
     void exchange_forward(const cplx* send, int begin, int count);    // send planes -> every rank's Y (after the compute so far)
     void exchange_inverse(const cplx* T, int k1_begin, int k1_count);  // T columns -> every rank's X
     void exchange_join();                                              // compute stream waits for the copies issued so far
+    // Peer-store exchange pipelined by plane chunks: forward axis 1 of planes [begin, begin+count)
+    // -> peers' Y, launched on the second (high-priority) stream as a persistent kernel confined to
+    // `max_ctas` SMs, so the NVLink-bound pass runs under the HBM-bound kernels of the next chunk.
+    void forward_mid_peer_planes(const cplx* W, int begin, int count, int max_ctas);
     ~DistSolver();
     void advance() { steps_taken_++; current_step_++; }
     double get_time() const { return (double)current_step_ * dt_; }

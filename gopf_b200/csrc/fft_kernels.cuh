@@ -32,7 +32,8 @@ struct PeerOut {
     cplx* base[GOPF_MAX_PEERS];
     long long block_off, a_stride, row_stride;
     int log, mask;
-    int n, pad;
+    int n;
+    int max_ctas;  // > 0: launch at most this many (persistent) CTAs
 };
 
 struct PassGeom {
@@ -241,15 +242,12 @@ __device__ __forceinline__ void pass_store_ptr(const PassIO& io, cplx (&v)[E], P
 
 // ---- strided axis (B > 1): tile = N x TX, TX adjacent lines ---------------------
 template <int N, int TX, bool PEER>
-__global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB(PlanFor<N>::T* TX))
-    k_pass_strided(const __grid_constant__ PassGeom g, const __grid_constant__ PassIO io, const cplx* __restrict__ tw) {
-    extern __shared__ __align__(16) unsigned char gopf_smem_raw[];
-    cplx* sm = reinterpret_cast<cplx*>(gopf_smem_raw);
+__device__ __forceinline__ void pass_strided_tile(const PassGeom& g, const PassIO& io, const cplx* __restrict__ tw,
+                                                  cplx* sm, long long tile) {
     constexpr int E = PlanFor<N>::E, T = PlanFor<N>::T;
     const int tid = threadIdx.x;
     const int l = tid % TX, t = tid / TX;
     const long long tilesB = g.B / TX;
-    const long long tile = blockIdx.x;
     const long long a = tile / tilesB;
     const long long b = (tile - a * tilesB) * TX + l;
     cplx v[E];
@@ -269,6 +267,23 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB(PlanFor<N>::T* TX
         pass_store_ptr<E>(io, v, [&](int m) -> cplx* { return peer_row(g.peer, a, t + T * m, b); });
     else
         pass_store_line<E>(io, v, at_out);
+}
+
+// PEER: persistent over tiles (grid-stride), so the launch can confine the NVLink-bound pass to
+// a few SMs (PeerOut::max_ctas) and leave the rest to the HBM-bound kernels of the next chunk
+// running on the compute stream.  Every thread has passed the barrier after the last exchange
+// read before it stores, so the next tile's first exchange write needs no extra barrier.
+template <int N, int TX, bool PEER>
+__global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB(PlanFor<N>::T* TX))
+    k_pass_strided(const __grid_constant__ PassGeom g, const __grid_constant__ PassIO io, const cplx* __restrict__ tw) {
+    extern __shared__ __align__(16) unsigned char gopf_smem_raw[];
+    cplx* sm = reinterpret_cast<cplx*>(gopf_smem_raw);
+    if (PEER) {
+        const long long tiles = g.A * (g.B / TX);
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) pass_strided_tile<N, TX, true>(g, io, tw, sm, tile);
+    } else {
+        pass_strided_tile<N, TX, false>(g, io, tw, sm, blockIdx.x);
+    }
 }
 
 // ---- contiguous axis (B == 1): LINES lines per CTA, position fastest ------------
@@ -334,7 +349,8 @@ cudaError_t launch_strided_n_tx(const PassGeom& g, const PassIO& io, const cplx*
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const long long tiles = g.A * (g.B / TX);
+    long long tiles = g.A * (g.B / TX);
+    if (g.peer.n > 0 && g.peer.max_ctas > 0 && tiles > g.peer.max_ctas) tiles = g.peer.max_ctas;
     kern<<<(unsigned)tiles, T * TX, smem, s>>>(g, io, tw);
     return cudaGetLastError();
 }

@@ -30,27 +30,6 @@ def run_steps(phases, all_to_all, S, A, B, nsteps: int, a_valid: bool) -> bool:
     return a_valid
 
 
-def run_steps_peer(phases, barrier, S, A, nsteps: int, x_valid: bool) -> bool:
-    """nsteps sharded Euler steps with the exchange fused into the producing passes (peer
-    stores over NVLink).  The receive buffers X and Y live in ``phases``; ``barrier()`` orders
-    every rank's earlier stream work before every rank's later stream work.  ``x_valid`` says X
-    already holds the first inverse pass of S.  Returns the new x_valid."""
-    for _ in range(nsteps):
-        if not x_valid:
-            barrier()                        # nobody is still reading X
-            phases.inverse_start_peer(S)     # S -> inverse axis 0 -> every rank's X
-            barrier()
-        phases.inverse_mid_x(A)              # X -> inverse axis 1 -> A
-        phases.real_step(A)                  # inverse axis 2, /N, g(c), forward axis 2
-        phases.forward_mid_peer(A)           # forward axis 1 -> every rank's Y
-        barrier()
-        phases.kspace_step_peer(S)           # Y: forward axis 0, Euler update of S, inverse axis 0 -> every rank's X
-        barrier()
-        phases.advance()
-        x_valid = True
-    return x_valid
-
-
 def chunks(extent: int, nchunks: int):
     """[(begin, count)] covering range(extent) in at most nchunks near-equal pieces."""
     nchunks = max(1, min(nchunks, extent))
@@ -61,6 +40,40 @@ def chunks(extent: int, nchunks: int):
         out.append((b, c))
         b += c
     return out
+
+
+def run_steps_peer(phases, barrier, S, A, nsteps: int, x_valid: bool, slab: int = 0, nchunks: int = 1,
+                   comm_ctas: int = 0) -> bool:
+    """nsteps sharded Euler steps with the exchange fused into the producing passes (peer
+    stores over NVLink).  The receive buffers X and Y live in ``phases``; ``barrier()`` orders
+    every rank's earlier stream work before every rank's later stream work.  ``x_valid`` says X
+    already holds the first inverse pass of S.  Returns the new x_valid.
+
+    nchunks > 1 pipelines the real-space side by plane chunks: the peer-storing pass of chunk c
+    (NVLink-bound; second stream, confined to ``comm_ctas`` SMs) runs under the HBM-bound
+    inverse_mid / real_step kernels of chunk c+1."""
+    parts = chunks(slab, nchunks) if nchunks > 1 and slab > 0 else None
+    for _ in range(nsteps):
+        if not x_valid:
+            barrier()                        # nobody is still reading X
+            phases.inverse_start_peer(S)     # S -> inverse axis 0 -> every rank's X
+            barrier()
+        if parts is None:
+            phases.inverse_mid_x(A)          # X -> inverse axis 1 -> A
+            phases.real_step(A)              # inverse axis 2, /N, g(c), forward axis 2
+            phases.forward_mid_peer(A)       # forward axis 1 -> every rank's Y
+        else:
+            for b, c in parts:
+                phases.inverse_mid_planes_x(A, b, c)
+                phases.real_step_planes(A, b, c)
+                phases.forward_mid_peer_planes(A, b, c, comm_ctas)
+            phases.exchange_join()
+        barrier()
+        phases.kspace_step_peer(S)           # Y: forward axis 0, Euler update of S, inverse axis 0 -> every rank's X
+        barrier()
+        phases.advance()
+        x_valid = True
+    return x_valid
 
 
 def run_steps_dma(phases, barrier, S, A, SEND, nsteps: int, x_valid: bool, slab: int, nchunks: int = 4) -> bool:
@@ -248,6 +261,9 @@ class CudaPhases:
     def exchange_join(self):
         check(lib().gopf_dist_exchange_join(self._h))
 
+    def forward_mid_peer_planes(self, W, begin: int, count: int, max_ctas: int):
+        check(lib().gopf_dist_forward_mid_peer_planes(self._h, self._p(W), int(begin), int(count), int(max_ctas)))
+
     def advance(self):
         check(lib().gopf_dist_advance(self._h))
 
@@ -277,7 +293,8 @@ class ShardedSolver:
     """pf.Solver for a slab-sharded cubic grid.  ``model`` is a gopf_b200.pf.Model whose single
     field's host ``Data`` holds THIS rank's slab (planes [rank*n/world, (rank+1)*n/world))."""
 
-    def __init__(self, model, n: int, dt: float, device: int, group=None, exchange: str = "peer", nchunks: int = 4):
+    def __init__(self, model, n: int, dt: float, device: int, group=None, exchange: str = "peer", nchunks: int = 8,
+                 comm_ctas: int = 48):
         """exchange = "peer": the transpose is fused into the producing passes as stores into
         the peers' receive buffers over NVLink (CUDA IPC mappings), with a tiny NCCL all-reduce
         as the stream barrier; "dma": the same receive buffers filled by copy-engine copies
@@ -297,6 +314,7 @@ class ShardedSolver:
             raise ValueError("exchange must be 'peer', 'dma' or 'nccl'")
         self.exchange = exchange
         self.nchunks = nchunks
+        self.comm_ctas = comm_ctas   # peer: SMs given to the NVLink-bound pass while it runs under the next chunk
         self.slab = n // self.world
         self.S, self.A = mk(), mk()
         self.B = mk() if exchange in ("nccl", "dma") else None
@@ -357,7 +375,8 @@ class ShardedSolver:
     def StepDevice(self, nsteps: int):
         with self.torch.cuda.stream(self.stream):
             if self.exchange == "peer":
-                self.a_valid = run_steps_peer(self.phases, self.barrier, self.S, self.A, nsteps, self.a_valid)
+                self.a_valid = run_steps_peer(self.phases, self.barrier, self.S, self.A, nsteps, self.a_valid, self.slab,
+                                              self.nchunks if self.world > 1 else 1, self.comm_ctas)
             elif self.exchange == "dma":
                 self.a_valid = run_steps_dma(self.phases, self.barrier, self.S, self.A, self.B, nsteps, self.a_valid,
                                              self.slab, self.nchunks)

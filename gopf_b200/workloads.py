@@ -98,3 +98,58 @@ def build_precipitate(pf, terms, elasticity, dims, *, expressions: bool, elastic
     m.AddEquation(eq_phase)
     solver = pf.NewSolver(m, dims, dt)
     return m, conc, phase, solver, vol
+
+
+# ---- cfg 5: examples/pfcPhases/main.go:38-89 scaled to 3-D, + white noise + Vandeven filter ----
+PFC_DT = 0.1
+PFC_LATTICE = 16.0          # main.go:30 uses a = 16 lattice spacing units (flag default)
+PFC_PEAK_WIDTH = 0.02       # main.go:66
+PFC_EFF_TEMP = 0.1
+PFC_NOISE_STRENGTH = 1e-4
+PFC_SEED = 11
+
+
+def pfc_initial(n_nodes: int, seed: int = PFC_SEED, mean_density: float = 0.0) -> np.ndarray:
+    """density = 0.3 (2u - 1) + mean (main.go:57-60 with the synthetic stream)."""
+    from . import synthetic
+    out = np.empty(n_nodes, dtype=np.complex128)
+    chunk = 1 << 24
+    for s in range(0, n_nodes, chunk):
+        m = min(chunk, n_nodes - s)
+        out[s:s + m] = 0.3 * (2.0 * synthetic.splitmix64_uniform(seed, m, s) - 1.0) + mean_density
+    return out
+
+
+def build_pfc(pf, terms, dims, *, noise=None, filt_order=5, pinned: bool = False, noise_seed: int = 7):
+    """Phase-field crystal: implicit pair-correlation term (two-peak set, main.go:63-72), mixed
+    ideal-mixture term (main.go:75-83), optional white noise (``noise`` = "device": the device
+    Philox stream through WhiteNoise.Generate; None: no noise) and Vandeven(filt_order) filter.
+    Returns (model, density, solver)."""
+    import math
+    n = int(np.prod(dims))
+    m = pf.NewModel()
+    if pinned:
+        f = pf.NewField("density", n, None, pinned=True)
+        f.Data[:] = pfc_initial(n)
+    else:
+        f = pf.NewField("density", n, pfc_initial(n))
+    m.AddField(f)
+    a = PFC_LATTICE
+    peaks = [terms.Peak(1.0, 2.0 * math.pi / a, PFC_PEAK_WIDTH, 4),
+             terms.Peak(1.0 / math.sqrt(2.0), 2.0 * math.pi / (a / math.sqrt(2.0)), PFC_PEAK_WIDTH, 4)]
+    term = terms.PairCorrlationTerm(terms.ReciprocalSpacePairCorrelation(PFC_EFF_TEMP, peaks), "density", 1.0, True)
+    ideal = terms.IdealMixtureTerm(terms.IdealMix(1.0, 1.0), "density", 1.0, True)
+    m.RegisterImplicitTerm("EXCESS", term, None)
+    m.RegisterMixedTerm("IDEAL", ideal, [ideal.DerivedField(n, m.Bricks)])
+    eq = "ddensity/dt = IDEAL + EXCESS"
+    if noise == "device":
+        m.RegisterFunction("NOISE", terms.WhiteNoise(PFC_NOISE_STRENGTH, seed=noise_seed).Generate)
+        eq += " + NOISE"
+    elif noise is not None:
+        m.RegisterFunction("NOISE", noise)
+        eq += " + NOISE"
+    m.AddEquation(eq)
+    solver = pf.NewSolver(m, dims, PFC_DT)
+    if filt_order is not None:
+        solver.Stepper.SetFilter(terms.NewVandeven(filt_order))
+    return m, f, solver

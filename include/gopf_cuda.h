@@ -251,6 +251,15 @@ int gopf_dist_kspace_step_cols(gopf_dist_solver* s, const void* t_in_c128, void*
 int gopf_dist_exchange_forward(gopf_dist_solver* s, const void* send_c128, int begin, int count);
 int gopf_dist_exchange_inverse(gopf_dist_solver* s, const void* t_c128, int k1_begin, int k1_count);
 int gopf_dist_exchange_join(gopf_dist_solver* s);
+/* Pipelined peer-store exchange: forward axis 1 of planes [begin, begin+count) -> every rank's Y,
+ * on the library's second (high-priority) stream after the compute stream's work so far, as a
+ * persistent kernel of at most max_ctas CTAs (0: no limit): the NVLink-bound pass of one chunk
+ * runs under the HBM-bound inverse_mid_planes / real_step_planes of the next.  exchange_join
+ * makes the compute stream wait for it.  One step:
+ *   for each plane chunk: inverse_mid_planes(X_local -> A); real_step_planes(A);
+ *                         forward_mid_peer_planes(A)
+ *   exchange_join; barrier; kspace_step_peer(S); barrier; advance()                        */
+int gopf_dist_forward_mid_peer_planes(gopf_dist_solver* s, const void* w_c128, int begin, int count, int max_ctas);
 int gopf_dist_advance(gopf_dist_solver* s);
 int gopf_dist_solver_get_time(gopf_dist_solver* s, double* t);
 int gopf_dist_solver_kernel_launches(gopf_dist_solver* s, int64_t* n, int reset);

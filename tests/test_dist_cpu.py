@@ -191,6 +191,10 @@ class NumpyDmaPhases(NumpyPeerPhases):
     def exchange_join(self):
         pass
 
+    def forward_mid_peer_planes(self, W, b, c, max_ctas):
+        self.forward_mid_planes(W, self._send, b, c)
+        self.exchange_forward(self._send, b, c)
+
 
 def _dma_worker(rank, world, port, n, split_steps, nchunks, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -214,7 +218,7 @@ def _dma_worker(rank, world, port, n, split_steps, nchunks, out_dir):
         tdist.destroy_process_group()
 
 
-def _peer_worker(rank, world, port, n, split_steps, out_dir):
+def _peer_worker(rank, world, port, n, split_steps, out_dir, nchunks=1):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     tdist.init_process_group("gloo", rank=rank, world_size=world)
@@ -223,12 +227,12 @@ def _peer_worker(rank, world, port, n, split_steps, out_dir):
         mk = lambda: torch.zeros(cells, dtype=torch.complex128)
         S, A = mk(), mk()
         A.numpy()[:] = synthetic.cahn_hilliard_initial(cells, 0, offset=rank * cells)
-        phases = NumpyPeerPhases(n, world, rank, synthetic.CAHN_HILLIARD_DT)
+        phases = NumpyDmaPhases(n, world, rank, synthetic.CAHN_HILLIARD_DT)
         gdist.upload_peer(phases, phases.barrier, A, S)
         valid = False
         mid = mk()
         for i, k in enumerate(split_steps):
-            valid = gdist.run_steps_peer(phases, phases.barrier, S, A, k, valid)
+            valid = gdist.run_steps_peer(phases, phases.barrier, S, A, k, valid, n // world, nchunks, 8)
             if i == 0:  # a download between epochs must not disturb the run (X stays valid)
                 valid = gdist.download_peer(phases, phases.barrier, S, A, mid, valid)
                 assert valid
@@ -295,10 +299,10 @@ def test_sharded_orchestration_matches_unsharded_oracle(tmp_path, world, n, spli
     assert err < 1e-12, err
 
 
-@pytest.mark.parametrize("world,n,split", [(2, 16, (3, 2)), (4, 16, (5,))])
-def test_peer_store_orchestration_matches_unsharded_oracle(tmp_path, world, n, split):
+@pytest.mark.parametrize("world,n,split,nchunks", [(2, 16, (3, 2), 1), (4, 16, (5,), 1), (2, 16, (2, 2), 4), (4, 16, (3,), 3)])
+def test_peer_store_orchestration_matches_unsharded_oracle(tmp_path, world, n, split, nchunks):
     nsteps = sum(split)
-    mp.spawn(_peer_worker, args=(world, _free_port(), n, split, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_peer_worker, args=(world, _free_port(), n, split, str(tmp_path), nchunks), nprocs=world, join=True)
     got = np.concatenate([np.load(tmp_path / f"slab{r}.npy") for r in range(world)])
     total = n ** 3
     m = opf.NewModel()
