@@ -1,0 +1,78 @@
+"""The CUDA path (through the C ABI) against the committed golden vectors of tests/golden/ --
+no oracle code runs in these tests.  Tolerance: relative L2 <= 1e-10 (BASELINE.json north_star);
+the k-table is bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from gopf_b200 import elasticity as gel
+from gopf_b200 import pf as gpf
+from gopf_b200 import pfutil as gpfutil
+from gopf_b200 import synthetic, workloads
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-10
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.mark.parametrize("dims", [[8, 16], [8, 8, 8]], ids=lambda d: "x".join(map(str, d)))
+def test_device_k_table_bit_exact(dims):
+    g = load("ktable.npz")
+    n = int(np.prod(dims))
+    got = gpfutil.NewFFTW(dims).freq_device(np.arange(n))
+    assert np.array_equal(got.reshape(n, -1)[:, :len(dims)], g[f"freq_{'x'.join(map(str, dims))}"])
+
+
+def test_fft_ramp():
+    g = load("fft_ramp_8x16.npz")
+    x = g["input"].copy()
+    gpfutil.NewFFTW([8, 16]).FFT(x)
+    assert rel_l2(x, g["forward"]) < 1e-13
+
+
+@pytest.mark.parametrize("generic", [False, True], ids=["fused", "generic"])
+@pytest.mark.parametrize("name,dims,stepper", [("ch_2d_32x32_euler.npz", [32, 32], "euler"), ("ch_3d_16_euler.npz", [16, 16, 16], "euler"),
+                                               ("ch_2d_32x32_rk4.npz", [32, 32], "rk4")])
+def test_cahn_hilliard_trajectories(name, dims, stepper, generic):
+    g = load(name)
+    n = int(np.prod(dims))
+    m = gpf.NewModel()
+    f = gpf.NewField("conc", n, synthetic.cahn_hilliard_initial(n, 0))
+    m.AddScalar(gpf.NewScalar("gamma", synthetic.CAHN_HILLIARD_GAMMA))
+    m.AddScalar(gpf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
+    m.AddField(f)
+    m.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
+    s = gpf.NewSolver(m, dims, synthetic.CAHN_HILLIARD_DT)
+    s.SetStepper(stepper)
+    if generic:
+        s.ForceGeneric(True)
+    done = 0
+    for k in sorted(int(key.split("_")[1]) for key in g.files):
+        s.Propagate(k - done)
+        done = k
+        assert rel_l2(f.Data, g[f"after_{k}"]) <= TOL
+
+
+@pytest.mark.parametrize("dims", [[32, 32], [16, 16, 16]], ids=lambda d: "x".join(map(str, d)))
+def test_precipitate(dims):
+    g = load(f"precipitate_{'x'.join(map(str, dims))}.npz")
+    m, conc, phase, s, vol = workloads.build_precipitate(gpf, gpf, gel, dims, expressions=True)
+    s.Solve(2, 5)
+    assert rel_l2(conc.Data, g["conc"]) <= TOL and rel_l2(phase.Data, g["phase"]) <= TOL
+    assert abs(s.LPMultiplier(0) - float(g["multiplier"][0])) <= 1e-9
+
+
+def test_pfc():
+    g = load("pfc_32x32_vandeven5.npz")
+    m, f, s = workloads.build_pfc(gpf, gpf, [32, 32], noise=None, filt_order=5)
+    s.Solve(2, 5)
+    assert rel_l2(f.Data, g["density"]) <= TOL
