@@ -45,7 +45,32 @@ struct PassGeom {
     long long node0; // reference node number of this array's first cell (slab offset when sharded)
     PeerOut peer;    // strided kernels only
     long long b0, bcount;  // fused k-space kernel: columns [b0, b0 + bcount) of B (chunked launches)
+    // Next-wave L2 prefetch (plain axis passes): a CTA asks L2 for the input tile of CTA
+    // blockIdx.x + pf_tiles (the one that takes its place on the SM, = resident CTAs of the launch),
+    // so DRAM keeps streaming while this tile is in its compute phase and the next wave's loads hit
+    // L2.  Measured on B200 (scripts/tune_prefetch.py): strided pass 256^3 5.95 -> 6.35 TB/s,
+    // 1024^3 4.33 -> 4.47 TB/s.  The fused kernels do not use it (k-space kernel: -15 %, two tiles
+    // per CTA oversubscribe L2; real-space kernel: neutral).  0: off.
+    long long pf_tiles;
 };
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// resident CTAs of a launch = prefetch distance (host)
+int prefetch_enabled();  // pass_launch.cu: GOPF_PREFETCH (default 1)
+template <class Kern>
+inline long long prefetch_distance(Kern kern, int threads, size_t smem) {
+    if (!prefetch_enabled()) return 0;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess || nb < 1) return 0;
+    return (long long)nb * sms;
+}
 
 __device__ __forceinline__ cplx* peer_row(const PeerOut& p, long long a, int j, long long b) {
     return p.base[j >> p.log] + (p.block_off + a * p.a_stride + (long long)(j & p.mask) * p.row_stride + b);
@@ -72,6 +97,7 @@ inline PassGeom make_geom(int n0, int n1, int n2, int axis) {
     g.peer = PeerOut{};
     g.b0 = 0;
     g.bcount = g.B;
+    g.pf_tiles = 0;
     return g;
 }
 
@@ -262,6 +288,19 @@ __device__ __forceinline__ void pass_strided_tile(const PassGeom& g, const PassI
                (size_t)(j & g.out.split_mask) * g.out.row_stride;
     };
     pass_load_line<E>(io, v, at_in, sm, [&](int m) -> int { return LayoutInterleaved<TX>::at(t + T * m, l); });
+    if (!PEER && g.pf_tiles > 0 && io.load_kind == LK_PLAIN) {
+        const long long tile2 = tile + g.pf_tiles;
+        if (tile2 < g.A * tilesB) {
+            const long long a2 = tile2 / tilesB;
+            const size_t ib2 = (size_t)a2 * g.in.a_stride + (size_t)((tile2 - a2 * tilesB) * TX + l);
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int j = t + T * m;
+                prefetch_l2(io.in + ib2 + (size_t)(j >> g.in.split_log) * g.in.split_stride +
+                            (size_t)(j & g.in.split_mask) * g.in.row_stride);
+            }
+        }
+    }
     line_fft<N, LayoutInterleaved<TX>, SyncCta>(v, t, l, sm, tw);
     if (PEER)
         pass_store_ptr<E>(io, v, [&](int m) -> cplx* { return peer_row(g.peer, a, t + T * m, b); });
@@ -311,6 +350,13 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
     cplx v[E];
     auto at = [&](int m) -> size_t { return base + p + T * m; };
     pass_load_line<E>(io, v, at, sm, [&](int m) -> int { return LayoutPadded<N>::at(p + T * m, l); });
+    if (g.pf_tiles > 0 && io.load_kind == LK_PLAIN) {
+        const long long line2 = line + g.pf_tiles * LINES;
+        if (line2 < g.A) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) prefetch_l2(io.in + (size_t)line2 * N + p + T * m);
+        }
+    }
     if (ContigCfg<N>::WARP_SYNC)
         line_fft<N, LayoutPadded<N>, SyncWarp>(v, p, l, sm, tw);
     else
@@ -351,7 +397,9 @@ cudaError_t launch_strided_n_tx(const PassGeom& g, const PassIO& io, const cplx*
     }
     long long tiles = g.A * (g.B / TX);
     if (g.peer.n > 0 && g.peer.max_ctas > 0 && tiles > g.peer.max_ctas) tiles = g.peer.max_ctas;
-    kern<<<(unsigned)tiles, T * TX, smem, s>>>(g, io, tw);
+    PassGeom gl = g;
+    if (g.peer.n == 0) gl.pf_tiles = prefetch_distance(kern, T * TX, smem);
+    kern<<<(unsigned)tiles, T * TX, smem, s>>>(gl, io, tw);
     return cudaGetLastError();
 }
 
@@ -385,7 +433,9 @@ cudaError_t launch_contig_n(const PassGeom& g, const PassIO& io, const cplx* tw,
         if (e != cudaSuccess) return e;
     }
     const long long blocks = (g.A + LINES - 1) / LINES;
-    kern<<<(unsigned)blocks, T * LINES, smem, s>>>(g, io, tw);
+    PassGeom gl = g;
+    gl.pf_tiles = prefetch_distance(kern, T * LINES, smem);
+    kern<<<(unsigned)blocks, T * LINES, smem, s>>>(gl, io, tw);
     return cudaGetLastError();
 }
 

@@ -1,7 +1,14 @@
 // Dispatch of one axis pass to the per-length instantiations (pass_inst_*.cu).
 #include "fft_kernels.cuh"
 
+#include <cstdlib>
+
 namespace gopf {
+
+int prefetch_enabled() {
+    const char* v = std::getenv("GOPF_PREFETCH");
+    return (v && *v) ? std::atoi(v) : 1;
+}
 
 #define GOPF_DECL(n) cudaError_t launch_pass_##n(const PassGeom&, int, const PassIO&, const cplx*, cudaStream_t);
 GOPF_DECL(2) GOPF_DECL(4) GOPF_DECL(8) GOPF_DECL(16) GOPF_DECL(32) GOPF_DECL(64) GOPF_DECL(128) GOPF_DECL(256)

@@ -10,18 +10,71 @@ namespace gopf {
 
 // ---- small kernels -------------------------------------------------------------------
 // generic pointwise update over every k (any shape, literal Freq from the node number)
+// Freq of node idx with 32-bit index arithmetic when the grid allows it (64-bit divisions cost
+// ~100 instructions each); same IEEE divides as ref_freq, so the result is bit-identical.
+__device__ __forceinline__ void ref_freq_fast(const FreqGeom& g, long long idx, bool small, double* res) {
+    if (!small) {
+        ref_freq(g, idx, res);
+        return;
+    }
+    const unsigned i = (unsigned)idx, d1 = (unsigned)g.d1, d0 = (unsigned)g.d0;
+    const unsigned q = i / d1, c = i - q * d1;
+    const unsigned d = q / d0, r = q - d * d0;
+    res[1] = (double)c / (double)g.d1;
+    res[0] = (double)r / (double)g.d0;
+    if (g.rank > 2) res[2] = (double)d / (double)g.d2;
+    for (int k = 0; k < g.rank; ++k)
+        if (res[k] > 0.5) res[k] -= 1.0;
+}
+
+// ImplicitTab: per field, filter(k) / (1 - dt*den(k)) tabulated once (the implicit side and the
+// modal filter depend on k only; the pair-correlation and viscosity multipliers cost exp / sqrt
+// per k).  NULL entries: evaluate literally.
+struct ImplicitTab {
+    const cplx* t[GOPF_MAX_FIELDS];
+};
+
 __global__ void __launch_bounds__(256)
-    k_update_generic(const __grid_constant__ DevKProgram P, SpectraPtrs sp, FreqGeom fg, long long n) {
+    k_update_generic(const __grid_constant__ DevKProgram P, SpectraPtrs sp, ImplicitTab tab, FreqGeom fg, long long n) {
+    const bool small = n < (1LL << 31);
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += (long long)gridDim.x * blockDim.x) {
         double f[3] = {0.0, 0.0, 0.0};
-        ref_freq(fg, idx, f);
+        ref_freq_fast(fg, idx, small, f);
         const KPoint kp = make_kpoint(f[0], f[1], f[2]);
         auto get = [&](int b) -> cplx { return sp.s[b][idx]; };
         for (int i = 0; i < P.n_fields; ++i) {
             const cplx d = sp.s[i][idx];
-            sp.s[i][idx] = euler_update(P, i, kp, d, get);  // later equations read the updated value
+            if (tab.t[i]) {
+                const DevEquation& q = P.eq[i];
+                cplx rhs = mk(0.0, 0.0);
+                for (int j = 0; j < q.n_rhs; ++j) rhs += eval_term(P, q.rhs[j], kp, get);
+                sp.s[i][idx] = mk(d.x + P.dt * rhs.x, d.y + P.dt * rhs.y) * tab.t[i][idx];
+            } else {
+                sp.s[i][idx] = euler_update(P, i, kp, d, get);  // later equations read the updated value
+            }
         }
+    }
+}
+
+// filter(k) / (1 - dt * den_i(k)) for every node (euler.go:33, util.go:125-132)
+__global__ void __launch_bounds__(256)
+    k_implicit_table(const __grid_constant__ DevKProgram P, int i, cplx* out, FreqGeom fg, long long n) {
+    const bool small = n < (1LL << 31);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        double f[3] = {0.0, 0.0, 0.0};
+        ref_freq_fast(fg, idx, small, f);
+        const KPoint kp = make_kpoint(f[0], f[1], f[2]);
+        const DevEquation& q = P.eq[i];
+        cplx den = mk(0.0, 0.0);
+        for (int j = 0; j < q.n_den; ++j) den += eval_term(P, q.den[j], kp, [&](int) -> cplx { return mk(1.0, 0.0); });
+        cplx r = cdiv(mk(1.0, 0.0), mk(1.0 - P.dt * den.x, -P.dt * den.y));
+        if (P.filter) {
+            const double sc = filter_eval(P.filter, P.filter_n, kp.frad * 2.0 / GOPF_PI);
+            r = mk(r.x * sc, r.y * sc);
+        }
+        out[idx] = r;
     }
 }
 
@@ -151,7 +204,7 @@ Solver::Solver(Model* m, int rank, const int* n, double dt, int device) : m_(m),
         if (f.n != plan_->N) throw Error("solver: Inconsistent domain size and number of grid points");
     std::memset(&S_, 0, sizeof(S_));
     std::memset(&R_, 0, sizeof(R_));
-    for (int i = 0; i < GOPF_MAX_FIELDS; ++i) Rw_[i] = rk_initial_[i] = rk_final_[i] = rk_k_[i] = nullptr;
+    for (int i = 0; i < GOPF_MAX_FIELDS; ++i) Rw_[i] = rk_initial_[i] = rk_final_[i] = rk_k_[i] = implicit_tab_[i] = nullptr;
     for (int i = 0; i < 3; ++i) sg_tmp_[i] = nullptr;
     for (int i = 0; i < GOPF_MAX_SPECIAL; ++i) {
         elast_mtab_[i] = nullptr;
@@ -170,6 +223,7 @@ Solver::~Solver() {
         if (rk_initial_[i]) cudaFree(rk_initial_[i]);
         if (rk_final_[i]) cudaFree(rk_final_[i]);
         if (rk_k_[i]) cudaFree(rk_k_[i]);
+        if (implicit_tab_[i]) cudaFree(implicit_tab_[i]);
     }
     for (int i = 0; i < 3; ++i)
         if (sg_tmp_[i]) cudaFree(sg_tmp_[i]);
@@ -339,6 +393,7 @@ void Solver::rebuild_program() {
     fused_prog_ = prog_;
     if (fused_) finalize_single_field_program(&fused_prog_, (int)m_->fields.size());
     prog_dirty_ = false;
+    implicit_tab_dirty_ = true;
 }
 
 // Program as seen by the fused single-field kernels: spectrum 0 = the field, 1 = the derived
@@ -521,17 +576,29 @@ void Solver::forward_derived(int d) {
         plan_->exec_device(out, -1, s);
         return;
     }
+    // Interpreted derived fields (registered functions, noise) are instruction-bound inside a pass
+    // (one CTA holds few warps; measured 0.76 TB/s at 512^3): evaluate them in a pointwise kernel
+    // at full occupancy and transform the result with plain passes (measured: see DESIGN.md 4.4).
+    const DevDerived& dd = m_->derived[d].dev;
+    const bool in_pass = dd.kind == DK_MONOMIAL || dd.kind == DK_TABLE;
+    if (!in_pass) {
+        const int F0 = (int)m_->fields.size();
+        const int id = tick("derived_pointwise", 16.0 * (double)plan_->N * (F0 + 1));
+        k_eval_derived<<<grid_for((long long)plan_->N), 256, 0, s>>>(dd, R_, out, step_no, (long long)plan_->N);
+        tock(id);
+        GOPF_CUDA(cudaGetLastError());
+    }
     for (int ax = 2; ax >= 0; --ax) {
         if (plan_->extent(ax) <= 1) continue;
         const PassGeom g = plan_->geom(ax);
         PassIO io = plain_io(out, out, false, 1.0);
-        if (ax == first_axis) {
+        if (ax == first_axis && in_pass) {
             io.load_kind = LK_DERIVED;
             io.D = m_->derived[d].dev;
             io.R = R_;
             io.step = step_no;
         }
-        const int id = tick(ax == first_axis ? "pass_forward_derived" : "pass_forward", cell);
+        const int id = tick(ax == first_axis && in_pass ? "pass_forward_derived" : "pass_forward", cell);
         cudaError_t e = launch_pass(g, plan_->tx_want, io, plan_->twiddle(ax), s);
         tock(id);
         if (e != cudaSuccess) throw Error(strf("derived forward pass axis %d: %s", ax, cudaGetErrorString(e)));
@@ -726,8 +793,34 @@ double Solver::lp_multiplier(int slot) {
 
 void Solver::launch_update(const DevKProgram& P) {
     const long long n = (long long)plan_->N;
-    const int id = tick("k_update", 32.0 * (double)n * P.n_fields);
-    k_update_generic<<<grid_for(n), 256, 0, stream()>>>(P, S_, plan_->freq_geom(), n);
+    // tabulate the implicit factor of equations whose denominator is expensive per k
+    ImplicitTab tab{};
+    for (int i = 0; i < P.n_fields; ++i) {
+        const DevEquation& q = P.eq[i];
+        bool expensive = P.filter != nullptr;
+        bool k_only = true;
+        for (int j = 0; j < q.n_den; ++j) {
+            if (q.den[j].kind == TK_SPECTRAL_VISC || q.den[j].kind == TK_PAIR_CORR) expensive = true;
+            if (q.den[j].brick >= 0 || q.den[j].kind == TK_VOLUME_LP || q.den[j].kind == TK_CONS_NOISE) k_only = false;
+        }
+        if (!(expensive && k_only)) continue;
+        if (!implicit_tab_[i]) GOPF_CUDA(cudaMalloc(&implicit_tab_[i], sizeof(cplx) * n));
+        if (implicit_tab_dirty_) {
+            k_implicit_table<<<grid_for(n), 256, 0, stream()>>>(P, i, implicit_tab_[i], plan_->freq_geom(), n);
+            GOPF_CUDA(cudaGetLastError());
+            launches_++;
+        }
+        tab.t[i] = implicit_tab_[i];
+    }
+    implicit_tab_dirty_ = false;
+    // algorithmic bytes: every spectrum the program reads + the fields it writes (+ tables)
+    int n_read = 0;
+    for (int b = 0; b < GOPF_MAX_SPECTRA; ++b)
+        if (S_.s[b]) n_read++;
+    int n_tab = 0;
+    for (int i = 0; i < P.n_fields; ++i) n_tab += tab.t[i] ? 1 : 0;
+    const int id = tick("k_update", 16.0 * (double)n * (n_read + P.n_fields + n_tab));
+    k_update_generic<<<grid_for(n), 256, 0, stream()>>>(P, S_, tab, plan_->freq_geom(), n);
     tock(id);
     GOPF_CUDA(cudaGetLastError());
 }

@@ -88,6 +88,8 @@ private:
     cplx* rk_final_[GOPF_MAX_FIELDS];
     cplx* rk_k_[GOPF_MAX_FIELDS];
     cplx* sg_tmp_[3];
+    cplx* implicit_tab_[GOPF_MAX_FIELDS];  // filter / (1 - dt*den) per field, when expensive per k (solver.cu)
+    bool implicit_tab_dirty_ = true;
     // HomogeneousModulusLinElast (pf/homoLinElast.go): tabulated multiplier M(k) per term slot,
     // RK4's snapshot of the real-space field, and "OnStepFinished has run at least once"
     double* elast_mtab_[GOPF_MAX_SPECIAL];
