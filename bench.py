@@ -378,6 +378,16 @@ def run_single_gpu(args):
     e2e["epoch10_value"] = n * 10 / (time.perf_counter() - t0)
 
     base = cpu_baseline(dims, 1, args.cpu_budget) if not args.no_cpu_baseline else None
+    # The sharded arm (N > 1) runs 1024^3 with the grid fixed (strong scaling); its 1-GPU point is
+    # measured here so the 1 -> N efficiency of that workload can be read off the N = 1 line too.
+    scaling_base = None
+    if args.scaling_base and G != 1024:
+        try:
+            del solver, model, conc
+            torch.cuda.empty_cache()
+            scaling_base = single_gpu_throughput(1024, dev, max(3, args.warmup), min(args.steps, 10))
+        except Exception as exc:  # e.g. not enough host memory for the 16 GiB pinned field
+            scaling_base = {"error": str(exc)[:200]}
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -390,7 +400,43 @@ def run_single_gpu(args):
     }
     if base is not None:
         line["cpu_baseline"] = base
+    if scaling_base is not None:
+        line["strong_scaling_base"] = scaling_base
     print(json.dumps(line), flush=True)
+
+
+def single_gpu_throughput(G, dev, warmup, steps):
+    """Device-resident throughput of the fused Cahn-Hilliard step at G^3 on one GPU (same seeded
+    field as the sharded arm)."""
+    import torch
+    from gopf_b200 import pf as gpf
+    from gopf_b200 import synthetic
+    n = G ** 3
+    model = gpf.NewModel()
+    conc = gpf.NewField("conc", n, None, pinned=True)
+    synthetic.cahn_hilliard_initial(n, 0, out=conc.Data)
+    model.AddScalar(gpf.NewScalar("gamma", synthetic.CAHN_HILLIARD_GAMMA))
+    model.AddScalar(gpf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
+    model.AddField(conc)
+    model.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
+    solver = gpf.NewSolver(model, [G, G, G], synthetic.CAHN_HILLIARD_DT, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    solver.SetStream(stream.cuda_stream)
+    solver.Upload()
+    solver.StepDevice(warmup)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    solver.StepDevice(steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak, _ = measured_hbm_peak()
+    value = n / (ms * 1e-3)
+    return {"workload": f"cahn-hilliard-3d-{G}^3-semi-implicit-euler", "n_gpus": 1, "value": value, "unit": METRIC,
+            "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "step_model_frac": value * BYTES_PER_CELL_UPDATE_3D / 1e9 / peak}
 
 
 def main():
@@ -402,6 +448,8 @@ def main():
     ap.add_argument("--grid", type=int, default=0, help="cubic grid edge (default 256 on 1 GPU, 1024 sharded)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scaling-base", dest="scaling_base", action="store_false",
+                    help="N = 1: skip the extra 1024^3 single-GPU measurement (strong-scaling base of the sharded arm)")
     ap.add_argument("--workload", default="ch", choices=["ch", "precipitate", "pfc"],
                     help="ch: Cahn-Hilliard (BASELINE.json configs 1-3, the metric's workload); precipitate: cfg 4; pfc: cfg 5")
     ap.add_argument("--exchange", default="peer", choices=["peer", "dma", "nccl"],
