@@ -412,6 +412,33 @@ int gopf_solver_set_stepper(gopf_solver* s, const char* name) {
     GOPF_API_END
 }
 
+int gopf_solver_set_newton_krylov(gopf_solver* s, int maxiter, double step_size, double tol, int stencil, int restart,
+                                  double inner_tol, int max_restarts) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    if (maxiter < 1 || !(step_size > 0.0) || !(tol > 0.0) || (stencil != 2 && stencil != 4 && stencil != 6) || restart < 1 ||
+        restart > 200 || !(inner_tol > 0.0) || max_restarts < 1)
+        throw Error("gopf_solver_set_newton_krylov: bad option (Stencil is 2, 4 or 6; Restart 1..200)");
+    NewtonKrylovOptions o;
+    o.maxiter = maxiter;
+    o.step_size = step_size;
+    o.tol = tol;
+    o.stencil = stencil;
+    o.restart = restart;
+    o.inner_tol = inner_tol;
+    o.max_restarts = max_restarts;
+    s->s->set_newton_krylov(o);
+    GOPF_API_END
+}
+
+int gopf_solver_newton_krylov_status(gopf_solver* s, int* converged, int64_t* residual_evaluations) {
+    GOPF_API_BEGIN
+    if (!s || !converged || !residual_evaluations) throw Error("NULL argument");
+    *converged = s->s->last_step_converged() ? 1 : 0;
+    *residual_evaluations = (int64_t)s->s->residual_evaluations();
+    GOPF_API_END
+}
+
 int gopf_solver_set_filter(gopf_solver* s, const double* table, int n) {
     GOPF_API_BEGIN
     if (!s) throw Error("solver is NULL");

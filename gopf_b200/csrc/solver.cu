@@ -204,7 +204,8 @@ Solver::Solver(Model* m, int rank, const int* n, double dt, int device) : m_(m),
         if (f.n != plan_->N) throw Error("solver: Inconsistent domain size and number of grid points");
     std::memset(&S_, 0, sizeof(S_));
     std::memset(&R_, 0, sizeof(R_));
-    for (int i = 0; i < GOPF_MAX_FIELDS; ++i) Rw_[i] = rk_initial_[i] = rk_final_[i] = rk_k_[i] = implicit_tab_[i] = nullptr;
+    for (int i = 0; i < GOPF_MAX_FIELDS; ++i)
+        Rw_[i] = rk_initial_[i] = rk_final_[i] = rk_k_[i] = implicit_tab_[i] = ie_orig_[i] = ie_rhs_prev_[i] = ie_res_[i] = nullptr;
     for (int i = 0; i < 3; ++i) sg_tmp_[i] = nullptr;
     for (int i = 0; i < GOPF_MAX_SPECIAL; ++i) {
         elast_mtab_[i] = nullptr;
@@ -224,7 +225,13 @@ Solver::~Solver() {
         if (rk_final_[i]) cudaFree(rk_final_[i]);
         if (rk_k_[i]) cudaFree(rk_k_[i]);
         if (implicit_tab_[i]) cudaFree(implicit_tab_[i]);
+        if (ie_orig_[i]) cudaFree(ie_orig_[i]);
+        if (ie_rhs_prev_[i]) cudaFree(ie_rhs_prev_[i]);
+        if (ie_res_[i]) cudaFree(ie_res_[i]);
     }
+    for (double* v : ie_vec_)
+        if (v) cudaFree(v);
+    if (ie_partial_) cudaFree(ie_partial_);
     for (int i = 0; i < 3; ++i)
         if (sg_tmp_[i]) cudaFree(sg_tmp_[i]);
     for (int i = 0; i < GOPF_MAX_SPECIAL; ++i) {
@@ -251,6 +258,9 @@ void Solver::synchronize() {
 void Solver::set_stepper(const std::string& name) {
     if (name == "euler") stepper_ = StepperKind::Euler;
     else if (name == "rk4") stepper_ = StepperKind::RK4;
+    // not a SetStepper name in the reference: there the user assigns solver.Stepper = &pf.ImplicitEuler{...}
+    // (pf/implicitEuler_test.go:193-198); the C ABI has no struct to assign, so the name selects it
+    else if (name == "implicit_euler") stepper_ = StepperKind::ImplicitEuler;
     else throw Error("Unknown stepper scheme");  // solver.go:101
     current_step_ = 0;  // SetStepper builds a fresh stepper struct (solver.go:90-99)
     decide_path();
@@ -312,7 +322,7 @@ void Solver::ensure_buffers() {
     if (fused_) {
         if (!W_) GOPF_CUDA(cudaMalloc(&W_, bytes));
     } else {
-        bool need_real = m_->n_work_spectra > 0;
+        bool need_real = m_->n_work_spectra > 0 || stepper_ == StepperKind::ImplicitEuler;
         for (size_t d = 0; d < m_->derived.size(); ++d) {
             if (!m_->derived[d].used) continue;
             need_real = true;
@@ -339,7 +349,7 @@ void Solver::ensure_buffers() {
                 GOPF_CUDA(cudaGetLastError());
                 launches_++;
             }
-            if (stepper_ == StepperKind::RK4 && !elast_phi_[u.slot]) {
+            if (stepper_ != StepperKind::Euler && !elast_phi_[u.slot]) {
                 GOPF_CUDA(cudaMalloc(&elast_phi_[u.slot], bytes));
                 GOPF_CUDA(cudaMemsetAsync(elast_phi_[u.slot], 0, bytes, stream()));
             }
@@ -533,7 +543,7 @@ void Solver::inverse_to_real(const cplx* spec, cplx* out) {
         }
     const double cell = 32.0 * (double)plan_->N;
     if (!all_fast || n_active == 0) {
-        GOPF_CUDA(cudaMemcpyAsync(out, spec, sizeof(cplx) * plan_->N, cudaMemcpyDeviceToDevice, s));
+        if (out != spec) GOPF_CUDA(cudaMemcpyAsync(out, spec, sizeof(cplx) * plan_->N, cudaMemcpyDeviceToDevice, s));
         plan_->exec_device(out, +1, s);
         k_scale<<<grid_for((long long)plan_->N), 256, 0, s>>>(out, inv_n, (long long)plan_->N);
         GOPF_CUDA(cudaGetLastError());
@@ -701,7 +711,7 @@ void Solver::elastic_terms() {
         for (int ax = 0; ax < 3; ++ax)
             if (plan_->extent(ax) > 1 && !plan_->axis_fast(ax))
                 throw Error("HomogeneousModulusLinElast needs power-of-two extents on the device path");
-        const cplx* phi = stepper_ == StepperKind::RK4 ? elast_phi_[u.slot] : Rw_[fi];
+        const cplx* phi = stepper_ != StepperKind::Euler ? elast_phi_[u.slot] : Rw_[fi];
         ElastParams E;
         const double e_density = make_elast_params(&E, u.stiffness, u.misfit, plan_->rank);
         int first_fwd = -1, last_inv = -1;
@@ -761,7 +771,7 @@ void Solver::elastic_terms() {
 // intermediate stages against the end-of-step snapshot, so it is taken here.
 void Solver::elastic_hooks() {
     if (!has_elastic()) return;
-    if (stepper_ == StepperKind::RK4)
+    if (stepper_ != StepperKind::Euler)
         for (const auto& kv : m_->user_terms) {
             const UserTerm& u = kv.second;
             if (u.kind != UserTermKind::HomogeneousModulusLinElast) continue;
@@ -853,6 +863,12 @@ void Solver::download() {
 
 // ---- steppers ------------------------------------------------------------------------
 void Solver::euler_step_generic() {
+    euler_update_generic();
+    volume_lp_hooks();                                       // solver.go:74-82
+    elastic_hooks();
+}
+
+void Solver::euler_update_generic() {
     bool any_derived = false;
     for (const DerivedSpec& d : m_->derived) any_derived |= d.used;
     const bool elastic = has_elastic();
@@ -864,8 +880,6 @@ void Solver::euler_step_generic() {
     squared_gradient_terms();
     if (elastic) elastic_terms();
     launch_update(prog_);                                    // euler.go:27-39
-    volume_lp_hooks();                                       // solver.go:74-82
-    elastic_hooks();
 }
 
 void Solver::euler_step_fused() {
@@ -971,6 +985,9 @@ void Solver::step(int nsteps) {
     for (int i = 0; i < nsteps; ++i) {
         if (stepper_ == StepperKind::RK4) {
             rk4_step();  // Step does not advance CurrentStep (rk4.go:130-135)
+        } else if (stepper_ == StepperKind::ImplicitEuler) {
+            implicit_euler_step();
+            current_step_++;  // implicitEuler.go:206
         } else {
             if (fused_) euler_step_fused();
             else euler_step_generic();

@@ -18,7 +18,19 @@
 
 namespace gopf {
 
-enum class StepperKind { Euler, RK4 };
+enum class StepperKind { Euler, RK4, ImplicitEuler };
+
+// Settings of the Newton-Krylov solve inside ImplicitEuler.Step (pf/implicitEuler.go:221-229
+// DefaultNonLinSolver; oracle/pf.py NewtonKrylov states the algorithm).
+struct NewtonKrylovOptions {
+    int maxiter = 50;
+    double step_size = 1e-3;
+    double tol = 1e-7;
+    int stencil = 2;       // central-difference points for J v: 2, 4 or 6 (the reference default is 6)
+    int restart = 30;      // GMRES restart length
+    double inner_tol = 1e-4;
+    int max_restarts = 4;
+};
 
 // shared by Solver and DistSolver (solver.cu)
 void finalize_single_field_program(DevKProgram* prog, int n_fields);
@@ -62,6 +74,9 @@ public:
     void synchronize();
     void force_generic(bool on);
     double lp_multiplier(int slot);
+    void set_newton_krylov(const NewtonKrylovOptions& o) { nk_ = o; }
+    bool last_step_converged() const { return ie_converged_; }
+    long long residual_evaluations() const { return ie_residual_evals_; }
 
 private:
     Model* m_;
@@ -100,6 +115,16 @@ private:
     DevKProgram fused_prog_;
     bool prog_dirty_ = true;
 
+    NewtonKrylovOptions nk_;
+    bool ie_converged_ = true;
+    long long ie_residual_evals_ = 0;
+    cplx* ie_orig_[GOPF_MAX_FIELDS];      // spectra at the start of the step
+    cplx* ie_rhs_prev_[GOPF_MAX_FIELDS];  // RHS at the start of the step
+    cplx* ie_res_[GOPF_MAX_FIELDS];       // residual work spectra
+    std::vector<double*> ie_vec_;         // x, F(x), b, s, w, tmp_p, tmp_m, then restart+1 Krylov vectors
+    double* ie_partial_ = nullptr;        // reduction partials (device) 
+    int ie_vec_restart_ = -1;
+
     bool profiling_ = false;
     std::vector<KernelTimer> timers_;
 
@@ -108,6 +133,15 @@ private:
     void rebuild_program();
     void decide_path();
     void euler_step_generic();
+    void euler_update_generic();   // the step without the OnStepFinished hooks
+    // ImplicitEuler (implicit_euler.cu)
+    void implicit_euler_step();
+    void ie_residual(const double* x, double* out);
+    void ie_jac_vec(const double* x, const double* v, double* out);
+    void ie_gmres(const double* x, const double* b, double* s);
+    void ie_ensure_buffers();
+    double ie_dot(const double* a, const double* b);
+    double ie_max_abs(const double* a);
     void euler_step_fused();
     void rk4_step();
     void inverse_to_real(const cplx* spec, cplx* real_out);           // IFFT + /N, out of place

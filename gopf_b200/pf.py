@@ -442,8 +442,69 @@ class _Stepper:
         self._solver.Propagate(1)
 
 
+class NewtonKrylov:
+    """Settings of the non-linear solve inside ImplicitEuler (nonlin.NewtonKrylov in the reference,
+    pf/implicitEuler.go:221-229)."""
+
+    def __init__(self, Maxiter=50, StepSize=1e-3, Tol=1e-7, Stencil=2, Restart=30, InnerTol=1e-4, MaxRestarts=4):
+        self.Maxiter, self.StepSize, self.Tol, self.Stencil = Maxiter, StepSize, Tol, Stencil
+        self.Restart, self.InnerTol, self.MaxRestarts = Restart, InnerTol, MaxRestarts
+
+
+class ImplicitEuler:
+    """pf.ImplicitEuler (pf/implicitEuler.go:20-229).  Assign to ``solver.Stepper`` as in the
+    reference (pf/implicitEuler_test.go:193-198); ``FT`` is accepted for signature parity and unused
+    (the device solver owns its transform)."""
+
+    def __init__(self, Dt: float, FT=None, NonlinSolver: Optional[NewtonKrylov] = None):
+        self.Dt, self.FT, self.NonlinSolver = Dt, FT, NonlinSolver
+        self._solver = None
+
+    def _attach(self, solver: "Solver"):
+        if abs(self.Dt - solver.Dt) > 0.0:
+            raise GopfError("ImplicitEuler.Dt must equal the solver's dt on the device path")
+        self._solver = solver
+        check(lib().gopf_solver_set_stepper(solver._h, b"implicit_euler"))
+        o = self.NonlinSolver or NewtonKrylov()
+        check(lib().gopf_solver_set_newton_krylov(solver._h, int(o.Maxiter), ctypes.c_double(o.StepSize), ctypes.c_double(o.Tol),
+                                                  int(o.Stencil), int(o.Restart), ctypes.c_double(o.InnerTol), int(o.MaxRestarts)))
+
+    def SetFilter(self, filt):
+        self._solver._set_filter(filt)
+
+    def GetTime(self) -> float:
+        t = ctypes.c_double(0.0)
+        check(lib().gopf_solver_get_time(self._solver._h, ctypes.byref(t)))
+        return t.value
+
+    def Step(self, m=None):
+        self._solver.Propagate(1)
+
+    @property
+    def Converged(self) -> bool:
+        c, n = ctypes.c_int(0), ctypes.c_int64(0)
+        check(lib().gopf_solver_newton_krylov_status(self._solver._h, ctypes.byref(c), ctypes.byref(n)))
+        return bool(c.value)
+
+    @property
+    def ResidualEvaluations(self) -> int:
+        c, n = ctypes.c_int(0), ctypes.c_int64(0)
+        check(lib().gopf_solver_newton_krylov_status(self._solver._h, ctypes.byref(c), ctypes.byref(n)))
+        return n.value
+
+
 class Solver:
     """pf.Solver (pf/solver.go:29-134) over ``gopf_solver``."""
+
+    @property
+    def Stepper(self):
+        return self._stepper
+
+    @Stepper.setter
+    def Stepper(self, st):
+        if isinstance(st, ImplicitEuler):
+            st._attach(self)
+        self._stepper = st
 
     def __init__(self, m: Model, domainSize, dt: float, device: int = -1):
         self.Model, self.Dt = m, dt

@@ -159,6 +159,17 @@ int gopf_vandeven_table(int order, double* out, int n);
 int gopf_solver_create(gopf_model* m, int rank, const int* domain_size, double dt, int device, gopf_solver** out);
 /* Solver.SetStepper("euler" | "rk4") (pf/solver.go:88-103) */
 int gopf_solver_set_stepper(gopf_solver* s, const char* name);
+/* solver.Stepper = &pf.ImplicitEuler{Dt, FT} (pf/implicitEuler.go:20-229) is selected with
+ * gopf_solver_set_stepper(s, "implicit_euler").  The non-linear solve is a Jacobian-free
+ * Newton-Krylov iteration on the device (gopf_b200/csrc/implicit_euler.cu); the reference
+ * delegates it to third-party modules that are not in its tree, so trajectories agree with it to
+ * the solver tolerance only.  Defaults = DefaultNonLinSolver (implicitEuler.go:221-229)
+ * except Stencil (2 instead of 6 residual evaluations per Jacobian-vector product). */
+int gopf_solver_set_newton_krylov(gopf_solver* s, int maxiter, double step_size, double tol, int stencil, int restart,
+                                  double inner_tol, int max_restarts);
+/* after a step: res.Converged of the last solve (the reference logs a warning when false,
+ * implicitEuler.go:202-204) and the residual evaluations so far */
+int gopf_solver_newton_krylov_status(gopf_solver* s, int* converged, int64_t* residual_evaluations);
 /* TimeStepper.SetFilter for a tabulated ModalFilter (pf/util.go:120-132, pf/vandeven.go:30-40);
  * table == NULL removes the filter */
 int gopf_solver_set_filter(gopf_solver* s, const double* table, int n);

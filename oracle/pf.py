@@ -707,6 +707,198 @@ class Euler:
 
 
 # ==========================================================================
+# pf/implicitEuler.go
+# ==========================================================================
+FD_STENCILS = {  # central-difference weights of d/dh at offsets +-1, +-2, +-3 (antisymmetric)
+    2: (0.5,),
+    4: (2.0 / 3.0, -1.0 / 12.0),
+    6: (0.75, -0.15, 1.0 / 60.0),
+}
+
+
+class NewtonKrylov:
+    """Jacobian-free Newton-Krylov solver for F(x) = 0.
+
+    PARITY UNPINNED: the reference delegates this to github.com/davidkleiven/gononlin v0.2.2
+    ``nonlin.NewtonKrylov`` with gonum.org/v1/exp ``linsolve.GMRES`` (pf/implicitEuler.go:190-201,
+    221-229); neither module is under /root/reference.  What the reference fixes are the settings
+    (Maxiter 50, StepSize 1e-3, Tol 1e-7, Stencil 6, un-restarted GMRES) and, through its tests,
+    the result to 5e-3 / 1e-3 against analytic solutions (pf/implicitEuler_test.go:31,43,55,67,208).
+    This class is the published algorithm those modules implement, stated once so that the CUDA
+    stepper (gopf_b200/csrc/implicit_euler.cu) can mirror it choice for choice:
+
+      Newton:  x <- x + s,  J(x) s = -F(x), until max|F(x)| < Tol or Maxiter iterations
+      J v   ~  sum_k w_k (F(x + k eps v) - F(x - k eps v)) / eps,  central stencil of `Stencil`
+               points, eps = StepSize * sqrt(len(x)) / |v|_2 (RMS perturbation = StepSize)
+      GMRES:   modified Gram-Schmidt Arnoldi, Givens rotations, restart `Restart`, stop at
+               |r| <= InnerTol * |F(x)| or after MaxRestarts cycles
+    Two converged runs agree to the solver tolerance, not to 1e-10.
+    """
+
+    def __init__(self, Maxiter=50, StepSize=1e-3, Tol=1e-7, Stencil=2, Restart=30, InnerTol=1e-4, MaxRestarts=4):
+        self.Maxiter, self.StepSize, self.Tol, self.Stencil = Maxiter, StepSize, Tol, Stencil
+        self.Restart, self.InnerTol, self.MaxRestarts = Restart, InnerTol, MaxRestarts
+        self.residual_evaluations = 0
+
+    def jac_vec(self, F, x, v, fx_unused=None):
+        nv = float(np.linalg.norm(v))
+        if nv == 0.0:
+            return np.zeros_like(v)
+        eps = self.StepSize * math.sqrt(x.shape[0]) / nv
+        out = np.zeros_like(x)
+        for k, w in enumerate(FD_STENCILS[self.Stencil], start=1):
+            out += w * (F(x + (k * eps) * v) - F(x - (k * eps) * v))
+            self.residual_evaluations += 2
+        return out / eps
+
+    def gmres(self, F, x, b):
+        """Solves J(x) s = b; returns s."""
+        n = x.shape[0]
+        s = np.zeros(n)
+        bnorm = float(np.linalg.norm(b))
+        if bnorm == 0.0:
+            return s
+        target = self.InnerTol * bnorm
+        for _cycle in range(self.MaxRestarts):
+            r = b - self.jac_vec(F, x, s) if np.any(s) else b.copy()
+            beta = float(np.linalg.norm(r))
+            if beta <= target:
+                break
+            m = self.Restart
+            V = np.zeros((m + 1, n))
+            H = np.zeros((m + 1, m))
+            cs, sn, g = np.zeros(m), np.zeros(m), np.zeros(m + 1)
+            V[0] = r / beta
+            g[0] = beta
+            k_used = 0
+            for j in range(m):
+                w = self.jac_vec(F, x, V[j])
+                for i in range(j + 1):
+                    H[i, j] = float(np.dot(w, V[i]))
+                    w -= H[i, j] * V[i]
+                H[j + 1, j] = float(np.linalg.norm(w))
+                if H[j + 1, j] > 0.0:
+                    V[j + 1] = w / H[j + 1, j]
+                for i in range(j):
+                    t = cs[i] * H[i, j] + sn[i] * H[i + 1, j]
+                    H[i + 1, j] = -sn[i] * H[i, j] + cs[i] * H[i + 1, j]
+                    H[i, j] = t
+                d = math.hypot(H[j, j], H[j + 1, j])
+                cs[j], sn[j] = (H[j, j] / d, H[j + 1, j] / d) if d > 0.0 else (1.0, 0.0)
+                H[j, j] = cs[j] * H[j, j] + sn[j] * H[j + 1, j]
+                H[j + 1, j] = 0.0
+                g[j + 1] = -sn[j] * g[j]
+                g[j] = cs[j] * g[j]
+                k_used = j + 1
+                if abs(g[j + 1]) <= target or H[j, j] == 0.0:
+                    break
+            y = np.zeros(k_used)
+            for i in range(k_used - 1, -1, -1):
+                acc = g[i] - float(np.dot(H[i, i + 1:k_used], y[i + 1:]))
+                y[i] = acc / H[i, i] if H[i, i] != 0.0 else 0.0
+            s += V[:k_used].T @ y
+            if abs(g[k_used]) <= target:
+                break
+        return s
+
+    def Solve(self, F, x0):
+        x = np.array(x0, dtype=np.float64)
+        converged = False
+        for _ in range(self.Maxiter):
+            fx = F(x)
+            self.residual_evaluations += 1
+            if float(np.max(np.abs(fx))) < self.Tol:
+                converged = True
+                break
+            x = x + self.gmres(F, x, -fx)
+        return x, converged
+
+
+class ImplicitEuler:
+    """pf/implicitEuler.go:20-207: exponential-integrator implicit step solved by Newton-Krylov,
+    one semi-implicit Euler step as the initial guess."""
+
+    def __init__(self, Dt: float, FT, Filter=None, NonlinSolver: Optional["NewtonKrylov"] = None):
+        self.Dt = Dt
+        self.FT = FT
+        self.Filter = Filter
+        self.CurrentStep = 0
+        self.NonlinSolver = NonlinSolver
+        self.last_converged = True
+
+    def GetTime(self) -> float:
+        return self.Dt * float(self.CurrentStep)
+
+    def SetFilter(self, filt):
+        self.Filter = filt  # implicitEuler.go:209-213: only the predictor sees it
+
+    def fft(self, m: Model):
+        m.SyncDerivedFields()
+        for f in m.Fields:
+            self.FT.FFT(f.Data)
+        for f in m.DerivedFields:
+            self.FT.FFT(f.Data)
+
+    def ifft(self, m: Model):
+        for f in m.Fields:
+            self.FT.IFFT(f.Data)
+            pfutil.div_real_scalar(f.Data, float(f.Data.shape[0]))
+
+    def nonlinearIntegral(self, denum, rhs, rhs_prev):
+        """:151-162, vectorised."""
+        c_dt = complex(self.Dt, 0.0)
+        a = rhs_prev
+        b = (rhs - rhs_prev) / c_dt
+        f = np.exp(denum * c_dt)
+        small = np.abs(denum) < 1e-5
+        safe = np.where(small, 1.0, denum)
+        general = a * (f - 1.0) / safe + b * (f - safe * c_dt - 1.0) / (safe * safe)
+        return np.where(small, 0.5 * c_dt * (rhs + rhs_prev * f), general)
+
+    def updateEquation(self, new_fields: np.ndarray, rhs_prev, orig_fields, m: Model) -> np.ndarray:
+        """:68-95."""
+        n = m.Fields[0].Data.shape[0]
+        for i, f in enumerate(m.Fields):  # vec2fields
+            f.Data[:] = new_fields[i * n:(i + 1) * n]
+        self.fft(m)
+        t = self.GetTime()
+        freq = as_frequency(self.FT.Freq)
+        c_dt = complex(self.Dt, 0.0)
+        out = np.zeros(len(m.Fields) * n, dtype=np.float64)
+        for i in range(len(m.Fields)):
+            rhs = m.GetRHS(i, freq, t)
+            denum = m.GetDenum(i, freq, t)
+            factor = np.exp(denum * c_dt)
+            integral = self.nonlinearIntegral(denum, rhs, rhs_prev[i * n:(i + 1) * n])
+            update = orig_fields[i] * factor + integral
+            res = np.ascontiguousarray(m.Fields[i].Data - update)
+            self.FT.IFFT(res)
+            pfutil.div_real_scalar(res, float(n))
+            out[i * n:(i + 1) * n] = res.real
+        return out
+
+    def Step(self, m: Model):
+        """:165-207."""
+        n = m.Fields[0].Data.shape[0]
+        t = self.GetTime()
+        freq = as_frequency(self.FT.Freq)
+        self.fft(m)
+        orig = [f.Data.copy() for f in m.Fields]
+        rhs_prev = np.concatenate([m.GetRHS(i, freq, t) for i in range(len(m.Fields))])
+        self.ifft(m)
+        explicit = Euler(self.Dt, self.FT, self.Filter)
+        explicit.CurrentStep = self.CurrentStep
+        explicit.Step(m)
+        x0 = np.concatenate([f.Data.real for f in m.Fields])
+        if self.NonlinSolver is None:
+            self.NonlinSolver = NewtonKrylov()
+        x, self.last_converged = self.NonlinSolver.Solve(lambda v: self.updateEquation(v, rhs_prev, orig, m), x0)
+        for i, f in enumerate(m.Fields):
+            f.Data[:] = x[i * n:(i + 1) * n]
+        self.CurrentStep += 1
+
+
+# ==========================================================================
 # pf/rk4.go
 # ==========================================================================
 class RK4:
