@@ -142,12 +142,22 @@ struct StageInfo {
 };
 
 // ---- shared-memory layouts -------------------------------------------------------
-// Strided-axis tiles: TX adjacent lines, line index fastest.  Any group of 8 threads
-// with equal position and consecutive line index touches one 128-B row: conflict free
-// for every stage without padding.
+// Strided-axis tiles: TX adjacent lines, line index fastest.  With TX = 8 a quarter-warp (the unit
+// of a 128-bit shared-memory access) holds one position and 8 lines = one 128-B row: conflict free
+// for every stage without padding.  With TX = 4 (2) it holds W = 2 (4) consecutive positions; the
+// gathers are still one row, but the radix-16 scatter of the first stage sends them 16 positions
+// apart, onto the same bank groups (2-way / 4-way conflicts: 21 % of the wavefronts of the
+// 1024-point pass in ncu).  XOR-ing the position's low bits (which pick the 64-B / 32-B part of
+// the row) with bits 4.. of the position keeps every access pattern of every plan on 8 distinct
+// bank groups (brute-force check over all plans and stages).  The map is a bijection inside each
+// aligned 8-cell group, so the tile size does not change.
 template <int TX>
 struct LayoutInterleaved {
-    static __device__ __forceinline__ int at(int pos, int l) { return pos * TX + l; }
+    enum { W = (TX >= 8 ? 1 : 8 / TX) };
+    static __device__ __forceinline__ int at(int pos, int l) {
+        const int a = pos * TX + l;
+        return W > 1 ? (a ^ (((pos >> 4) & (W - 1)) * TX)) : a;
+    }
     static constexpr int elems(int n, int lines) { return n * lines; }
 };
 // Contiguous-axis lines: position fastest, one pad cell per 16 so that the radix-16
@@ -165,6 +175,60 @@ struct SyncCta {
 struct SyncWarp {
     static __device__ __forceinline__ void run() { __syncwarp(); }
 };
+
+// a[k] *= W_N^{k*bh}, k = 1 .. R-1.  Only the power-of-two multiples W^{bh}, W^{2bh}, W^{4bh},
+// W^{8bh} come from the table (4 loads instead of 15 at radix 16); the others are products.  The
+// passes are limited by the load/store queues, not by the fp64 pipe (ncu: fp64 pipe 24 % busy,
+// lg_throttle + mio_throttle stalls dominate at 1024-point lines), so trading loads for DFMAs pays.
+// Each product costs about 1.5 ulp of the unit-modulus twiddle, far inside the 1e-10 tolerance.
+template <int R>
+__device__ __forceinline__ void twiddle_mul(cplx (&a)[R], const cplx* __restrict__ tw, int bh) {
+    if (R == 2) {
+        a[1] = a[1] * ld_tab(tw + bh);
+    } else if (R == 4) {
+        const cplx w1 = ld_tab(tw + bh), w2 = ld_tab(tw + 2 * bh);
+        a[1] = a[1] * w1;
+        a[2] = a[2] * w2;
+        a[3] = a[3] * (w1 * w2);
+    } else if (R == 8) {
+        const cplx w1 = ld_tab(tw + bh), w2 = ld_tab(tw + 2 * bh), w4 = ld_tab(tw + 4 * bh);
+        const cplx w3 = w1 * w2;
+        a[1] = a[1] * w1;
+        a[2] = a[2] * w2;
+        a[3] = a[3] * w3;
+        a[4] = a[4] * w4;
+        a[5] = a[5] * (w4 * w1);
+        a[6] = a[6] * (w4 * w2);
+        a[7] = a[7] * (w4 * w3);
+    } else {  // 16
+        const cplx w1 = ld_tab(tw + bh), w2 = ld_tab(tw + 2 * bh), w4 = ld_tab(tw + 4 * bh), w8 = ld_tab(tw + 8 * bh);
+        const cplx w3 = w1 * w2;
+        a[1] = a[1] * w1;
+        a[2] = a[2] * w2;
+        a[3] = a[3] * w3;
+        a[4] = a[4] * w4;
+        a[8] = a[8] * w8;
+        a[12] = a[12] * (w8 * w4);
+        {
+            const cplx w5 = w4 * w1;
+            a[5] = a[5] * w5;
+            a[13] = a[13] * (w8 * w5);
+        }
+        {
+            const cplx w6 = w4 * w2;
+            a[6] = a[6] * w6;
+            a[14] = a[14] * (w8 * w6);
+        }
+        {
+            const cplx w7 = w4 * w3;
+            a[7] = a[7] * w7;
+            a[15] = a[15] * (w8 * w7);
+        }
+        a[9] = a[9] * (w8 * w1);
+        a[10] = a[10] * (w8 * w2);
+        a[11] = a[11] * (w8 * w3);
+    }
+}
 
 // ---- one stage -------------------------------------------------------------------
 template <int N, int S, class Layout, class Sync>
@@ -186,8 +250,7 @@ __device__ __forceinline__ void fft_stage(cplx (&v)[PlanFor<N>::E], int t, int l
             const int b = t + T * i;
             const int bl = b & (L - 1);
             const int bh = b - bl;  // (b div L) * L
-#pragma unroll
-            for (int k = 1; k < R; ++k) a[k] = a[k] * ld_tab(tw + k * bh);
+            twiddle_mul<R>(a, tw, bh);
             const int base = bl + (bh * R);
 #pragma unroll
             for (int k = 0; k < R; ++k) sm[Layout::at(base + L * k, l)] = a[k];

@@ -132,13 +132,13 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
         if (LATE) {
             // the line is live in registers here: walk the rows with two running addresses in a
             // rolled loop instead of materialising E address pairs
-            unsigned dst = (unsigned)__cvta_generic_to_shared(sS + Lay::at(t, l));
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(sS);
             const cplx* src = S + base + (size_t)t * strideB;
             const size_t src_step = (size_t)T * strideB;
 #pragma unroll 1
             for (int m = 0; m < E; ++m) {
+                const unsigned dst = sbase + (unsigned)(Lay::at(t + T * m, l) * (int)sizeof(cplx));
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
-                dst += (unsigned)(T * TX * sizeof(cplx));
                 src += src_step;
             }
         } else {
@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
     cplx v[E];
 #pragma unroll
     for (int m = 0; m < E; ++m) v[m] = W[base + (size_t)(t + T * m) * strideB];
+
     // Reference Freq components [row, col, depth] = FFTW axes [1, 2, 0] (fftWrap.go:42-74).
     // Two of them are fixed along this thread's line, the third runs with j.
     double fa, fb;        // the two fixed components
