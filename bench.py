@@ -33,11 +33,11 @@ FALLBACK_HBM_GBS = 6650.0         # B200_PROFILING.md fallback when MEASURED_PEA
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
-# capture (profiles/r1b_ncu_full_step.md), keyed by (kernel class, cubic grid edge)
-NCU_TRAFFIC = {("fused_kspace", 256): 536.918784e6 + 482.359040e6,
-               ("fused_real", 256): 268.504832e6 + 209.955840e6,
-               ("pass_inverse_mid", 256): 268.507904e6 + 212.805632e6,
-               ("pass_forward_mid", 256): 268.555008e6 + 211.119872e6}
+# capture (profiles/r1c_ncu_full_step.md), keyed by (kernel class, cubic grid edge)
+NCU_TRAFFIC = {("fused_kspace", 256): 536.918016e6 + 479.948032e6,
+               ("fused_real", 256): 268.504064e6 + 210.432768e6,
+               ("pass_inverse_mid", 256): 268.747008e6 + 209.792256e6,
+               ("pass_forward_mid", 256): 268.631296e6 + 209.894144e6}
 
 
 def measured_hbm_peak():
@@ -354,7 +354,7 @@ def run_single_gpu(args):
     top = kernels[0]
     roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": top["gbs"] / peak, "traffic": NCU_TRAFFIC.get((top["kernel"], G)),
-                "traffic_source": "profiles/r1b_ncu_full_step.md" if (top["kernel"], G) in NCU_TRAFFIC else None,
+                "traffic_source": "profiles/r1c_ncu_full_step.md" if (top["kernel"], G) in NCU_TRAFFIC else None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": top["algorithmic_bytes"], "avg_launch_ms": top["avg_ms"],
                 "step_model": {"bytes_per_cell_update": BYTES_PER_CELL_UPDATE_3D,

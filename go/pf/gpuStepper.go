@@ -81,6 +81,14 @@ func NewGPUStepper(m *Model, domainSize []int, dt float64, scheme string, exprs 
 		switch v := t.(type) {
 		case *SpectralViscosity:
 			gpuCheck(C.gopf_model_register_spectral_viscosity(st.model, cn, C.double(v.Eps), C.double(v.DissipationThreshold), C.int(v.Power)))
+		case *TensorialHessian:
+			cf := cstr(v.Field)
+			k := make([]C.double, len(v.K))
+			for i, x := range v.K {
+				k[i] = C.double(x)
+			}
+			gpuCheck(C.gopf_model_register_tensorial_hessian(st.model, cn, cf, &k[0], C.int(len(k))))
+			C.free(unsafe.Pointer(cf))
 		case *VolumeConservingLP:
 			cf, ci := cstr(v.Field), cstr(v.Indicator)
 			gpuCheck(C.gopf_model_register_volume_conserving_lp(st.model, cn, cf, ci, C.double(v.Dt)))

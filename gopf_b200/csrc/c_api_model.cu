@@ -208,6 +208,21 @@ int gopf_model_register_squared_gradient(gopf_model* m, const char* name, const 
     GOPF_API_END
 }
 
+int gopf_model_register_tensorial_hessian(gopf_model* m, const char* name, const char* field, const double* k, int n_coeff) {
+    GOPF_API_BEGIN
+    if (!m || !k) throw Error("NULL argument");
+    if (n_coeff != 4 && n_coeff != 9) throw Error("TensorialHessian: K must hold 4 (2-D) or 9 (3-D) coefficients");
+    UserTerm u;
+    u.name = need(name, "name");
+    u.cls = UserTermClass::Implicit;
+    u.kind = UserTermKind::TensorialHessian;
+    u.field = field ? field : "";
+    u.hessian.d = n_coeff == 9 ? 3 : 2;
+    for (int i = 0; i < n_coeff; ++i) u.hessian.K[i] = k[i];
+    m->m.register_user_term(u);
+    GOPF_API_END
+}
+
 int gopf_model_register_homogeneous_modulus_lin_elast(gopf_model* m, const char* name, const char* field,
                                                       const double* stiffness81, const double* misfit9) {
     GOPF_API_BEGIN

@@ -421,6 +421,11 @@ CompiledEquation Model::build(const std::string& eq) {
                     apply_prefixes(&d, prefixes);
                     ce.den.push_back(d);
                     break;
+                case UserTermKind::TensorialHessian:
+                    d.kind = TK_TENSOR_HESSIAN;
+                    apply_prefixes(&d, prefixes);
+                    ce.den.push_back(d);
+                    break;
                 case UserTermKind::PairCorrelation:
                     d.kind = TK_PAIR_CORR;
                     d.lap = u.laplacian ? 1 : 0;
@@ -514,12 +519,13 @@ void Model::init() {
     if (equations.size() > fields.size()) throw Error("model: more equations than fields");
     for (DerivedSpec& d : derived) d.used = false;
     // assign parameter slots / work spectra to the registered user terms
-    int n_sv = 0, n_pc = 0, n_cn = 0, n_lp = 0, n_el = 0;
+    int n_sv = 0, n_pc = 0, n_cn = 0, n_lp = 0, n_el = 0, n_th = 0;
     n_work_spectra = 0;
     for (auto& kv : user_terms) {
         UserTerm& u = kv.second;
         switch (u.kind) {
             case UserTermKind::SpectralViscosity: u.slot = n_sv++; break;
+            case UserTermKind::TensorialHessian: u.slot = n_th++; break;
             case UserTermKind::PairCorrelation:
             case UserTermKind::ExplicitPairCorrelation: u.slot = n_pc++; break;
             case UserTermKind::ConservativeNoise: u.slot = n_cn++; break;
@@ -535,7 +541,7 @@ void Model::init() {
         }
     }
     if (n_sv > GOPF_MAX_SPECIAL || n_pc > GOPF_MAX_SPECIAL || n_cn > GOPF_MAX_SPECIAL || n_lp > GOPF_MAX_SPECIAL ||
-        n_el > GOPF_MAX_SPECIAL)
+        n_el > GOPF_MAX_SPECIAL || n_th > GOPF_MAX_SPECIAL)
         throw Error(strf("model: at most %d terms of each special kind", GOPF_MAX_SPECIAL));
     if (n_spectra() > GOPF_MAX_SPECTRA) throw Error(strf("model: at most %d spectra", GOPF_MAX_SPECTRA));
     compiled.clear();
@@ -564,6 +570,7 @@ void Model::fill_program(DevKProgram* P, double dt, int rank) const {
         if (u.slot < 0) continue;
         switch (u.kind) {
             case UserTermKind::SpectralViscosity: P->sv[u.slot] = u.sv; break;
+            case UserTermKind::TensorialHessian: P->th[u.slot] = u.hessian; break;
             case UserTermKind::PairCorrelation:
             case UserTermKind::ExplicitPairCorrelation:
                 P->pc[u.slot] = u.pc;

@@ -31,7 +31,7 @@ struct DerivedSpec {
 };
 
 enum class UserTermClass { Implicit, Explicit, Mixed };
-enum class UserTermKind { SpectralViscosity, PairCorrelation, ExplicitPairCorrelation, IdealMixture, ConservativeNoise, VolumeConservingLP, SquaredGradient, HomogeneousModulusLinElast };
+enum class UserTermKind { SpectralViscosity, PairCorrelation, ExplicitPairCorrelation, IdealMixture, ConservativeNoise, VolumeConservingLP, SquaredGradient, HomogeneousModulusLinElast, TensorialHessian };
 
 struct UserTerm {
     std::string name;
@@ -50,6 +50,7 @@ struct UserTerm {
     int work_spectrum = -1;  // SquaredGradient / elastic term: spectrum index its result is written to
     double stiffness[81] = {0};  // HomogeneousModulusLinElast.MatProp (elasticity.Rank4.Data, rank4.go:22-24)
     double misfit[9] = {0};      // HomogeneousModulusLinElast.Misfit, row-major 3x3
+    TensorHessianParams hessian = {};  // TensorialHessian.K
 };
 
 struct CompiledEquation {

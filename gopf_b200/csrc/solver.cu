@@ -217,6 +217,7 @@ Solver::Solver(Model* m, int rank, const int* n, double dt, int device) : m_(m),
 
 Solver::~Solver() {
     cudaSetDevice(plan_->device);
+    drop_graph();
     for (int i = 0; i < GOPF_MAX_SPECTRA; ++i)
         if (S_.s[i]) cudaFree(S_.s[i]);
     for (int i = 0; i < GOPF_MAX_FIELDS; ++i) {
@@ -248,6 +249,56 @@ Solver::~Solver() {
             cudaEventDestroy(ev.first);
             cudaEventDestroy(ev.second);
         }
+}
+
+// ---- CUDA graph replay -------------------------------------------------------------------
+// Below ~1 M cells the fused step is a handful of kernels of a few microseconds each and the
+// host launch rate bounds it (128^2: 16.6 us per 2-kernel step).  One graph of GRAPH_STEPS steps
+// is captured from the stream and replayed; anything that changes a kernel argument drops it.
+static const int GRAPH_STEPS = 8;
+
+void Solver::drop_graph() {
+    if (graph_exec_) {
+        cudaGraphExecDestroy(graph_exec_);
+        graph_exec_ = nullptr;
+    }
+    graph_steps_ = 0;
+}
+
+bool Solver::graph_applicable() const {
+    if (graph_disabled_ || !fused_ || profiling_ || stepper_ != StepperKind::Euler || !w_valid_) return false;
+    if (plan_->N > (size_t)1 << 20) return false;
+    const int k = m_->derived[fused_derived_].dev.kind;
+    return k == DK_MONOMIAL || k == DK_RPN;  // noise / table fields take the step number as a kernel argument
+}
+
+bool Solver::build_graph(int steps) {
+    cudaStream_t s = stream();
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        graph_disabled_ = true;
+        return false;
+    }
+    bool ok = true;
+    const long long launches_before = launches_;
+    try {
+        for (int i = 0; i < steps; ++i) euler_step_fused();
+    } catch (...) {
+        ok = false;
+    }
+    launches_ = launches_before;  // capturing launches nothing
+    if (cudaStreamEndCapture(s, &graph) != cudaSuccess || !graph) ok = false;
+    if (ok && cudaGraphInstantiate(&graph_exec_, graph, 0) != cudaSuccess) ok = false;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+        cudaGetLastError();
+        graph_exec_ = nullptr;
+        graph_disabled_ = true;
+        return false;
+    }
+    graph_steps_ = steps;
+    return true;
 }
 
 void Solver::synchronize() {
@@ -396,6 +447,7 @@ void Solver::ensure_buffers() {
 
 void Solver::rebuild_program() {
     if (!prog_dirty_) return;
+    drop_graph();
     m_->fill_program(&prog_, dt_, plan_->rank);
     prog_.filter = d_filter_;
     prog_.filter_n = filter_n_;
@@ -982,7 +1034,26 @@ void Solver::step(int nsteps) {
     plan_->use_device();
     ensure_buffers();
     rebuild_program();
-    for (int i = 0; i < nsteps; ++i) {
+    int done = 0;
+    if (fused_ && stepper_ == StepperKind::Euler && nsteps > GRAPH_STEPS) {
+        // the first step runs eagerly (it also produces W when it is not valid yet and sets every
+        // kernel's attributes); whole blocks of GRAPH_STEPS steps are then replayed from the graph
+        euler_step_fused();
+        current_step_++;
+        steps_taken_++;
+        done = 1;
+        if (graph_applicable() && (graph_exec_ || build_graph(GRAPH_STEPS))) {
+            const long long per_block = (plan_->rank == 3 ? 4 : 2) * (long long)graph_steps_;
+            while (nsteps - done >= graph_steps_) {
+                GOPF_CUDA(cudaGraphLaunch(graph_exec_, stream()));
+                launches_ += per_block;
+                current_step_ += graph_steps_;
+                steps_taken_ += graph_steps_;
+                done += graph_steps_;
+            }
+        }
+    }
+    for (int i = done; i < nsteps; ++i) {
         if (stepper_ == StepperKind::RK4) {
             rk4_step();  // Step does not advance CurrentStep (rk4.go:130-135)
         } else if (stepper_ == StepperKind::ImplicitEuler) {

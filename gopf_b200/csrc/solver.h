@@ -53,7 +53,10 @@ public:
 
     void set_stepper(const std::string& name);   // Solver.SetStepper (solver.go:88-103)
     void set_filter(const double* table, int n);  // TimeStepper.SetFilter with a tabulated ModalFilter
-    void set_stream(cudaStream_t s) { user_stream_ = s; }
+    void set_stream(cudaStream_t s) {
+        user_stream_ = s;
+        drop_graph();
+    }
     void upload();              // host Field.Data -> device spectra
     void step(int nsteps);      // nsteps x Stepper.Step on device-resident state
     void download();            // device spectra -> real-space host Field.Data
@@ -114,6 +117,14 @@ private:
     DevKProgram prog_;
     DevKProgram fused_prog_;
     bool prog_dirty_ = true;
+
+    // CUDA-graph replay of the fused step on small grids (launch-bound: 2-4 kernels of a few us)
+    cudaGraphExec_t graph_exec_ = nullptr;
+    int graph_steps_ = 0;
+    bool graph_disabled_ = false;
+    void drop_graph();
+    bool graph_applicable() const;
+    bool build_graph(int steps);
 
     NewtonKrylovOptions nk_;
     bool ie_converged_ = true;

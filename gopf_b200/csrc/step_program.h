@@ -30,7 +30,8 @@ enum TermKind {
     TK_SPECTRAL_VISC = 1,  // coef * (-eps Q(|f|) |f|^p) * L^lap            spectralViscosity.go:44-54
     TK_PAIR_CORR = 2,      // coef * (-A C2(2 pi |f|)) [* brick] * L^lap    pairCorrelationTerm.go:37-51,96-110
     TK_CONS_NOISE = 3,     // coef * sum_c 2i sin(pi f_c) xi_c * L^lap      noise.go:60-78
-    TK_VOLUME_LP = 4       // coef * lambda * [brick] * L^lap               volumeConserving.go:19-29
+    TK_VOLUME_LP = 4,      // coef * lambda * [brick] * L^lap               volumeConserving.go:19-29
+    TK_TENSOR_HESSIAN = 5  // coef * (-4 pi^2 sum_ij K_ij f_i f_j) * L^lap  tensorialHessian.go:38-63
 };
 
 struct DevTerm {
@@ -59,6 +60,11 @@ struct PairCorrParams {
     double num_planes[GOPF_MAX_PEAKS];
 };
 
+struct TensorHessianParams {
+    double K[9];  // row-major d x d (d = 3 when 9 coefficients were given, else 2; tensorialHessian.go:65-71)
+    int d, pad;
+};
+
 struct ConsNoiseParams {
     int dim;
     int brick[3];  // spectrum index of the current component fields
@@ -73,6 +79,7 @@ struct DevKProgram {
     SpectralViscParams sv[GOPF_MAX_SPECIAL];
     PairCorrParams pc[GOPF_MAX_SPECIAL];
     ConsNoiseParams cn[GOPF_MAX_SPECIAL];
+    TensorHessianParams th[GOPF_MAX_SPECIAL];
     const double* lp_multiplier[GOPF_MAX_SPECIAL];  // device scalars (VolumeConservingLP.Multiplier)
     // Single-field fast form (fused kernels): when every term of eq[0] is a monomial with a
     // real coefficient the update collapses to polynomials in L = -(2 pi |f|)^2:
@@ -170,6 +177,15 @@ __device__ __forceinline__ cplx eval_term(const DevKProgram& P, const DevTerm& t
                     val += mk(-s2 * xi.y, s2 * xi.x);  // (0 + i s2) * xi
                 }
             }
+            break;
+        }
+        case TK_TENSOR_HESSIAN: {
+            const TensorHessianParams& h = P.th[t.param];
+            double acc = 0.0;
+            for (int j = 0; j < P.rank; ++j) acc += -4.0 * GOPF_PI * GOPF_PI * kp.f[j] * kp.f[j] * h.K[j * h.d + j];
+            for (int j = 0; j < P.rank; ++j)
+                for (int k = j + 1; k < P.rank; ++k) acc += -8.0 * GOPF_PI * GOPF_PI * kp.f[j] * kp.f[k] * h.K[j * h.d + k];
+            val = mk(acc, 0.0);
             break;
         }
         case TK_VOLUME_LP: {

@@ -100,6 +100,19 @@ class SpectralViscosity:
                                                             ctypes.c_double(self.DissipationThreshold), int(self.Power)))
 
 
+class TensorialHessian:
+    """pf.TensorialHessian (pf/tensorialHessian.go:17-74), implicit."""
+
+    def __init__(self, K, Field: str = ""):
+        self.K, self.Field = [float(v) for v in K], Field
+
+    def _register(self, m: "Model", name: str, cls: str):
+        if cls != "implicit":
+            raise GopfError("TensorialHessian is an implicit term")
+        k = (ctypes.c_double * len(self.K))(*self.K)
+        check(lib().gopf_model_register_tensorial_hessian(m._h, _s(name), _s(self.Field), k, len(self.K)))
+
+
 class Peak:
     """pfc.Peak (pfc/pairCorrelation.go:8-13)."""
 

@@ -120,6 +120,9 @@ int gopf_model_register_volume_conserving_lp(gopf_model* m, const char* name, co
                                              const char* indicator, double dt);
 /* RegisterExplicitTerm(name, &SquaredGradient{Field, Factor}) (pf/squareGradientTerm.go:14-68) */
 int gopf_model_register_squared_gradient(gopf_model* m, const char* name, const char* field, double factor);
+/* RegisterImplicitTerm(name, &TensorialHessian{Field, K}) (pf/tensorialHessian.go:17-74):
+ * sum_ij K_ij d_i d_j acting on the equation's own field; K row-major, 4 (2-D) or 9 (3-D) values */
+int gopf_model_register_tensorial_hessian(gopf_model* m, const char* name, const char* field, const double* k, int n_coeff);
 /* RegisterExplicitTerm(name, NewHomogeneousModolus(fieldName, domainSize, matProp, misfit))
  * (pf/homoLinElast.go:30-150).  stiffness81 = elasticity.Rank4.Data (index i*27+j*9+k*3+l,
  * elasticity/rank4.go:10-24), misfit9 = the 3x3 misfit strain, row-major.  The term's private

@@ -145,6 +145,36 @@ class SpectralViscosity:
         pass
 
 
+class TensorialHessian:
+    """pf/tensorialHessian.go:17-74: implicit term sum_ij K_ij d_i d_j, i.e. the multiplier
+    -4 pi^2 sum_j f_j^2 K_jj - 8 pi^2 sum_{j<k} f_j f_k K_jk."""
+
+    def __init__(self, K, Field: str = ""):
+        self.Field = Field
+        self.K = [float(v) for v in K]
+
+    def GetCoeff(self, i: int, j: int) -> float:
+        d = 3 if len(self.K) == 9 else 2  # :65-71
+        return self.K[i * d + j]
+
+    def Construct(self, bricks):
+        def fn(freq, t, field: np.ndarray):
+            f = as_frequency(freq).table(field.shape[0])
+            dim = f.shape[1]
+            acc = np.zeros(field.shape[0], dtype=np.float64)
+            for j in range(dim):
+                acc += -4.0 * math.pi * math.pi * f[:, j] * f[:, j] * self.GetCoeff(j, j)
+            for j in range(dim):
+                for k in range(j + 1, dim):
+                    acc += -8.0 * math.pi * math.pi * f[:, j] * f[:, k] * self.GetCoeff(j, k)
+            field[:] = acc
+
+        return fn
+
+    def OnStepFinished(self, t, bricks):
+        pass
+
+
 # ==========================================================================
 # pf/noise.go
 # ==========================================================================

@@ -126,3 +126,18 @@ def test_vandeven_table_matches_oracle():
         got = gpf.NewVandeven(order).Data
         exp = terms.NewVandeven(order).Data
         assert np.max(np.abs(got - exp)) < 1e-15
+
+
+def test_hessian_with_model_term_counts():
+    # pf/tensorialHessian_test.go:105-146 through the C ABI parser
+    from gopf_b200 import pf as gpf
+    N = 16
+    m = gpf.NewModel()
+    m.AddField(gpf.NewField("conc1", N * N))
+    m.AddField(gpf.NewField("conc2", N * N))
+    m.RegisterImplicitTerm("HESSIAN", gpf.TensorialHessian([1.0, 2.0, 2.0, 2.0]), None)
+    m.AddEquation("dconc1/dt = HESSIAN")
+    m.AddEquation("dconc2/dt = -conc2")
+    m.Init()
+    rhs = m.RHS
+    assert len(rhs[0].Terms) == 0 and len(rhs[0].Denum) == 1

@@ -240,3 +240,40 @@ def test_explicit_pair_corr_term(laplace):
     term.Construct({"myfield": field})(freq, 0.0, result)
     expect = 2.5 * freq(0)[0] ** 2 * 4.0 * math.pi * math.pi if laplace else -2.5
     assert np.max(np.abs(result.real - expect)) < 1e-10 and np.all(result.imag == 0.0)
+
+
+def test_tensorial_hessian():
+    # pf/tensorialHessian_test.go:11-103: K picks d2/dx2, d2/dy2 or the mixed derivative of a polynomial bump
+    N = 64
+    i = np.arange(N * N)
+    y, x = (i % N) / float(N), (i // N) / float(N)
+    px = 16.0 * (x * x - 2.0 * x ** 3 + x ** 4)
+    py = 16.0 * (y * y - 2.0 * y ** 3 + y ** 4)
+    want = {
+        "dx2": 16.0 * (2.0 - 12.0 * x + 12.0 * x * x) * py / float(N * N),
+        "dy2": px * 16.0 * (2.0 - 12.0 * y + 12.0 * y * y) / float(N * N),
+        "dxdy": 16.0 * (2.0 * x - 6.0 * x * x + 4.0 * x ** 3) * 16.0 * (2.0 * y - 6.0 * y * y + 4.0 * y ** 3) / float(N * N),
+    }
+    ft = pfutil.NewFFTW([N, N])
+    data = (px * py).astype(np.complex128)
+    ft.FFT(data)
+    for K, key, tol in [([1.0, 0.0, 0.0, 0.0], "dx2", 1e-3), ([0.0, 0.0, 0.0, 1.0], "dy2", 1e-3), ([0.0, 0.5, 0.5, 0.0], "dxdy", 1e-6)]:
+        res = np.zeros(N * N, dtype=np.complex128)
+        terms.TensorialHessian(K).Construct({})(ft.Freq, 0.0, res)
+        res *= data
+        ft.IFFT(res)
+        res /= N * N
+        assert np.max(np.abs(res.real - want[key])) < tol and np.max(np.abs(res.imag)) < tol
+
+
+def test_hessian_with_model():
+    # pf/tensorialHessian_test.go:105-146: an implicit user term adds no explicit term
+    N = 16
+    m = pf.NewModel()
+    m.AddField(pf.NewField("conc1", N * N, np.arange(N * N, dtype=np.float64).astype(np.complex128)))
+    m.AddField(pf.NewField("conc2", N * N, np.arange(N * N, dtype=np.float64).astype(np.complex128)))
+    m.RegisterImplicitTerm("HESSIAN", terms.TensorialHessian([1.0, 2.0, 2.0, 2.0]), None)
+    m.AddEquation("dconc1/dt = HESSIAN")
+    m.AddEquation("dconc2/dt = -conc2")
+    m.Init()
+    assert len(m.RHS[0].Terms) == 0 and len(m.RHS[0].Denum) == 1

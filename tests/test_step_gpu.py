@@ -519,3 +519,43 @@ def test_elastic_term_rk4_vs_oracle():
     gs.Solve(2, 3)
     osolver.Solve(2, 3)
     assert rel_l2(gconc.Data, oconc.Data) <= TOL and rel_l2(gphase.Data, ophase.Data) <= TOL
+
+
+@pytest.mark.parametrize("dims,K", [([64, 64], [1.0, 0.3, 0.3, 2.0]), ([16, 16, 16], [1.0, 0.2, 0.1, 0.2, 2.0, 0.3, 0.1, 0.3, 0.5])],
+                         ids=["2d", "3d"])
+def test_tensorial_hessian_anisotropic_diffusion_vs_oracle(dims, K):
+    # pf.TensorialHessian (pf/tensorialHessian.go:17-74) as the implicit part of a diffusion equation
+    n = opfutil.prod_int(dims)
+    init = synthetic.cahn_hilliard_initial(n, 5)
+    outs = []
+    for mod, tmod in ((gpf, gpf), (opf, oterms)):
+        m = mod.NewModel()
+        f = mod.NewField("conc", n, init.copy())
+        m.AddField(f)
+        m.RegisterImplicitTerm("HESSIAN", tmod.TensorialHessian(K), None)
+        m.AddEquation("dconc/dt = HESSIAN - conc^3")
+        s = mod.NewSolver(m, dims, 0.05)
+        s.Solve(2, 10)
+        outs.append(f.Data.copy())
+    assert rel_l2(outs[0], outs[1]) <= TOL
+    assert rel_l2(outs[0], init) > 0.1
+
+
+@pytest.mark.parametrize("dims", [[128, 128], [32, 32, 32]], ids=lambda d: "x".join(map(str, d)))
+def test_graph_replay_equals_eager_launches(dims):
+    # small grids replay a captured CUDA graph of 8 fused steps; one step per call never does
+    (gm1, gf1), _ = ch_models(dims)
+    (gm2, gf2), _ = ch_models(dims)
+    s1 = gpf.NewSolver(gm1, dims, 0.1)
+    s1.Upload()
+    s1.StepDevice(35)   # 1 eager + 4 graph launches + 2 eager
+    s1.StepDevice(20)   # the graph is reused
+    s1.Download()
+    s2 = gpf.NewSolver(gm2, dims, 0.1)
+    s2.Upload()
+    for _ in range(55):
+        s2.StepDevice(1)
+    s2.Download()
+    assert np.array_equal(gf1.Data, gf2.Data)
+    assert abs(s1.Stepper.GetTime() - 5.5) < 1e-12 and abs(s2.Stepper.GetTime() - 5.5) < 1e-12
+    assert s1.KernelLaunches() == s2.KernelLaunches()
