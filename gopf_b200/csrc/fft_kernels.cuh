@@ -48,9 +48,10 @@ struct PassGeom {
     // Next-wave L2 prefetch (plain axis passes): a CTA asks L2 for the input tile of CTA
     // blockIdx.x + pf_tiles (the one that takes its place on the SM, = resident CTAs of the launch),
     // so DRAM keeps streaming while this tile is in its compute phase and the next wave's loads hit
-    // L2.  Measured on B200 (scripts/tune_prefetch.py): strided pass 256^3 5.95 -> 6.35 TB/s,
-    // 1024^3 4.33 -> 4.47 TB/s.  The fused kernels do not use it (k-space kernel: -15 %, two tiles
-    // per CTA oversubscribe L2; real-space kernel: neutral).  0: off.
+    // L2.  Off by default (GOPF_PREFETCH=1 enables it): inside the fused Cahn-Hilliard step the
+    // middle-axis passes gained 4-7 % (scripts/tune_prefetch.py), but isolated passes along the
+    // slowest axis lost up to 30 % (scripts/tune_axis0.py: 512^3 2996 -> 2017 GB/s at TX 4) and the
+    // fused kernels 15 %.  0: off.
     long long pf_tiles;
 };
 
@@ -227,6 +228,40 @@ __device__ __forceinline__ void pass_load_line(const PassIO& io, cplx (&v)[E], A
         const cplx* __restrict__ in = io.in;
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = in[at(m)];
+    } else if (io.load_kind == LK_ELAST_H) {
+        // simple arithmetic on one or two loads per cell: keep every load of the thread in flight
+        // like the plain case (the rolled loop below serialises them: 1.3 vs 1.0 ms per 512^3 pass)
+        const cplx* __restrict__ phi = io.g[0];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = phi[at(m)];
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const double p = v[m].x;
+            v[m] = mk(3.0 * p * p - 2.0 * p * p * p, 0.0);
+        }
+    } else if (io.load_kind == LK_ELAST_R) {
+        const cplx* __restrict__ in = io.in;
+        const double* __restrict__ phi = reinterpret_cast<const double*>(io.g[0]);
+        double p[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = in[at(m)];
+#pragma unroll
+        for (int m = 0; m < E; ++m) p[m] = phi[2 * at(m)];  // real part only
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const double h = 3.0 * p[m] * p[m] - 2.0 * p[m] * p[m] * p[m], dh = 6.0 * p[m] - 6.0 * p[m] * p[m];
+            v[m] = mk(dh * v[m].x - io.aux * (h * dh), dh * v[m].y);
+        }
+    } else if (io.load_kind == LK_MUL_TABLE) {
+        const cplx* __restrict__ in = io.in;
+        const double* __restrict__ tab = io.rtab;
+        double w[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = in[at(m)];
+#pragma unroll
+        for (int m = 0; m < E; ++m) w[m] = tab[at(m)];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = mk(v[m].x * w[m], v[m].y * w[m]);
     } else {
 #pragma unroll 1
         for (int m = 0; m < E; ++m) sm[sat(m)] = pass_load_slow(io, at(m));
@@ -365,7 +400,15 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
 }
 
 // ---- launch-side helpers ------------------------------------------------------------
+int pass_tx_override();  // pass_launch.cu: GOPF_PASS_TX (tuning; 0 = none)
+
 inline int pick_tx(int N, long long B, int want, bool peer = false) {
+    const int forced = pass_tx_override();
+    if (forced > 0 && !peer) {
+        int tx = forced;
+        while (tx > 1 && ((long long)N * tx * 16 > 200 * 1024 || (B % tx) != 0)) tx >>= 1;
+        return tx;
+    }
     // Peer stores go out over NVLink in row segments of TX cells: 128-B segments reach 717 GB/s,
     // 64-B ones 438 GB/s (scripts/peer_store_probe.cu), so the peer-writing passes take TX >= 8
     // even where a narrower tile is the faster local choice.
@@ -374,11 +417,14 @@ inline int pick_tx(int N, long long B, int want, bool peer = false) {
         while (tx > 1 && ((long long)N * tx * 16 > 128 * 1024 || (B % tx) != 0)) tx >>= 1;
         return tx < 2 ? ((B % 2 == 0) ? 2 : 1) : tx;
     }
-    // Lines of >= 512 cells: a 128-B-wide tile would be the only CTA on its SM (registers), with
-    // no other tile's loads in flight behind it; two 64-B-wide tiles per SM measure faster
-    // (scripts/tune_pass.py, B200: N=1024 4.4 vs 4.0 TB/s, N=512 4.6 vs 3.8 TB/s).
-    // Exception: 1024-cell lines at plane-sized row strides keep 128-B segments (3.9 vs 3.6 TB/s).
-    if (N >= 512 && want > 4 && !(N >= 1024 && B >= 16384)) want = 4;
+    // Tile width by measurement (scripts/tune_axis0.py, B200, GB/s of the 32 B/cell pass, TX 4 / 8 / 16):
+    //   256^3  slowest axis 4656 / 5762 / 5972   middle axis 5428 / 6347 / 6168
+    //   512^3  slowest axis 2996 / 5073 / 4446   middle axis 5569 / 6023 / 4469
+    //   1024   slowest axis 3874 / 4028 / 4013   middle axis 4797 / 3900 / 3888
+    // Row segments of 128 B matter most where the row stride is large (slowest axis); 1024-cell
+    // lines along the middle axis prefer two 64-KB tiles per SM over one 128-KB tile.
+    if (N >= 1024 && B < 16384 && want > 4) want = 4;
+    else if (N <= 256 && B >= 16384 && want == 8) want = 16;
     int tx = want;
     while (tx > 1 && ((long long)N * tx * 16 > 128 * 1024)) tx >>= 1;
     while (tx > 1 && (B % tx) != 0) tx >>= 1;

@@ -5,9 +5,14 @@
 
 namespace gopf {
 
+int pass_tx_override() {
+    const char* v = std::getenv("GOPF_PASS_TX");
+    return (v && *v) ? std::atoi(v) : 0;
+}
+
 int prefetch_enabled() {
     const char* v = std::getenv("GOPF_PREFETCH");
-    return (v && *v) ? std::atoi(v) : 1;
+    return (v && *v) ? std::atoi(v) : 0;
 }
 
 #define GOPF_DECL(n) cudaError_t launch_pass_##n(const PassGeom&, int, const PassIO&, const cplx*, cudaStream_t);

@@ -34,26 +34,60 @@ struct ImplicitTab {
     const cplx* t[GOPF_MAX_FIELDS];
 };
 
+// C cells per thread.  Measured at 512^3 (cfg 4): C = 4 is 40 % slower than C = 1 (registers cost
+// more occupancy than the extra loads in flight give back), so the kernel runs C = 1.
+template <int C>
+__device__ __forceinline__ void update_cells(const DevKProgram& P, const SpectraPtrs& sp, const ImplicitTab& tab,
+                                             const FreqGeom& fg, bool small, const long long (&idx)[C]) {
+    KPoint kp[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        double f[3] = {0.0, 0.0, 0.0};
+        ref_freq_fast(fg, idx[c], small, f);
+        kp[c] = make_kpoint(f[0], f[1], f[2]);
+    }
+    for (int i = 0; i < P.n_fields; ++i) {
+        const DevEquation& q = P.eq[i];
+        cplx d[C], rhs[C], den[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            d[c] = sp.s[i][idx[c]];
+            rhs[c] = den[c] = mk(0.0, 0.0);
+        }
+        for (int j = 0; j < q.n_rhs; ++j) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) rhs[c] += eval_term(P, q.rhs[j], kp[c], [&](int b) -> cplx { return sp.s[b][idx[c]]; });
+        }
+        if (tab.t[i]) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                sp.s[i][idx[c]] = mk(d[c].x + P.dt * rhs[c].x, d[c].y + P.dt * rhs[c].y) * tab.t[i][idx[c]];
+        } else {
+            for (int j = 0; j < q.n_den; ++j) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) den[c] += eval_term(P, q.den[j], kp[c], [&](int b) -> cplx { return sp.s[b][idx[c]]; });
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const cplx num = mk(d[c].x + P.dt * rhs[c].x, d[c].y + P.dt * rhs[c].y);
+                cplx r = cdiv(num, mk(1.0 - P.dt * den[c].x, -P.dt * den[c].y));  // euler.go:33
+                if (P.filter) {
+                    const double sc = filter_eval(P.filter, P.filter_n, kp[c].frad * 2.0 / GOPF_PI);
+                    r = mk(r.x * sc, r.y * sc);
+                }
+                sp.s[i][idx[c]] = r;  // later equations read the updated value (euler.go:27-39)
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
     k_update_generic(const __grid_constant__ DevKProgram P, SpectraPtrs sp, ImplicitTab tab, FreqGeom fg, long long n) {
     const bool small = n < (1LL << 31);
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (long long)gridDim.x * blockDim.x) {
-        double f[3] = {0.0, 0.0, 0.0};
-        ref_freq_fast(fg, idx, small, f);
-        const KPoint kp = make_kpoint(f[0], f[1], f[2]);
-        auto get = [&](int b) -> cplx { return sp.s[b][idx]; };
-        for (int i = 0; i < P.n_fields; ++i) {
-            const cplx d = sp.s[i][idx];
-            if (tab.t[i]) {
-                const DevEquation& q = P.eq[i];
-                cplx rhs = mk(0.0, 0.0);
-                for (int j = 0; j < q.n_rhs; ++j) rhs += eval_term(P, q.rhs[j], kp, get);
-                sp.s[i][idx] = mk(d.x + P.dt * rhs.x, d.y + P.dt * rhs.y) * tab.t[i][idx];
-            } else {
-                sp.s[i][idx] = euler_update(P, i, kp, d, get);  // later equations read the updated value
-            }
-        }
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+        const long long idx[1] = {i};
+        update_cells<1>(P, sp, tab, fg, small, idx);
     }
 }
 
