@@ -31,6 +31,7 @@ import "C"
 
 import (
 	"fmt"
+	"os"
 	"unsafe"
 )
 
@@ -186,6 +187,33 @@ func (st *GPUStepper) SetFilter(filter ModalFilter) {
 		return
 	}
 	panic("gopfcuda: only tabulated filters (pf.Vandeven) run on the device")
+}
+
+// SetNewtonKrylov forwards the settings of ImplicitEuler.NonlinSolver (pf/implicitEuler.go:221-229)
+// to the device solver; scheme "implicit_euler" replaces &pf.ImplicitEuler{Dt, FT}.  InnerMethod has
+// no counterpart: the device runs its own restarted GMRES (restart 30, inner tolerance 1e-4).
+func (st *GPUStepper) SetNewtonKrylov(maxiter int, stepSize, tol float64, stencil int) {
+	gpuCheck(C.gopf_solver_set_newton_krylov(st.solver, C.int(maxiter), C.double(stepSize), C.double(tol), C.int(stencil), 30, 1e-4, 4))
+}
+
+// Converged reports res.Converged of the last implicit step (the reference logs a warning when
+// it is false, pf/implicitEuler.go:202-204)
+func (st *GPUStepper) Converged() bool {
+	var c C.int
+	var n C.int64_t
+	gpuCheck(C.gopf_solver_newton_krylov_status(st.solver, &c, &n))
+	return c != 0
+}
+
+// SaveReal writes the real part of field i of the device-resident state as big-endian float64,
+// byte for byte what Field.SaveReal writes (pf/model.go:35-41, pf/fileIO.go:85-95); the byte swap
+// runs on the device and only 8 bytes per cell cross PCIe.
+func (st *GPUStepper) SaveReal(i int, n int, fname string) {
+	buf := make([]byte, 8*n)
+	gpuCheck(C.gopf_solver_download_real(st.solver, C.int(i), (*C.double)(unsafe.Pointer(&buf[0])), 1))
+	if err := os.WriteFile(fname, buf, 0644); err != nil {
+		panic(err)
+	}
 }
 
 // GetTime returns the current time (pf.TimeStepper)

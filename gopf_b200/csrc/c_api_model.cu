@@ -427,6 +427,13 @@ int gopf_solver_set_stepper(gopf_solver* s, const char* name) {
     GOPF_API_END
 }
 
+int gopf_solver_download_real(gopf_solver* s, int field_index, double* host_out, int big_endian) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->download_real(field_index, host_out, big_endian != 0);
+    GOPF_API_END
+}
+
 int gopf_solver_set_newton_krylov(gopf_solver* s, int maxiter, double step_size, double tol, int stencil, int restart,
                                   double inner_tol, int max_restarts) {
     GOPF_API_BEGIN

@@ -112,6 +112,22 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// real part of every cell; big-endian byte order on request (encoding/binary.BigEndian in
+// pf/fileIO.go:85-95 SaveFloat64)
+__global__ void k_real_part(const cplx* __restrict__ in, double* __restrict__ out, int big_endian, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double v = in[i].x;
+        if (big_endian) {
+            const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+            const unsigned lo = (unsigned)u, hi = (unsigned)(u >> 32);
+            const unsigned long long sw =
+                ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | (unsigned long long)__byte_perm(hi, 0, 0x0123);
+            v = __longlong_as_double((long long)sw);
+        }
+        out[i] = v;
+    }
+}
+
 __global__ void k_scale(cplx* a, double s, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         a[i] = mk(a[i].x * s, a[i].y * s);
@@ -276,6 +292,7 @@ Solver::~Solver() {
     for (int i = 0; i < GOPF_MAX_SPECTRA; ++i)
         if (d_table_[i]) cudaFree(d_table_[i]);
     if (W_) cudaFree(W_);
+    if (d_real_out_) cudaFree(d_real_out_);
     if (d_filter_) cudaFree(d_filter_);
     if (d_lp_state_) cudaFree(d_lp_state_);
     for (KernelTimer& t : timers_)
@@ -944,6 +961,23 @@ void Solver::download() {
         inverse_to_real(S_.s[i], Rw_[i]);  // euler.go:42-45
         GOPF_CUDA(cudaMemcpyAsync(m_->fields[i].host, Rw_[i], sizeof(cplx) * plan_->N, cudaMemcpyDeviceToHost, s));
     }
+    GOPF_CUDA(cudaStreamSynchronize(s));
+}
+
+void Solver::download_real(int field, double* host_out, bool big_endian) {
+    if (!on_device_) throw Error("solver: nothing on the device to download");
+    if (field < 0 || field >= (int)m_->fields.size()) throw Error("download_real: field index out of range");
+    if (!host_out) throw Error("download_real: host_out is NULL");
+    plan_->use_device();
+    ensure_buffers();
+    cudaStream_t s = stream();
+    const long long n = (long long)plan_->N;
+    if (!d_real_out_) GOPF_CUDA(cudaMalloc(&d_real_out_, sizeof(double) * n));
+    inverse_to_real(S_.s[field], Rw_[field]);  // euler.go:42-45
+    k_real_part<<<grid_for(n), 256, 0, s>>>(Rw_[field], d_real_out_, big_endian ? 1 : 0, n);
+    GOPF_CUDA(cudaGetLastError());
+    launches_++;
+    GOPF_CUDA(cudaMemcpyAsync(host_out, d_real_out_, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     GOPF_CUDA(cudaStreamSynchronize(s));
 }
 

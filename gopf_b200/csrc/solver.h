@@ -60,6 +60,9 @@ public:
     void upload();              // host Field.Data -> device spectra
     void step(int nsteps);      // nsteps x Stepper.Step on device-resident state
     void download();            // device spectra -> real-space host Field.Data
+    // Real part of field i only, optionally byte-swapped to big-endian on the device: the payload of
+    // Field.SaveReal / Float64IO.SaveFields (pf/model.go:35-41, pf/fileIO.go:57-62) at half the D2H bytes
+    void download_real(int field, double* host_out, bool big_endian);
     void propagate(int nsteps)  // Solver.Propagate on host buffers (solver.go:70-84)
     {
         upload();
@@ -99,6 +102,7 @@ private:
     RealPtrs R_;               // real-space fields (generic path)
     cplx* Rw_[GOPF_MAX_FIELDS];
     cplx* W_ = nullptr;        // fused work array
+    double* d_real_out_ = nullptr;  // staging for download_real
     double* d_filter_ = nullptr;
     int filter_n_ = 0;
     double* d_lp_state_ = nullptr;  // per VolumeConservingLP: multiplier, current integral, first flag

@@ -563,6 +563,25 @@ class Solver:
     def Download(self):
         check(lib().gopf_solver_download(self._h))
 
+    def DownloadReal(self, field_index: int, big_endian: bool = False) -> np.ndarray:
+        """Real part of one field from the device-resident state (float64; '>f8' when big_endian)."""
+        n = self.Model.Fields[field_index].Data.shape[0]
+        out = np.empty(n, dtype=np.float64)
+        check(lib().gopf_solver_download_real(self._h, int(field_index), out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                              1 if big_endian else 0))
+        return out.view(">f8") if big_endian else out
+
+    def SolveOnDevice(self, nepochs: int, nsteps: int):
+        """Solver.Solve with the state resident on the device between epochs: one upload, callbacks
+        after every epoch (they read what they need through DownloadReal / Download; host Field.Data
+        is NOT refreshed for them), one download at the end."""
+        self.Upload()
+        for i in range(nepochs):
+            self.StepDevice(nsteps)
+            for cb in self.Callbacks:
+                cb(self, i + self.StartEpoch)
+        self.Download()
+
     def Synchronize(self):
         check(lib().gopf_solver_synchronize(self._h))
 
@@ -628,6 +647,32 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+
+class Float64IO:
+    """pf.Float64IO (pf/fileIO.go:47-62): big-endian float64 of the real part of every field, one
+    file per field and epoch, named <prefix>_<field>_<epoch>.bin.  ``from_device`` = True reads the
+    device-resident state (for Solver.SolveOnDevice callbacks); False writes host Field.Data."""
+
+    def __init__(self, prefix: str, from_device: bool = False):
+        self.Prefix, self.from_device = prefix, from_device
+
+    def SaveFields(self, s: "Solver", epoch: int):
+        for i, f in enumerate(s.Model.Fields):
+            fname = f"{self.Prefix}_{f.Name}_{epoch}.bin"
+            if self.from_device:
+                s.DownloadReal(i, big_endian=True).tofile(fname)  # bytes are already big-endian
+            else:
+                np.ascontiguousarray(f.Data.real).astype(">f8").tofile(fname)
+
+
+def NewFloat64IO(prefix: str, from_device: bool = False) -> Float64IO:
+    return Float64IO(prefix, from_device)
+
+
+def LoadFloat64(fname: str) -> np.ndarray:
+    """pf.LoadFloat64 (pf/fileIO.go:66-83)."""
+    return np.fromfile(fname, dtype=">f8").astype(np.float64)
 
 
 def NewSolver(m: Model, domainSize, dt: float, device: int = -1) -> Solver:

@@ -197,6 +197,11 @@ int gopf_solver_kernel_launches(gopf_solver* s, int64_t* n, int reset);
 int gopf_solver_get_spectrum(gopf_solver* s, int index, double* host_c128);
 /* VolumeConservingLP.Multiplier of the slot-th registered term */
 int gopf_solver_lp_multiplier(gopf_solver* s, int slot, double* value);
+/* Real part of field `field_index` (N doubles) from the device-resident state, big-endian byte
+ * order on request: the payload of Field.SaveReal / Float64IO.SaveFields (pf/model.go:35-41,
+ * pf/fileIO.go:57-62, 85-95) for epoch callbacks of device-resident runs, at half the D2H bytes of
+ * gopf_solver_download.  The swap to big endian runs on the device. */
+int gopf_solver_download_real(gopf_solver* s, int field_index, double* host_out, int big_endian);
 /* per-kernel CUDA-event timing over the following gopf_solver_step calls */
 int gopf_solver_profile_begin(gopf_solver* s);
 int gopf_solver_profile_end(gopf_solver* s, int* n_kernels);

@@ -559,3 +559,27 @@ def test_graph_replay_equals_eager_launches(dims):
     assert np.array_equal(gf1.Data, gf2.Data)
     assert abs(s1.Stepper.GetTime() - 5.5) < 1e-12 and abs(s2.Stepper.GetTime() - 5.5) < 1e-12
     assert s1.KernelLaunches() == s2.KernelLaunches()
+
+
+def test_float64_io_from_device_matches_host_path(tmp_path):
+    # pf.Float64IO.SaveFields (pf/fileIO.go:57-62): big-endian float64 of the real part; the
+    # device-resident epoch loop writes the same bytes as the host path after the same steps
+    dims = [32, 32, 32]
+    (gm1, gf1), (om, of) = ch_models(dims)
+    (gm2, gf2), _ = ch_models(dims)
+    s1 = gpf.NewSolver(gm1, dims, 0.1)
+    s1.AddCallback(gpf.NewFloat64IO(str(tmp_path / "host")).SaveFields)
+    s1.Solve(3, 4)
+    s2 = gpf.NewSolver(gm2, dims, 0.1)
+    s2.AddCallback(gpf.NewFloat64IO(str(tmp_path / "dev"), from_device=True).SaveFields)
+    s2.SolveOnDevice(3, 4)
+    osolver = opf.NewSolver(om, dims, 0.1)
+    osolver.Solve(3, 4)
+    for epoch in range(3):
+        a = gpf.LoadFloat64(str(tmp_path / f"host_conc_{epoch}.bin"))
+        b = gpf.LoadFloat64(str(tmp_path / f"dev_conc_{epoch}.bin"))
+        assert a.shape[0] == 32 ** 3 and rel_l2(a, b) < 1e-13
+    raw = (tmp_path / "dev_conc_2.bin").read_bytes()
+    assert raw == np.ascontiguousarray(s2.DownloadReal(0)).astype(">f8").tobytes()  # byte order: big endian
+    assert rel_l2(gpf.LoadFloat64(str(tmp_path / "dev_conc_2.bin")), of.Data.real) <= TOL
+    assert rel_l2(gf2.Data, of.Data) <= TOL
