@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes
 
-from ._lib import check, lib
+from ._lib import GopfError, check, lib
 
 
 def run_steps(phases, all_to_all, S, A, B, nsteps: int, a_valid: bool) -> bool:
@@ -320,31 +320,53 @@ class ShardedSolver:
         self.B = mk() if exchange in ("nccl", "dma") else None
         self.a_valid = False   # nccl: A holds the first inverse pass of S; peer: X does
         self.on_device = False
-        if exchange in ("peer", "dma"):
-            self._map_peers()
+        if exchange in ("peer", "dma") and not self._map_peers():
+            self.exchange = "nccl"   # same kernels, classic all-to-all between the phases
+            if self.B is None:
+                self.B = mk()
         # One real stream for kernels, copies and the collective's stream dependencies.  (The
         # legacy default stream has handle 0, which the C ABI reads as "use the plan's stream".)
         self.stream = torch.cuda.Stream(device=self.device)
         self.phases.set_stream(self.stream.cuda_stream)
 
-    def _map_peers(self):
+    def _map_peers(self) -> bool:
         """Allocate this rank's receive buffers and map every other rank's (CUDA IPC handles
-        travel through one all_gather)."""
+        travel through one all_gather).  Returns False -- on EVERY rank -- when any rank could not
+        export or map a buffer (e.g. a container without CUDA IPC), so that all ranks switch to the
+        NCCL exchange together; the reason goes to stderr."""
+        import sys
         torch, tdist = self.torch, self.tdist
-        self.phases.peer_alloc()
-        mine = self.phases.peer_export(0) + self.phases.peer_export(1)
+        mine, err = bytes(128), None
+        try:
+            self.phases.peer_alloc()
+            mine = self.phases.peer_export(0) + self.phases.peer_export(1)
+        except GopfError as e:
+            err = e
         if self.world > 1:
-            send = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+            send = torch.tensor(list(mine) + [0 if err is None else 1], dtype=torch.uint8, device=self.device)
             recv = [torch.empty_like(send) for _ in range(self.world)]
             tdist.all_gather(recv, send, group=self.group)
-            handles = [bytes(t.cpu().tolist()) for t in recv]
+            rows = [bytes(t.cpu().tolist()) for t in recv]
         else:
-            handles = [mine]
-        for q, h in enumerate(handles):
-            if q != self.rank:
-                self.phases.peer_import(0, q, h[:64])
-                self.phases.peer_import(1, q, h[64:])
+            rows = [mine + bytes([0 if err is None else 1])]
+        if err is None and not any(r[128] for r in rows):
+            try:
+                for q, h in enumerate(rows):
+                    if q != self.rank:
+                        self.phases.peer_import(0, q, h[:64])
+                        self.phases.peer_import(1, q, h[64:128])
+            except GopfError as e:
+                err = e
+        ok = torch.tensor([0 if (err is not None or any(r[128] for r in rows)) else 1], dtype=torch.int32, device=self.device)
+        if self.world > 1:
+            tdist.all_reduce(ok, op=tdist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            if err is not None:
+                print(f"gopf_b200.dist: rank {self.rank}: peer mapping failed ({err}); all ranks use the NCCL exchange",
+                      file=sys.stderr, flush=True)
+            return False
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        return True
 
     def barrier(self):
         """Cross-rank barrier in stream order: the all-reduce cannot complete on any rank

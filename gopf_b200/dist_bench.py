@@ -74,6 +74,7 @@ def run(args):
     comm_ctas = getattr(args, "comm_ctas", 48)
     solver = gdist.ShardedSolver(model, n, synthetic.CAHN_HILLIARD_DT, device=local, exchange=exchange, nchunks=nchunks,
                                  comm_ctas=comm_ctas)
+    exchange = solver.exchange  # what actually runs (peer mapping can fall back to nccl on every rank)
     stream = solver.stream
 
     solver.Upload()
