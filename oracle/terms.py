@@ -520,3 +520,152 @@ class HomogeneousModulusLinElast:
 
 def NewHomogeneousModolus(field_name, domain_size, mat_prop, misfit, workers: int = 1):
     return HomogeneousModulusLinElast(field_name, domain_size, mat_prop, misfit, workers)
+
+
+# ==========================================================================
+# the remaining catalog (oracle first; no device implementation yet)
+# pf/gradientCalculator.go, pf/advection.go, pf/sourceTerm.go, pf/negative_value_penalty.go
+# ==========================================================================
+class GradientCalculator:
+    """pf/gradientCalculator.go:19-58: d/dx_Comp of a real-space array, pseudo-spectrally; the
+    +0.5 Nyquist frequency is zeroed unless KeepNyquist."""
+
+    def __init__(self, FT, Comp: int, KeepNyquist: bool = False):
+        self.FT, self.Comp, self.KeepNyquist = FT, Comp, KeepNyquist
+
+    def Calculate(self, indata: np.ndarray, data: np.ndarray):
+        data[:] = indata
+        self.FT.FFT(data)
+        f = as_frequency(self.FT.Freq).table(data.shape[0])[:, self.Comp].copy()
+        if not self.KeepNyquist:
+            f[np.abs(f - 0.5) < 1e-10] = 0.0
+        data *= 1j * 2.0 * math.pi * f
+        self.FT.IFFT(data)
+        data /= float(data.shape[0])
+
+    def ToDerivedField(self, name: str, N: int, brick):
+        from .pf import DerivedField  # local import: pf imports nothing from terms
+
+        def calc(data: np.ndarray):
+            data[:] = brick.Get(np.arange(N))
+            self.Calculate(data.copy(), data)
+
+        return DerivedField(np.zeros(N, dtype=np.complex128), name, calc)
+
+
+class DivGrad:
+    """pf/gradientCalculator.go:60-134: div(F grad field), F a function of the bricks."""
+
+    def __init__(self, Field: str, F):
+        self.Field, self.F = Field, F
+
+    def FuncName(self) -> str:
+        return f"DivGrad_{self.Field}_Func"
+
+    def GradName(self, comp: int) -> str:
+        return f"GRAD_{self.Field}_{comp}"
+
+    def PrepareModel(self, N: int, m, FT):
+        from .pf import DerivedField
+        dim = len(FT.Freq(0))
+        for d in range(dim):
+            grad = GradientCalculator(FT, d, False)
+            m.RegisterDerivedField(grad.ToDerivedField(self.GradName(d), N, m.Bricks[self.Field]))
+
+            def calc(data: np.ndarray, d=d):
+                idx = np.arange(N)
+                data[:] = self.F(idx, m.Bricks) * m.Bricks[self.GradName(d)].Get(idx)
+
+            m.RegisterDerivedField(DerivedField(np.zeros(N, dtype=np.complex128), self.FuncName() + self.GradName(d), calc))
+
+    def Construct(self, bricks):
+        def fn(freq, t, field: np.ndarray):
+            f = as_frequency(freq).table(field.shape[0])
+            field[:] = 0.0
+            for d in range(f.shape[1]):
+                field += (1j * 2.0 * math.pi * f[:, d]) * bricks[self.FuncName() + self.GradName(d)].Get(np.arange(field.shape[0]))
+
+        return fn
+
+    def OnStepFinished(self, t, bricks=None):
+        pass
+
+
+class Advection:
+    """pf/advection.go:10-96: -(v . grad field) through gradient derived fields."""
+
+    def __init__(self, Field: str, VelocityFields):
+        self.Field, self.VelocityFields = Field, list(VelocityFields)
+
+    def GradName(self, comp: int) -> str:
+        return f"{self.Field}_{comp}"
+
+    def GetName(self) -> str:
+        return "".join(self.VelocityFields) + "DotGrad" + self.Field
+
+    def AllFieldsExist(self, m) -> bool:
+        return all(m.IsBrickName(v) for v in self.VelocityFields) and m.IsBrickName(self.Field)
+
+    def PrepareModel(self, N: int, m, FT):
+        from .pf import DerivedField
+        dim = len(FT.Freq(0))
+        if len(self.VelocityFields) != dim:
+            raise RuntimeError("Advection: Inconsistent number of velocity fields")
+        if not self.AllFieldsExist(m):
+            raise RuntimeError("Advection: Make sure that field and all the velocity fields are added to the model")
+        for d in range(dim):
+            m.RegisterDerivedField(GradientCalculator(FT, d).ToDerivedField(self.GradName(d), N, m.Bricks[self.Field]))
+
+        def calc(data: np.ndarray):
+            idx = np.arange(N)
+            data[:] = 0.0
+            for d in range(len(self.VelocityFields)):
+                data += m.Bricks[self.VelocityFields[d]].Get(idx) * m.Bricks[self.GradName(d)].Get(idx)
+
+        m.RegisterDerivedField(DerivedField(np.zeros(N, dtype=np.complex128), self.GetName(), calc))
+
+    def Construct(self, bricks):
+        def fn(freq, t, field: np.ndarray):
+            field[:] = -bricks[self.GetName()].Get(np.arange(field.shape[0]))
+
+        return fn
+
+    def OnStepFinished(self, t, bricks=None):
+        pass
+
+
+class Source:
+    """pf/sourceTerm.go:10-30: f(t) exp(-2 pi i k . pos) -- the transform of a point source."""
+
+    def __init__(self, pos, f):
+        self.Pos = [float(p) for p in pos]
+        self.f = f
+
+    def Eval(self, freq, t: float, data: np.ndarray):
+        k = as_frequency(freq).table(data.shape[0])
+        data[:] = complex(self.f(t), 0.0) * np.exp(-1j * 2.0 * math.pi * (k @ np.asarray(self.Pos)))
+
+
+def NewSource(pos, f) -> Source:
+    return Source(pos, f)
+
+
+class NegativeValuePenalty:
+    """pf/negative_value_penalty.go:5-38."""
+
+    def __init__(self, Prefactor: float, Exponent: int, Field: str):
+        self.Prefactor, self.Exponent, self.Field = Prefactor, Exponent, Field
+
+    def Penalty(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        p = float(self.Exponent)
+        with np.errstate(invalid="ignore"):
+            val = -2.0 * self.Prefactor * p * np.power(np.where(x > 0.0, 1.0, x), p - 1.0)
+        return np.where(x > 0.0, 0.0, val)
+
+    def Evaluate(self, i, bricks):
+        return self.Penalty(np.real(bricks[self.Field].Get(i))).astype(np.complex128)
+
+
+def NewDefaultNegativeValuePenalty(field: str) -> NegativeValuePenalty:
+    return NegativeValuePenalty(1500.0, 3, field)

@@ -1,0 +1,121 @@
+"""Oracle restatements of the remaining catalog terms (GradientCalculator,
+DivGrad, Advection, Source, NegativeValuePenalty) pinned to the reference's own tests.  These have
+no device implementation yet; the oracle goes first so that one can be checked against it.
+No GPU needed."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import pf, pfutil, terms
+
+SIGMA = 1.0 / 10.0
+
+
+def test_gradient_calculator():
+    # pf/gradientCalculator_test.go:11-41
+    N = 16
+    i = np.arange(N * N)
+    x = (i % N) / float(N)
+    data = (x * x - 2 * x ** 3 + x ** 4).astype(np.complex128)
+    expect = (2.0 * x - 6.0 * x * x + 4.0 * x ** 3) / float(N)
+    grad = terms.GradientCalculator(pfutil.NewFFTW([N, N]), 1)
+    got = np.zeros(N * N, dtype=np.complex128)
+    grad.Calculate(data, got)
+    assert np.max(np.abs(got.real - expect)) < 1e-4 and np.max(np.abs(got.imag)) < 1e-4
+
+
+def test_div_grad():
+    # pf/gradientCalculator_test.go:64-160: div(c grad c) of a Gaussian
+    dg = terms.DivGrad("myfield", lambda idx, b: b["myfield"].Get(idx))
+    assert dg.FuncName() == "DivGrad_myfield_Func" and dg.GradName(1) == "GRAD_myfield_1"
+    N = 64
+    i = np.arange(N * N)
+    x = (i % N) / float(N) - 0.5
+    y = (i // N) / float(N) - 0.5
+    data = np.exp(-0.5 * (x * x + y * y) / (SIGMA * SIGMA))
+    want = ((2.0 * x * x + 2.0 * y * y) / (SIGMA * SIGMA) - 2.0) * data * data / (SIGMA * SIGMA)
+    m = pf.NewModel()
+    field = pf.NewField("myfield", N * N, data.astype(np.complex128))
+    m.AddField(field)
+    ft = pfutil.NewFFTW([N, N])
+    dg.PrepareModel(N * N, m, ft)
+    m.Init()
+    rhs = dg.Construct(m.Bricks)
+    for f in m.Fields:
+        ft.FFT(f.Data)
+    for d in m.DerivedFields:
+        ft.FFT(d.Data)
+    res = np.zeros(N * N, dtype=np.complex128)
+    rhs(ft.Freq, 0.0, res)
+    ft.IFFT(res)
+    res /= N * N
+    re = res.real * float(N * N)
+    ok = (np.abs(re - want) < 1e-3) | (np.abs(re - want) < want * 1e-3)
+    assert np.all(ok)
+    assert np.max(np.abs(res.imag)) < 1e-10
+
+
+def _gauss(N):
+    i = np.arange(N * N)
+    x = (i % N) / float(N) - 0.5
+    y = (i // N) / float(N) - 0.5
+    return x, y, np.exp(-0.5 * (x * x + y * y) / (SIGMA * SIGMA))
+
+
+@pytest.mark.parametrize("case", ["vx", "vy", "linear"])
+def test_advection(case):
+    # pf/advection_test.go:94-170
+    N = 64
+    x, y, g = _gauss(N)
+    vx, vy = np.zeros(N * N, dtype=np.complex128), np.zeros(N * N, dtype=np.complex128)
+    if case == "vx":
+        vx[:] = 1.0
+        expect = y * g / (SIGMA * SIGMA)
+    elif case == "vy":
+        vy[:] = 1.0
+        expect = x * g / (SIGMA * SIGMA)
+    else:
+        vx[:] = x
+        expect = y * x * g / (SIGMA * SIGMA)
+    m = pf.NewModel()
+    m.AddField(pf.NewField("conc", N * N, g.astype(np.complex128)))
+    m.AddField(pf.NewField("vx", N * N, vx))
+    m.AddField(pf.NewField("vy", N * N, vy))
+    adv = terms.Advection("conc", ["vx", "vy"])
+    ft = pfutil.NewFFTW([N, N])
+    adv.PrepareModel(N * N, m, ft)
+    m.Init()
+    res = np.zeros(N * N, dtype=np.complex128)
+    adv.Construct(m.Bricks)(ft.Freq, 0.0, res)
+    assert np.max(np.abs(res.real * N - expect)) < 1e-3 and np.max(np.abs(res.imag * N)) < 1e-3
+
+
+def test_advection_panics():
+    # pf/advection_test.go:172-216
+    m = pf.NewModel()
+    adv = terms.Advection("conc", ["vx"])
+    ft = pfutil.NewFFTW([8, 8])
+    with pytest.raises(RuntimeError):
+        adv.PrepareModel(64, m, ft)
+    for name in ("conc", "vx", "vy"):
+        m.AddField(pf.NewField(name, 64))
+    with pytest.raises(RuntimeError):
+        adv.PrepareModel(64, m, ft)  # wrong number of velocity fields
+    terms.Advection("conc", ["vx", "vy"]).PrepareModel(64, m, ft)
+
+
+def test_source_term():
+    # pf/sourceTerm_test.go:19-31
+    src = terms.NewSource([2.5], lambda t: 2.0 * t)
+    data = np.zeros(2, dtype=np.complex128)
+    src.Eval(pf.Frequency(lambda i: [float(i)], lambda cnt: np.arange(cnt, dtype=np.float64).reshape(-1, 1)), 2.0, data)
+    expect = 4.0 * np.exp(-1j * 2.0 * math.pi * 2.5 * np.array([0.0, 1.0]))
+    assert np.max(np.abs(data - expect)) < 1e-10
+
+
+def test_negative_value_penalty():
+    # pf/negative_value_penalty_test.go:8-36
+    nvp = terms.NewDefaultNegativeValuePenalty("myfield")
+    for value, expect in [(1.0, 0.0), (0.0, 0.0), (-1.0, -2.0 * nvp.Prefactor * float(nvp.Exponent))]:
+        assert abs(float(nvp.Penalty(value)) - expect) < 1e-6
