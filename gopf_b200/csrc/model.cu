@@ -313,7 +313,7 @@ struct ExprCompiler {
                 static const std::map<std::string, RpnOp> fn = {
                     {"H", OP_H}, {"dH", OP_DH}, {"Landau", OP_LANDAU}, {"dLandau", OP_DLANDAU},
                     {"exp", OP_EXP}, {"log", OP_LOG}, {"sin", OP_SIN}, {"cos", OP_COS},
-                    {"tanh", OP_TANH}, {"sqrt", OP_SQRT}, {"abs", OP_ABS}};
+                    {"tanh", OP_TANH}, {"sqrt", OP_SQRT}, {"abs", OP_ABS}, {"negpart", OP_NEGPART}};
                 auto it = fn.find(id);
                 if (it == fn.end()) fail("unknown function '" + id + "'");
                 emit(it->second);

@@ -233,7 +233,8 @@ enum RpnOp {
     OP_DH,          // 6x - 6x^2          (pf/homoLinElast.go:15-17)
     OP_LANDAU,      // x^2 - 2x^3 + x^4
     OP_DLANDAU,     // 2x - 6x^2 + 4x^3
-    OP_EXP, OP_LOG, OP_SIN, OP_COS, OP_TANH, OP_SQRT, OP_ABS
+    OP_EXP, OP_LOG, OP_SIN, OP_COS, OP_TANH, OP_SQRT, OP_ABS,
+    OP_NEGPART      // min(x, 0): NegativeValuePenalty acts on negative values only (pf/negative_value_penalty.go:15-21)
 };
 
 struct DevDerived {
@@ -340,6 +341,7 @@ __device__ __forceinline__ cplx eval_derived(const DevDerived& D, Fld fld, unsig
             case OP_TANH: st[sp - 1] = tanh(st[sp - 1]); break;
             case OP_SQRT: st[sp - 1] = sqrt(st[sp - 1]); break;
             case OP_ABS: st[sp - 1] = fabs(st[sp - 1]); break;
+            case OP_NEGPART: st[sp - 1] = fmin(st[sp - 1], 0.0); break;
             default: break;
         }
     }

@@ -100,6 +100,25 @@ class SpectralViscosity:
                                                             ctypes.c_double(self.DissipationThreshold), int(self.Power)))
 
 
+class NegativeValuePenalty:
+    """pf.NegativeValuePenalty (pf/negative_value_penalty.go:5-38).  ``Evaluate`` is what the
+    reference passes to RegisterFunction; here it is the equivalent device expression:
+    Penalty(x) = x > 0 ? 0 : -2 P p x^(p-1) = -2 P p negpart(x)^(p-1) for p > 1."""
+
+    def __init__(self, Prefactor: float, Exponent: int, Field: str):
+        if Exponent < 2:
+            raise GopfError("NegativeValuePenalty: the device expression needs Exponent >= 2")
+        self.Prefactor, self.Exponent, self.Field = Prefactor, Exponent, Field
+
+    @property
+    def Evaluate(self) -> str:
+        return f"-2.0*({self.Prefactor!r})*{float(self.Exponent)!r}*negpart({self.Field})^{self.Exponent - 1}"
+
+
+def NewDefaultNegativeValuePenalty(field: str) -> NegativeValuePenalty:
+    return NegativeValuePenalty(1500.0, 3, field)
+
+
 class TensorialHessian:
     """pf.TensorialHessian (pf/tensorialHessian.go:17-74), implicit."""
 

@@ -88,7 +88,8 @@ int gopf_model_add_scalar(gopf_model* m, const char* name, double re, double im)
 int gopf_model_add_equation(gopf_model* m, const char* equation);
 /* Model.RegisterFunction (pf/model.go:400-412) with the GenericFunction given as a
  * real-valued expression over real parts of fields and scalars:
- * + - * / ^ ( ), H dH Landau dLandau exp log sin cos tanh sqrt abs re() im() */
+ * + - * / ^ ( ), H dH Landau dLandau exp log sin cos tanh sqrt abs negpart re() im();
+ * negpart(x) = min(x, 0) expresses NegativeValuePenalty.Evaluate (pf/negative_value_penalty.go:15-27) */
 int gopf_model_register_function(gopf_model* m, const char* name, const char* expression);
 /* RegisterFunction(name, WhiteNoise{Strength}.Generate) (pf/noise.go:11-23): N(0, 2*Strength)
  * per node per step from a counter-based Philox stream (seed, step, node) */

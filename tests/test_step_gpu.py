@@ -583,3 +583,24 @@ def test_float64_io_from_device_matches_host_path(tmp_path):
     assert raw == np.ascontiguousarray(s2.DownloadReal(0)).astype(">f8").tobytes()  # byte order: big endian
     assert rel_l2(gpf.LoadFloat64(str(tmp_path / "dev_conc_2.bin")), of.Data.real) <= TOL
     assert rel_l2(gf2.Data, of.Data) <= TOL
+
+
+def test_negative_value_penalty_vs_oracle():
+    # pf.NegativeValuePenalty (pf/negative_value_penalty.go) as a registered function: acts on the
+    # negative part of the field only
+    dims = [32, 32]
+    n = 32 * 32
+    init = synthetic.cahn_hilliard_initial(n, 9) * 0.2   # values in [-0.2, 0.2)
+    outs = []
+    for mod, tmod in ((gpf, gpf), (opf, oterms)):
+        m = mod.NewModel()
+        f = mod.NewField("density", n, init.copy())
+        m.AddField(f)
+        nvp = tmod.NegativeValuePenalty(5.0, 3, "density")
+        m.RegisterFunction("PENALTY", nvp.Evaluate)
+        m.AddEquation("ddensity/dt = LAP density - PENALTY")
+        s = mod.NewSolver(m, dims, 0.01)
+        s.Solve(2, 10)
+        outs.append(f.Data.copy())
+    assert rel_l2(outs[0], outs[1]) <= TOL
+    assert np.mean(outs[0].real) > np.mean(init.real) + 1e-4   # the penalty pushed negative values up
