@@ -58,6 +58,10 @@ type FunctionExprs map[string]string
 func NewGPUStepper(m *Model, domainSize []int, dt float64, scheme string, exprs FunctionExprs) *GPUStepper {
 	st := &GPUStepper{Dt: dt}
 	gpuCheck(C.gopf_model_create(&st.model))
+	// cgo pointer rule: the library keeps the Field.Data pointer for the model's lifetime, so the
+	// backing arrays must not be Go-heap memory.  Allocate them with gopf_host_alloc (page-locked,
+	// C-owned) and hand them to pf.NewField(name, N, data), which adopts a caller slice
+	// (pf/model.go:44-57); INTEGRATION.md section 2 shows the helper.
 	for _, f := range m.Fields {
 		name := cstr(f.Name)
 		gpuCheck(C.gopf_model_add_field(st.model, name, C.int64_t(len(f.Data)), (*C.double)(unsafe.Pointer(&f.Data[0]))))
