@@ -669,3 +669,77 @@ class NegativeValuePenalty:
 
 def NewDefaultNegativeValuePenalty(field: str) -> NegativeValuePenalty:
     return NegativeValuePenalty(1500.0, 3, field)
+
+
+# ==========================================================================
+# pf/chargeTransport.go
+# ==========================================================================
+VOIGT_3D = ((0, 5, 4), (5, 1, 3), (4, 3, 2))
+VOIGT_2D = ((0, 2), (2, 1))
+
+
+def voigtIndex(i: int, j: int, dim: int) -> int:
+    """pf/chargeTransport.go:151-171."""
+    return VOIGT_2D[i][j] if dim == 2 else VOIGT_3D[i][j]
+
+
+class ChargeTransport:
+    """pf/chargeTransport.go:9-149: d rho/dt += div(sigma (grad phi - E_ext)) with the potential from
+    Poisson's equation in k-space.  ``Conductivity(i)`` returns the Voigt components at node i
+    (vectorised here: an (N, n_voigt) array for an index array)."""
+
+    def __init__(self, Conductivity, ExternalField, Field: str, FT):
+        self.Conductivity, self.ExternalField, self.Field, self.FT = Conductivity, list(ExternalField), Field, FT
+
+    def _sigma(self, N: int, dim: int) -> np.ndarray:
+        s = self.Conductivity(np.arange(N))
+        s = np.asarray(s, dtype=np.float64)
+        if s.ndim == 1:  # a constant tensor
+            s = np.broadcast_to(s, (N, s.shape[0]))
+        return s
+
+    def current(self, brick, N: int) -> np.ndarray:
+        """:38-71 -- returns effCurrent as (dim, N)."""
+        k = as_frequency(self.FT.Freq).table(N)
+        dim = k.shape[1]
+        k_sq = np.sum(k * k, axis=1)
+        sigma = self._sigma(N, dim)
+        rho = brick.Get(np.arange(N))
+        eff_current = np.zeros((dim, N), dtype=np.complex128)
+        for d in range(dim):
+            keep = np.abs(np.abs(k[:, d]) - 0.5) > 1e-10
+            eff_field = np.where(keep, rho * (1j * k[:, d] / (2.0 * math.pi * k_sq + 1e-16)), 0.0).astype(np.complex128)
+            self.FT.IFFT(eff_field)
+            eff_field /= float(N)
+            eff_field -= complex(self.ExternalField[d], 0.0)
+            for d2 in range(dim):
+                eff_current[d2] += sigma[:, voigtIndex(d, d2, dim)] * eff_field
+        return eff_current
+
+    def Construct(self, bricks):
+        def fn(freq, t, field: np.ndarray):
+            N = field.shape[0]
+            k = as_frequency(freq).table(N)
+            dim = k.shape[1]
+            field[:] = 0.0
+            eff_current = self.current(bricks[self.Field], N)
+            for d2 in range(dim):
+                work = np.ascontiguousarray(eff_current[d2])
+                self.FT.FFT(work)
+                keep = np.abs(np.abs(k[:, d2]) - 0.5) > 1e-10
+                field += np.where(keep, (1j * 2.0 * math.pi * k[:, d2]) * work, 0.0)
+
+        return fn
+
+    def Current(self, density, N: int, realspace: bool):
+        """:104-146."""
+        if realspace:
+            from .pf import NewField
+            r = np.array(density.Get(np.arange(N)), dtype=np.complex128)
+            self.FT.FFT(r)
+            density = NewField("ftDensity", N, r)
+        cur = self.current(density, N)
+        return [-cur[d].real for d in range(cur.shape[0])]
+
+    def OnStepFinished(self, t, bricks):
+        pass

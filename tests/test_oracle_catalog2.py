@@ -119,3 +119,36 @@ def test_negative_value_penalty():
     nvp = terms.NewDefaultNegativeValuePenalty("myfield")
     for value, expect in [(1.0, 0.0), (0.0, 0.0), (-1.0, -2.0 * nvp.Prefactor * float(nvp.Exponent))]:
         assert abs(float(nvp.Penalty(value)) - expect) < 1e-6
+
+
+@pytest.mark.parametrize("case", ["zero", "sine"])
+def test_charge_transport(case):
+    # pf/chargeTransport_test.go:10-133
+    N = 32
+    idx = np.arange(N * N)
+    x = np.array([pfutil.pos([N, N], int(i))[0] for i in idx]) / float(N)
+    if case == "zero":
+        rho = np.zeros(N * N)
+        want_div = np.zeros(N * N)
+        want_cur = [np.ones(N * N), np.zeros(N * N)]
+    else:
+        rho = np.sin(2.0 * math.pi * x)
+        want_div = -np.sin(2.0 * math.pi * x)
+        want_cur = [1.0 - float(N) * np.cos(2.0 * math.pi * x) / (2.0 * math.pi), np.zeros(N * N)]
+    ft = pfutil.NewFFTW([N, N])
+    ct = terms.ChargeTransport(lambda i: np.array([1.0, 1.0, 0.0]), [1.0, 0.0], "density", ft)
+    field = pf.NewField("density", N * N, rho.astype(np.complex128))
+    orig = field.Data.copy()
+    ft.FFT(field.Data)
+    result = np.zeros(N * N, dtype=np.complex128)
+    ct.Construct({"density": field})(ft.Freq, 0.0, result)
+    ft.IFFT(result)
+    result /= N * N
+    assert np.max(np.abs(result.real - want_div)) < 1e-10 and np.max(np.abs(result.imag)) < 1e-10
+    cur = ct.Current(field, N * N, False)
+    for d in range(2):
+        assert np.max(np.abs(cur[d] - want_cur[d])) < 1e-10
+    field.Data[:] = orig
+    cur_real = ct.Current(field, N * N, True)
+    for d in range(2):
+        assert np.max(np.abs(cur_real[d] - cur[d])) < 1e-10
