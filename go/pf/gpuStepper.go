@@ -17,6 +17,11 @@
 // RegisterFunctionExpr, user terms must be catalog types (type switch below).  Anything else panics
 // at construction, not in the middle of a run.
 //
+// cgo note: a file that uses //export may only DECLARE C functions in its preamble; the two static
+// helpers above are definitions, so in a real checkout they live in a second file of the package
+// (gpuStepper_helpers.go with the same preamble minus the extern).  Kept here so the binding reads
+// top to bottom.
+//
 // NOT COMPILED IN THIS REPOSITORY'S CI (no Go toolchain in the image); gopf_b200/pf.py is the
 // binding the tests exercise, call for call.
 package pf
@@ -25,7 +30,13 @@ package pf
 #cgo CFLAGS: -I${SRCDIR}/../../include
 #cgo LDFLAGS: -L${SRCDIR}/../../gopf_b200/lib -lgopfcuda
 #include <stdlib.h>
+#include <stdint.h>
 #include "gopf_cuda.h"
+
+// defined below with //export: calls the Go TimeDepSource registered under the index in `user`
+extern double gopfSourceTrampoline(double t, void* user);
+static gopf_time_fn gopf_source_trampoline_ptr(void) { return (gopf_time_fn)gopfSourceTrampoline; }
+static void* gopf_index_as_ptr(uintptr_t i) { return (void*)i; }
 */
 import "C"
 
@@ -40,6 +51,15 @@ type GPUStepper struct {
 	model  *C.gopf_model
 	solver *C.gopf_solver
 	Dt     float64
+}
+
+// TimeDepSource closures of the model's point sources (pf/sourceTerm.go:11); the C library calls
+// them back on the host once per right-hand-side evaluation through gopfSourceTrampoline.
+var gpuSourceFuncs []TimeDepSource
+
+//export gopfSourceTrampoline
+func gopfSourceTrampoline(t C.double, user unsafe.Pointer) C.double {
+	return C.double(gpuSourceFuncs[int(uintptr(user))-1](float64(t)))
 }
 
 func gpuCheck(status C.int) {
@@ -132,6 +152,24 @@ func NewGPUStepper(m *Model, domainSize []int, dt float64, scheme string, exprs 
 			C.free(unsafe.Pointer(cf))
 		case *ConservativeNoise:
 			gpuCheck(C.gopf_model_register_conservative_noise(st.model, cn, C.double(v.Strength), C.int(v.Dim), C.uint32_t(v.UniquePrefix), 0))
+		case *ChargeTransport:
+			// Conductivity(i) is a Go closure (pf/chargeTransport.go:29-37): tabulate it once,
+			// component-major [n_voigt][N]; the library copies the table
+			n := len(m.Fields[0].Data)
+			nv := len(v.Conductivity(0))
+			tab := make([]C.double, nv*n)
+			for i := 0; i < n; i++ {
+				for c, x := range v.Conductivity(i) {
+					tab[c*n+i] = C.double(x)
+				}
+			}
+			ext := make([]C.double, len(v.ExternalField))
+			for i, x := range v.ExternalField {
+				ext[i] = C.double(x)
+			}
+			cf := cstr(v.Field)
+			gpuCheck(C.gopf_model_register_charge_transport(st.model, cn, cf, &tab[0], C.int(nv), C.int64_t(n), &ext[0], C.int(len(ext))))
+			C.free(unsafe.Pointer(cf))
 		default:
 			panic(fmt.Sprintf("gopfcuda: term %s (%T) has no device implementation", name, t))
 		}
@@ -149,6 +187,17 @@ func NewGPUStepper(m *Model, domainSize []int, dt float64, scheme string, exprs 
 		ce := cstr(eq)
 		gpuCheck(C.gopf_model_add_equation(st.model, ce))
 		C.free(unsafe.Pointer(ce))
+	}
+	for eqNo, srcs := range m.AllSources { // pf/model.go:151-154, 291-294
+		for i := range srcs {
+			pos := make([]C.double, len(srcs[i].Pos))
+			for k, x := range srcs[i].Pos {
+				pos[k] = C.double(x)
+			}
+			gpuSourceFuncs = append(gpuSourceFuncs, srcs[i].f)
+			gpuCheck(C.gopf_model_add_source(st.model, C.int(eqNo), &pos[0], C.int(len(pos)),
+				C.gopf_source_trampoline_ptr(), C.gopf_index_as_ptr(C.uintptr_t(len(gpuSourceFuncs)))))
+		}
 	}
 	dims := make([]C.int, len(domainSize))
 	for i, v := range domainSize {
@@ -218,6 +267,20 @@ func (st *GPUStepper) SaveReal(i int, n int, fname string) {
 	if err := os.WriteFile(fname, buf, 0644); err != nil {
 		panic(err)
 	}
+}
+
+// ChargeCurrent is ChargeTransport.Current (pf/chargeTransport.go:121-146) for the term registered
+// as name, evaluated on the device-resident state: res[d][i] = -real(current_d[i]).
+func (st *GPUStepper) ChargeCurrent(name string, dim int, n int) [][]float64 {
+	flat := make([]float64, dim*n)
+	cn := cstr(name)
+	defer C.free(unsafe.Pointer(cn))
+	gpuCheck(C.gopf_solver_charge_current(st.solver, cn, (*C.double)(unsafe.Pointer(&flat[0]))))
+	res := make([][]float64, dim)
+	for d := 0; d < dim; d++ {
+		res[d] = flat[d*n : (d+1)*n]
+	}
+	return res
 }
 
 // GetTime returns the current time (pf.TimeStepper)

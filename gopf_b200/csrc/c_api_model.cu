@@ -238,6 +238,62 @@ int gopf_model_register_homogeneous_modulus_lin_elast(gopf_model* m, const char*
     GOPF_API_END
 }
 
+int gopf_model_register_charge_transport(gopf_model* m, const char* name, const char* field, const double* conductivity,
+                                         int n_voigt, int64_t n_nodes, const double* external_field, int n_ext) {
+    GOPF_API_BEGIN
+    if (!m || !conductivity || !external_field) throw Error("NULL argument");
+    if (n_voigt != 3 && n_voigt != 6)
+        throw Error("ChargeTransport: the conductivity has 3 (2-D) or 6 (3-D) Voigt components");
+    const int dim = n_voigt == 3 ? 2 : 3;
+    if (n_ext < dim) throw Error(strf("ChargeTransport: ExternalField needs %d components", dim));
+    if (n_nodes <= 0) throw Error("ChargeTransport: empty conductivity table");
+    UserTerm u;
+    u.name = need(name, "name");
+    u.cls = UserTermClass::Explicit;
+    u.kind = UserTermKind::ChargeTransport;
+    u.field = need(field, "field");
+    u.n_voigt = n_voigt;
+    u.conductivity.assign(conductivity, conductivity + (size_t)n_voigt * (size_t)n_nodes);
+    for (int k = 0; k < dim; ++k) u.external_field[k] = external_field[k];
+    m->m.register_user_term(u);
+    GOPF_API_END
+}
+
+int gopf_model_add_source(gopf_model* m, int eq_no, const double* pos, int n_pos, gopf_time_fn f, void* user) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    m->m.add_source(eq_no, pos, n_pos, f, user);
+    GOPF_API_END
+}
+
+int gopf_charge_transport_multipliers(int rank, const double* freq, int64_t count, double* field_mult, double* div_mult) {
+    GOPF_API_BEGIN
+    if (!freq) throw Error("NULL argument");
+    if (rank != 2 && rank != 3) throw Error("gopf_charge_transport_multipliers: rank must be 2 or 3");
+    for (int64_t i = 0; i < count; ++i)
+        for (int c = 0; c < rank; ++c) {
+            if (field_mult) field_mult[(int64_t)c * count + i] = ct_field_multiplier(freq + (size_t)rank * i, rank, c);
+            if (div_mult) div_mult[(int64_t)c * count + i] = ct_divergence_multiplier(freq + (size_t)rank * i, c);
+        }
+    GOPF_API_END
+}
+
+int gopf_charge_transport_voigt_index(int i, int j, int dim, int* out) {
+    GOPF_API_BEGIN
+    if (!out) throw Error("NULL argument");
+    if ((dim != 2 && dim != 3) || i < 0 || j < 0 || i >= dim || j >= dim) throw Error("voigtIndex: index out of range");
+    *out = ct_voigt(i, j, dim);
+    GOPF_API_END
+}
+
+int gopf_source_eval(int rank, const double* freq, int64_t count, const double* pos, double amp, double* out) {
+    GOPF_API_BEGIN
+    if (!freq || !pos || !out) throw Error("NULL argument");
+    if (rank < 1 || rank > 3) throw Error("gopf_source_eval: rank must be 1..3");
+    for (int64_t i = 0; i < count; ++i) source_value(freq + (size_t)rank * i, pos, rank, amp, &out[2 * i], &out[2 * i + 1]);
+    GOPF_API_END
+}
+
 // ---- elasticity package helpers (host) ---------------------------------------------------
 static inline int r4(int i, int j, int k, int l) { return i * 27 + j * 9 + k * 3 + l; }
 
@@ -552,6 +608,13 @@ int gopf_solver_lp_multiplier(gopf_solver* s, int slot, double* value) {
     GOPF_API_BEGIN
     if (!s || !value) throw Error("NULL argument");
     *value = s->s->lp_multiplier(slot);
+    GOPF_API_END
+}
+
+int gopf_solver_charge_current(gopf_solver* s, const char* name, double* host_out) {
+    GOPF_API_BEGIN
+    if (!s || !host_out) throw Error("NULL argument");
+    s->s->charge_current(need(name, "name"), host_out);
     GOPF_API_END
 }
 

@@ -206,6 +206,7 @@ void Solver::ie_residual(const double* x, double* out) {
     for (size_t d = 0; d < m_->derived.size(); ++d)  // SyncDerivedFields + fft of the derived fields
         if (m_->derived[d].used) forward_derived((int)d);
     squared_gradient_terms();
+    catalog_terms();
     if (has_elastic()) elastic_terms();
     SpectraPtrs orig{}, rp{}, res{};
     for (int i = 0; i < F; ++i) {
@@ -333,6 +334,7 @@ void Solver::implicit_euler_step() {
     for (size_t d = 0; d < m_->derived.size(); ++d)
         if (m_->derived[d].used) forward_derived((int)d);
     squared_gradient_terms();
+    catalog_terms();
     if (has_elastic()) elastic_terms();
     SpectraPtrs rp{};
     for (int i = 0; i < F; ++i) {

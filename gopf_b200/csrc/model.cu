@@ -59,6 +59,28 @@ void Model::add_equation(const std::string& eq_in) {
     field_name_from_leibniz(split(eq, "=")[0]);
     equations.push_back(eq);
     update_derived_fields(eq);
+    sources.emplace_back();  // model.go:161
+    initialised = false;
+}
+
+// model.go:151-154.  The reference indexes AllSources[eqNo] directly (a Go panic when the equation
+// does not exist yet) and Source.Eval takes Dot(freq, Pos) over the frequency components
+// (sourceTerm.go:28, pfutil/sliceOperations.go:52-58), so Pos needs at least `rank` entries; that is
+// checked when the solver knows the rank.
+void Model::add_source(int eq_no, const double* pos, int npos, SourceFn f, void* user) {
+    if (eq_no < 0 || eq_no >= (int)sources.size())
+        throw Error(strf("AddSource: index out of range [%d] with length %d", eq_no, (int)sources.size()));
+    if (!pos || npos < 1 || npos > 3) throw Error("AddSource: Pos must hold 1..3 coordinates");
+    if (!f) throw Error("AddSource: the time function is NULL");
+    if ((int)sources[eq_no].size() >= GOPF_MAX_SOURCES)
+        throw Error(strf("AddSource: at most %d sources per equation", GOPF_MAX_SOURCES));
+    SourceSpec s;
+    s.pos[0] = s.pos[1] = s.pos[2] = 0.0;
+    for (int k = 0; k < npos; ++k) s.pos[k] = pos[k];
+    s.npos = npos;
+    s.fn = f;
+    s.user = user;
+    sources[eq_no].push_back(s);
     initialised = false;
 }
 
@@ -490,6 +512,17 @@ CompiledEquation Model::build(const std::string& eq) {
                     apply_prefixes(&d, prefixes);
                     ce.rhs.push_back(d);
                     break;
+                case UserTermKind::ChargeTransport:
+                    // the solver fills the work spectrum with the whole term (chargeTransport.go:94-119)
+                    if (field_index(u.field) < 0) throw Error("ChargeTransport: unknown field " + u.field);
+                    if (u.conductivity.size() != (size_t)u.n_voigt * N)
+                        throw Error(strf("ChargeTransport: conductivity table holds %zu values, expected %d x %zu",
+                                         u.conductivity.size(), u.n_voigt, N));
+                    d.kind = TK_MONOMIAL;
+                    d.brick = u.work_spectrum;
+                    apply_prefixes(&d, prefixes);
+                    ce.rhs.push_back(d);
+                    break;
                 case UserTermKind::HomogeneousModulusLinElast:
                     // the solver fills the work spectrum with the whole term (homoLinElast.go:47-99)
                     if (field_index(u.field) < 0) throw Error("HomogeneousModulusLinElast: unknown field " + u.field);
@@ -519,7 +552,7 @@ void Model::init() {
     if (equations.size() > fields.size()) throw Error("model: more equations than fields");
     for (DerivedSpec& d : derived) d.used = false;
     // assign parameter slots / work spectra to the registered user terms
-    int n_sv = 0, n_pc = 0, n_cn = 0, n_lp = 0, n_el = 0, n_th = 0;
+    int n_sv = 0, n_pc = 0, n_cn = 0, n_lp = 0, n_el = 0, n_th = 0, n_ct = 0;
     n_work_spectra = 0;
     for (auto& kv : user_terms) {
         UserTerm& u = kv.second;
@@ -534,14 +567,22 @@ void Model::init() {
                 u.slot = n_el++;
                 u.work_spectrum = (int)(fields.size() + derived.size()) + n_work_spectra++;
                 break;
+            case UserTermKind::ChargeTransport:
+                u.slot = n_ct++;
+                u.work_spectrum = (int)(fields.size() + derived.size()) + n_work_spectra++;
+                break;
             case UserTermKind::SquaredGradient:
                 u.work_spectrum = (int)(fields.size() + derived.size()) + n_work_spectra++;
                 break;
             default: break;
         }
     }
+    // one work spectrum per equation that has point sources (model.go:291-294)
+    source_spectrum.assign(equations.size(), -1);
+    for (size_t e = 0; e < equations.size() && e < sources.size(); ++e)
+        if (!sources[e].empty()) source_spectrum[e] = (int)(fields.size() + derived.size()) + n_work_spectra++;
     if (n_sv > GOPF_MAX_SPECIAL || n_pc > GOPF_MAX_SPECIAL || n_cn > GOPF_MAX_SPECIAL || n_lp > GOPF_MAX_SPECIAL ||
-        n_el > GOPF_MAX_SPECIAL || n_th > GOPF_MAX_SPECIAL)
+        n_el > GOPF_MAX_SPECIAL || n_th > GOPF_MAX_SPECIAL || n_ct > GOPF_MAX_SPECIAL)
         throw Error(strf("model: at most %d terms of each special kind", GOPF_MAX_SPECIAL));
     if (n_spectra() > GOPF_MAX_SPECTRA) throw Error(strf("model: at most %d spectra", GOPF_MAX_SPECTRA));
     compiled.clear();
@@ -563,6 +604,18 @@ void Model::fill_program(DevKProgram* P, double dt, int rank) const {
             q.n_den = (int)compiled[i].den.size();
             for (int j = 0; j < q.n_rhs; ++j) q.rhs[j] = compiled[i].rhs[j];
             for (int j = 0; j < q.n_den; ++j) q.den[j] = compiled[i].den[j];
+            if (i < source_spectrum.size() && source_spectrum[i] >= 0) {  // + sum of the sources (model.go:291-294)
+                if (q.n_rhs >= GOPF_MAX_TERMS)
+                    throw Error(strf("equation %d: more than %d terms on one side", (int)i, GOPF_MAX_TERMS));
+                DevTerm t;
+                t.cre = 1.0;
+                t.cim = 0.0;
+                t.brick = source_spectrum[i];
+                t.lap = 0;
+                t.kind = TK_MONOMIAL;
+                t.param = 0;
+                q.rhs[q.n_rhs++] = t;
+            }
         }
     }
     for (const auto& kv : user_terms) {

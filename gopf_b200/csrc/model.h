@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "catalog_terms.cuh"
 #include "parser.h"
 #include "step_program.h"
 
@@ -31,7 +32,7 @@ struct DerivedSpec {
 };
 
 enum class UserTermClass { Implicit, Explicit, Mixed };
-enum class UserTermKind { SpectralViscosity, PairCorrelation, ExplicitPairCorrelation, IdealMixture, ConservativeNoise, VolumeConservingLP, SquaredGradient, HomogeneousModulusLinElast, TensorialHessian };
+enum class UserTermKind { SpectralViscosity, PairCorrelation, ExplicitPairCorrelation, IdealMixture, ConservativeNoise, VolumeConservingLP, SquaredGradient, HomogeneousModulusLinElast, TensorialHessian, ChargeTransport };
 
 struct UserTerm {
     std::string name;
@@ -51,6 +52,21 @@ struct UserTerm {
     double stiffness[81] = {0};  // HomogeneousModulusLinElast.MatProp (elasticity.Rank4.Data, rank4.go:22-24)
     double misfit[9] = {0};      // HomogeneousModulusLinElast.Misfit, row-major 3x3
     TensorHessianParams hessian = {};  // TensorialHessian.K
+    // ChargeTransport (chargeTransport.go:29-47): Conductivity(i) tabulated per node, component-major
+    // [n_voigt][N]; ExternalField
+    std::vector<double> conductivity;
+    int n_voigt = 0;
+    double external_field[3] = {0.0, 0.0, 0.0};
+};
+
+// pf.Source (sourceTerm.go:10-22): the amplitude is a host function of time, evaluated once per
+// RHS evaluation and handed to the device as a scalar
+typedef double (*SourceFn)(double t, void* user);
+struct SourceSpec {
+    double pos[3];
+    int npos;
+    SourceFn fn;
+    void* user;
 };
 
 struct CompiledEquation {
@@ -72,6 +88,8 @@ public:
     std::map<std::string, UserTerm> user_terms;
     std::vector<std::string> equations;  // spaces stripped (model.go:158)
     std::vector<CompiledEquation> compiled;
+    std::vector<std::vector<SourceSpec>> sources;  // Model.AllSources (model.go:125, 161)
+    std::vector<int> source_spectrum;              // per equation: work spectrum of its sources, -1 if none
     int n_work_spectra = 0;
     bool initialised = false;
 
@@ -83,6 +101,7 @@ public:
     void register_white_noise(const std::string& name, double strength, unsigned long long seed);
     void register_table_field(const std::string& name, const double* values, long long n_steps);
     void register_user_term(const UserTerm& t);
+    void add_source(int eq_no, const double* pos, int npos, SourceFn f, void* user);  // AddSource (model.go:151-154)
     void register_derived_monomial(const std::string& desc);  // RegisterDerivedField for a monomial description
     void init();                                               // Model.Init (model.go:244-260)
 

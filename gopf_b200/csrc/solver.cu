@@ -291,6 +291,7 @@ Solver::~Solver() {
     }
     for (int i = 0; i < GOPF_MAX_SPECTRA; ++i)
         if (d_table_[i]) cudaFree(d_table_[i]);
+    free_catalog_buffers();
     if (W_) cudaFree(W_);
     if (d_real_out_) cudaFree(d_real_out_);
     if (d_filter_) cudaFree(d_filter_);
@@ -998,6 +999,7 @@ void Solver::euler_update_generic() {
             if (m_->derived[d].used) forward_derived((int)d);  // euler.go:22-24
     }
     squared_gradient_terms();
+    catalog_terms();
     if (elastic) elastic_terms();
     launch_update(prog_);                                    // euler.go:27-39
 }
@@ -1067,6 +1069,7 @@ void Solver::rk4_step() {
                 if (m_->derived[d].used) forward_derived((int)d);
         }
         squared_gradient_terms();
+        catalog_terms();
         if (has_elastic()) elastic_terms();
         k_rk4_rhs<<<grid_for(n), 256, 0, s>>>(prog_, S_, kf, fg, n);
         GOPF_CUDA(cudaGetLastError());

@@ -80,6 +80,9 @@ public:
     void synchronize();
     void force_generic(bool on);
     double lp_multiplier(int slot);
+    // ChargeTransport.Current (chargeTransport.go:121-146) of the term registered as `name`:
+    // host_out[d*N + i] = -real(current_d[i]) from the device-resident spectrum
+    void charge_current(const std::string& name, double* host_out);
     void set_newton_krylov(const NewtonKrylovOptions& o) { nk_ = o; }
     bool last_step_converged() const { return ie_converged_; }
     long long residual_evaluations() const { return ie_residual_evals_; }
@@ -118,6 +121,9 @@ private:
     cplx* elast_phi_[GOPF_MAX_SPECIAL];
     bool elast_valid_ = false;
     double* d_table_[GOPF_MAX_SPECTRA];
+    // ChargeTransport (catalog_terms.cu): conductivity tables per term slot, one current component
+    double* ct_sigma_[GOPF_MAX_SPECIAL] = {nullptr, nullptr};
+    cplx* ct_tmp_ = nullptr;
     DevKProgram prog_;
     DevKProgram fused_prog_;
     bool prog_dirty_ = true;
@@ -165,6 +171,12 @@ private:
     void eval_real_fields();
     void squared_gradient_terms();
     void elastic_terms();
+    void catalog_terms();            // ChargeTransport + point sources (catalog_terms.cu)
+    void charge_transport_terms();
+    void source_terms();
+    void free_catalog_buffers();
+    template <class Emit>
+    void charge_current_components(const UserTerm& u, const cplx* rho, Emit emit);
     void elastic_hooks();
     bool has_elastic() const;
     void volume_lp_hooks();

@@ -302,6 +302,79 @@ def NewHomogeneousModolus(fieldName: str, domainSize, matProp, misfit) -> Homoge
     return HomogeneousModulusLinElast(fieldName, domainSize, matProp, misfit)
 
 
+def voigtIndex(i: int, j: int, dim: int) -> int:
+    """pf/chargeTransport.go:151-171."""
+    out = ctypes.c_int(0)
+    check(lib().gopf_charge_transport_voigt_index(int(i), int(j), int(dim), ctypes.byref(out)))
+    return out.value
+
+
+class ChargeTransport:
+    """pf.ChargeTransport (pf/chargeTransport.go:29-146).  ``Conductivity`` is the reference's
+    ``func(i int) []float64``; a Go closure cannot run on the device, so it is tabulated once at
+    registration (a callable of a node-index array returning (N, n_voigt) or one constant tensor,
+    or the (N, n_voigt) array itself).  ``FT`` is accepted for signature parity and unused: the
+    device solver's own transform is the term's transform."""
+
+    def __init__(self, Conductivity, ExternalField, Field: str, FT=None):
+        self.Conductivity, self.ExternalField, self.Field, self.FT = Conductivity, [float(e) for e in ExternalField], Field, FT
+        self._model: Optional["Model"] = None
+        self._name = ""
+
+    def _table(self, N: int) -> np.ndarray:
+        s = self.Conductivity(np.arange(N)) if callable(self.Conductivity) else self.Conductivity
+        s = np.asarray(s, dtype=np.float64)
+        if s.ndim == 1:
+            s = np.broadcast_to(s, (N, s.shape[0]))
+        if s.ndim != 2 or s.shape[0] != N or s.shape[1] not in (3, 6):
+            raise GopfError("ChargeTransport: Conductivity must give 3 (2-D) or 6 (3-D) Voigt components per node")
+        return np.ascontiguousarray(s.T)  # component-major [n_voigt][N]
+
+    def _register(self, m: "Model", name: str, cls: str):
+        if cls != "explicit":
+            raise GopfError("ChargeTransport is an explicit term")
+        tab = self._table(m.NumNodes())
+        ext = np.ascontiguousarray(self.ExternalField, dtype=np.float64)
+        pd = ctypes.POINTER(ctypes.c_double)
+        check(lib().gopf_model_register_charge_transport(m._h, _s(name), _s(self.Field), tab.ctypes.data_as(pd),
+                                                         int(tab.shape[0]), ctypes.c_int64(tab.shape[1]),
+                                                         ext.ctypes.data_as(pd), int(ext.shape[0])))
+        self._model, self._name = m, name
+
+    def Current(self, density=None, N: Optional[int] = None, realspace: bool = True):
+        """ChargeTransport.Current (:121-146) evaluated on the device-resident state of the solver
+        the term's model belongs to: a list of ``dim`` real arrays, minus the real part of the current.
+        ``density`` / ``realspace`` are accepted for signature parity; the device spectrum of the
+        term's field is the density."""
+        if self._model is None or not self._model._solvers:
+            raise GopfError("ChargeTransport.Current: the term is not registered with a model that has a solver")
+        solver = self._model._solvers[-1]
+        n = self._model.NumNodes()
+        dim = len(self.ExternalField)
+        out = np.empty((dim, n), dtype=np.float64)
+        check(lib().gopf_solver_charge_current(solver._h, _s(self._name), out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        return [out[d] for d in range(dim)]
+
+    def OnStepFinished(self, t, bricks=None):
+        pass
+
+
+_TIME_FN = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.c_double, ctypes.c_void_p)
+
+
+class Source:
+    """pf.Source (pf/sourceTerm.go:13-22): a point source at ``Pos`` with amplitude ``f(t)``."""
+
+    def __init__(self, pos, f: Callable[[float], float]):
+        self.Pos = [float(p) for p in pos]
+        self.f = f
+        self._cb = _TIME_FN(lambda t, _user: float(f(t)))  # kept alive with the Source
+
+
+def NewSource(pos, f) -> Source:
+    return Source(pos, f)
+
+
 class Vandeven:
     """pf.Vandeven (pf/vandeven.go:8-40): Data is the 1000-point table."""
 
@@ -338,6 +411,7 @@ class Model:
         self.Bricks = {}
         self.Equations: List[str] = []
         self._solvers = []
+        self._sources: List["Source"] = []  # keeps the ctypes callbacks alive
 
     def AddField(self, f: Field):
         check(lib().gopf_model_add_field(self._h, _s(f.Name), ctypes.c_int64(f.Data.shape[0]),
@@ -352,6 +426,14 @@ class Model:
     def AddEquation(self, eq: str):
         check(lib().gopf_model_add_equation(self._h, _s(eq)))
         self.Equations.append(eq.replace(" ", ""))
+
+    def AddSource(self, eqNo: int, s: "Source"):
+        """Model.AddSource (pf/model.go:151-154).  The time function runs on the host, once per
+        right-hand-side evaluation."""
+        pos = np.ascontiguousarray(s.Pos, dtype=np.float64)
+        check(lib().gopf_model_add_source(self._h, int(eqNo), pos.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                          int(pos.shape[0]), s._cb, None))
+        self._sources.append(s)
 
     def RegisterFunction(self, name: str, F):
         """F: expression string, or WhiteNoise(...).Generate."""

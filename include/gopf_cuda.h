@@ -131,6 +131,31 @@ int gopf_model_register_tensorial_hessian(gopf_model* m, const char* name, const
  * (OnStepFinished, :130-134), so the term vanishes during the first step -- replicated. */
 int gopf_model_register_homogeneous_modulus_lin_elast(gopf_model* m, const char* name, const char* field,
                                                       const double* stiffness81, const double* misfit9);
+/* RegisterExplicitTerm(name, &ChargeTransport{Conductivity, ExternalField, Field, FT})
+ * (pf/chargeTransport.go:29-119): minus the divergence of the current j = sigma (E_ind - E_ext) with
+ * the induced field from Poisson's equation in k-space.  The Go closure Conductivity(i) is
+ * tabulated by the caller: conductivity[v * n_nodes + i] = Conductivity(i)[v], n_voigt = 3 in 2-D
+ * (s_xx, s_yy, s_xy) or 6 in 3-D (s_xx, s_yy, s_zz, s_xz, s_yz, s_xy); the table is copied.
+ * external_field holds n_ext = rank values. */
+int gopf_model_register_charge_transport(gopf_model* m, const char* name, const char* field,
+                                         const double* conductivity, int n_voigt, int64_t n_nodes,
+                                         const double* external_field, int n_ext);
+/* Model.AddSource(eqNo, pf.NewSource(pos, f)) (pf/model.go:151-154, pf/sourceTerm.go:10-30): adds
+ * f(t) * exp(-i 2 pi Freq(k) . pos) to the right-hand side of equation eq_no.  f is the reference's
+ * TimeDepSource as a C callback; it is called on the host once per right-hand-side evaluation
+ * with t = TimeStepper.GetTime() and `user`.  pos holds n_pos >= rank coordinates. */
+typedef double (*gopf_time_fn)(double t, void* user);
+int gopf_model_add_source(gopf_model* m, int eq_no, const double* pos, int n_pos, gopf_time_fn f, void* user);
+/* Host evaluation of the per-k factors the ChargeTransport / Source kernels apply (same
+ * __host__ __device__ code, gopf_b200/csrc/catalog_terms.cuh), for `count` frequency vectors
+ * freq[count][rank]: field_mult[c][i] (pf/chargeTransport.go:64-73), div_mult[c][i] (:106-112),
+ * component-major [rank][count]; either output may be NULL. */
+int gopf_charge_transport_multipliers(int rank, const double* freq, int64_t count, double* field_mult,
+                                      double* div_mult);
+/* voigtIndex(i, j, dim) (pf/chargeTransport.go:151-171) */
+int gopf_charge_transport_voigt_index(int i, int j, int dim, int* out);
+/* Source.Eval on the host (pf/sourceTerm.go:25-30): out_c128[i] = amp * exp(-i 2 pi freq[i] . pos) */
+int gopf_source_eval(int rank, const double* freq, int64_t count, const double* pos, double amp, double* out_c128);
 /* elasticity.CubicMaterial / Isotropic / Rank4.Rotate / Rank4.ContractLast / EnergyDensity
  * (elasticity/rank4.go:39-128, linearElasticity.go:86-98): host-side tensor helpers */
 int gopf_elasticity_cubic_material(double c11, double c12, double c44, double* out81);
@@ -198,6 +223,10 @@ int gopf_solver_kernel_launches(gopf_solver* s, int64_t* n, int reset);
 int gopf_solver_get_spectrum(gopf_solver* s, int index, double* host_c128);
 /* VolumeConservingLP.Multiplier of the slot-th registered term */
 int gopf_solver_lp_multiplier(gopf_solver* s, int slot, double* value);
+/* ChargeTransport.Current(density, N, realspace) (pf/chargeTransport.go:121-146) for the term
+ * registered as `name`, evaluated on the device-resident spectrum of its field:
+ * host_out[d * N + i] = -real(current_d[i]), d < rank */
+int gopf_solver_charge_current(gopf_solver* s, const char* name, double* host_out);
 /* Real part of field `field_index` (N doubles) from the device-resident state, big-endian byte
  * order on request: the payload of Field.SaveReal / Float64IO.SaveFields (pf/model.go:35-41,
  * pf/fileIO.go:57-62, 85-95) for epoch callbacks of device-resident runs, at half the D2H bytes of

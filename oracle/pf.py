@@ -381,6 +381,10 @@ class Model:
     def AddScalar(self, s: Scalar):
         self.Bricks[s.Name] = s
 
+    # model.go:151-154
+    def AddSource(self, eq_no: int, s):
+        self.AllSources[eq_no].append(s)
+
     # model.go:157-162
     def AddEquation(self, eq: str):
         eq = eq.replace(" ", "")
