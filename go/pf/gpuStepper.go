@@ -269,6 +269,58 @@ func (st *GPUStepper) SaveReal(i int, n int, fname string) {
 	}
 }
 
+// NewGPUSDD mirrors a configured pf.SDD (pf/sdd.go:86-129) onto the device: scheme "sdd", the
+// orientation vector (already normalised by Init / SetInitialOrientation) and the exported settings.
+// Call SyncSDD(&sdd) after changing a setting; Monitor / CurrentStep / orientation are read back by
+// PullSDD(&sdd) (e.g. from a Solver callback).
+func NewGPUSDD(m *Model, domainSize []int, sdd *SDD, exprs FunctionExprs) *GPUStepper {
+	st := NewGPUStepper(m, domainSize, sdd.Dt, "sdd", exprs)
+	if sdd.initialized {
+		gpuCheck(C.gopf_solver_sdd_set_orientation(st.solver, (*C.double)(unsafe.Pointer(&sdd.orientation[0])), C.int64_t(len(sdd.orientation))))
+	}
+	st.SyncSDD(sdd)
+	return st
+}
+
+func (st *GPUStepper) sddSet(key string, v float64) {
+	ck := cstr(key)
+	defer C.free(unsafe.Pointer(ck))
+	gpuCheck(C.gopf_solver_sdd_set(st.solver, ck, C.double(v)))
+}
+
+func (st *GPUStepper) sddGet(key string) float64 {
+	ck := cstr(key)
+	defer C.free(unsafe.Pointer(ck))
+	var v C.double
+	gpuCheck(C.gopf_solver_sdd_get(st.solver, ck, &v))
+	return float64(v)
+}
+
+// SyncSDD pushes the exported fields of the SDD struct (set_orientation overwrote InitDimerLength
+// with the norm of the unit vector, so it is pushed again here)
+func (st *GPUStepper) SyncSDD(sdd *SDD) {
+	st.sddSet("Alpha", sdd.Alpha)
+	st.sddSet("Dt", sdd.Dt)
+	st.sddSet("TimeConstants.Orientation", sdd.TimeConstants.Orientation)
+	st.sddSet("TimeConstants.DimerLength", sdd.TimeConstants.DimerLength)
+	st.sddSet("MinDimerLength", sdd.MinDimerLength)
+	st.sddSet("InitDimerLength", sdd.InitDimerLength)
+	st.sddSet("CurrentStep", float64(sdd.CurrentStep))
+}
+
+// PullSDD refreshes Monitor, CurrentStep and the orientation vector from the device
+func (st *GPUStepper) PullSDD(sdd *SDD) {
+	sdd.CurrentStep = int(st.sddGet("CurrentStep"))
+	sdd.Monitor.MaxForce = st.sddGet("Monitor.MaxForce")
+	sdd.Monitor.ForcePowerSpectrum = st.sddGet("Monitor.ForcePowerSpectrum")
+	sdd.Monitor.MaxTorque = st.sddGet("Monitor.MaxTorque")
+	sdd.Monitor.FieldNorm = st.sddGet("Monitor.FieldNorm")
+	sdd.Monitor.FieldNormChange = st.sddGet("Monitor.FieldNormChange")
+	if sdd.initialized {
+		gpuCheck(C.gopf_solver_sdd_get_orientation(st.solver, (*C.double)(unsafe.Pointer(&sdd.orientation[0]))))
+	}
+}
+
 // ChargeCurrent is ChargeTransport.Current (pf/chargeTransport.go:121-146) for the term registered
 // as name, evaluated on the device-resident state: res[d][i] = -real(current_d[i]).
 func (st *GPUStepper) ChargeCurrent(name string, dim int, n int) [][]float64 {

@@ -611,6 +611,34 @@ int gopf_solver_lp_multiplier(gopf_solver* s, int slot, double* value) {
     GOPF_API_END
 }
 
+int gopf_solver_sdd_set_orientation(gopf_solver* s, const double* orientation, int64_t len) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->sdd_set_orientation(orientation, (long long)len);
+    GOPF_API_END
+}
+
+int gopf_solver_sdd_get_orientation(gopf_solver* s, double* host_out) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->sdd_get_orientation(host_out);
+    GOPF_API_END
+}
+
+int gopf_solver_sdd_set(gopf_solver* s, const char* key, double value) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->sdd_set(need(key, "key"), value);
+    GOPF_API_END
+}
+
+int gopf_solver_sdd_get(gopf_solver* s, const char* key, double* value) {
+    GOPF_API_BEGIN
+    if (!s || !value) throw Error("NULL argument");
+    *value = s->s->sdd_get(need(key, "key"));
+    GOPF_API_END
+}
+
 int gopf_solver_charge_current(gopf_solver* s, const char* name, double* host_out) {
     GOPF_API_BEGIN
     if (!s || !host_out) throw Error("NULL argument");

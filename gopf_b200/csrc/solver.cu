@@ -292,6 +292,7 @@ Solver::~Solver() {
     for (int i = 0; i < GOPF_MAX_SPECTRA; ++i)
         if (d_table_[i]) cudaFree(d_table_[i]);
     free_catalog_buffers();
+    sdd_free_buffers();
     if (W_) cudaFree(W_);
     if (d_real_out_) cudaFree(d_real_out_);
     if (d_filter_) cudaFree(d_filter_);
@@ -364,6 +365,11 @@ void Solver::set_stepper(const std::string& name) {
     // not a SetStepper name in the reference: there the user assigns solver.Stepper = &pf.ImplicitEuler{...}
     // (pf/implicitEuler_test.go:193-198); the C ABI has no struct to assign, so the name selects it
     else if (name == "implicit_euler") stepper_ = StepperKind::ImplicitEuler;
+    // likewise solver.Stepper = &sdd (pf/sdd_test.go:86); settings through sdd_set / sdd_set_orientation
+    else if (name == "sdd") {
+        stepper_ = StepperKind::SDD;
+        sdd_ = SddState();  // NewSDD (sdd.go:120-129)
+    }
     else throw Error("Unknown stepper scheme");  // solver.go:101
     current_step_ = 0;  // SetStepper builds a fresh stepper struct (solver.go:90-99)
     decide_path();
@@ -375,6 +381,7 @@ void Solver::force_generic(bool on) {
 }
 
 void Solver::set_filter(const double* table, int n) {
+    if (stepper_ == StepperKind::SDD && table && n > 1) throw Error("SDD: Does not support modal filters");  // sdd.go:431-433
     plan_->use_device();
     if (d_filter_) {
         cudaFree(d_filter_);
@@ -1127,6 +1134,8 @@ void Solver::step(int nsteps) {
     for (int i = done; i < nsteps; ++i) {
         if (stepper_ == StepperKind::RK4) {
             rk4_step();  // Step does not advance CurrentStep (rk4.go:130-135)
+        } else if (stepper_ == StepperKind::SDD) {
+            sdd_step();  // advances its own CurrentStep (sdd.go:299)
         } else if (stepper_ == StepperKind::ImplicitEuler) {
             implicit_euler_step();
             current_step_++;  // implicitEuler.go:206

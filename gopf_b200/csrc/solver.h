@@ -18,7 +18,7 @@
 
 namespace gopf {
 
-enum class StepperKind { Euler, RK4, ImplicitEuler };
+enum class StepperKind { Euler, RK4, ImplicitEuler, SDD };
 
 // Settings of the Newton-Krylov solve inside ImplicitEuler.Step (pf/implicitEuler.go:221-229
 // DefaultNonLinSolver; oracle/pf.py NewtonKrylov states the algorithm).
@@ -30,6 +30,20 @@ struct NewtonKrylovOptions {
     int restart = 30;      // GMRES restart length
     double inner_tol = 1e-4;
     int max_restarts = 4;
+};
+
+// pf.SDD (pf/sdd.go:86-129): settings and monitor of the shrinking-dimer stepper
+struct SddState {
+    double alpha = 0.5;             // SDD.Alpha
+    double tau_orientation = 1.0;   // TimeConstants.Orientation
+    double tau_dimer_length = 1.0;  // TimeConstants.DimerLength
+    double dt = 0.0;                // SDD.Dt: must be set explicitly (checkTimeStep, :131-135)
+    double min_dimer_length = 0.0;
+    double init_dimer_length = 0.0;
+    long long current_step = 0;
+    bool initialized = false;
+    // SDDMonitor (:25-53)
+    double max_force = 0.0, force_power_spectrum = 0.0, max_torque = 0.0, field_norm = 0.0, field_norm_change = 0.0;
 };
 
 // shared by Solver and DistSolver (solver.cu)
@@ -69,7 +83,15 @@ public:
         step(nsteps);
         download();
     }
-    double get_time() const { return (double)current_step_ * dt_; }
+    double get_time() const {
+        if (stepper_ == StepperKind::SDD) return (double)sdd_.current_step * sdd_.dt;  // sdd.go:359-361
+        return (double)current_step_ * dt_;
+    }
+    // pf.SDD (sdd.cu): SetInitialOrientation (sdd.go:413-427), settings / monitor by name, orientation
+    void sdd_set_orientation(const double* orient, long long len);
+    void sdd_set(const std::string& key, double value);
+    double sdd_get(const std::string& key);
+    void sdd_get_orientation(double* host_out);
     bool fused() const { return fused_; }
     long long kernel_launches() const { return launches_; }
     void reset_launch_count() { launches_ = 0; }
@@ -145,6 +167,21 @@ private:
     std::vector<double*> ie_vec_;         // x, F(x), b, s, w, tmp_p, tmp_m, then restart+1 Krylov vectors
     double* ie_partial_ = nullptr;        // reduction partials (device) 
     int ie_vec_restart_ = -1;
+
+    // SDD (sdd.cu)
+    SddState sdd_;
+    double* sdd_orient_ = nullptr;           // orientation vector, F x N reals
+    cplx* sdd_vhat_[GOPF_MAX_FIELDS] = {};   // FFT of the orientation blocks
+    cplx* sdd_rs_[GOPF_MAX_FIELDS] = {};     // RHS at the start image, then the torque
+    cplx* sdd_re_[GOPF_MAX_FIELDS] = {};     // RHS at the end image
+    cplx* sdd_work_ = nullptr;
+    cplx* sdd_d_ = nullptr;
+    double* sdd_partial_ = nullptr;
+    void sdd_step();
+    void sdd_ensure_buffers();
+    void sdd_free_buffers();
+    double sdd_dimer_length(double t) const;
+    void sdd_collect(int n_sums, unsigned blocks, double* sums, double* mx);
 
     bool profiling_ = false;
     std::vector<KernelTimer> timers_;

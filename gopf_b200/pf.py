@@ -17,6 +17,7 @@ raise ``GopfError`` where the reference panics.
 from __future__ import annotations
 
 import ctypes
+import math
 from typing import Callable, List, Optional
 
 import numpy as np
@@ -607,6 +608,114 @@ class ImplicitEuler:
         return n.value
 
 
+class SDDTimeConstants:
+    """pf.SDDTimeConstants (pf/sdd.go:14-23)."""
+
+    def __init__(self, Orientation: float = 1.0, DimerLength: float = 1.0):
+        self.Orientation, self.DimerLength = Orientation, DimerLength
+
+
+class SDDMonitor:
+    """pf.SDDMonitor (pf/sdd.go:25-53), refreshed from the device after every Propagate."""
+
+    def __init__(self):
+        self.MaxForce = self.ForcePowerSpectrum = self.MaxTorque = self.FieldNorm = self.FieldNormChange = 0.0
+
+
+class SDD:
+    """pf.SDD (pf/sdd.go:86-443), the shrinking-dimer saddle-point stepper.  Used like the reference:
+    ``sdd = NewSDD(domainSize, model); sdd.Init(...); sdd.Dt = dt; solver.Stepper = sdd``.  The struct's
+    exported fields are plain attributes here; they are pushed to the device before every Propagate
+    (the reference reads them through the pointer at every step) and CurrentStep / Monitor / the
+    orientation are read back after it."""
+
+    _KEYS = ("Alpha", "Dt", "MinDimerLength", "InitDimerLength")
+
+    def __init__(self, domainSize, model: "Model"):
+        self.TimeConstants = SDDTimeConstants(1.0, 1.0)
+        self.Alpha = 0.5
+        self.Dt = 0.0
+        self.CurrentStep = 0
+        self.MinDimerLength = 0.0
+        self.Monitor = SDDMonitor()
+        self.InitDimerLength = 0.0
+        self._orientation = np.zeros(model.NumNodes() * len(model.Fields), dtype=np.float64)
+        self._initialized = False
+        self._orientation_dirty = False
+        self._solver: Optional["Solver"] = None
+
+    # -- reference API (host arithmetic of :359-427 is plain float math and stays on the host)
+    def Init(self, init, final):
+        self.SetInitialOrientation(np.concatenate([(b.Data - a.Data).real for a, b in zip(init, final)]))
+
+    def SetInitialOrientation(self, orient):
+        orient = np.asarray(orient, dtype=np.float64)
+        if orient.shape[0] != self._orientation.shape[0]:
+            raise GopfError("Inconsistent length of the passed orientaiton vector")
+        self.InitDimerLength = math.sqrt(float(np.dot(orient, orient)))
+        self._orientation = orient / self.InitDimerLength
+        self._initialized = True
+        self._orientation_dirty = True
+
+    def GetTime(self) -> float:
+        return float(self.CurrentStep) * self.Dt
+
+    def DimerLength(self, t: float) -> float:
+        l = self.InitDimerLength * math.exp(-t / self.TimeConstants.DimerLength)
+        return self.MinDimerLength if l < self.MinDimerLength else l
+
+    def RequiredDimerLengthTime(self, l: float) -> float:
+        return self.TimeConstants.DimerLength * math.log(self.InitDimerLength / l)
+
+    def SetFilter(self, filt):
+        raise GopfError("SDD: Does not support modal filters")
+
+    def Step(self, m=None):
+        self._solver.Propagate(1)
+
+    @property
+    def orientation(self) -> np.ndarray:
+        return self._orientation
+
+    # -- device plumbing
+    def _attach(self, solver: "Solver"):
+        self._solver = solver
+        check(lib().gopf_solver_set_stepper(solver._h, b"sdd"))
+        self._orientation_dirty = self._initialized
+
+    def _push(self):
+        h = self._solver._h
+        if self._orientation_dirty:
+            o = np.ascontiguousarray(self._orientation)
+            check(lib().gopf_solver_sdd_set_orientation(h, o.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.c_int64(o.shape[0])))
+            self._orientation_dirty = False
+        for k in self._KEYS:
+            check(lib().gopf_solver_sdd_set(h, _s(k), ctypes.c_double(getattr(self, k))))
+        check(lib().gopf_solver_sdd_set(h, b"TimeConstants.Orientation", ctypes.c_double(self.TimeConstants.Orientation)))
+        check(lib().gopf_solver_sdd_set(h, b"TimeConstants.DimerLength", ctypes.c_double(self.TimeConstants.DimerLength)))
+        check(lib().gopf_solver_sdd_set(h, b"CurrentStep", ctypes.c_double(self.CurrentStep)))
+
+    def _pull(self):
+        h = self._solver._h
+        v = ctypes.c_double(0.0)
+
+        def get(key):
+            check(lib().gopf_solver_sdd_get(h, _s(key), ctypes.byref(v)))
+            return v.value
+
+        self.CurrentStep = int(get("CurrentStep"))
+        for k in ("MaxForce", "ForcePowerSpectrum", "MaxTorque", "FieldNorm", "FieldNormChange"):
+            setattr(self.Monitor, k, get("Monitor." + k))
+        if self._initialized:
+            out = np.empty_like(self._orientation)
+            check(lib().gopf_solver_sdd_get_orientation(h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+            self._orientation = out
+
+
+def NewSDD(domainSize, model: "Model") -> SDD:
+    return SDD(domainSize, model)
+
+
 class Solver:
     """pf.Solver (pf/solver.go:29-134) over ``gopf_solver``."""
 
@@ -616,7 +725,7 @@ class Solver:
 
     @Stepper.setter
     def Stepper(self, st):
-        if isinstance(st, ImplicitEuler):
+        if isinstance(st, (ImplicitEuler, SDD)):
             st._attach(self)
         self._stepper = st
 
@@ -644,7 +753,11 @@ class Solver:
 
     def Propagate(self, nsteps: int):
         """Solver.Propagate on the host Field.Data arrays (upload, steps, download)."""
+        if isinstance(self._stepper, SDD):
+            self._stepper._push()
         check(lib().gopf_solver_propagate(self._h, int(nsteps)))
+        if isinstance(self._stepper, SDD):
+            self._stepper._pull()
 
     def Solve(self, nepochs: int, nsteps: int):
         for i in range(nepochs):
@@ -659,7 +772,11 @@ class Solver:
         check(lib().gopf_solver_upload(self._h))
 
     def StepDevice(self, nsteps: int):
+        if isinstance(self._stepper, SDD):
+            self._stepper._push()
         check(lib().gopf_solver_step(self._h, int(nsteps)))
+        if isinstance(self._stepper, SDD):
+            self._stepper._pull()
 
     def Download(self):
         check(lib().gopf_solver_download(self._h))

@@ -223,6 +223,21 @@ int gopf_solver_kernel_launches(gopf_solver* s, int64_t* n, int reset);
 int gopf_solver_get_spectrum(gopf_solver* s, int index, double* host_c128);
 /* VolumeConservingLP.Multiplier of the slot-th registered term */
 int gopf_solver_lp_multiplier(gopf_solver* s, int slot, double* value);
+/* pf.SDD, the shrinking-dimer saddle-point stepper (pf/sdd.go:86-470), selected with
+ * gopf_solver_set_stepper(s, "sdd") (the reference assigns solver.Stepper = &sdd; selecting it is
+ * NewSDD: Alpha 0.5, time constants 1, orientation zeros, not initialised).
+ * sdd_set_orientation = SDD.SetInitialOrientation (:413-427): n_fields * n_nodes reals, normalised,
+ * their length becomes InitDimerLength; SDD.Init(init, final) (:390-408) is the same call with
+ * real(final - init).  sdd_set / sdd_get address the struct's exported fields by their Go names:
+ * "Alpha", "Dt" (must be set: a step with Dt < 1e-16 fails like the reference's panic),
+ * "TimeConstants.Orientation", "TimeConstants.DimerLength", "MinDimerLength", "InitDimerLength",
+ * "CurrentStep"; sdd_get also "DimerLength" (at GetTime()) and the SDDMonitor fields
+ * "Monitor.MaxForce", "Monitor.ForcePowerSpectrum", "Monitor.MaxTorque", "Monitor.FieldNorm",
+ * "Monitor.FieldNormChange" (:25-53).  A modal filter is refused (:431-433). */
+int gopf_solver_sdd_set_orientation(gopf_solver* s, const double* orientation, int64_t len);
+int gopf_solver_sdd_get_orientation(gopf_solver* s, double* host_out);
+int gopf_solver_sdd_set(gopf_solver* s, const char* key, double value);
+int gopf_solver_sdd_get(gopf_solver* s, const char* key, double* value);
 /* ChargeTransport.Current(density, N, realspace) (pf/chargeTransport.go:121-146) for the term
  * registered as `name`, evaluated on the device-resident spectrum of its field:
  * host_out[d * N + i] = -real(current_d[i]), d < rank */
