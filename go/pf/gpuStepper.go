@@ -321,6 +321,26 @@ func (st *GPUStepper) PullSDD(sdd *SDD) {
 	}
 }
 
+// SaveUint8 is Uint8IO.SaveFields for field i (pf/fileIO.go:29-44) from the device-resident state:
+// min / max reduction and the 0..255 scaling run on the device, n bytes cross PCIe.
+func (st *GPUStepper) SaveUint8(i int, n int, fname string) {
+	buf := make([]byte, n)
+	gpuCheck(C.gopf_solver_download_uint8(st.solver, C.int(i), (*C.uint8_t)(unsafe.Pointer(&buf[0])), nil, nil))
+	if err := os.WriteFile(fname, buf, 0644); err != nil {
+		panic(err)
+	}
+}
+
+// TermEnergy is IdealMixtureTerm.GetEnergy / PairCorrlationTerm.GetEnergy
+// (pf/pairCorrelationTerm.go:58-84, 185-193) of the term registered as name, on the device state.
+func (st *GPUStepper) TermEnergy(name string) float64 {
+	cn := cstr(name)
+	defer C.free(unsafe.Pointer(cn))
+	var e C.double
+	gpuCheck(C.gopf_solver_term_energy(st.solver, cn, &e))
+	return float64(e)
+}
+
 // ChargeCurrent is ChargeTransport.Current (pf/chargeTransport.go:121-146) for the term registered
 // as name, evaluated on the device-resident state: res[d][i] = -real(current_d[i]).
 func (st *GPUStepper) ChargeCurrent(name string, dim int, n int) [][]float64 {

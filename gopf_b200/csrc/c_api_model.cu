@@ -132,6 +132,8 @@ int gopf_model_register_ideal_mixture(gopf_model* m, const char* name, const cha
     u.field = need(field, "field");
     u.prefactor = prefactor;
     u.laplacian = laplacian != 0;
+    u.c3 = c3;
+    u.c4 = c4;
     m->m.register_user_term(u);
     if (register_derived) {
         // IdealMixtureTerm.DerivedField (pairCorrelationTerm.go:144-156): 3*c3'*v*v + 4*c4'*v*v*v,
@@ -636,6 +638,20 @@ int gopf_solver_sdd_get(gopf_solver* s, const char* key, double* value) {
     GOPF_API_BEGIN
     if (!s || !value) throw Error("NULL argument");
     *value = s->s->sdd_get(need(key, "key"));
+    GOPF_API_END
+}
+
+int gopf_solver_term_energy(gopf_solver* s, const char* name, double* energy) {
+    GOPF_API_BEGIN
+    if (!s || !energy) throw Error("NULL argument");
+    *energy = s->s->term_energy(need(name, "name"));
+    GOPF_API_END
+}
+
+int gopf_solver_download_uint8(gopf_solver* s, int field_index, uint8_t* host_out, double* min_real, double* max_real) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->download_uint8(field_index, host_out, min_real, max_real);
     GOPF_API_END
 }
 

@@ -41,6 +41,7 @@ struct UserTerm {
     std::string field;       // PairCorrelation.Field / IdealMixture.Field / VolumeLP.Field / SquaredGradient.Field
     std::string indicator;   // VolumeConservingLP.Indicator
     double prefactor = 1.0;  // Prefactor / Factor
+    double c3 = 0.0, c4 = 0.0;  // IdealMixtureTerm.IdealMix (pfc/ideal.go:20-23)
     bool laplacian = false;
     SpectralViscParams sv{};
     PairCorrParams pc{};

@@ -105,6 +105,10 @@ public:
     // ChargeTransport.Current (chargeTransport.go:121-146) of the term registered as `name`:
     // host_out[d*N + i] = -real(current_d[i]) from the device-resident spectrum
     void charge_current(const std::string& name, double* host_out);
+    // IdealMixtureTerm.GetEnergy / PairCorrlationTerm.GetEnergy (pairCorrelationTerm.go:58-84, 185-193)
+    double term_energy(const std::string& name);
+    // Uint8IO.SaveFields payload (fileIO.go:29-44, util.go:108-117) + pfutil.MinReal / MaxReal
+    void download_uint8(int field, unsigned char* host_out, double* mn, double* mx);
     void set_newton_krylov(const NewtonKrylovOptions& o) { nk_ = o; }
     bool last_step_converged() const { return ie_converged_; }
     long long residual_evaluations() const { return ie_residual_evals_; }
@@ -146,6 +150,8 @@ private:
     // ChargeTransport (catalog_terms.cu): conductivity tables per term slot, one current component
     double* ct_sigma_[GOPF_MAX_SPECIAL] = {nullptr, nullptr};
     cplx* ct_tmp_ = nullptr;
+    double* obs_partial_ = nullptr;
+    void observe(const cplx* a, const cplx* b, int mode, const double* q, double* sum, double* mn, double* mx);
     DevKProgram prog_;
     DevKProgram fused_prog_;
     bool prog_dirty_ = true;

@@ -147,6 +147,15 @@ class ReciprocalSpacePairCorrelation:
         self.EffTemp, self.Peaks = EffTemp, Peaks
 
 
+def _term_energy(term) -> float:
+    m = getattr(term, "_model", None)
+    if m is None or not m._solvers:
+        raise GopfError("GetEnergy: the term is not registered with a model that has a solver")
+    e = ctypes.c_double(0.0)
+    check(lib().gopf_solver_term_energy(m._solvers[-1]._h, _s(term._name), ctypes.byref(e)))
+    return e.value
+
+
 class PairCorrlationTerm:
     """pf.PairCorrlationTerm (pf/pairCorrelationTerm.go:22-51), implicit."""
 
@@ -166,6 +175,12 @@ class PairCorrlationTerm:
             1 if self.Laplacian else 0, ctypes.c_double(self.PairCorrFunc.EffTemp), len(pk),
             dbl([p.PlaneDensity for p in pk]), dbl([p.Location for p in pk]), dbl([p.Width for p in pk]),
             int_array([p.NumPlanes for p in pk])))
+        self._model, self._name = m, name
+
+    def GetEnergy(self, bricks=None, ft=None, domainSize=None) -> float:
+        """PairCorrlationTerm.GetEnergy (pf/pairCorrelationTerm.go:58-84) on the device-resident state
+        of the model's solver; the arguments are accepted for signature parity."""
+        return _term_energy(self)
 
 
 class ExplicitPairCorrelationTerm(PairCorrlationTerm):
@@ -203,6 +218,11 @@ class IdealMixtureTerm:
         check(lib().gopf_model_register_ideal_mixture(
             m._h, _s(name), _s(self.Field), ctypes.c_double(self.IdealMix.C3), ctypes.c_double(self.IdealMix.C4),
             ctypes.c_double(self.Prefactor), 1 if self.Laplacian else 0, 1 if with_derived else 0))
+        self._model, self._name = m, name
+
+    def GetEnergy(self, bricks=None, nodes=None) -> float:
+        """IdealMixtureTerm.GetEnergy (pf/pairCorrelationTerm.go:185-193) on the device-resident state."""
+        return _term_energy(self)
 
 
 class WhiteNoise:
@@ -413,6 +433,7 @@ class Model:
         self.Equations: List[str] = []
         self._solvers = []
         self._sources: List["Source"] = []  # keeps the ctypes callbacks alive
+        self.ImplicitTerms, self.ExplicitTerms, self.MixedTerms = {}, {}, {}  # model.go:120-123
 
     def AddField(self, f: Field):
         check(lib().gopf_model_add_field(self._h, _s(f.Name), ctypes.c_int64(f.Data.shape[0]),
@@ -473,15 +494,18 @@ class Model:
 
     def RegisterImplicitTerm(self, name: str, t, dFields=None):
         t._register(self, name, "implicit")
+        self.ImplicitTerms[name] = t
 
     def RegisterExplicitTerm(self, name: str, t, dFields=None):
         if isinstance(t, ConservativeNoise):
             t._register(self, name, "explicit", self._wants_derived(dFields, "cons_noise_derived"))
         else:
             t._register(self, name, "explicit")
+        self.ExplicitTerms[name] = t
 
     def RegisterMixedTerm(self, name: str, t, dFields=None):
         t._register(self, name, "mixed", self._wants_derived(dFields, "ideal_mixture_derived"))
+        self.MixedTerms[name] = t
 
     def Init(self):
         check(lib().gopf_model_init(self._h))
@@ -789,6 +813,16 @@ class Solver:
                                               1 if big_endian else 0))
         return out.view(">f8") if big_endian else out
 
+    def DownloadUint8(self, field_index: int):
+        """(uint8 array, min, max): RealPartAsUint8 of one field from the device-resident state with
+        pfutil.MinReal / MaxReal (pf/util.go:108-117, pf/fileIO.go:31-34), 1 byte per cell over PCIe."""
+        n = self.Model.Fields[field_index].Data.shape[0]
+        out = np.empty(n, dtype=np.uint8)
+        mn, mx = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        check(lib().gopf_solver_download_uint8(self._h, int(field_index), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                               ctypes.byref(mn), ctypes.byref(mx)))
+        return out, mn.value, mx.value
+
     def SolveOnDevice(self, nepochs: int, nsteps: int):
         """Solver.Solve with the state resident on the device between epochs: one upload, callbacks
         after every epoch (they read what they need through DownloadReal / Download; host Field.Data
@@ -882,6 +916,35 @@ class Float64IO:
                 s.DownloadReal(i, big_endian=True).tofile(fname)  # bytes are already big-endian
             else:
                 np.ascontiguousarray(f.Data.real).astype(">f8").tofile(fname)
+
+
+def RealPartAsUint8(data: np.ndarray, mn: float, mx: float) -> np.ndarray:
+    """pf.RealPartAsUint8 (pf/util.go:108-117) on a host array."""
+    if abs(mx - mn) < 1e-10:
+        mx = mn + 1.0
+    return ((255.0 * (np.asarray(data).real - mn)) / (mx - mn)).astype(np.uint8)
+
+
+class Uint8IO:
+    """pf.Uint8IO (pf/fileIO.go:15-44): every field's real part scaled to 0..255, one file per field and
+    epoch, named <prefix>_<field>_<epoch>.bin.  ``from_device`` = True quantises on the device
+    (Solver.SolveOnDevice callbacks); False uses host Field.Data."""
+
+    def __init__(self, prefix: str, from_device: bool = False):
+        self.Prefix, self.from_device = prefix, from_device
+
+    def SaveFields(self, s: "Solver", epoch: int):
+        for i, f in enumerate(s.Model.Fields):
+            fname = f"{self.Prefix}_{f.Name}_{epoch}.bin"
+            if self.from_device:
+                s.DownloadUint8(i)[0].tofile(fname)
+            else:
+                re = f.Data.real
+                RealPartAsUint8(f.Data, float(re.min()), float(re.max())).tofile(fname)
+
+
+def NewUint8IO(prefix: str, from_device: bool = False) -> Uint8IO:
+    return Uint8IO(prefix, from_device)
 
 
 def NewFloat64IO(prefix: str, from_device: bool = False) -> Float64IO:

@@ -247,6 +247,15 @@ int gopf_solver_charge_current(gopf_solver* s, const char* name, double* host_ou
  * pf/fileIO.go:57-62, 85-95) for epoch callbacks of device-resident runs, at half the D2H bytes of
  * gopf_solver_download.  The swap to big endian runs on the device. */
 int gopf_solver_download_real(gopf_solver* s, int field_index, double* host_out, int big_endian);
+/* Uint8IO.SaveFields payload of one field (pf/fileIO.go:29-44): pfutil.MinReal / MaxReal of the
+ * device-resident field (returned in min_real / max_real, either may be NULL) and RealPartAsUint8
+ * (pf/util.go:108-117), uint8(255 * (re - min) / (max - min)), N bytes -- 1/16 of the D2H bytes of
+ * gopf_solver_download.  This is the epoch callback of examples/cahnHilliard (config 1). */
+int gopf_solver_download_uint8(gopf_solver* s, int field_index, uint8_t* host_out, double* min_real, double* max_real);
+/* IdealMixtureTerm.GetEnergy (pf/pairCorrelationTerm.go:185-193) or PairCorrlationTerm.GetEnergy
+ * (:58-84) of the term registered as `name`, evaluated on the device-resident state (the energy
+ * observer of examples/pfcPhases, config 5) */
+int gopf_solver_term_energy(gopf_solver* s, const char* name, double* energy);
 /* per-kernel CUDA-event timing over the following gopf_solver_step calls */
 int gopf_solver_profile_begin(gopf_solver* s);
 int gopf_solver_profile_end(gopf_solver* s, int* n_kernels);

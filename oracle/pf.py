@@ -656,6 +656,20 @@ def is_implicit(t, bricks, N: int, freq) -> bool:
 # ==========================================================================
 # pf/util.go:120-132 modal filter
 # ==========================================================================
+def RealPartAsUint8(data: np.ndarray, mn: float, mx: float) -> np.ndarray:
+    """pf/util.go:108-117: the real part scaled such that min -> 0 and max -> 255, truncated."""
+    if abs(mx - mn) < 1e-10:
+        mx = mn + 1.0
+    return ((255.0 * (np.asarray(data).real - mn)) / (mx - mn)).astype(np.uint8)
+
+
+def uint8_payload(data: np.ndarray) -> np.ndarray:
+    """Uint8IO.SaveFields for one field (pf/fileIO.go:31-34): pfutil.MinReal / MaxReal
+    (pfutil/sliceOperations.go:60-81), then RealPartAsUint8."""
+    re_ = np.asarray(data).real
+    return RealPartAsUint8(data, float(re_.min()), float(re_.max()))
+
+
 def apply_modal_filter(filt, freq, data: np.ndarray):
     f = as_frequency(freq).table(data.shape[0])
     f_rad = np.sqrt(np.sum(f * f, axis=1))  # sqrt(pfutil.Dot(f, f))
