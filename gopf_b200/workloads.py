@@ -153,3 +153,106 @@ def build_pfc(pf, terms, dims, *, noise=None, filt_order=5, pinned: bool = False
     if filt_order is not None:
         solver.Stepper.SetFilter(terms.NewVandeven(filt_order))
     return m, f, solver
+
+
+# ---- examples/electricConductivity/main.go:60-160: charge relaxation in a polycrystal -------------
+CHARGE_DT = 0.1                     # main.go:93
+CHARGE_EXTERNAL_FIELD = [1.0, 0.0]  # main.go:134
+CHARGE_REF_CONDUCTIVITY = (1.0, 3.0)  # main.go:119: diag(1, 3) rotated per grain
+
+
+def charge_conductivity(dims) -> np.ndarray:
+    """(N, 3) Voigt conductivity [s_xx, s_yy, s_xy] of a 2-D polycrystal: vertical stripes of grains,
+    grain g rotated by g*pi/9 (main.go:122-125), smooth blend at the boundaries (the example blurs
+    the grain indicator fields, main.go:62-84)."""
+    import math
+    n0, n1 = dims
+    idx = np.arange(n0 * n1)
+    c = idx % n1
+    n_grains = 4
+    pos = c / float(n1) * n_grains
+    g0 = np.floor(pos).astype(int) % n_grains
+    g1 = (g0 + 1) % n_grains
+    w = np.clip((pos - np.floor(pos) - 0.8) / 0.2, 0.0, 1.0)  # blend over the last fifth of a grain
+    out = np.zeros((n0 * n1, 3))
+    s1, s2 = CHARGE_REF_CONDUCTIVITY
+    for g, weight in ((g0, 1.0 - w), (g1, w)):
+        ang = g * math.pi / 9.0
+        ca, sa = np.cos(ang), np.sin(ang)
+        out[:, 0] += weight * (s1 * ca * ca + s2 * sa * sa)
+        out[:, 1] += weight * (s1 * sa * sa + s2 * ca * ca)
+        out[:, 2] += weight * ((s1 - s2) * ca * sa)
+    return out
+
+
+def build_charge(pf, terms, dims, ft=None):
+    """density field with d rho/dt = MINUS_DIV_CURRENT (main.go:131-140).  ``ft`` is the
+    FourierTransform the reference's struct carries (needed by the oracle, unused on the device).
+    Returns (model, density, term, solver)."""
+    from . import synthetic
+    n = int(np.prod(dims))
+    sigma = charge_conductivity(dims)
+    m = pf.NewModel()
+    init = (0.05 * (2.0 * synthetic.splitmix64_uniform(3, n) - 1.0)).astype(np.complex128)
+    f = pf.NewField("density", n, init)
+    m.AddField(f)
+    term = terms.ChargeTransport(lambda i: sigma[i], CHARGE_EXTERNAL_FIELD, "density", ft)
+    m.RegisterExplicitTerm("MINUS_DIV_CURRENT", term, None)
+    m.AddEquation("ddensity/dt = MINUS_DIV_CURRENT")
+    return m, f, term, pf.NewSolver(m, dims, CHARGE_DT)
+
+
+# ---- diffusion with two time-dependent point sources (pf/sourceTerm.go, pf/model.go:151-154) ------
+def build_sourced_diffusion(pf, terms, dims):
+    import math
+    from . import synthetic
+    n = int(np.prod(dims))
+    rank = len(dims)
+    m = pf.NewModel()
+    f = pf.NewField("conc", n, (0.05 * (2.0 * synthetic.splitmix64_uniform(5, n) - 1.0)).astype(np.complex128))
+    m.AddField(f)
+    m.AddScalar(pf.NewScalar("D", 0.8))
+    m.AddEquation("dconc/dt = D*LAP conc - conc^3")
+    m.AddSource(0, terms.NewSource([3.0, 5.0, 2.0][:rank], lambda t: 2.0 * t + 0.5))
+    m.AddSource(0, terms.NewSource([10.5, 1.25, 7.0][:rank], lambda t: math.cos(3.0 * t)))
+    return m, f, pf.NewSolver(m, dims, 0.05)
+
+
+# ---- pf/sdd_test.go:163-246 (TestClassicalNucleation): critical nucleus by shrinking dimer ---------
+SDD_GAMMA, SDD_RHO, SDD_DT = 0.5, 0.05, 0.7
+
+
+def _disc(n: int, radius: int) -> np.ndarray:
+    """-1 outside / +1 inside a centred disc, blurred by the 5 x 5 periodic box (insertCircleAtCenter +
+    pfutil.Blur with BoxKernel{Width: 2}, sdd_test.go:151-161, 199-205)."""
+    i = np.arange(n * n)
+    dx, dy = i // n - n // 2, i % n - n // 2
+    v = np.where(dx * dx + dy * dy <= radius * radius, 1.0, -1.0).reshape(n, n)
+    acc = np.zeros_like(v)
+    for dr in range(-2, 3):
+        for dc in range(-2, 3):
+            acc += np.roll(np.roll(v, dr, axis=0), dc, axis=1)
+    return (acc / 25.0).reshape(-1)
+
+
+def build_sdd_nucleation(pf, new_sdd, n: int, *, expressions: bool):
+    """Returns (model, phi, sdd, solver) with the stepper assigned, as the reference test does."""
+    rho = SDD_RHO
+    phi = pf.NewField("phi", n * n, _disc(n, 12).astype(np.complex128))
+    m = pf.NewModel()
+    m.AddField(phi)
+    m.AddScalar(pf.NewScalar("gamma", SDD_GAMMA))
+    if expressions:
+        m.RegisterFunction("MINUS_CHEM_POT", f"(1.0 - phi*phi)*(phi + {3.0 * rho / 4.0!r})")
+    else:
+        m.RegisterFunction("MINUS_CHEM_POT", lambda i, b: (1.0 - b["phi"].Get(i) ** 2) * (b["phi"].Get(i) + 3.0 * rho / 4.0))
+    m.AddEquation("dphi/dt = MINUS_CHEM_POT + gamma*LAP phi")
+    sdd = new_sdd([n, n], m)
+    sdd.InitDimerLength = 1.0
+    sdd.MinDimerLength = 5e-6
+    sdd.Dt = SDD_DT
+    sdd.Init([pf.NewField("a", n * n, _disc(n, 10).astype(np.complex128))],
+             [pf.NewField("b", n * n, _disc(n, 15).astype(np.complex128))])
+    solver = pf.NewSolver(m, [n, n], SDD_DT)
+    solver.Stepper = sdd
+    return m, phi, sdd, solver

@@ -17,6 +17,7 @@ from gopf_b200 import synthetic, workloads  # noqa: E402  (inputs only: seeded s
 from oracle import elasticity as oel  # noqa: E402
 from oracle import pf as opf  # noqa: E402
 from oracle import pfutil as opfutil  # noqa: E402
+from oracle import sdd as osdd  # noqa: E402
 from oracle import terms as oterms  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -90,6 +91,28 @@ def main():
         for j in range(i, 3):
             tot += (1.0 if i == j else 2.0) * A[i, j] * oel.Strain(disp, f3, i, j)
     np.savez_compressed(os.path.join(OUT, "khachaturyan_8.npz"), indicator_hat=H, contracted_strain_hat=tot, freq3=f3)
+    # ChargeTransport, point sources, SDD, the epoch observers
+    dims = [32, 32]
+    m, f, term, s = workloads.build_charge(opf, oterms, dims, opfutil.NewFFTW(dims))
+    s.Solve(2, 3)
+    cur = term.Current(f, 32 * 32, True)
+    np.savez_compressed(os.path.join(OUT, "charge_transport_32x32.npz"), density=f.Data, current=np.stack(cur))
+    for dims in ([16, 32], [16, 16, 16]):
+        m, f, s = workloads.build_sourced_diffusion(opf, oterms, dims)
+        s.Solve(2, 5)
+        np.savez_compressed(os.path.join(OUT, f"sources_{'x'.join(map(str, dims))}.npz"), conc=f.Data)
+    m, phi, sdd, s = workloads.build_sdd_nucleation(opf, osdd.NewSDD, 64, expressions=False)
+    s.Solve(1, 60)
+    np.savez_compressed(os.path.join(OUT, "sdd_nucleation_64x64.npz"), phi=phi.Data, orientation=sdd.orientation,
+                        monitor=np.array([sdd.Monitor.MaxForce, sdd.Monitor.ForcePowerSpectrum, sdd.Monitor.MaxTorque,
+                                          sdd.Monitor.FieldNorm, sdd.Monitor.FieldNormChange]))
+    # Uint8IO payload of the 2-D Cahn-Hilliard field after 10 steps and the pfcPhases energy observer
+    traj = ch([32, 32], [10])
+    m, f, s = workloads.build_pfc(opf, oterms, [32, 32], noise=None, filt_order=None)
+    s.Solve(1, 5)
+    np.savez_compressed(os.path.join(OUT, "observers.npz"), ch_uint8=opf.uint8_payload(traj["after_10"]),
+                        pfc_energy=np.array([m.MixedTerms["IDEAL"].GetEnergy(m.Bricks, 1024),
+                                             m.ImplicitTerms["EXCESS"].GetEnergy(m.Bricks, s.FT, [32, 32])]))
     print("golden vectors written to", OUT)
 
 

@@ -76,3 +76,54 @@ def test_pfc():
     m, f, s = workloads.build_pfc(gpf, gpf, [32, 32], noise=None, filt_order=5)
     s.Solve(2, 5)
     assert rel_l2(f.Data, g["density"]) <= TOL
+
+
+# ---- ChargeTransport, point sources, SDD, epoch observers ---------------------
+def test_charge_transport():
+    g = load("charge_transport_32x32.npz")
+    m, f, term, s = workloads.build_charge(gpf, gpf, [32, 32])
+    s.Solve(2, 3)
+    assert rel_l2(f.Data, g["density"]) <= TOL
+    assert rel_l2(np.stack(term.Current()), g["current"]) <= TOL
+
+
+@pytest.mark.parametrize("dims", [[16, 32], [16, 16, 16]], ids=lambda d: "x".join(map(str, d)))
+def test_point_sources(dims):
+    g = load(f"sources_{'x'.join(map(str, dims))}.npz")
+    m, f, s = workloads.build_sourced_diffusion(gpf, gpf, dims)
+    s.Solve(2, 5)
+    assert rel_l2(f.Data, g["conc"]) <= TOL
+
+
+def test_sdd_nucleation():
+    g = load("sdd_nucleation_64x64.npz")
+    m, phi, sdd, s = workloads.build_sdd_nucleation(gpf, gpf.NewSDD, 64, expressions=True)
+    s.Solve(1, 60)
+    assert rel_l2(phi.Data, g["phi"]) <= TOL
+    assert rel_l2(sdd.orientation, g["orientation"]) <= 1e-7  # conditioning ~ 1 / MinDimerLength
+    mon = np.array([sdd.Monitor.MaxForce, sdd.Monitor.ForcePowerSpectrum, sdd.Monitor.MaxTorque, sdd.Monitor.FieldNorm,
+                    sdd.Monitor.FieldNormChange])
+    assert np.allclose(mon, g["monitor"], rtol=1e-7, atol=1e-9)
+
+
+def test_observers():
+    g = load("observers.npz")
+    n = 32 * 32
+    m = gpf.NewModel()
+    f = gpf.NewField("conc", n, synthetic.cahn_hilliard_initial(n, 0))
+    m.AddScalar(gpf.NewScalar("gamma", synthetic.CAHN_HILLIARD_GAMMA))
+    m.AddScalar(gpf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
+    m.AddField(f)
+    m.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
+    s = gpf.NewSolver(m, [32, 32], synthetic.CAHN_HILLIARD_DT)
+    s.Upload()
+    s.StepDevice(10)
+    got, mn, mx = s.DownloadUint8(0)
+    # the trajectory agrees to 1e-10, so a cell within that of a quantisation boundary may land on
+    # either side: at most one level, on a handful of cells
+    assert np.max(np.abs(got.astype(int) - g["ch_uint8"].astype(int))) <= 1
+    assert np.mean(got != g["ch_uint8"]) < 0.01
+    m, f, s = workloads.build_pfc(gpf, gpf, [32, 32], noise=None, filt_order=None)
+    s.Solve(1, 5)
+    e = np.array([m.MixedTerms["IDEAL"].GetEnergy(), m.ImplicitTerms["EXCESS"].GetEnergy()])
+    assert np.allclose(e, g["pfc_energy"], rtol=1e-10, atol=0.0)
