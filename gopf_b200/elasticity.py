@@ -66,3 +66,24 @@ def KhachaturyanMultiplier(matProp: Rank4, misfit, dim: int, freq3) -> np.ndarra
     out = np.zeros(f.shape[0], dtype=np.float64)
     check(lib().gopf_elasticity_multiplier(_p(matProp.Data), _p(mis), int(dim), _p(f), ctypes.c_int64(f.shape[0]), _p(out)))
     return out
+
+
+def StrainFactor(matProp: Rank4, misfit, freq3, i: int, j: int) -> np.ndarray:
+    """s_ij(k) with eps^_ij = s_ij H^ (csrc/elastic_energy.cu; Displacements + Strain,
+    elasticity/linearElasticity.go:16-83) for an (n, 3) array of padded frequencies, on the host."""
+    f = np.ascontiguousarray(freq3, dtype=np.float64).reshape(-1, 3)
+    mis = np.ascontiguousarray(misfit, dtype=np.float64).reshape(9)
+    out = np.zeros(f.shape[0], dtype=np.float64)
+    check(lib().gopf_elasticity_strain_factor(_p(matProp.Data), _p(mis), _p(f), ctypes.c_int64(f.shape[0]), int(i), int(j), _p(out)))
+    return out
+
+
+def HomogeneousModulusEnergy(indicator, domainSize, misfit, matProp: Rank4, device: int = -1) -> float:
+    """elasticity.HomogeneousModulusEnergy (elasticity/linearElasticity.go:101-165) on the device."""
+    ind = np.ascontiguousarray(indicator, dtype=np.complex128)
+    mis = np.ascontiguousarray(misfit, dtype=np.float64).reshape(9)
+    dims = (ctypes.c_int * len(domainSize))(*[int(v) for v in domainSize])
+    out = ctypes.c_double()
+    check(lib().gopf_elasticity_homogeneous_modulus_energy(len(domainSize), dims, _p(ind.view(np.float64)), _p(mis),
+                                                           _p(matProp.Data), int(device), ctypes.byref(out)))
+    return out.value

@@ -163,6 +163,18 @@ int gopf_elasticity_isotropic(double bulk_mod, double poisson, double* out81);
 int gopf_elasticity_rotate(double* inout81, const double* rot9);
 int gopf_elasticity_contract_last(const double* stiffness81, const double* tensor9, double* out9);
 int gopf_elasticity_energy_density(const double* stiffness81, const double* strain9, double* out);
+/* elasticity.HomogeneousModulusEnergy(indicator, domainSize, misfit, matProp)
+ * (elasticity/linearElasticity.go:101-165) on the device: elastic energy per unit precipitate volume of
+ * the inclusion `indicator_c128` (host, N complex128, not modified; the reference transforms it in place
+ * and back).  device = -1: current device.  Post-processing, not a step kernel. */
+int gopf_elasticity_homogeneous_modulus_energy(int rank, const int* n, const double* indicator_c128,
+                                               const double* misfit9, const double* stiffness81, int device,
+                                               double* energy);
+/* the real per-k factor s_ij(k) with eps^_ij = s_ij H^ used by that call (Displacements + Strain,
+ * elasticity/linearElasticity.go:16-83), evaluated on the host for `count` padded frequency vectors
+ * freq3[count][3] by the same __host__ __device__ code */
+int gopf_elasticity_strain_factor(const double* stiffness81, const double* misfit9, const double* freq3, int64_t count,
+                                  int i, int j, double* out);
 /* The real multiplier M(k) the device applies between the transforms of the elastic term
  * (gopf_b200/csrc/elastic.cuh), evaluated on the host for `count` frequency triples
  * [f_row, f_col, f_depth] -- parity tests against elasticity.Displacements + Strain. */

@@ -69,3 +69,27 @@ def test_khachaturyan_multiplier_equals_literal_chain(dims, material):
     M = gel.KhachaturyanMultiplier(cg, misfit, dim, f3)
     assert M[0] == 0.0  # zero mode (linearElasticity.go:43-46)
     assert np.max(np.abs(M * H - total)) <= 1e-13 * np.max(np.abs(total))
+
+
+@pytest.mark.parametrize("dims", [[8, 8, 8], [8, 16]], ids=lambda d: "x".join(map(str, d)))
+def test_strain_factor_matches_literal_displacement_strain_chain(dims):
+    # s_ij(k) H^ (csrc/elastic_energy.cu) against EffectiveForce -> Displacements -> Strain
+    # (elasticity/effectiveForce.go:26-35, linearElasticity.go:16-83) on a random H^, all six
+    # components, force components looped over comp < 3 as HomogeneousModulusEnergy does (:114-119)
+    from gopf_b200 import elasticity as gel
+    f = opfutil.NewFFTW(dims).freq_table()
+    f3 = oel.pad3(f)
+    n = f3.shape[0]
+    C = oel.CubicMaterial(110.0, 60.0, 30.0)
+    mis = np.array([[0.05, 0.01, 0.0], [0.01, -0.01, 0.02], [0.0, 0.02, 0.03]])
+    rng = np.random.default_rng(9)
+    H = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    eff = oel.EffectiveForce(C, mis)
+    force = np.stack([eff.Get(c, f, H) for c in range(3)], axis=1)
+    disp = oel.Displacements(force, f3, C)
+    gC = gel.CubicMaterial(110.0, 60.0, 30.0)
+    for i in range(3):
+        for j in range(i, 3):
+            want = oel.Strain(disp, f3, i, j)
+            got = gel.StrainFactor(gC, mis, f3, i, j) * H
+            assert np.max(np.abs(got - want)) <= 1e-12 * max(1.0, np.max(np.abs(want))), (i, j)

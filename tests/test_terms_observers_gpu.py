@@ -93,3 +93,30 @@ def test_energy_of_other_terms_is_refused():
     assert lib().gopf_solver_term_energy(s._h, b"SG", ctypes.byref(e)) != 0
     assert b"no energy" in lib().gopf_last_error()
     assert lib().gopf_solver_term_energy(s._h, b"NOPE", ctypes.byref(e)) != 0
+
+
+def test_homogeneous_modulus_energy_vs_oracle_and_eshelby():
+    # elasticity/linearElasticity.go:101-165; elasticity/linearElasticity_test.go:11-49 (Eshelby's
+    # dilatational sphere within 5 % on a 64^3 grid)
+    from gopf_b200 import elasticity as gel
+    from oracle import elasticity as oel
+    N = 32
+    mis = np.array([[0.05, 0.01, 0.0], [0.01, -0.01, 0.02], [0.0, 0.02, 0.03]])
+    ind = oel.Ellipsoid(N, 6.0, 4.0, 5.0)
+    want = oel.HomogeneousModulusEnergy(ind, [N, N, N], mis, oel.CubicMaterial(110.0, 60.0, 30.0))
+    got = gel.HomogeneousModulusEnergy(ind, [N, N, N], mis, gel.CubicMaterial(110.0, 60.0, 30.0))
+    assert abs(got - want) <= 1e-10 * abs(want)
+    # 2-D: the function still loops the force over three components and pads the frequencies (:114-132)
+    i = np.arange(N * N)
+    ind2 = ((((i // N) - N // 2) / 7.0) ** 2 + (((i % N) - N // 2) / 4.0) ** 2 <= 1.0).astype(np.complex128)
+    want = oel.HomogeneousModulusEnergy(ind2, [N, N], mis, oel.Isotropic(60.0, 0.3))
+    got = gel.HomogeneousModulusEnergy(ind2, [N, N], mis, gel.Isotropic(60.0, 0.3))
+    assert abs(got - want) <= 1e-10 * abs(want)
+    # the reference's own known answer
+    N = 64
+    poisson, bulk, eps = 0.3, 50.0, 0.05
+    shear = oel.Shear(bulk, poisson)
+    energy = gel.HomogeneousModulusEnergy(oel.Ellipsoid(N, 10.0, 10.0, 10.0), [N, N, N], np.diag([eps, eps, eps]),
+                                          gel.Isotropic(bulk, poisson))
+    expect = oel.EshelbyEnergyDensityDilatational(poisson, shear, eps)
+    assert abs(energy - expect) < 0.05 * expect
