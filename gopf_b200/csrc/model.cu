@@ -70,6 +70,9 @@ void Model::add_equation(const std::string& eq_in) {
 void Model::add_source(int eq_no, const double* pos, int npos, SourceFn f, void* user) {
     if (eq_no < 0 || eq_no >= (int)sources.size())
         throw Error(strf("AddSource: index out of range [%d] with length %d", eq_no, (int)sources.size()));
+    if (attached_solvers > 0)
+        throw Error("AddSource: a solver has already been compiled from this model; add the sources before NewSolver "
+                    "(the reference reads AllSources live, the device program is compiled once)");
     if (!pos || npos < 1 || npos > 3) throw Error("AddSource: Pos must hold 1..3 coordinates");
     if (!f) throw Error("AddSource: the time function is NULL");
     if ((int)sources[eq_no].size() >= GOPF_MAX_SOURCES)

@@ -93,6 +93,7 @@ public:
     std::vector<int> source_spectrum;              // per equation: work spectrum of its sources, -1 if none
     int n_work_spectra = 0;
     bool initialised = false;
+    int attached_solvers = 0;  // solvers compiled from this model (their programs do not follow later edits)
 
     // pf.Model API (model.go:141-162, 322-418)
     void add_field(const std::string& name, size_t n, double* host);

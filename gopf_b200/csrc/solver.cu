@@ -263,9 +263,11 @@ Solver::Solver(Model* m, int rank, const int* n, double dt, int device) : m_(m),
     }
     for (int i = 0; i < GOPF_MAX_SPECTRA; ++i) d_table_[i] = nullptr;
     decide_path();
+    m_->attached_solvers++;
 }
 
 Solver::~Solver() {
+    m_->attached_solvers--;
     cudaSetDevice(plan_->device);
     drop_graph();
     for (int i = 0; i < GOPF_MAX_SPECTRA; ++i)

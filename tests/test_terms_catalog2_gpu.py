@@ -144,3 +144,17 @@ def test_source_position_shorter_than_rank_is_an_error():
     gs = gpf.NewSolver(gm, dims, 0.1)
     with pytest.raises(gpf.GopfError, match="coordinates"):
         gs.Propagate(1)
+
+
+def test_add_source_after_new_solver_is_refused():
+    # the reference reads Model.AllSources live at every GetRHS (pf/model.go:291-294); the device
+    # program is compiled once by NewSolver, so a later AddSource must fail loudly, not be ignored
+    dims = [16, 16]
+    (gm, gf), _ = _source_models(dims, np.zeros(256), [([3.0, 2.0], lambda t: 1.0)])
+    gs = gpf.NewSolver(gm, dims, 0.1)
+    with pytest.raises(gpf.GopfError, match="before NewSolver"):
+        gm.AddSource(0, gpf.NewSource([1.0, 1.0], lambda t: 1.0))
+    gs.Propagate(2)
+    assert np.max(np.abs(gf.Data)) > 0.0
+    gs.close()
+    gm.AddSource(0, gpf.NewSource([1.0, 1.0], lambda t: 1.0))  # no solver attached any more
