@@ -389,7 +389,16 @@ class Source:
     def __init__(self, pos, f: Callable[[float], float]):
         self.Pos = [float(p) for p in pos]
         self.f = f
-        self._cb = _TIME_FN(lambda t, _user: float(f(t)))  # kept alive with the Source
+        self._error: Optional[BaseException] = None
+
+        def call(t, _user):  # an exception cannot cross the C frame: keep it, poison the amplitude
+            try:
+                return float(f(t))
+            except BaseException as e:  # noqa: BLE001 -- re-raised by Solver after the C call returns
+                self._error = e
+                return float("nan")
+
+        self._cb = _TIME_FN(call)  # kept alive with the Source
 
 
 def NewSource(pos, f) -> Source:
@@ -780,6 +789,7 @@ class Solver:
         if isinstance(self._stepper, SDD):
             self._stepper._push()
         check(lib().gopf_solver_propagate(self._h, int(nsteps)))
+        self._reraise_source_errors()
         if isinstance(self._stepper, SDD):
             self._stepper._pull()
 
@@ -791,6 +801,12 @@ class Solver:
             for mon in self.Monitors:
                 mon.Add(self.Model.Bricks)
 
+    def _reraise_source_errors(self):
+        for src in self.Model._sources:
+            if src._error is not None:
+                err, src._error = src._error, None
+                raise GopfError(f"Source time function raised {err!r}") from err
+
     # -- device-resident control
     def Upload(self):
         check(lib().gopf_solver_upload(self._h))
@@ -799,6 +815,7 @@ class Solver:
         if isinstance(self._stepper, SDD):
             self._stepper._push()
         check(lib().gopf_solver_step(self._h, int(nsteps)))
+        self._reraise_source_errors()
         if isinstance(self._stepper, SDD):
             self._stepper._pull()
 

@@ -158,3 +158,15 @@ def test_add_source_after_new_solver_is_refused():
     assert np.max(np.abs(gf.Data)) > 0.0
     gs.close()
     gm.AddSource(0, gpf.NewSource([1.0, 1.0], lambda t: 1.0))  # no solver attached any more
+
+
+def test_exception_in_source_time_function_is_reported():
+    dims = [16, 16]
+
+    def bad(t):
+        raise ValueError("boom")
+
+    (gm, gf), _ = _source_models(dims, np.zeros(256), [([3.0, 2.0], bad)])
+    gs = gpf.NewSolver(gm, dims, 0.1)
+    with pytest.raises(gpf.GopfError, match="boom"):
+        gs.Propagate(1)
