@@ -215,6 +215,8 @@ def run_general_workload(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     solver.SetStream(stream.cuda_stream)
+    # registered functions and the k-space update as NVRTC images (profiles/r1d_jit_notes.md)
+    solver.SetJit(not args.no_jit)
     solver.Upload()
     solver.StepDevice(args.warmup)
     torch.cuda.synchronize()
@@ -269,7 +271,7 @@ def run_general_workload(args):
             "data": "synthetic",
             "config": {"workload": W["name"].format(G=G), "grid": dims, "stepper": "euler",
                        "cache": f"arrays of {16 * n / 2**20:.0f} MiB each exceed the 126 MB L2 (no flush needed)",
-                       "path": "general multi-field path"},
+                       "path": "general multi-field path", "specialised_kernels": solver.JitKernels()},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
     if not args.no_cpu_baseline:
         # oracle on a bounded sample: the same model at 64^3 (cells/s is size-normalised), single thread
@@ -450,6 +452,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scaling-base", dest="scaling_base", action="store_false",
                     help="N = 1: skip the extra 1024^3 single-GPU measurement (strong-scaling base of the sharded arm)")
+    ap.add_argument("--no-jit", action="store_true",
+                    help="general workloads: interpreter kernels instead of the NVRTC-specialised ones")
     ap.add_argument("--workload", default="ch", choices=["ch", "precipitate", "pfc"],
                     help="ch: Cahn-Hilliard (BASELINE.json configs 1-3, the metric's workload); precipitate: cfg 4; pfc: cfg 5")
     ap.add_argument("--exchange", default="peer", choices=["peer", "dma", "nccl"],

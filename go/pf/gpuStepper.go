@@ -356,6 +356,24 @@ func (st *GPUStepper) ChargeCurrent(name string, dim int, n int) [][]float64 {
 }
 
 // GetTime returns the current time (pf.TimeStepper)
+// SetJit switches the run-time specialisation on or off: registered functions and the k-space
+// update are then compiled for this model by NVRTC at the next step instead of being interpreted.
+// Default: the GOPF_JIT environment variable.
+func (st *GPUStepper) SetJit(on bool) {
+	v := C.int(0)
+	if on {
+		v = 1
+	}
+	gpuCheck(C.gopf_solver_set_jit(st.solver, v))
+}
+
+// JitKernels returns how many kernels currently run as compiled images (0: interpreter kernels).
+func (st *GPUStepper) JitKernels() int {
+	var n C.int
+	gpuCheck(C.gopf_solver_jit_kernels(st.solver, &n))
+	return int(n)
+}
+
 func (st *GPUStepper) GetTime() float64 {
 	var t C.double
 	gpuCheck(C.gopf_solver_get_time(st.solver, &t))

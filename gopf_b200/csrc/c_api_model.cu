@@ -63,6 +63,86 @@ int gopf_model_register_function(gopf_model* m, const char* name, const char* ex
     GOPF_API_END
 }
 
+static const DevDerived& registered_function(gopf_model* m, const char* name) {
+    if (!m) throw Error("model is NULL");
+    const std::string n = need(name, "name");
+    for (const DerivedSpec& d : m->m.derived)
+        if (d.name == n) {
+            if (d.dev.kind != DK_RPN) throw Error("'" + n + "' is not a registered function");
+            return d.dev;
+        }
+    throw Error("no derived field named '" + n + "'");
+}
+
+int gopf_model_function_source(gopf_model* m, const char* name, int kernel, char* buf, int64_t len, int64_t* needed) {
+    GOPF_API_BEGIN
+    const DevDerived& D = registered_function(m, name);
+    const std::string src = kernel ? jit::derived_kernel_source(D, nullptr) : jit::expression_source(D, nullptr);
+    if (needed) *needed = (int64_t)src.size() + 1;
+    if (buf) {
+        if (len < (int64_t)src.size() + 1) throw Error("gopf_model_function_source: buffer too small");
+        std::memcpy(buf, src.c_str(), src.size() + 1);
+    }
+    GOPF_API_END
+}
+
+int gopf_model_function_compile(gopf_model* m, const char* name, int64_t* cubin_bytes) {
+    GOPF_API_BEGIN
+    const DevDerived& D = registered_function(m, name);
+    std::vector<char> cubin;
+    std::string log;
+    if (!jit::compile_cubin(jit::derived_kernel_source(D, nullptr), &cubin, &log)) throw Error("jit: " + log);
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    GOPF_API_END
+}
+
+static std::string kupdate_source_of(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, int with_filter,
+                                    long long* nodes) {
+    if (!m || !n) throw Error("NULL argument");
+    if (rank != 2 && rank != 3) throw Error("rank must be 2 or 3");
+    m->m.init();
+    DevKProgram P;
+    m->m.fill_program(&P, dt, rank);
+    // stand-in addresses (the image is inspected, never launched): non-NULL where the solver would set one
+    if (with_filter) {
+        P.filter = reinterpret_cast<const double*>(uintptr_t(0x7f0000000000ull));
+        P.filter_n = 1000;
+    }
+    for (int i = 0; i < GOPF_MAX_SPECIAL; ++i) P.lp_multiplier[i] = reinterpret_cast<const double*>(uintptr_t(0x7f0000100000ull) + 24u * i);
+    FreqGeom fg;
+    fg.rank = rank;
+    fg.d0 = n[0];
+    fg.d1 = n[1];
+    fg.d2 = rank > 2 ? n[2] : 1;
+    long long N = 1;
+    for (int i = 0; i < rank; ++i) N *= n[i];
+    if (nodes) *nodes = N;
+    return jit::kupdate_kernel_source(P, fg, N, tab_mask);
+}
+
+int gopf_model_kupdate_source(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, int with_filter,
+                              char* buf, int64_t len, int64_t* needed) {
+    GOPF_API_BEGIN
+    const std::string src = kupdate_source_of(m, rank, n, dt, tab_mask, with_filter, nullptr);
+    if (needed) *needed = (int64_t)src.size() + 1;
+    if (buf) {
+        if (len < (int64_t)src.size() + 1) throw Error("gopf_model_kupdate_source: buffer too small");
+        std::memcpy(buf, src.c_str(), src.size() + 1);
+    }
+    GOPF_API_END
+}
+
+int gopf_model_kupdate_compile(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, int with_filter,
+                               int64_t* cubin_bytes) {
+    GOPF_API_BEGIN
+    std::vector<char> cubin;
+    std::string log;
+    if (!jit::compile_cubin(kupdate_source_of(m, rank, n, dt, tab_mask, with_filter, nullptr), &cubin, &log))
+        throw Error("jit: " + log);
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    GOPF_API_END
+}
+
 int gopf_model_register_white_noise(gopf_model* m, const char* name, double strength, uint64_t seed) {
     GOPF_API_BEGIN
     if (!m) throw Error("model is NULL");
@@ -586,6 +666,27 @@ int gopf_solver_force_generic(gopf_solver* s, int on) {
     GOPF_API_BEGIN
     if (!s) throw Error("solver is NULL");
     s->s->force_generic(on != 0);
+    GOPF_API_END
+}
+
+int gopf_solver_set_jit(gopf_solver* s, int on) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->set_jit(on != 0);
+    GOPF_API_END
+}
+
+int gopf_solver_jit_kernels(gopf_solver* s, int* count) {
+    GOPF_API_BEGIN
+    if (!s || !count) throw Error("NULL argument");
+    *count = s->s->jit_kernels();
+    GOPF_API_END
+}
+
+int gopf_solver_jit_log(gopf_solver* s, char* buf, int len) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    copy_name(s->s->jit_log(), buf, len);
     GOPF_API_END
 }
 

@@ -3,8 +3,12 @@
 // so host slices map 1:1 onto device arrays and every global access is a
 // 128-bit LDG/STG.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#else
+typedef unsigned int uint32_t;  // NVRTC has no <stdint.h>
+#endif
 
 namespace gopf {
 

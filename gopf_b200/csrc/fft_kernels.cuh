@@ -8,6 +8,7 @@
 //   B = product of faster extents (inner stride), A = product of slower extents.
 #pragma once
 #include "fft_engine.cuh"
+#include "kupdate.cuh"
 #include "step_program.h"
 
 namespace gopf {
@@ -100,28 +101,6 @@ inline PassGeom make_geom(int n0, int n1, int n2, int axis) {
     g.bcount = g.B;
     g.pf_tiles = 0;
     return g;
-}
-
-// Reference k-table geometry.  Freq() decomposes the node number with
-// Dimensions[1] / Dimensions[0] (pfutil/fftWrap.go:42-54), which matches the FFTW
-// row-major layout for every 2-D shape and for cubic 3-D shapes only.
-struct FreqGeom {
-    int rank;
-    int d0, d1, d2;  // reference Dimensions[0..2] (d2 = 1 for rank 2)
-};
-
-// Literal restatement of FFTWWrapper.Freq for node i (pfutil/fftWrap.go:57-74).
-__host__ __device__ inline void ref_freq(const FreqGeom& g, long long i, double* res) {
-    long long c = i % g.d1;
-    long long r = (i / g.d1) % g.d0;
-    res[1] = (double)c / (double)g.d1;
-    res[0] = (double)r / (double)g.d0;
-    if (g.rank > 2) {
-        long long d = i / ((long long)g.d0 * g.d1);
-        res[2] = (double)d / (double)g.d2;
-    }
-    for (int k = 0; k < g.rank; ++k)
-        if (res[k] > 0.5) res[k] -= 1.0;
 }
 
 struct RealPtrs {

@@ -9,86 +9,9 @@
 namespace gopf {
 
 // ---- small kernels -------------------------------------------------------------------
-// generic pointwise update over every k (any shape, literal Freq from the node number)
-// Freq of node idx with 32-bit index arithmetic when the grid allows it (64-bit divisions cost
-// ~100 instructions each); same IEEE divides as ref_freq, so the result is bit-identical.
-__device__ __forceinline__ void ref_freq_fast(const FreqGeom& g, long long idx, bool small, double* res) {
-    if (!small) {
-        ref_freq(g, idx, res);
-        return;
-    }
-    const unsigned i = (unsigned)idx, d1 = (unsigned)g.d1, d0 = (unsigned)g.d0;
-    const unsigned q = i / d1, c = i - q * d1;
-    const unsigned d = q / d0, r = q - d * d0;
-    res[1] = (double)c / (double)g.d1;
-    res[0] = (double)r / (double)g.d0;
-    if (g.rank > 2) res[2] = (double)d / (double)g.d2;
-    for (int k = 0; k < g.rank; ++k)
-        if (res[k] > 0.5) res[k] -= 1.0;
-}
-
-// ImplicitTab: per field, filter(k) / (1 - dt*den(k)) tabulated once (the implicit side and the
-// modal filter depend on k only; the pair-correlation and viscosity multipliers cost exp / sqrt
-// per k).  NULL entries: evaluate literally.
-struct ImplicitTab {
-    const cplx* t[GOPF_MAX_FIELDS];
-};
-
-// C cells per thread.  Measured at 512^3 (cfg 4): C = 4 is 40 % slower than C = 1 (registers cost
-// more occupancy than the extra loads in flight give back), so the kernel runs C = 1.
-template <int C>
-__device__ __forceinline__ void update_cells(const DevKProgram& P, const SpectraPtrs& sp, const ImplicitTab& tab,
-                                             const FreqGeom& fg, bool small, const long long (&idx)[C]) {
-    KPoint kp[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        double f[3] = {0.0, 0.0, 0.0};
-        ref_freq_fast(fg, idx[c], small, f);
-        kp[c] = make_kpoint(f[0], f[1], f[2]);
-    }
-    for (int i = 0; i < P.n_fields; ++i) {
-        const DevEquation& q = P.eq[i];
-        cplx d[C], rhs[C], den[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            d[c] = sp.s[i][idx[c]];
-            rhs[c] = den[c] = mk(0.0, 0.0);
-        }
-        for (int j = 0; j < q.n_rhs; ++j) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) rhs[c] += eval_term(P, q.rhs[j], kp[c], [&](int b) -> cplx { return sp.s[b][idx[c]]; });
-        }
-        if (tab.t[i]) {
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-                sp.s[i][idx[c]] = mk(d[c].x + P.dt * rhs[c].x, d[c].y + P.dt * rhs[c].y) * tab.t[i][idx[c]];
-        } else {
-            for (int j = 0; j < q.n_den; ++j) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) den[c] += eval_term(P, q.den[j], kp[c], [&](int b) -> cplx { return sp.s[b][idx[c]]; });
-            }
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const cplx num = mk(d[c].x + P.dt * rhs[c].x, d[c].y + P.dt * rhs[c].y);
-                cplx r = cdiv(num, mk(1.0 - P.dt * den[c].x, -P.dt * den[c].y));  // euler.go:33
-                if (P.filter) {
-                    const double sc = filter_eval(P.filter, P.filter_n, kp[c].frad * 2.0 / GOPF_PI);
-                    r = mk(r.x * sc, r.y * sc);
-                }
-                sp.s[i][idx[c]] = r;  // later equations read the updated value (euler.go:27-39)
-            }
-        }
-    }
-}
-
 __global__ void __launch_bounds__(256)
     k_update_generic(const __grid_constant__ DevKProgram P, SpectraPtrs sp, ImplicitTab tab, FreqGeom fg, long long n) {
-    const bool small = n < (1LL << 31);
-    const long long nthreads = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
-        const long long idx[1] = {i};
-        update_cells<1>(P, sp, tab, fg, small, idx);
-    }
+    update_all(P, sp, tab, fg, n);
 }
 
 // filter(k) / (1 - dt * den_i(k)) for every node (euler.go:33, util.go:125-132)
@@ -249,6 +172,7 @@ Solver::Solver(Model* m, int rank, const int* n, double dt, int device) : m_(m),
     if (rank != 2 && rank != 3)
         throw Error(strf("solver: rank must be 2 or 3 (got %d); FFTWWrapper.Freq indexes res[1] (fftWrap.go:61)", rank));
     m_->init();  // NewSolver calls m.Init() (solver.go:42)
+    jit_on_ = jit::enabled();
     plan_.reset(new FftPlan(rank, n, device));
     for (const HostField& f : m_->fields)  // solver.go:55-60
         if (f.n != plan_->N) throw Error("solver: Inconsistent domain size and number of grid points");
@@ -293,6 +217,8 @@ Solver::~Solver() {
     }
     for (int i = 0; i < GOPF_MAX_SPECTRA; ++i)
         if (d_table_[i]) cudaFree(d_table_[i]);
+    for (jit::Kernel* k : jit_derived_) jit::unload(k);
+    jit::unload(jit_kupdate_);
     free_catalog_buffers();
     sdd_free_buffers();
     if (W_) cudaFree(W_);
@@ -678,6 +604,51 @@ void Solver::inverse_to_real(const cplx* spec, cplx* out) {
 
 void Solver::forward_in_place(cplx* data) { plan_->exec_device(data, -1, stream()); }
 
+// A registered function (or noise / table) evaluated at every node into `out`.  Registered
+// functions run as NVRTC-compiled straight-line kernels when the specialisation is on and
+// compiles; otherwise (and for every other kind) the RPN interpreter kernel does the work.
+void Solver::derived_pointwise(int d, cplx* out, unsigned long long step_no, cudaStream_t s) {
+    const DevDerived& dd = m_->derived[d].dev;
+    const long long n = (long long)plan_->N;
+    if (jit_on_ && dd.kind == DK_RPN) {
+        if (jit_derived_.size() != m_->derived.size()) {
+            jit_derived_.assign(m_->derived.size(), nullptr);
+            jit_tried_.assign(m_->derived.size(), 0);
+        }
+        if (!jit_tried_[d]) {
+            jit_tried_[d] = 1;
+            std::string log;
+            std::vector<char> cubin;
+            try {
+                if (jit::compile_cubin(jit::derived_kernel_source(dd, nullptr), &cubin, &log))
+                    jit_derived_[d] = jit::load(cubin, "gopf_jit_derived", &log);
+            } catch (const std::exception& e) {
+                log = e.what();
+            }
+            if (!jit_derived_[d]) jit_log_ += "derived '" + m_->derived[d].name + "': " + log + "\n";
+        }
+        if (jit_derived_[d]) {
+            const cplx* f[GOPF_MAX_FIELDS];
+            for (int i = 0; i < GOPF_MAX_FIELDS; ++i) f[i] = R_.r[i];
+            long long nn = n;
+            void* args[] = {&f[0], &f[1], &f[2], &f[3], &out, &nn};
+            std::string log;
+            if (!jit::launch(jit_derived_[d], grid_for((n + 1) / 2), 256, args, s, &log))
+                throw Error("jit launch of derived '" + m_->derived[d].name + "': " + log);
+            return;
+        }
+    }
+    k_eval_derived<<<grid_for(n), 256, 0, s>>>(dd, R_, out, step_no, n);
+    GOPF_CUDA(cudaGetLastError());
+}
+
+int Solver::jit_kernels() const {
+    int c = jit_kupdate_ ? 1 : 0;
+    for (const jit::Kernel* k : jit_derived_)
+        if (k) c++;
+    return c;
+}
+
 void Solver::forward_derived(int d) {
     cudaStream_t s = stream();
     const int F = (int)m_->fields.size();
@@ -692,9 +663,7 @@ void Solver::forward_derived(int d) {
     const double cell = 32.0 * (double)plan_->N;
     const unsigned long long step_no = (unsigned long long)steps_taken_;
     if (!all_fast || first_axis < 0) {
-        k_eval_derived<<<grid_for((long long)plan_->N), 256, 0, s>>>(m_->derived[d].dev, R_, out, step_no,
-                                                                     (long long)plan_->N);
-        GOPF_CUDA(cudaGetLastError());
+        derived_pointwise(d, out, step_no, s);
         launches_++;
         plan_->exec_device(out, -1, s);
         return;
@@ -707,9 +676,8 @@ void Solver::forward_derived(int d) {
     if (!in_pass) {
         const int F0 = (int)m_->fields.size();
         const int id = tick("derived_pointwise", 16.0 * (double)plan_->N * (F0 + 1));
-        k_eval_derived<<<grid_for((long long)plan_->N), 256, 0, s>>>(dd, R_, out, step_no, (long long)plan_->N);
+        derived_pointwise(d, out, step_no, s);
         tock(id);
-        GOPF_CUDA(cudaGetLastError());
     }
     for (int ax = 2; ax >= 0; --ax) {
         if (plan_->extent(ax) <= 1) continue;
@@ -943,9 +911,45 @@ void Solver::launch_update(const DevKProgram& P) {
     int n_tab = 0;
     for (int i = 0; i < P.n_fields; ++i) n_tab += tab.t[i] ? 1 : 0;
     const int id = tick("k_update", 16.0 * (double)n * (n_read + P.n_fields + n_tab));
-    k_update_generic<<<grid_for(n), 256, 0, stream()>>>(P, S_, tab, plan_->freq_geom(), n);
+    if (!launch_update_jit(P, tab)) {
+        k_update_generic<<<grid_for(n), 256, 0, stream()>>>(P, S_, tab, plan_->freq_geom(), n);
+        GOPF_CUDA(cudaGetLastError());
+    }
     tock(id);
-    GOPF_CUDA(cudaGetLastError());
+}
+
+// The same update compiled for exactly this program (jit.h).  The image is keyed on the
+// program bytes (they hold the filter / multiplier addresses too) and on which fields have a
+// tabulated implicit factor; any change recompiles.  false: not specialised, run the generic kernel.
+bool Solver::launch_update_jit(const DevKProgram& P, const ImplicitTab& tab) {
+    if (!jit_on_) return false;
+    unsigned mask = 0;
+    for (int i = 0; i < P.n_fields; ++i)
+        if (tab.t[i]) mask |= 1u << i;
+    std::string key(reinterpret_cast<const char*>(&P), sizeof(P));
+    key.push_back((char)mask);
+    if (key != jit_kupdate_key_) {
+        jit::unload(jit_kupdate_);
+        jit_kupdate_ = nullptr;
+        jit_kupdate_key_ = key;
+        std::string log;
+        std::vector<char> cubin;
+        try {
+            if (jit::compile_cubin(jit::kupdate_kernel_source(P, plan_->freq_geom(), (long long)plan_->N, mask), &cubin, &log))
+                jit_kupdate_ = jit::load(cubin, "gopf_jit_kupdate", &log);
+        } catch (const std::exception& e) {
+            log = e.what();
+        }
+        if (!jit_kupdate_) jit_log_ += "k_update: " + log + "\n";
+    }
+    if (!jit_kupdate_) return false;
+    SpectraPtrs sp = S_;
+    ImplicitTab t = tab;
+    void* args[] = {&sp, &t};
+    std::string log;
+    if (!jit::launch(jit_kupdate_, grid_for((long long)plan_->N), 256, args, stream(), &log))
+        throw Error("jit launch of k_update: " + log);
+    return true;
 }
 
 // ---- host synchronisation ------------------------------------------------------------

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "fft_plan.h"
+#include "jit.h"
 #include "elastic.cuh"
 #include "model.h"
 #include "step_kernels.cuh"
@@ -111,6 +112,11 @@ public:
     void download_uint8(int field, unsigned char* host_out, double* mn, double* mx);
     void set_newton_krylov(const NewtonKrylovOptions& o) { nk_ = o; }
     bool last_step_converged() const { return ie_converged_; }
+    // run-time specialisation (jit.h): switch, and how many kernels (registered functions, the
+    // k-space update) currently run as compiled images
+    void set_jit(bool on) { jit_on_ = on; }
+    int jit_kernels() const;
+    const std::string& jit_log() const { return jit_log_; }
     long long residual_evaluations() const { return ie_residual_evals_; }
 
 private:
@@ -163,6 +169,17 @@ private:
     void drop_graph();
     bool graph_applicable() const;
     bool build_graph(int steps);
+
+    // Registered functions compiled to straight-line sm_100a code at first use (jit.h); a NULL
+    // entry keeps the interpreter kernel for that derived field
+    std::vector<jit::Kernel*> jit_derived_;
+    std::vector<char> jit_tried_;
+    bool jit_on_ = false;
+    std::string jit_log_;
+    void derived_pointwise(int d, cplx* out, unsigned long long step_no, cudaStream_t s);
+    jit::Kernel* jit_kupdate_ = nullptr;  // k_update compiled for the current program, NULL: generic kernel
+    std::string jit_kupdate_key_;
+    bool launch_update_jit(const DevKProgram& P, const ImplicitTab& tab);
 
     NewtonKrylovOptions nk_;
     bool ie_converged_ = true;

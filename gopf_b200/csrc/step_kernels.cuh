@@ -21,10 +21,6 @@
 
 namespace gopf {
 
-struct SpectraPtrs {
-    cplx* s[GOPF_MAX_SPECTRA];  // fields first (k-space state, updated in place), then derived / work spectra
-};
-
 struct FreqTabs {
     const double* f0;  // per normalised FFTW axis 0, 1, 2: wrap(idx / n), fftWrap.go:57-74
     const double* f1;

@@ -9,9 +9,24 @@
 //                   functions (pf/model.go:400-412) as an RPN over real parts, and
 //                   white noise (pf/noise.go:20-23).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 #include "cplx.cuh"
+
+// Device pointers of the program (modal-filter table, VolumeConservingLP multipliers).  The
+// run-time specialisation (jit.cu) defines these as literal addresses so that the program itself
+// can be a compile-time constant.
+#ifndef GOPF_FILTER
+#define GOPF_FILTER(P) ((P).filter)
+#define GOPF_LP(P, slot) ((P).lp_multiplier[slot])
+#endif
+// Loops over the program (terms, peaks, powers): their trip counts are literals in the run-time
+// specialisation, which asks for full unrolling; the library build leaves them rolled.
+#ifndef GOPF_JIT_UNROLL
+#define GOPF_JIT_UNROLL
+#endif
 
 namespace gopf {
 
@@ -111,6 +126,7 @@ __device__ __forceinline__ KPoint make_kpoint(double f0, double f1, double f2) {
 
 __device__ __forceinline__ double ipow(double x, int n) {
     double r = 1.0;
+    GOPF_JIT_UNROLL
     for (int i = 0; i < n; ++i) r *= x;
     return r;
 }
@@ -127,6 +143,7 @@ __device__ __forceinline__ double sv_interpolant(double f, double peak) {
 // pfc/pairCorrelation.go:27-37
 __device__ __forceinline__ double pair_corr_eval(const PairCorrParams& p, double k) {
     double result = 0.0;
+    GOPF_JIT_UNROLL
     for (int i = 0; i < p.n_peaks; ++i) {
         const double pref = exp(-p.eff_temp * p.eff_temp * k * k / (2.0 * p.plane_density[i] * p.num_planes[i]));
         const double z = (k - p.location[i]) / p.width[i];
@@ -169,6 +186,7 @@ __device__ __forceinline__ cplx eval_term(const DevKProgram& P, const DevTerm& t
         case TK_CONS_NOISE: {
             const ConsNoiseParams& c = P.cn[t.param];
             val = mk(0.0, 0.0);
+            GOPF_JIT_UNROLL
             for (int comp = 0; comp < c.dim; ++comp) {
                 const double f = kp.f[comp];
                 if (fabs(fabs(f) - 0.5) > 1e-6) {
@@ -182,14 +200,17 @@ __device__ __forceinline__ cplx eval_term(const DevKProgram& P, const DevTerm& t
         case TK_TENSOR_HESSIAN: {
             const TensorHessianParams& h = P.th[t.param];
             double acc = 0.0;
+            GOPF_JIT_UNROLL
             for (int j = 0; j < P.rank; ++j) acc += -4.0 * GOPF_PI * GOPF_PI * kp.f[j] * kp.f[j] * h.K[j * h.d + j];
+            GOPF_JIT_UNROLL
             for (int j = 0; j < P.rank; ++j)
+                GOPF_JIT_UNROLL
                 for (int k = j + 1; k < P.rank; ++k) acc += -8.0 * GOPF_PI * GOPF_PI * kp.f[j] * kp.f[k] * h.K[j * h.d + k];
             val = mk(acc, 0.0);
             break;
         }
         case TK_VOLUME_LP: {
-            const double lam = *P.lp_multiplier[t.param];
+            const double lam = *GOPF_LP(P, t.param);
             val = get(t.brick) * lam;
             break;
         }
@@ -207,13 +228,15 @@ template <class Get>
 __device__ __forceinline__ cplx euler_update(const DevKProgram& P, int i, const KPoint& kp, cplx d, Get get) {
     const DevEquation& q = P.eq[i];
     cplx rhs = mk(0.0, 0.0), den = mk(0.0, 0.0);
+    GOPF_JIT_UNROLL
     for (int j = 0; j < q.n_rhs; ++j) rhs += eval_term(P, q.rhs[j], kp, get);
+    GOPF_JIT_UNROLL
     for (int j = 0; j < q.n_den; ++j) den += eval_term(P, q.den[j], kp, get);
     const cplx num = mk(d.x + P.dt * rhs.x, d.y + P.dt * rhs.y);
     const cplx dn = mk(1.0 - P.dt * den.x, -P.dt * den.y);
     cplx r = cdiv(num, dn);
-    if (P.filter) {
-        const double s = filter_eval(P.filter, P.filter_n, kp.frad * 2.0 / GOPF_PI);
+    if (GOPF_FILTER(P)) {
+        const double s = filter_eval(GOPF_FILTER(P), P.filter_n, kp.frad * 2.0 / GOPF_PI);
         r = mk(r.x * s, r.y * s);
     }
     return r;

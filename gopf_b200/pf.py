@@ -477,6 +477,36 @@ class Model:
             raise GopfError("RegisterFunction: arbitrary closures cannot run on the device; pass an expression "
                             "string (see include/gopf_cuda.h) or WhiteNoise(...).Generate")
 
+    def FunctionSource(self, name: str, kernel: bool = False) -> str:
+        """C source the registered function `name` compiles to (kernel=True: the CUDA unit for NVRTC)."""
+        need = ctypes.c_int64(0)
+        check(lib().gopf_model_function_source(self._h, _s(name), 1 if kernel else 0, None, ctypes.c_int64(0),
+                                               ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        check(lib().gopf_model_function_source(self._h, _s(name), 1 if kernel else 0, buf, need, None))
+        return buf.value.decode("utf-8")
+
+    def FunctionCompile(self, name: str) -> int:
+        """NVRTC-compile the function's kernel for sm_100a (needs no GPU); returns the cubin size."""
+        n = ctypes.c_int64(0)
+        check(lib().gopf_model_function_compile(self._h, _s(name), ctypes.byref(n)))
+        return n.value
+
+    def KUpdateSource(self, dims, dt: float, tab_mask: int = 0, with_filter: bool = False) -> str:
+        """CUDA unit the k-space update of this model is specialised to (inspection / compile checks)."""
+        need = ctypes.c_int64(0)
+        args = (self._h, len(dims), int_array(dims), ctypes.c_double(dt), ctypes.c_uint(tab_mask), 1 if with_filter else 0)
+        check(lib().gopf_model_kupdate_source(*args, None, ctypes.c_int64(0), ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        check(lib().gopf_model_kupdate_source(*args, buf, need, None))
+        return buf.value.decode("utf-8")
+
+    def KUpdateCompile(self, dims, dt: float, tab_mask: int = 0, with_filter: bool = False) -> int:
+        n = ctypes.c_int64(0)
+        check(lib().gopf_model_kupdate_compile(self._h, len(dims), int_array(dims), ctypes.c_double(dt),
+                                               ctypes.c_uint(tab_mask), 1 if with_filter else 0, ctypes.byref(n)))
+        return n.value
+
     def RegisterTableField(self, name: str, values: np.ndarray):
         values = np.ascontiguousarray(values, dtype=np.float64)
         if values.ndim != 2:
@@ -872,6 +902,21 @@ class Solver:
 
     def ForceGeneric(self, on: bool = True):
         check(lib().gopf_solver_force_generic(self._h, 1 if on else 0))
+
+    def SetJit(self, on: bool = True):
+        """Compile registered functions with NVRTC into straight-line kernels at first use
+        (default: the GOPF_JIT environment variable)."""
+        check(lib().gopf_solver_set_jit(self._h, 1 if on else 0))
+
+    def JitKernels(self) -> int:
+        n = ctypes.c_int(0)
+        check(lib().gopf_solver_jit_kernels(self._h, ctypes.byref(n)))
+        return n.value
+
+    def JitLog(self) -> str:
+        buf = ctypes.create_string_buffer(4096)
+        check(lib().gopf_solver_jit_log(self._h, buf, 4096))
+        return buf.value.decode("utf-8", "replace")
 
     def KernelLaunches(self, reset: bool = False) -> int:
         n = ctypes.c_int64(0)

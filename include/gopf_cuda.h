@@ -77,6 +77,22 @@ int gopf_fft_plan_destroy(gopf_fft_plan* plan);
  * come from the reference's catalog.  Anything else fails here, loudly. */
 /* pf.NewModel (pf/model.go:130-138) */
 int gopf_model_create(gopf_model** out);
+/* The C source the registered function `name` compiles to: `static inline double gopf_expr(r0, i0,
+ * ..., r3, i3)` over the real / imaginary parts of fields 0..3 (kernel = 0), or the whole CUDA
+ * translation unit handed to NVRTC (kernel = 1).  *needed = bytes including the terminator; buf
+ * may be NULL to query.  Host only, no GPU. */
+int gopf_model_function_source(gopf_model* m, const char* name, int kernel, char* buf, int64_t len, int64_t* needed);
+/* NVRTC-compile that translation unit for sm_100a; *cubin_bytes = size of the image.  No GPU needed. */
+int gopf_model_function_compile(gopf_model* m, const char* name, int64_t* cubin_bytes);
+/* The CUDA translation unit the k-space update of this model (pf/euler.go:27-39) is specialised to
+ * on an n[0] x n[1] (x n[2]) grid: the compiled term list as a constant image, grid geometry and
+ * node count as literals.  tab_mask bit i: field i uses a tabulated implicit factor; with_filter:
+ * a modal filter is set.  Device addresses are stand-ins, so the result is for inspection and
+ * compile checks only.  Calls Model.Init.  Host only, no GPU. */
+int gopf_model_kupdate_source(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, int with_filter,
+                              char* buf, int64_t len, int64_t* needed);
+int gopf_model_kupdate_compile(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, int with_filter,
+                               int64_t* cubin_bytes);
 /* pf.NewField + Model.AddField (pf/model.go:44-57, 141-144).  host_c128 is the
  * caller-owned Field.Data backing array of n_nodes complex128; it is read by
  * gopf_solver_upload/propagate and written by gopf_solver_download/propagate,
@@ -229,6 +245,15 @@ int gopf_solver_get_time(gopf_solver* s, double* t);
 /* 1 when the single-field fused kernels are in use, 0 for the general path */
 int gopf_solver_is_fused(gopf_solver* s, int* fused);
 int gopf_solver_force_generic(gopf_solver* s, int on);
+/* Run-time specialisation of registered functions (Model.RegisterFunction, pf/model.go:400-412):
+ * the expression is compiled with NVRTC into a straight-line sm_100a kernel at first use instead
+ * of being interpreted per cell.  Off unless GOPF_JIT=1 is in the environment when the solver is
+ * created; gopf_solver_set_jit overrides that.  A function that fails to compile keeps the
+ * interpreter kernel (both are device paths); gopf_solver_jit_log tells why. */
+int gopf_solver_set_jit(gopf_solver* s, int on);
+/* number of derived fields currently evaluated by compiled kernels */
+int gopf_solver_jit_kernels(gopf_solver* s, int* count);
+int gopf_solver_jit_log(gopf_solver* s, char* buf, int len);
 /* kernels launched by this solver since creation / since the last reset */
 int gopf_solver_kernel_launches(gopf_solver* s, int64_t* n, int reset);
 /* k-space spectrum of field / derived field `index` -> host (debug / tests) */
