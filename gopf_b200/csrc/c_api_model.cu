@@ -96,19 +96,20 @@ int gopf_model_function_compile(gopf_model* m, const char* name, int64_t* cubin_
     GOPF_API_END
 }
 
-static std::string kupdate_source_of(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, int with_filter,
-                                    long long* nodes) {
+static std::string kupdate_source_of(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask,
+                                    uint64_t filter_addr, int filter_n, uint64_t lp_addr) {
     if (!m || !n) throw Error("NULL argument");
     if (rank != 2 && rank != 3) throw Error("rank must be 2 or 3");
     m->m.init();
     DevKProgram P;
     m->m.fill_program(&P, dt, rank);
-    // stand-in addresses (the image is inspected, never launched): non-NULL where the solver would set one
-    if (with_filter) {
-        P.filter = reinterpret_cast<const double*>(uintptr_t(0x7f0000000000ull));
-        P.filter_n = 1000;
+    if (filter_addr) {
+        P.filter = reinterpret_cast<const double*>(uintptr_t(filter_addr));
+        P.filter_n = filter_n;
     }
-    for (int i = 0; i < GOPF_MAX_SPECIAL; ++i) P.lp_multiplier[i] = reinterpret_cast<const double*>(uintptr_t(0x7f0000100000ull) + 24u * i);
+    // the solver keeps {multiplier, integral, first flag} per VolumeConservingLP slot (solver.cu)
+    if (lp_addr)
+        for (int i = 0; i < GOPF_MAX_SPECIAL; ++i) P.lp_multiplier[i] = reinterpret_cast<const double*>(uintptr_t(lp_addr)) + 3 * i;
     FreqGeom fg;
     fg.rank = rank;
     fg.d0 = n[0];
@@ -116,14 +117,13 @@ static std::string kupdate_source_of(gopf_model* m, int rank, const int* n, doub
     fg.d2 = rank > 2 ? n[2] : 1;
     long long N = 1;
     for (int i = 0; i < rank; ++i) N *= n[i];
-    if (nodes) *nodes = N;
     return jit::kupdate_kernel_source(P, fg, N, tab_mask);
 }
 
-int gopf_model_kupdate_source(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, int with_filter,
-                              char* buf, int64_t len, int64_t* needed) {
+int gopf_model_kupdate_source(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, uint64_t filter_addr,
+                              int filter_n, uint64_t lp_addr, char* buf, int64_t len, int64_t* needed) {
     GOPF_API_BEGIN
-    const std::string src = kupdate_source_of(m, rank, n, dt, tab_mask, with_filter, nullptr);
+    const std::string src = kupdate_source_of(m, rank, n, dt, tab_mask, filter_addr, filter_n, lp_addr);
     if (needed) *needed = (int64_t)src.size() + 1;
     if (buf) {
         if (len < (int64_t)src.size() + 1) throw Error("gopf_model_kupdate_source: buffer too small");
@@ -132,14 +132,46 @@ int gopf_model_kupdate_source(gopf_model* m, int rank, const int* n, double dt, 
     GOPF_API_END
 }
 
-int gopf_model_kupdate_compile(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, int with_filter,
-                               int64_t* cubin_bytes) {
+int gopf_model_kupdate_compile(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, uint64_t filter_addr,
+                               int filter_n, uint64_t lp_addr, int64_t* cubin_bytes) {
     GOPF_API_BEGIN
     std::vector<char> cubin;
     std::string log;
-    if (!jit::compile_cubin(kupdate_source_of(m, rank, n, dt, tab_mask, with_filter, nullptr), &cubin, &log))
+    if (!jit::compile_cubin(kupdate_source_of(m, rank, n, dt, tab_mask, filter_addr, filter_n, lp_addr), &cubin, &log))
         throw Error("jit: " + log);
     if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    GOPF_API_END
+}
+
+// raw program images: see the header
+static void copy_image(const void* src, size_t size, void* buf, int64_t len, int64_t* needed) {
+    if (needed) *needed = (int64_t)size;
+    if (buf) {
+        if (len < (int64_t)size) throw Error("image buffer too small");
+        std::memcpy(buf, src, size);
+    }
+}
+
+int gopf_model_program_image(gopf_model* m, int rank, double dt, void* buf, int64_t len, int64_t* needed) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    if (rank != 2 && rank != 3) throw Error("rank must be 2 or 3");
+    m->m.init();
+    DevKProgram P;
+    m->m.fill_program(&P, dt, rank);
+    copy_image(&P, sizeof(P), buf, len, needed);
+    GOPF_API_END
+}
+
+int gopf_model_derived_image(gopf_model* m, int index, void* buf, int64_t len, int64_t* needed, int* used) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    m->m.init();
+    if (index < 0 || index >= (int)m->m.derived.size()) throw Error("derived field index out of range");
+    DevDerived D = m->m.derived[index].dev;
+    D.table = nullptr;  // a device address when a solver is attached; the caller supplies its own
+    copy_image(&D, sizeof(D), buf, len, needed);
+    if (used) *used = m->m.derived[index].used ? 1 : 0;
     GOPF_API_END
 }
 

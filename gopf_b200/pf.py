@@ -492,19 +492,20 @@ class Model:
         check(lib().gopf_model_function_compile(self._h, _s(name), ctypes.byref(n)))
         return n.value
 
-    def KUpdateSource(self, dims, dt: float, tab_mask: int = 0, with_filter: bool = False) -> str:
-        """CUDA unit the k-space update of this model is specialised to (inspection / compile checks)."""
+    def KUpdateSource(self, dims, dt: float, tab_mask: int = 0, filter_addr: int = 0, filter_n: int = 0, lp_addr: int = 0) -> str:
+        """CUDA unit the k-space update of this model is specialised to (inspection, compile checks, tests)."""
         need = ctypes.c_int64(0)
-        args = (self._h, len(dims), int_array(dims), ctypes.c_double(dt), ctypes.c_uint(tab_mask), 1 if with_filter else 0)
+        args = (self._h, len(dims), int_array(dims), ctypes.c_double(dt), ctypes.c_uint(tab_mask), ctypes.c_uint64(filter_addr),
+                int(filter_n), ctypes.c_uint64(lp_addr))
         check(lib().gopf_model_kupdate_source(*args, None, ctypes.c_int64(0), ctypes.byref(need)))
         buf = ctypes.create_string_buffer(need.value)
         check(lib().gopf_model_kupdate_source(*args, buf, need, None))
         return buf.value.decode("utf-8")
 
-    def KUpdateCompile(self, dims, dt: float, tab_mask: int = 0, with_filter: bool = False) -> int:
+    def KUpdateCompile(self, dims, dt: float, tab_mask: int = 0, filter_addr: int = 0, filter_n: int = 0, lp_addr: int = 0) -> int:
         n = ctypes.c_int64(0)
-        check(lib().gopf_model_kupdate_compile(self._h, len(dims), int_array(dims), ctypes.c_double(dt),
-                                               ctypes.c_uint(tab_mask), 1 if with_filter else 0, ctypes.byref(n)))
+        check(lib().gopf_model_kupdate_compile(self._h, len(dims), int_array(dims), ctypes.c_double(dt), ctypes.c_uint(tab_mask),
+                                               ctypes.c_uint64(filter_addr), int(filter_n), ctypes.c_uint64(lp_addr), ctypes.byref(n)))
         return n.value
 
     def RegisterTableField(self, name: str, values: np.ndarray):

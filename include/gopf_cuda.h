@@ -86,13 +86,23 @@ int gopf_model_function_source(gopf_model* m, const char* name, int kernel, char
 int gopf_model_function_compile(gopf_model* m, const char* name, int64_t* cubin_bytes);
 /* The CUDA translation unit the k-space update of this model (pf/euler.go:27-39) is specialised to
  * on an n[0] x n[1] (x n[2]) grid: the compiled term list as a constant image, grid geometry and
- * node count as literals.  tab_mask bit i: field i uses a tabulated implicit factor; with_filter:
- * a modal filter is set.  Device addresses are stand-ins, so the result is for inspection and
- * compile checks only.  Calls Model.Init.  Host only, no GPU. */
-int gopf_model_kupdate_source(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, int with_filter,
-                              char* buf, int64_t len, int64_t* needed);
-int gopf_model_kupdate_compile(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, int with_filter,
-                               int64_t* cubin_bytes);
+ * node count as literals.  tab_mask bit i: field i uses a tabulated implicit factor.  filter_addr /
+ * filter_n: address and length of the modal-filter table to bake in (0: no filter); lp_addr: address
+ * of the VolumeConservingLP state, three doubles per slot (0: none).  The solver passes its device
+ * addresses; these entry points exist for inspection, compile checks and tests/host_emul (which
+ * compiles the unit for the host and passes host addresses).  Calls Model.Init.  Host only, no GPU. */
+int gopf_model_kupdate_source(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, uint64_t filter_addr,
+                              int filter_n, uint64_t lp_addr, char* buf, int64_t len, int64_t* needed);
+int gopf_model_kupdate_compile(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, uint64_t filter_addr,
+                               int filter_n, uint64_t lp_addr, int64_t* cubin_bytes);
+/* Raw images of what the model compiles to: the k-space program (struct DevKProgram of
+ * gopf_b200/csrc/step_program.h, device pointers NULL) and derived field `index` (struct DevDerived;
+ * index counts derived fields in registration order, spectrum index = number of fields + index).
+ * For inspection and for tests/host_emul, which compiles the same headers for the host and runs the
+ * evaluators against the oracle without a GPU.  *needed = size of the struct; buf may be NULL.
+ * Both call Model.Init.  Host only. */
+int gopf_model_program_image(gopf_model* m, int rank, double dt, void* buf, int64_t len, int64_t* needed);
+int gopf_model_derived_image(gopf_model* m, int index, void* buf, int64_t len, int64_t* needed, int* used);
 /* pf.NewField + Model.AddField (pf/model.go:44-57, 141-144).  host_c128 is the
  * caller-owned Field.Data backing array of n_nodes complex128; it is read by
  * gopf_solver_upload/propagate and written by gopf_solver_download/propagate,

@@ -1,0 +1,303 @@
+"""The device evaluators of the general path, compiled for the HOST, against the oracle -- no GPU.
+
+`gopf_b200/csrc/kupdate.cuh`, `step_program.h` and `cplx.cuh` are header-only device code: the k-space
+update of pf/euler.go:27-39 with every catalog term, the derived-field evaluators of
+pf/model.go:237-241 (monomials with Go's cmplx.Pow, registered functions, Philox noise, tables), the
+literal `Freq`, the modal filter.  tests/host_emul/ compiles exactly these headers with g++ behind a
+small CUDA shim; `EmulatedSolver` below wires them to the programs the C++ model compiles
+(`gopf_model_program_image`, `gopf_model_derived_image`), with scipy's FFT standing where the CUDA
+transforms are.  The step-level device tests of tests/test_step_gpu.py that stay on the
+semi-implicit Euler general path are then run unchanged against it, so the oracle checks the
+product's own evaluator source on CPU.  This is test infrastructure: nothing in gopf_b200/ can reach
+it, and the transforms, the fused kernels and the launch code remain covered by the device tests only.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+import types
+
+import numpy as np
+import pytest
+import scipy.fft
+
+from gopf_b200 import pf as gpf
+from gopf_b200._lib import check, lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MAX_SPECTRA, MAX_FIELDS = 16, 4
+DP = ctypes.POINTER(ctypes.c_double)
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    if not shutil.which("g++"):
+        pytest.skip("g++ not available")
+    so = tmp_path_factory.mktemp("emul") / "emul.so"
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-I", os.path.join(ROOT, "gopf_b200", "csrc"),
+                    "-o", str(so), os.path.join(ROOT, "tests", "host_emul", "emul.cpp")], check=True)
+    dll = ctypes.CDLL(str(so))
+    dll.emul_sizeof_program.restype = ctypes.c_int
+    dll.emul_sizeof_derived.restype = ctypes.c_int
+    return dll
+
+
+def _image(fn, *args, tail=()):
+    need = ctypes.c_int64(0)
+    check(fn(*args, None, ctypes.c_int64(0), ctypes.byref(need), *tail))
+    buf = ctypes.create_string_buffer(need.value)
+    return buf, need
+
+
+class EmulatedSolver:
+    """gopf_b200.pf.Solver's surface, semi-implicit Euler on the general path, on the host."""
+
+    IsFused = False
+
+    def __init__(self, dll, m, dims, dt):
+        self.dll, self.Model, self.dims, self.Dt = dll, m, [int(d) for d in dims], dt
+        self.Callbacks, self.Monitors, self.StartEpoch = [], [], 0
+        self.filter = None
+        self.steps = 0
+        self.launches = 0
+        self.Stepper = types.SimpleNamespace(SetFilter=self._set_filter, GetTime=lambda: self.steps * self.Dt, Dt=dt)
+        self.rank = len(dims)
+        self.N = int(np.prod(dims))
+        for f in m.Fields:
+            if f.Data.shape[0] != self.N:  # solver.go:55-60
+                raise gpf.GopfError("solver: Inconsistent domain size and number of grid points")
+        h = m._h
+        buf, need = _image(lib().gopf_model_program_image, h, self.rank, ctypes.c_double(dt))
+        assert need.value == dll.emul_sizeof_program(), "emulation and library disagree on sizeof(DevKProgram)"
+        check(lib().gopf_model_program_image(h, self.rank, ctypes.c_double(dt), buf, need, None))
+        self.program = buf
+        nd = ctypes.c_int(0)
+        check(lib().gopf_model_num_derived_fields(h, ctypes.byref(nd)))
+        self.derived = []
+        for d in range(nd.value):
+            used = ctypes.c_int(0)
+            dbuf, dneed = _image(lib().gopf_model_derived_image, h, d, tail=(None,))
+            assert dneed.value == dll.emul_sizeof_derived()
+            check(lib().gopf_model_derived_image(h, d, dbuf, dneed, None, ctypes.byref(used)))
+            self.derived.append((dbuf, bool(used.value)))
+        if len(m.Fields) + nd.value > MAX_SPECTRA:
+            raise gpf.GopfError("too many spectra")
+        self.tables = getattr(m, "_emul_tables", [])
+
+    # -- the surface the tests use
+    def _set_filter(self, filt):
+        self.filter = None if filt is None else np.ascontiguousarray(filt.Data, dtype=np.float64)
+
+    def ForceGeneric(self, on=True):
+        pass
+
+    def KernelLaunches(self, reset=False):
+        return self.launches
+
+    def Solve(self, nepochs, nsteps):
+        for i in range(nepochs):
+            self.Propagate(nsteps)
+            for cb in self.Callbacks:
+                cb(self, i + self.StartEpoch)
+            for mon in self.Monitors:
+                mon.Add(self.Model.Bricks)
+
+    def Propagate(self, nsteps):
+        fields = self.Model.Fields
+        S = [self._fft(f.Data) for f in fields]  # upload: euler.go:19-21
+        for _ in range(nsteps):
+            self._step(S)
+        for f, s in zip(fields, S):  # download: euler.go:42-45
+            f.Data[:] = self._ifft(s)
+
+    # -- one Solver::euler_update_generic
+    def _fft(self, x):
+        return np.ascontiguousarray(scipy.fft.fftn(x.reshape(self.dims)).reshape(-1))
+
+    def _ifft(self, x):
+        return np.ascontiguousarray(scipy.fft.ifftn(x.reshape(self.dims)).reshape(-1))  # includes the 1/N
+
+    def _step(self, S):
+        F = len(S)
+        spectra = list(S) + [None] * (MAX_SPECTRA - F)
+        if any(used for _, used in self.derived):
+            R = [self._ifft(s) for s in S]
+            rp = (DP * MAX_FIELDS)(*[R[i].ctypes.data_as(DP) if i < F else None for i in range(MAX_FIELDS)])
+            table_no = 0
+            for d, (dbuf, used) in enumerate(self.derived):
+                kind = ctypes.c_int.from_buffer(dbuf).value
+                table, tn = None, 0
+                if kind == 3:  # DK_TABLE
+                    tab = self.tables[table_no]
+                    table_no += 1
+                    table, tn = tab.ctypes.data_as(DP), tab.shape[1]
+                if not used:
+                    continue
+                out = np.empty(self.N, dtype=np.complex128)
+                self.dll.emul_derived(dbuf, rp, table, ctypes.c_longlong(tn), out.ctypes.data_as(DP),
+                                      ctypes.c_ulonglong(self.steps), ctypes.c_longlong(self.N))
+                spectra[F + d] = self._fft(out)
+                self.launches += 1
+        sp = (DP * MAX_SPECTRA)(*[s.ctypes.data_as(DP) if s is not None else None for s in spectra])
+        filt = self.filter.ctypes.data_as(DP) if self.filter is not None else None
+        fn = self.filter.shape[0] if self.filter is not None else 0
+        d = self.dims
+        self.dll.emul_update(self.program, sp, None, filt, fn, None, None, self.rank, d[0], d[1], d[2] if self.rank > 2 else 1,
+                             ctypes.c_longlong(self.N))
+        self.launches += 1
+        self.steps += 1
+
+
+class _RecordingModel(gpf.Model):
+    """gopf_b200.pf.Model that also keeps the host copy of prescribed table fields for the emulation."""
+
+    def RegisterTableField(self, name, values):
+        super().RegisterTableField(name, values)
+        self.__dict__.setdefault("_emul_tables", []).append(np.ascontiguousarray(values, dtype=np.float64))
+
+
+@pytest.fixture()
+def T(emul, monkeypatch):
+    """tests/test_step_gpu.py with its `gpf` bound to the host emulation."""
+    import test_step_gpu as mod
+
+    shim = types.SimpleNamespace(**{k: getattr(gpf, k) for k in dir(gpf) if not k.startswith("__")})
+    shim.NewModel = _RecordingModel
+    shim.NewSolver = lambda m, dims, dt, device=-1: EmulatedSolver(emul, m, dims, dt)
+    monkeypatch.setattr(mod, "gpf", shim)
+    return mod
+
+
+# ---- the device tests that stay on the Euler general path, run against the emulation ------------------
+@pytest.mark.parametrize("dims", [[128, 128], [64, 256], [32, 32, 32]], ids=lambda d: "x".join(map(str, d)))
+def test_cahn_hilliard_100_steps(T, dims):
+    T.test_cahn_hilliard_100_steps(dims, True)
+
+
+def test_euler_decays(T):
+    T.test_euler_exponential_decay()
+    T.test_euler_square_decay()
+
+
+def test_solver_diffusion(T):
+    T.test_solver_diffusion()
+
+
+def test_gauss_seidel_field_ordering(T):
+    T.test_gauss_seidel_field_ordering()
+
+
+@pytest.mark.parametrize("dims", [[32, 32], [16, 16, 16]], ids=lambda d: "x".join(map(str, d)))
+def test_reaction_diffusion_three_fields(T, dims):
+    T.test_reaction_diffusion_three_fields(dims)
+
+
+@pytest.mark.parametrize("lap", [False, True], ids=["nolap", "lap"])
+def test_pfc_pair_correlation_ideal_mixture(T, lap):
+    T.test_pfc_pair_correlation_ideal_mixture_vs_oracle(lap)
+
+
+def test_pfc_with_vandeven_filter_and_prescribed_noise(T):
+    T.test_pfc_with_vandeven_filter_and_prescribed_noise_vs_oracle()
+
+
+def test_spectral_viscosity(T):
+    T.test_spectral_viscosity_vs_oracle()
+
+
+def test_white_noise_statistics(T):
+    T.test_white_noise_statistics()
+
+
+def test_conservative_noise(T):
+    T.test_conservative_noise_properties()
+    T.test_conservative_noise_prescribed_currents_vs_oracle()
+
+
+@pytest.mark.parametrize("dims,K", [([64, 64], [1.0, 0.3, 0.3, 2.0]), ([16, 16, 16], [1.0, 0.2, 0.1, 0.2, 2.0, 0.3, 0.1, 0.3, 0.5])],
+                         ids=["2d", "3d"])
+def test_tensorial_hessian(T, dims, K):
+    T.test_tensorial_hessian_anisotropic_diffusion_vs_oracle(dims, K)
+
+
+def test_negative_value_penalty(T):
+    T.test_negative_value_penalty_vs_oracle()
+
+
+# ---- the specialised k-space update (jit.cu), the very unit NVRTC receives, compiled for the host -----
+class _Spectra(ctypes.Structure):
+    _fields_ = [("s", DP * MAX_SPECTRA)]
+
+
+class _Tabs(ctypes.Structure):
+    _fields_ = [("t", DP * MAX_FIELDS)]
+
+
+class SpecialisedEmulatedSolver(EmulatedSolver):
+    """EmulatedSolver whose update is `gopf_jit_kupdate`: program image as constant words, grid geometry,
+    node count and the (host) address of the filter table as literals."""
+
+    build_dir = None
+    calls = 0
+
+    def _step(self, S):
+        if not hasattr(self, "_kernel") or self._filter_id != id(self.filter):
+            self._filter_id = id(self.filter)
+            addr = self.filter.ctypes.data if self.filter is not None else 0
+            fn = self.filter.shape[0] if self.filter is not None else 0
+            src = self.Model.KUpdateSource(self.dims, self.Dt, 0, filter_addr=addr, filter_n=fn)
+            assert "jit_prog_words" in src
+            SpecialisedEmulatedSolver.serial = getattr(SpecialisedEmulatedSolver, "serial", 0) + 1
+            stem = os.path.join(self.build_dir, f"unit_{SpecialisedEmulatedSolver.serial}")
+            with open(stem + ".cpp", "w") as f:
+                f.write('#include "cuda_shim.h"\n' + src)
+            subprocess.run(["g++", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-I", os.path.join(ROOT, "gopf_b200", "csrc"),
+                            "-I", os.path.join(ROOT, "tests", "host_emul"), "-o", stem + ".so", stem + ".cpp"], check=True)
+            self._kernel = ctypes.CDLL(stem + ".so").gopf_jit_kupdate
+            self._kernel.argtypes = [_Spectra, _Tabs]
+            self._kernel.restype = None
+        generic_update = self.dll.emul_update
+
+        def specialised(program, sp, tabs, filt, fn, lp0, lp1, rank, d0, d1, d2, n):
+            self._kernel(_Spectra(sp), _Tabs())
+            SpecialisedEmulatedSolver.calls += 1
+
+        self.dll = types.SimpleNamespace(emul_update=specialised, emul_derived=self.dll.emul_derived)
+        try:
+            super()._step(S)
+        finally:
+            self.dll = types.SimpleNamespace(emul_update=generic_update, emul_derived=self.dll.emul_derived)
+
+
+@pytest.fixture()
+def TS(emul, monkeypatch, tmp_path):
+    import test_step_gpu as mod
+
+    SpecialisedEmulatedSolver.build_dir = str(tmp_path)
+    shim = types.SimpleNamespace(**{k: getattr(gpf, k) for k in dir(gpf) if not k.startswith("__")})
+    shim.NewModel = _RecordingModel
+    shim.NewSolver = lambda m, dims, dt, device=-1: SpecialisedEmulatedSolver(emul, m, dims, dt)
+    monkeypatch.setattr(mod, "gpf", shim)
+    return mod
+
+
+def test_specialised_update_unit_on_the_host(TS):
+    SpecialisedEmulatedSolver.calls = 0
+    TS.test_cahn_hilliard_100_steps([64, 256], True)  # non-square: d0, d1 literals in the right order
+    TS.test_reaction_diffusion_three_fields([16, 16, 16])
+    TS.test_pfc_with_vandeven_filter_and_prescribed_noise_vs_oracle()  # filter address as a literal
+    TS.test_spectral_viscosity_vs_oracle()
+    TS.test_conservative_noise_prescribed_currents_vs_oracle()
+    TS.test_tensorial_hessian_anisotropic_diffusion_vs_oracle([16, 16, 16], [1.0, 0.2, 0.1, 0.2, 2.0, 0.3, 0.1, 0.3, 0.5])
+    assert SpecialisedEmulatedSolver.calls > 200  # every step above went through gopf_jit_kupdate
+
+
+def test_emulated_freq_is_the_reference_k_table(emul):
+    from oracle import pfutil as opfutil
+    for dims in ([8, 16], [6, 10], [8, 8, 8]):
+        n = int(np.prod(dims))
+        out = np.zeros((n, 3))
+        emul.emul_freq(len(dims), dims[0], dims[1], dims[2] if len(dims) > 2 else 1, ctypes.c_longlong(n), out.ctypes.data_as(DP))
+        ft = opfutil.NewFFTW(dims)
+        want = np.array([ft.Freq(i) for i in range(n)])
+        assert np.array_equal(out[:, :len(dims)], want)

@@ -201,10 +201,11 @@ def test_kspace_update_specialises_to_a_folded_image(kind, tab_mask, with_filter
         m, dt = workloads.build_precipitate(shim, shim, gel, dims, expressions=True)[0], workloads.PRECIPITATE_DT
     else:
         m, dt = workloads.build_pfc(shim, shim, dims, noise="device")[0], workloads.PFC_DT
-    src = m.KUpdateSource(dims, dt, tab_mask, with_filter)
+    stand_in = dict(filter_addr=0x7F0000000000 if with_filter else 0, filter_n=1000, lp_addr=0x7F0000100000)
+    src = m.KUpdateSource(dims, dt, tab_mask, **stand_in)
     assert '#include "kupdate.cuh"' in src and "jit_prog_words" in src and "{3, 8, 8, 8}" in src
     assert ("GOPF_FILTER(P) ((const double*)0x0ull)" in src) == (not with_filter)
-    assert m.KUpdateCompile(dims, dt, tab_mask, with_filter) > 1000
+    assert m.KUpdateCompile(dims, dt, tab_mask, **stand_in) > 1000
     if not shutil.which("cuobjdump"):
         return
     cubin = str(sorted(tmp_path.glob("*.cubin"))[-1])
