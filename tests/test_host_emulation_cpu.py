@@ -224,6 +224,52 @@ def test_negative_value_penalty(T):
     T.test_negative_value_penalty_vs_oracle()
 
 
+# ---- seeded random models: parser -> program -> evaluators against the oracle, numerically ---------------
+@pytest.mark.parametrize("seed", range(80))
+def test_random_models_step_like_the_oracle(emul, seed):
+    """The equations of tests/test_parser_fuzz_cpu.py (the reference's grammar: signs, scalar powers,
+    LAP^n prefixes, products of field powers, names of fields absent from the model), stepped."""
+    import random
+
+    from oracle import pf as opf
+    from oracle import pfutil as opfutil
+    from test_parser_fuzz_cpu import FIELDS, SCALARS, random_equation
+
+    rng = random.Random(1000 + seed)
+    dims = rng.choice([[8, 8], [4, 16], [4, 4, 4]])
+    n = int(np.prod(dims))
+    names = FIELDS[:rng.choice([1, 2, 3])]
+    eqs = [random_equation(rng, f) for f in names]
+    dt = 1e-3
+    res = []
+    for mod in (gpf, opf):
+        m = _RecordingModel() if mod is gpf else mod.NewModel()
+        fields = []
+        for k, name in enumerate(names):
+            f = mod.NewField(name, n, (0.6 + 0.3 * opfutil.splitmix64_uniform(seed * 7 + k, n)).astype(np.complex128))
+            m.AddField(f)
+            fields.append(f)
+        for sname, val in SCALARS:
+            m.AddScalar(mod.NewScalar(sname, val))
+        try:
+            for eq in eqs:
+                m.AddEquation(eq)
+            solver = EmulatedSolver(emul, m, dims, dt) if mod is gpf else mod.NewSolver(m, dims, dt)
+            solver.Solve(1, 3)
+            res.append([f.Data.copy() for f in fields])
+        except Exception as e:  # noqa: BLE001 -- the reference panics; either side raises its own type
+            res.append(e)
+    failed = [isinstance(r, Exception) for r in res]
+    assert failed[0] == failed[1], (eqs, res)
+    if failed[0]:
+        return
+    for a, b in zip(*res):
+        if not np.all(np.isfinite(b)) or np.max(np.abs(b)) > 1e8:
+            assert not np.all(np.isfinite(a)) or np.max(np.abs(a)) > 1e6, eqs  # blown up on both sides
+            continue
+        assert np.linalg.norm(a - b) <= 1e-9 * max(np.linalg.norm(b), 1e-300), (eqs, dims)
+
+
 # ---- the specialised k-space update (jit.cu), the very unit NVRTC receives, compiled for the host -----
 class _Spectra(ctypes.Structure):
     _fields_ = [("s", DP * MAX_SPECTRA)]
