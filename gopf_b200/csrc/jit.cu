@@ -190,6 +190,15 @@ std::string kupdate_kernel_source(const DevKProgram& P_in, const FreqGeom& fg, l
     static_assert(sizeof(DevKProgram) % 8 == 0, "DevKProgram is laid down as 64-bit words");
     DevKProgram P;
     std::memcpy(&P, &P_in, sizeof(P));
+    // a literal NULL behind a dereference is undefined behaviour the compiler may turn into an empty kernel
+    for (int i = 0; i < P.n_fields; ++i)
+        for (int side = 0; side < 2; ++side) {
+            const DevTerm* t = side ? P.eq[i].den : P.eq[i].rhs;
+            const int nt = side ? P.eq[i].n_den : P.eq[i].n_rhs;
+            for (int j = 0; j < nt; ++j)
+                if (t[j].kind == TK_VOLUME_LP && (t[j].param < 0 || t[j].param >= GOPF_MAX_SPECIAL || !P.lp_multiplier[t[j].param]))
+                    throw Error("jit: VolumeConservingLP term without a multiplier address");
+        }
     std::string src;
     src += strf("#define GOPF_FILTER(P) ((const double*)0x%llxull)\n", (unsigned long long)(uintptr_t)P.filter);
     src += "#define GOPF_LP(P, slot) (";
@@ -209,12 +218,25 @@ std::string kupdate_kernel_source(const DevKProgram& P_in, const FreqGeom& fg, l
     for (size_t i = 0; i < words; ++i) src += strf("%s0x%llxull,", i % 6 == 0 ? "\n    " : " ", w[i]);
     src += "\n};\n}  // namespace gopf\n";
     src += strf(
-        "extern \"C\" __global__ void __launch_bounds__(256) gopf_jit_kupdate(gopf::SpectraPtrs sp, gopf::ImplicitTab tab) {\n"
-        "    const gopf::DevKProgram& P = *reinterpret_cast<const gopf::DevKProgram*>(gopf::jit_prog_words);\n"
-        "    const gopf::FreqGeom fg = {%d, %d, %d, %d};\n"
-        "    gopf::update_all(P, sp, tab, fg, %lldLL);\n"
-        "}\n",
+        "#define GOPF_JIT_PROGRAM (*reinterpret_cast<const gopf::DevKProgram*>(gopf::jit_prog_words))\n"
+        "#define GOPF_JIT_GEOM {%d, %d, %d, %d}\n"
+        "#define GOPF_JIT_NODES %lldLL\n",
         fg.rank, fg.d0, fg.d1, fg.d2, n);
+    src +=
+        "extern \"C\" __global__ void __launch_bounds__(256) gopf_jit_kupdate(gopf::SpectraPtrs sp, gopf::ImplicitTab tab) {\n"
+        "    const gopf::FreqGeom fg = GOPF_JIT_GEOM;\n"
+        "    gopf::update_all(GOPF_JIT_PROGRAM, sp, tab, fg, GOPF_JIT_NODES);\n"
+        "}\n"
+        // the RK4 passes of the same program (pf/rk4.go:29-127)
+        "extern \"C\" __global__ void __launch_bounds__(256) gopf_jit_rk4_rhs(gopf::SpectraPtrs sp, gopf::SpectraPtrs kout) {\n"
+        "    const gopf::FreqGeom fg = GOPF_JIT_GEOM;\n"
+        "    gopf::rk4_rhs_all(GOPF_JIT_PROGRAM, sp, kout, fg, GOPF_JIT_NODES);\n"
+        "}\n"
+        "extern \"C\" __global__ void __launch_bounds__(256) gopf_jit_rk4_point(int mode, double fdt, gopf::SpectraPtrs field,\n"
+        "        gopf::SpectraPtrs initial, gopf::SpectraPtrs final_, gopf::SpectraPtrs kf) {\n"
+        "    const gopf::FreqGeom fg = GOPF_JIT_GEOM;\n"
+        "    gopf::rk4_point_all(GOPF_JIT_PROGRAM, mode, fdt, field, initial, final_, kf, fg, GOPF_JIT_NODES);\n"
+        "}\n";
     return src;
 }
 

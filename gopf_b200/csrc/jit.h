@@ -34,8 +34,9 @@ std::string expression_source(const DevDerived& D, unsigned* used_mask);
 // Full translation unit: gopf_expr + extern "C" __global__ gopf_jit_derived(f0..f3, out, n)
 std::string derived_kernel_source(const DevDerived& D, unsigned* used_mask);
 
-// Translation unit of the specialised k-space update: extern "C" __global__
-// gopf_jit_kupdate(SpectraPtrs sp, ImplicitTab tab).  P.filter / P.lp_multiplier are taken as the
+// Translation unit of the specialised k-space kernels: extern "C" __global__
+// gopf_jit_kupdate(SpectraPtrs sp, ImplicitTab tab), gopf_jit_rk4_rhs(SpectraPtrs sp, SpectraPtrs kout),
+// gopf_jit_rk4_point(int mode, double fdt, SpectraPtrs field, initial, final_, kf).  P.filter / P.lp_multiplier are taken as the
 // literal device addresses to bake in; tab_mask bit i = field i has a tabulated implicit factor.
 std::string kupdate_kernel_source(const DevKProgram& P, const FreqGeom& fg, long long n, unsigned tab_mask);
 

@@ -127,4 +127,111 @@ __device__ __forceinline__ void update_all(const DevKProgram& P, const SpectraPt
     }
 }
 
+// filter(k) / (1 - dt * den_i(k)) for every node (euler.go:33, util.go:125-132)
+__device__ __forceinline__ void implicit_table_all(const DevKProgram& P, int i, cplx* out, const FreqGeom& fg, long long n) {
+    const bool small = n < (1LL << 31);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        double f[3] = {0.0, 0.0, 0.0};
+        ref_freq_fast(fg, idx, small, f);
+        const KPoint kp = make_kpoint(f[0], f[1], f[2]);
+        const DevEquation& q = P.eq[i];
+        cplx den = mk(0.0, 0.0);
+        GOPF_JIT_UNROLL
+        for (int j = 0; j < q.n_den; ++j) den += eval_term(P, q.den[j], kp, [&](int) -> cplx { return mk(1.0, 0.0); });
+        cplx r = cdiv(mk(1.0, 0.0), mk(1.0 - P.dt * den.x, -P.dt * den.y));
+        if (GOPF_FILTER(P)) {
+            const double sc = filter_eval(GOPF_FILTER(P), P.filter_n, kp.frad * 2.0 / GOPF_PI);
+            r = mk(r.x * sc, r.y * sc);
+        }
+        out[idx] = r;
+    }
+}
+
+// VolumeConservingLP.OnStepFinished (pf/volumeConserving.go:31-50).  sum_i Re c_i is the
+// DC mode of the updated spectrum, the indicator integral the DC mode of the indicator
+// spectrum.  state = {multiplier, current integral, first-update flag}
+__device__ __forceinline__ void volume_lp_update(double* state, const cplx* field_spec, const cplx* indicator_spec, double dt) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double field_integral = field_spec[0].x;
+        const double indicator_integral = indicator_spec[0].x;
+        if (state[2] != 0.0) {
+            state[1] = field_integral;
+            state[2] = 0.0;
+        } else {
+            const double delta = field_integral - state[1];
+            state[1] = field_integral;
+            state[0] = state[0] - delta / (dt * indicator_integral);
+        }
+    }
+}
+
+// RK4 pointwise passes (pf/rk4.go:58-68, 77-84, 87-96, 101-111, 123-126)
+__device__ __forceinline__ void rk4_rhs_all(const DevKProgram& P, const SpectraPtrs& sp, const SpectraPtrs& kout,
+                                            const FreqGeom& fg, long long n) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        double f[3] = {0.0, 0.0, 0.0};
+        ref_freq(fg, idx, f);
+        const KPoint kp = make_kpoint(f[0], f[1], f[2]);
+        auto get = [&](int b) -> cplx { return sp.s[b][idx]; };
+        GOPF_JIT_UNROLL
+        for (int i = 0; i < P.n_fields; ++i) {
+            const DevEquation& q = P.eq[i];
+            cplx rhs = mk(0.0, 0.0);
+            GOPF_JIT_UNROLL
+            for (int j = 0; j < q.n_rhs; ++j) rhs += eval_term(P, q.rhs[j], kp, get);
+            kout.s[i][idx] = rhs;
+        }
+    }
+}
+
+// mode 0: final += fdt*k ; field = initial                       (PrepareNextCorrection)
+// mode 1: field = (field + fdt*k) / (1 - fdt*den)                 (correction, first loop)
+// mode 2: final /= (1 - fdt*den); field = final; filter           (end of Step)
+__device__ __forceinline__ void rk4_point_all(const DevKProgram& P, int mode, double fdt, SpectraPtrs field,
+                                              SpectraPtrs initial, SpectraPtrs final_, SpectraPtrs kf, FreqGeom fg,
+                                              long long n) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (long long)gridDim.x * blockDim.x) {
+        KPoint kp;
+        if (mode != 0) {
+            double f[3] = {0.0, 0.0, 0.0};
+            ref_freq(fg, idx, f);
+            kp = make_kpoint(f[0], f[1], f[2]);
+        }
+        auto get = [&](int b) -> cplx { return field.s[b][idx]; };
+        GOPF_JIT_UNROLL
+        for (int i = 0; i < P.n_fields; ++i) {
+            if (mode == 0) {
+                const cplx k = kf.s[i][idx];
+                cplx fv = final_.s[i][idx];
+                fv = mk(fv.x + fdt * k.x, fv.y + fdt * k.y);
+                final_.s[i][idx] = fv;
+                field.s[i][idx] = initial.s[i][idx];
+                continue;
+            }
+            const DevEquation& q = P.eq[i];
+            cplx den = mk(0.0, 0.0);
+            GOPF_JIT_UNROLL
+            for (int j = 0; j < q.n_den; ++j) den += eval_term(P, q.den[j], kp, get);
+            const cplx dn = mk(1.0 - fdt * den.x, -fdt * den.y);
+            if (mode == 1) {
+                const cplx k = kf.s[i][idx];
+                cplx fv = field.s[i][idx];
+                fv = mk(fv.x + fdt * k.x, fv.y + fdt * k.y);
+                field.s[i][idx] = cdiv(fv, dn);
+            } else {
+                cplx fv = cdiv(final_.s[i][idx], dn);
+                final_.s[i][idx] = fv;
+                if (GOPF_FILTER(P)) {
+                    const double s = filter_eval(GOPF_FILTER(P), P.filter_n, kp.frad * 2.0 / GOPF_PI);
+                    fv = mk(fv.x * s, fv.y * s);
+                }
+                field.s[i][idx] = fv;
+            }
+        }
+    }
+}
+
 }  // namespace gopf

@@ -14,25 +14,9 @@ __global__ void __launch_bounds__(256)
     update_all(P, sp, tab, fg, n);
 }
 
-// filter(k) / (1 - dt * den_i(k)) for every node (euler.go:33, util.go:125-132)
 __global__ void __launch_bounds__(256)
     k_implicit_table(const __grid_constant__ DevKProgram P, int i, cplx* out, FreqGeom fg, long long n) {
-    const bool small = n < (1LL << 31);
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (long long)gridDim.x * blockDim.x) {
-        double f[3] = {0.0, 0.0, 0.0};
-        ref_freq_fast(fg, idx, small, f);
-        const KPoint kp = make_kpoint(f[0], f[1], f[2]);
-        const DevEquation& q = P.eq[i];
-        cplx den = mk(0.0, 0.0);
-        for (int j = 0; j < q.n_den; ++j) den += eval_term(P, q.den[j], kp, [&](int) -> cplx { return mk(1.0, 0.0); });
-        cplx r = cdiv(mk(1.0, 0.0), mk(1.0 - P.dt * den.x, -P.dt * den.y));
-        if (P.filter) {
-            const double sc = filter_eval(P.filter, P.filter_n, kp.frad * 2.0 / GOPF_PI);
-            r = mk(r.x * sc, r.y * sc);
-        }
-        out[idx] = r;
-    }
+    implicit_table_all(P, i, out, fg, n);
 }
 
 // real part of every cell; big-endian byte order on request (encoding/binary.BigEndian in
@@ -62,22 +46,8 @@ __global__ void __launch_bounds__(256)
         out[i] = eval_derived(D, [&](int f) -> cplx { return R.r[f][i]; }, step, i);
 }
 
-// VolumeConservingLP.OnStepFinished (pf/volumeConserving.go:31-50).  sum_i Re c_i is the
-// DC mode of the updated spectrum, the indicator integral the DC mode of the indicator
-// spectrum.  state = {multiplier, current integral, first-update flag}
 __global__ void k_volume_lp_update(double* state, const cplx* field_spec, const cplx* indicator_spec, double dt) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const double field_integral = field_spec[0].x;
-        const double indicator_integral = indicator_spec[0].x;
-        if (state[2] != 0.0) {
-            state[1] = field_integral;
-            state[2] = 0.0;
-        } else {
-            const double delta = field_integral - state[1];
-            state[1] = field_integral;
-            state[0] = state[0] - delta / (dt * indicator_integral);
-        }
-    }
+    volume_lp_update(state, field_spec, indicator_spec, dt);
 }
 
 // M(k) of the elastic term for every node (elastic.cuh); time-independent, tabulated once.
@@ -91,68 +61,15 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// RK4 pointwise kernels (pf/rk4.go:58-68, 77-84, 87-96, 101-111, 123-126)
 __global__ void __launch_bounds__(256)
     k_rk4_rhs(const __grid_constant__ DevKProgram P, SpectraPtrs sp, SpectraPtrs kout, FreqGeom fg, long long n) {
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (long long)gridDim.x * blockDim.x) {
-        double f[3] = {0.0, 0.0, 0.0};
-        ref_freq(fg, idx, f);
-        const KPoint kp = make_kpoint(f[0], f[1], f[2]);
-        auto get = [&](int b) -> cplx { return sp.s[b][idx]; };
-        for (int i = 0; i < P.n_fields; ++i) {
-            const DevEquation& q = P.eq[i];
-            cplx rhs = mk(0.0, 0.0);
-            for (int j = 0; j < q.n_rhs; ++j) rhs += eval_term(P, q.rhs[j], kp, get);
-            kout.s[i][idx] = rhs;
-        }
-    }
+    rk4_rhs_all(P, sp, kout, fg, n);
 }
 
-// mode 0: final += fdt*k ; field = initial                       (PrepareNextCorrection)
-// mode 1: field = (field + fdt*k) / (1 - fdt*den)                 (correction, first loop)
-// mode 2: final /= (1 - fdt*den); field = final; filter           (end of Step)
 __global__ void __launch_bounds__(256)
     k_rk4_point(const __grid_constant__ DevKProgram P, int mode, double fdt, SpectraPtrs field, SpectraPtrs initial,
                 SpectraPtrs final_, SpectraPtrs kf, FreqGeom fg, long long n) {
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (long long)gridDim.x * blockDim.x) {
-        KPoint kp;
-        if (mode != 0) {
-            double f[3] = {0.0, 0.0, 0.0};
-            ref_freq(fg, idx, f);
-            kp = make_kpoint(f[0], f[1], f[2]);
-        }
-        auto get = [&](int b) -> cplx { return field.s[b][idx]; };
-        for (int i = 0; i < P.n_fields; ++i) {
-            if (mode == 0) {
-                const cplx k = kf.s[i][idx];
-                cplx fv = final_.s[i][idx];
-                fv = mk(fv.x + fdt * k.x, fv.y + fdt * k.y);
-                final_.s[i][idx] = fv;
-                field.s[i][idx] = initial.s[i][idx];
-                continue;
-            }
-            const DevEquation& q = P.eq[i];
-            cplx den = mk(0.0, 0.0);
-            for (int j = 0; j < q.n_den; ++j) den += eval_term(P, q.den[j], kp, get);
-            const cplx dn = mk(1.0 - fdt * den.x, -fdt * den.y);
-            if (mode == 1) {
-                const cplx k = kf.s[i][idx];
-                cplx fv = field.s[i][idx];
-                fv = mk(fv.x + fdt * k.x, fv.y + fdt * k.y);
-                field.s[i][idx] = cdiv(fv, dn);
-            } else {
-                cplx fv = cdiv(final_.s[i][idx], dn);
-                final_.s[i][idx] = fv;
-                if (P.filter) {
-                    const double s = filter_eval(P.filter, P.filter_n, kp.frad * 2.0 / GOPF_PI);
-                    fv = mk(fv.x * s, fv.y * s);
-                }
-                field.s[i][idx] = fv;
-            }
-        }
-    }
+    rk4_point_all(P, mode, fdt, field, initial, final_, kf, fg, n);
 }
 
 // Go's cmplx.Pow leaves an O(1e-16) imaginary residue on negative real scalars (m1 = -1
@@ -219,6 +136,8 @@ Solver::~Solver() {
         if (d_table_[i]) cudaFree(d_table_[i]);
     for (jit::Kernel* k : jit_derived_) jit::unload(k);
     jit::unload(jit_kupdate_);
+    jit::unload(jit_rk4_rhs_);
+    jit::unload(jit_rk4_point_);
     free_catalog_buffers();
     sdd_free_buffers();
     if (W_) cudaFree(W_);
@@ -918,31 +837,40 @@ void Solver::launch_update(const DevKProgram& P) {
     tock(id);
 }
 
-// The same update compiled for exactly this program (jit.h).  The image is keyed on the
+// The k-space kernels compiled for exactly this program (jit.h).  The images are keyed on the
 // program bytes (they hold the filter / multiplier addresses too) and on which fields have a
-// tabulated implicit factor; any change recompiles.  false: not specialised, run the generic kernel.
-bool Solver::launch_update_jit(const DevKProgram& P, const ImplicitTab& tab) {
+// tabulated implicit factor; any change recompiles.  false: not specialised.
+bool Solver::ensure_jit_program(const DevKProgram& P, unsigned tab_mask) {
     if (!jit_on_) return false;
-    unsigned mask = 0;
-    for (int i = 0; i < P.n_fields; ++i)
-        if (tab.t[i]) mask |= 1u << i;
     std::string key(reinterpret_cast<const char*>(&P), sizeof(P));
-    key.push_back((char)mask);
+    key.push_back((char)tab_mask);
     if (key != jit_kupdate_key_) {
         jit::unload(jit_kupdate_);
-        jit_kupdate_ = nullptr;
+        jit::unload(jit_rk4_rhs_);
+        jit::unload(jit_rk4_point_);
+        jit_kupdate_ = jit_rk4_rhs_ = jit_rk4_point_ = nullptr;
         jit_kupdate_key_ = key;
         std::string log;
         std::vector<char> cubin;
         try {
-            if (jit::compile_cubin(jit::kupdate_kernel_source(P, plan_->freq_geom(), (long long)plan_->N, mask), &cubin, &log))
+            if (jit::compile_cubin(jit::kupdate_kernel_source(P, plan_->freq_geom(), (long long)plan_->N, tab_mask), &cubin, &log)) {
                 jit_kupdate_ = jit::load(cubin, "gopf_jit_kupdate", &log);
+                jit_rk4_rhs_ = jit::load(cubin, "gopf_jit_rk4_rhs", &log);
+                jit_rk4_point_ = jit::load(cubin, "gopf_jit_rk4_point", &log);
+            }
         } catch (const std::exception& e) {
             log = e.what();
         }
-        if (!jit_kupdate_) jit_log_ += "k_update: " + log + "\n";
+        if (!jit_kupdate_ || !jit_rk4_rhs_ || !jit_rk4_point_) jit_log_ += "k-space kernels: " + log + "\n";
     }
-    if (!jit_kupdate_) return false;
+    return jit_kupdate_ && jit_rk4_rhs_ && jit_rk4_point_;
+}
+
+bool Solver::launch_update_jit(const DevKProgram& P, const ImplicitTab& tab) {
+    unsigned mask = 0;
+    for (int i = 0; i < P.n_fields; ++i)
+        if (tab.t[i]) mask |= 1u << i;
+    if (!ensure_jit_program(P, mask)) return false;
     SpectraPtrs sp = S_;
     ImplicitTab t = tab;
     void* args[] = {&sp, &t};
@@ -1084,13 +1012,27 @@ void Solver::rk4_step() {
         squared_gradient_terms();
         catalog_terms();
         if (has_elastic()) elastic_terms();
-        k_rk4_rhs<<<grid_for(n), 256, 0, s>>>(prog_, S_, kf, fg, n);
-        GOPF_CUDA(cudaGetLastError());
+        if (ensure_jit_program(prog_, 0)) {
+            SpectraPtrs sp = S_, ko = kf;
+            void* args[] = {&sp, &ko};
+            std::string log;
+            if (!jit::launch(jit_rk4_rhs_, grid_for(n), 256, args, s, &log)) throw Error("jit launch of rk4_rhs: " + log);
+        } else {
+            k_rk4_rhs<<<grid_for(n), 256, 0, s>>>(prog_, S_, kf, fg, n);
+            GOPF_CUDA(cudaGetLastError());
+        }
         launches_++;
     };
     auto point = [&](int mode, double fdt) {
-        k_rk4_point<<<grid_for(n), 256, 0, s>>>(prog_, mode, fdt, S_, init, fin, kf, fg, n);
-        GOPF_CUDA(cudaGetLastError());
+        if (ensure_jit_program(prog_, 0)) {
+            SpectraPtrs f = S_, a = init, b = fin, c = kf;
+            void* args[] = {&mode, &fdt, &f, &a, &b, &c};
+            std::string log;
+            if (!jit::launch(jit_rk4_point_, grid_for(n), 256, args, s, &log)) throw Error("jit launch of rk4_point: " + log);
+        } else {
+            k_rk4_point<<<grid_for(n), 256, 0, s>>>(prog_, mode, fdt, S_, init, fin, kf, fg, n);
+            GOPF_CUDA(cudaGetLastError());
+        }
         launches_++;
     };
     for (int i = 0; i < F; ++i) {  // rk4.go:36-43

@@ -177,8 +177,12 @@ private:
     bool jit_on_ = false;
     std::string jit_log_;
     void derived_pointwise(int d, cplx* out, unsigned long long step_no, cudaStream_t s);
-    jit::Kernel* jit_kupdate_ = nullptr;  // k_update compiled for the current program, NULL: generic kernel
+    // k-space kernels compiled for the current program (one image, three entry points); NULL: generic kernels
+    jit::Kernel* jit_kupdate_ = nullptr;
+    jit::Kernel* jit_rk4_rhs_ = nullptr;
+    jit::Kernel* jit_rk4_point_ = nullptr;
     std::string jit_kupdate_key_;
+    bool ensure_jit_program(const DevKProgram& P, unsigned tab_mask);
     bool launch_update_jit(const DevKProgram& P, const ImplicitTab& tab);
 
     NewtonKrylovOptions nk_;

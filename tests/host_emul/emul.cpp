@@ -34,6 +34,58 @@ void emul_update(const void* program, double** spectra, const double** tabs, con
     update_all(P, sp, tab, fg, n);
 }
 
+static DevKProgram load_program(const void* program, const double* filter, int filter_n, const double* lp0, const double* lp1) {
+    DevKProgram P;
+    memcpy(&P, program, sizeof(P));
+    P.filter = filter;
+    P.filter_n = filter ? filter_n : 0;
+    P.lp_multiplier[0] = lp0;
+    P.lp_multiplier[1] = lp1;
+    return P;
+}
+
+static SpectraPtrs load_spectra(double** spectra) {
+    SpectraPtrs sp;
+    for (int i = 0; i < GOPF_MAX_SPECTRA; ++i) sp.s[i] = spectra ? reinterpret_cast<cplx*>(spectra[i]) : nullptr;
+    return sp;
+}
+
+static FreqGeom geom(int rank, int d0, int d1, int d2) {
+    FreqGeom fg;
+    fg.rank = rank;
+    fg.d0 = d0;
+    fg.d1 = d1;
+    fg.d2 = d2;
+    return fg;
+}
+
+// implicit_table_all: filter(k) / (1 - dt den_i(k)) for every node
+void emul_implicit_table(const void* program, const double* filter, int filter_n, int i, double* out, int rank, int d0,
+                         int d1, int d2, long long n) {
+    const DevKProgram P = load_program(program, filter, filter_n, nullptr, nullptr);
+    implicit_table_all(P, i, reinterpret_cast<cplx*>(out), geom(rank, d0, d1, d2), n);
+}
+
+// volume_lp_update (pf/volumeConserving.go:31-50) on state = {multiplier, integral, first flag}
+void emul_volume_lp_update(double* state, const double* field_spec, const double* indicator_spec, double dt) {
+    volume_lp_update(state, reinterpret_cast<const cplx*>(field_spec), reinterpret_cast<const cplx*>(indicator_spec), dt);
+}
+
+// the RK4 passes (pf/rk4.go:29-127)
+void emul_rk4_rhs(const void* program, double** spectra, double** kout, const double* lp0, const double* lp1, int rank,
+                  int d0, int d1, int d2, long long n) {
+    const DevKProgram P = load_program(program, nullptr, 0, lp0, lp1);
+    rk4_rhs_all(P, load_spectra(spectra), load_spectra(kout), geom(rank, d0, d1, d2), n);
+}
+
+void emul_rk4_point(const void* program, const double* filter, int filter_n, const double* lp0, const double* lp1, int mode,
+                    double fdt, double** field, double** initial, double** final_, double** kf, int rank, int d0, int d1,
+                    int d2, long long n) {
+    const DevKProgram P = load_program(program, filter, filter_n, lp0, lp1);
+    rk4_point_all(P, mode, fdt, load_spectra(field), load_spectra(initial), load_spectra(final_), load_spectra(kf),
+                  geom(rank, d0, d1, d2), n);
+}
+
 // eval_derived (pf/model.go:237-241) at every node: fields = GOPF_MAX_FIELDS pointers to real-space
 // complex128 arrays, out = n complex128.
 void emul_derived(const void* derived, const double** fields, const double* table, long long table_n, double* out,

@@ -49,6 +49,29 @@ def _image(fn, *args, tail=()):
     return buf, need
 
 
+class _Term(ctypes.Structure):  # DevTerm (step_program.h)
+    _fields_ = [("cre", ctypes.c_double), ("cim", ctypes.c_double), ("brick", ctypes.c_int), ("lap", ctypes.c_int),
+                ("kind", ctypes.c_int), ("param", ctypes.c_int)]
+
+
+class _Equation(ctypes.Structure):  # DevEquation: GOPF_MAX_TERMS = 8
+    _fields_ = [("n_rhs", ctypes.c_int), ("n_den", ctypes.c_int), ("rhs", _Term * 8), ("den", _Term * 8)]
+
+
+class _ProgramHead(ctypes.Structure):  # the leading members of DevKProgram: GOPF_MAX_FIELDS = 4
+    _fields_ = [("rank", ctypes.c_int), ("n_fields", ctypes.c_int), ("dt", ctypes.c_double), ("eq", _Equation * MAX_FIELDS)]
+
+
+class ProgramView:
+    def __init__(self, buf):
+        self.head = _ProgramHead.from_buffer(buf)
+        self.n_fields = self.head.n_fields
+
+    def den_terms(self, i):
+        q = self.head.eq[i]
+        return [q.den[j] for j in range(q.n_den)]
+
+
 class EmulatedSolver:
     """gopf_b200.pf.Solver's surface, semi-implicit Euler on the general path, on the host."""
 
@@ -58,9 +81,10 @@ class EmulatedSolver:
         self.dll, self.Model, self.dims, self.Dt = dll, m, [int(d) for d in dims], dt
         self.Callbacks, self.Monitors, self.StartEpoch = [], [], 0
         self.filter = None
-        self.steps = 0
+        self.current_step = 0  # Euler.CurrentStep; RK4.Step never advances it (rk4.go:130-135)
+        self.steps_taken = 0   # counter of the noise stream
         self.launches = 0
-        self.Stepper = types.SimpleNamespace(SetFilter=self._set_filter, GetTime=lambda: self.steps * self.Dt, Dt=dt)
+        self.Stepper = types.SimpleNamespace(SetFilter=self._set_filter, GetTime=lambda: self.current_step * self.Dt, Dt=dt)
         self.rank = len(dims)
         self.N = int(np.prod(dims))
         for f in m.Fields:
@@ -83,10 +107,26 @@ class EmulatedSolver:
         if len(m.Fields) + nd.value > MAX_SPECTRA:
             raise gpf.GopfError("too many spectra")
         self.tables = getattr(m, "_emul_tables", [])
+        self.stepper = "euler"
+        self.lp_state = np.array([0.0, 0.0, 1.0] * 2)  # per slot: Multiplier, CurrentIntegral, IsFirstUpdate (solver.cu)
+        # VolumeConservingLP terms: slots in name order (std::map in model.cu), field / indicator spectrum
+        names = m.AllFieldNames()
+        self.lp_terms = [(names.index(t.Field), names.index(t.Indicator), t.Dt)
+                         for _, t in sorted(m.ExplicitTerms.items()) if isinstance(t, gpf.VolumeConservingLP)]
+        self.tabs = None
 
     # -- the surface the tests use
+    def SetStepper(self, name):
+        if name not in ("euler", "rk4"):
+            raise gpf.GopfError("Unknown stepper scheme")
+        self.stepper = name
+
+    def LPMultiplier(self, slot=0):
+        return float(self.lp_state[3 * slot])
+
     def _set_filter(self, filt):
         self.filter = None if filt is None else np.ascontiguousarray(filt.Data, dtype=np.float64)
+        self.tabs = None
 
     def ForceGeneric(self, on=True):
         pass
@@ -103,11 +143,22 @@ class EmulatedSolver:
                 mon.Add(self.Model.Bricks)
 
     def Propagate(self, nsteps):
-        fields = self.Model.Fields
-        S = [self._fft(f.Data) for f in fields]  # upload: euler.go:19-21
+        self.Upload()
+        self.StepDevice(nsteps)
+        self.Download()
+
+    def Upload(self):  # euler.go:19-21
+        self.S = [self._fft(f.Data) for f in self.Model.Fields]
+
+    def StepDevice(self, nsteps):
         for _ in range(nsteps):
-            self._step(S)
-        for f, s in zip(fields, S):  # download: euler.go:42-45
+            if self.stepper == "rk4":
+                self._rk4_step(self.S)
+            else:
+                self._step(self.S)
+
+    def Download(self):  # euler.go:42-45
+        for f, s in zip(self.Model.Fields, self.S):
             f.Data[:] = self._ifft(s)
 
     # -- one Solver::euler_update_generic
@@ -117,7 +168,38 @@ class EmulatedSolver:
     def _ifft(self, x):
         return np.ascontiguousarray(scipy.fft.ifftn(x.reshape(self.dims)).reshape(-1))  # includes the 1/N
 
-    def _step(self, S):
+    def _ptrs(self, arrays, count):
+        return (DP * count)(*[a.ctypes.data_as(DP) if a is not None else None for a in arrays])
+
+    def _geom(self):
+        d = self.dims
+        return self.rank, d[0], d[1], d[2] if self.rank > 2 else 1, ctypes.c_longlong(self.N)
+
+    def _filter_args(self):
+        if self.filter is None:
+            return None, 0
+        return self.filter.ctypes.data_as(DP), self.filter.shape[0]
+
+    def _lp_args(self):
+        base = self.lp_state.ctypes.data
+        return ctypes.cast(base, DP), ctypes.cast(base + 24, DP)
+
+    def _implicit_tabs(self):
+        """Solver::launch_update: tabulate filter / (1 - dt den) when it is expensive per k and depends on k only."""
+        if self.tabs is None:
+            P = ProgramView(self.program)
+            self.tabs = [None] * MAX_FIELDS
+            for i in range(P.n_fields):
+                den = P.den_terms(i)
+                expensive = self.filter is not None or any(t.kind in (1, 2) for t in den)  # TK_SPECTRAL_VISC, TK_PAIR_CORR
+                k_only = all(t.brick < 0 and t.kind not in (3, 4) for t in den)            # TK_CONS_NOISE, TK_VOLUME_LP
+                if expensive and k_only:
+                    out = np.empty(self.N, dtype=np.complex128)
+                    self.dll.emul_implicit_table(self.program, *self._filter_args(), i, out.ctypes.data_as(DP), *self._geom())
+                    self.tabs[i] = out
+        return self.tabs
+
+    def _derived_spectra(self, S):
         F = len(S)
         spectra = list(S) + [None] * (MAX_SPECTRA - F)
         if any(used for _, used in self.derived):
@@ -135,17 +217,52 @@ class EmulatedSolver:
                     continue
                 out = np.empty(self.N, dtype=np.complex128)
                 self.dll.emul_derived(dbuf, rp, table, ctypes.c_longlong(tn), out.ctypes.data_as(DP),
-                                      ctypes.c_ulonglong(self.steps), ctypes.c_longlong(self.N))
+                                      ctypes.c_ulonglong(self.steps_taken), ctypes.c_longlong(self.N))
                 spectra[F + d] = self._fft(out)
                 self.launches += 1
-        sp = (DP * MAX_SPECTRA)(*[s.ctypes.data_as(DP) if s is not None else None for s in spectra])
-        filt = self.filter.ctypes.data_as(DP) if self.filter is not None else None
-        fn = self.filter.shape[0] if self.filter is not None else 0
-        d = self.dims
-        self.dll.emul_update(self.program, sp, None, filt, fn, None, None, self.rank, d[0], d[1], d[2] if self.rank > 2 else 1,
-                             ctypes.c_longlong(self.N))
+        return spectra
+
+    def _step(self, S):  # Solver::euler_step_generic
+        spectra = self._derived_spectra(S)
+        tabs = self._implicit_tabs() if self.use_tabs else [None] * MAX_FIELDS
+        self.dll.emul_update(self.program, self._ptrs(spectra, MAX_SPECTRA), self._ptrs(tabs, MAX_FIELDS), *self._filter_args(),
+                             *self._lp_args(), *self._geom())
         self.launches += 1
-        self.steps += 1
+        for slot, (fi, ii, dt) in enumerate(self.lp_terms):  # Solver::volume_lp_hooks
+            state = ctypes.cast(self.lp_state.ctypes.data + 24 * slot, DP)
+            self.dll.emul_volume_lp_update(state, spectra[fi].ctypes.data_as(DP), spectra[ii].ctypes.data_as(DP), ctypes.c_double(dt))
+        self.current_step += 1
+        self.steps_taken += 1
+
+    use_tabs = True
+
+    def _rk4_step(self, S):  # Solver::rk4_step (pf/rk4.go:29-74); S is updated in place
+        F = len(S)
+        init = [s.copy() for s in S]
+        fin = [s.copy() for s in S]
+        kf = [np.zeros(self.N, dtype=np.complex128) for _ in S]
+        pad = [None] * (MAX_SPECTRA - F)
+
+        def sync_and_rhs():
+            spectra = self._derived_spectra(S)
+            self.dll.emul_rk4_rhs(self.program, self._ptrs(spectra, MAX_SPECTRA), self._ptrs(kf + pad, MAX_SPECTRA),
+                                  *self._lp_args(), *self._geom())
+            self.launches += 1
+            return spectra
+
+        def point(mode, fdt, spectra):
+            self.dll.emul_rk4_point(self.program, *self._filter_args(), *self._lp_args(), mode, ctypes.c_double(fdt),
+                                    self._ptrs(spectra, MAX_SPECTRA), self._ptrs(init + pad, MAX_SPECTRA),
+                                    self._ptrs(fin + pad, MAX_SPECTRA), self._ptrs(kf + pad, MAX_SPECTRA), *self._geom())
+            self.launches += 1
+
+        dt = self.Dt
+        for first, second in (((0, dt / 6.0), (1, 0.5 * dt)), ((0, dt / 3.0), (1, 0.5 * dt)), ((0, dt / 3.0), (1, 1.0 * dt)),
+                              ((0, dt / 6.0), (2, dt))):
+            spectra = sync_and_rhs()
+            point(*first, spectra)
+            point(*second, spectra)
+        self.steps_taken += 1
 
 
 class _RecordingModel(gpf.Model):
@@ -224,6 +341,36 @@ def test_negative_value_penalty(T):
     T.test_negative_value_penalty_vs_oracle()
 
 
+def test_rk4(T):
+    T.test_rk4_simple_model_and_implicit()
+    T.test_rk4_cahn_hilliard_vs_oracle([32, 32])
+    T.test_rk4_cahn_hilliard_vs_oracle([16, 16, 16])
+
+
+def test_two_phase_functions_and_volume_constraint(T):
+    T.test_two_phase_functions_and_volume_constraint_vs_oracle()
+
+
+def test_tabulated_and_literal_implicit_side_agree(emul, monkeypatch):
+    """pfc with pair correlation + Vandeven filter: launch_update tabulates filter / (1 - dt den); the
+    literal evaluation of the same factor must give the same trajectory."""
+    import test_step_gpu as mod
+
+    out = []
+    for use_tabs in (True, False):
+        shim = types.SimpleNamespace(**{k: getattr(gpf, k) for k in dir(gpf) if not k.startswith("__")})
+        shim.NewModel = _RecordingModel
+        cls = type("S", (EmulatedSolver,), {"use_tabs": use_tabs})
+        shim.NewSolver = lambda m, dims, dt, device=-1, cls=cls: cls(emul, m, dims, dt)
+        monkeypatch.setattr(mod, "gpf", shim)
+        (gm, gf, gs), _ = mod.pfc_models([32, 32], True, filt_order=5)
+        gs.Solve(2, 10)
+        if use_tabs:
+            assert gs.tabs is not None and gs.tabs[0] is not None
+        out.append(gf.Data.copy())
+    assert np.linalg.norm(out[0] - out[1]) <= 1e-13 * np.linalg.norm(out[1])
+
+
 # ---- seeded random models: parser -> program -> evaluators against the oracle, numerically ---------------
 @pytest.mark.parametrize("seed", range(80))
 def test_random_models_step_like_the_oracle(emul, seed):
@@ -283,15 +430,23 @@ class SpecialisedEmulatedSolver(EmulatedSolver):
     """EmulatedSolver whose update is `gopf_jit_kupdate`: program image as constant words, grid geometry,
     node count and the (host) address of the filter table as literals."""
 
+    use_tabs = False
+
     build_dir = None
     calls = 0
 
     def _step(self, S):
+        self._with_unit(super()._step, S)
+
+    def _rk4_step(self, S):
+        self._with_unit(super()._rk4_step, S)
+
+    def _with_unit(self, step, S):
         if not hasattr(self, "_kernel") or self._filter_id != id(self.filter):
             self._filter_id = id(self.filter)
             addr = self.filter.ctypes.data if self.filter is not None else 0
             fn = self.filter.shape[0] if self.filter is not None else 0
-            src = self.Model.KUpdateSource(self.dims, self.Dt, 0, filter_addr=addr, filter_n=fn)
+            src = self.Model.KUpdateSource(self.dims, self.Dt, 0, filter_addr=addr, filter_n=fn, lp_addr=self.lp_state.ctypes.data)
             assert "jit_prog_words" in src
             SpecialisedEmulatedSolver.serial = getattr(SpecialisedEmulatedSolver, "serial", 0) + 1
             stem = os.path.join(self.build_dir, f"unit_{SpecialisedEmulatedSolver.serial}")
@@ -299,20 +454,35 @@ class SpecialisedEmulatedSolver(EmulatedSolver):
                 f.write('#include "cuda_shim.h"\n' + src)
             subprocess.run(["g++", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-I", os.path.join(ROOT, "gopf_b200", "csrc"),
                             "-I", os.path.join(ROOT, "tests", "host_emul"), "-o", stem + ".so", stem + ".cpp"], check=True)
-            self._kernel = ctypes.CDLL(stem + ".so").gopf_jit_kupdate
+            unit = ctypes.CDLL(stem + ".so")
+            self._kernel = unit.gopf_jit_kupdate
             self._kernel.argtypes = [_Spectra, _Tabs]
             self._kernel.restype = None
-        generic_update = self.dll.emul_update
-
+            self._rk4_rhs = unit.gopf_jit_rk4_rhs
+            self._rk4_rhs.argtypes = [_Spectra, _Spectra]
+            self._rk4_rhs.restype = None
+            self._rk4_point = unit.gopf_jit_rk4_point
+            self._rk4_point.argtypes = [ctypes.c_int, ctypes.c_double, _Spectra, _Spectra, _Spectra, _Spectra]
+            self._rk4_point.restype = None
         def specialised(program, sp, tabs, filt, fn, lp0, lp1, rank, d0, d1, d2, n):
-            self._kernel(_Spectra(sp), _Tabs())
+            self._kernel(_Spectra(sp), _Tabs())  # tab_mask 0: the literal implicit side
             SpecialisedEmulatedSolver.calls += 1
 
-        self.dll = types.SimpleNamespace(emul_update=specialised, emul_derived=self.dll.emul_derived)
+        def rk4_rhs(program, sp, kout, lp0, lp1, rank, d0, d1, d2, n):
+            self._rk4_rhs(_Spectra(sp), _Spectra(kout))
+            SpecialisedEmulatedSolver.calls += 1
+
+        def rk4_point(program, filt, fn, lp0, lp1, mode, fdt, field, initial, final_, kf, rank, d0, d1, d2, n):
+            self._rk4_point(mode, fdt, _Spectra(field), _Spectra(initial), _Spectra(final_), _Spectra(kf))
+            SpecialisedEmulatedSolver.calls += 1
+
+        real = self.dll
+        self.dll = types.SimpleNamespace(emul_update=specialised, emul_rk4_rhs=rk4_rhs, emul_rk4_point=rk4_point,
+                                         emul_derived=real.emul_derived, emul_volume_lp_update=real.emul_volume_lp_update)
         try:
-            super()._step(S)
+            step(S)
         finally:
-            self.dll = types.SimpleNamespace(emul_update=generic_update, emul_derived=self.dll.emul_derived)
+            self.dll = real
 
 
 @pytest.fixture()
@@ -336,6 +506,14 @@ def test_specialised_update_unit_on_the_host(TS):
     TS.test_conservative_noise_prescribed_currents_vs_oracle()
     TS.test_tensorial_hessian_anisotropic_diffusion_vs_oracle([16, 16, 16], [1.0, 0.2, 0.1, 0.2, 2.0, 0.3, 0.1, 0.3, 0.5])
     assert SpecialisedEmulatedSolver.calls > 200  # every step above went through gopf_jit_kupdate
+
+
+def test_specialised_rk4_and_volume_constraint_units_on_the_host(TS):
+    SpecialisedEmulatedSolver.calls = 0
+    TS.test_rk4_simple_model_and_implicit()
+    TS.test_rk4_cahn_hilliard_vs_oracle([16, 16, 16])
+    assert SpecialisedEmulatedSolver.calls > 100
+    TS.test_two_phase_functions_and_volume_constraint_vs_oracle()  # the multiplier's address as a literal
 
 
 def test_emulated_freq_is_the_reference_k_table(emul):

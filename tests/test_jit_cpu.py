@@ -146,14 +146,15 @@ def test_function_source_is_refused_for_other_derived_fields():
         m.FunctionSource("nope")
 
 
-def _resource_usage(cubin):
+def _resource_usage(cubin, function=None):
     out = subprocess.run(["cuobjdump", "-res-usage", cubin], check=True, capture_output=True, text=True).stdout
-    m = re.search(r"REG:(\d+) STACK:(\d+)", out)
+    pattern = r"REG:(\d+) STACK:(\d+)" if function is None else rf"Function {function}:\s+REG:(\d+) STACK:(\d+)"
+    m = re.search(pattern, out)
     return int(m.group(1)), int(m.group(2))
 
 
-def _sass_counts(cubin):
-    sass = subprocess.run(["cuobjdump", "-sass", cubin], check=True, capture_output=True, text=True).stdout
+def _sass_counts(cubin, function):
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", function, cubin], check=True, capture_output=True, text=True).stdout
     ops = re.findall(r"^\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", sass, flags=re.M)
     return ops
 
@@ -209,11 +210,22 @@ def test_kspace_update_specialises_to_a_folded_image(kind, tab_mask, with_filter
     if not shutil.which("cuobjdump"):
         return
     cubin = str(sorted(tmp_path.glob("*.cubin"))[-1])
-    regs, stack = _resource_usage(cubin)
-    ops = _sass_counts(cubin)
-    assert stack == 0 and regs <= 64, (regs, stack)
+    for fn in ("gopf_jit_rk4_rhs", "gopf_jit_rk4_point"):  # the RK4 passes of the same program
+        regs, stack = _resource_usage(cubin, fn)
+        rk_ops = _sass_counts(cubin, fn)
+        assert stack == 0 and len(rk_ops) > 50 and not any(o.startswith(("LDL", "STL")) for o in rk_ops), (fn, regs, stack)
+    regs, stack = _resource_usage(cubin, "gopf_jit_kupdate")
+    ops = _sass_counts(cubin, "gopf_jit_kupdate")
+    assert stack == 0 and regs <= 64 and len(ops) > 100, (regs, stack, len(ops))
     assert not any(o.startswith(("LDL", "STL")) for o in ops)
     # the program image is folded away: the only global loads left are the 16-byte spectrum / table cells
     loads = [o for o in ops if o.startswith("LDG")]
     assert loads and all(o.startswith("LDG.E.128") or o.startswith("LDG.E.64") for o in loads), sorted(set(loads))
     assert len(loads) <= 12, len(loads)
+
+
+def test_specialisation_refuses_a_null_multiplier_address():
+    shim = _host_only(gpf)
+    m = workloads.build_precipitate(shim, shim, gel, [8, 8, 8], expressions=True)[0]
+    with pytest.raises(gpf.GopfError, match="without a multiplier address"):
+        m.KUpdateSource([8, 8, 8], workloads.PRECIPITATE_DT, 0, lp_addr=0)
