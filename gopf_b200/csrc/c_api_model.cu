@@ -504,6 +504,23 @@ int gopf_elasticity_multiplier(const double* c, const double* misfit, int dim, c
     GOPF_API_END
 }
 
+int gopf_has_kspace_noise(void) {
+#ifdef GOPF_KNOISE
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+int gopf_model_set_kspace_noise(gopf_model* m, int on) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    if (m->m.attached_solvers > 0) throw Error("model: a solver has been compiled from this model already");
+    m->m.kspace_noise = on != 0;
+    m->m.initialised = false;
+    GOPF_API_END
+}
+
 int gopf_model_init(gopf_model* m) {
     GOPF_API_BEGIN
     if (!m) throw Error("model is NULL");

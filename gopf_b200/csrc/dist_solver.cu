@@ -30,6 +30,7 @@ DistSolver::DistSolver(Model* m, int n, int world, int rank, double dt, int devi
     const int dims[3] = {n, n, n};
     plan_.reset(new FftPlan(3, dims, device));
     m->fill_program(&prog_, dt, 3);
+    if (program_has_knoise(prog_)) throw Error("dist solver: k-space noise is not wired into the sharded path");
     prog_.filter = nullptr;
     prog_.filter_n = 0;
     finalize_single_field_program(&prog_, 1);

@@ -167,8 +167,7 @@ __device__ __forceinline__ void volume_lp_update(double* state, const cplx* fiel
 }
 
 // RK4 pointwise passes (pf/rk4.go:58-68, 77-84, 87-96, 101-111, 123-126)
-__device__ __forceinline__ void rk4_rhs_all(const DevKProgram& P, const SpectraPtrs& sp, const SpectraPtrs& kout,
-                                            const FreqGeom& fg, long long n) {
+__device__ __forceinline__ void rk4_rhs_all(const DevKProgram& P, SpectraPtrs sp, SpectraPtrs kout, FreqGeom fg, long long n) {
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
          idx += (long long)gridDim.x * blockDim.x) {
         double f[3] = {0.0, 0.0, 0.0};

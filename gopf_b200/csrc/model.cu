@@ -540,6 +540,22 @@ CompiledEquation Model::build(const std::string& eq) {
             ce.den.push_back(concrete_term(t));
         } else {
             DevTerm d = concrete_term(t);
+            const int di = d.brick - (int)fields.size();
+            if (kspace_noise && di >= 0 && di < (int)derived.size() && derived[di].dev.kind == DK_WHITE_NOISE) {
+                // + c * L^n * NOISE: the noise spectrum is drawn at the k-point, the field is never transformed
+                int slot = -1;
+                for (const auto& ks : knoise_slots)
+                    if (ks.second == di) slot = ks.first;
+                if (slot < 0) {
+                    slot = knoise_base_ + (int)knoise_slots.size();
+                    if (slot >= GOPF_MAX_SPECIAL)
+                        throw Error(strf("model: at most %d TensorialHessian terms and k-space noise fields together", GOPF_MAX_SPECIAL));
+                    knoise_slots.push_back({slot, di});
+                }
+                d.kind = TK_WHITE_NOISE_K;
+                d.brick = -1;
+                d.param = slot;
+            }
             if (d.brick >= 0) mark_used(d.brick);
             ce.rhs.push_back(d);
         }
@@ -589,6 +605,8 @@ void Model::init() {
         throw Error(strf("model: at most %d terms of each special kind", GOPF_MAX_SPECIAL));
     if (n_spectra() > GOPF_MAX_SPECTRA) throw Error(strf("model: at most %d spectra", GOPF_MAX_SPECTRA));
     compiled.clear();
+    knoise_slots.clear();
+    knoise_base_ = n_th;  // k-space noise borrows the TensorHessianParams slots after the real ones
     for (const std::string& eq : equations) compiled.push_back(build(eq));
     // equation i must evolve field i (Euler.Step pairs m.RHS[i] with m.Fields[i], euler.go:27-31)
     initialised = true;
@@ -620,6 +638,13 @@ void Model::fill_program(DevKProgram* P, double dt, int rank) const {
                 q.rhs[q.n_rhs++] = t;
             }
         }
+    }
+    for (const auto& ks : knoise_slots) {  // step_program.h TensorHessianParams: amplitude, seed bits, step bits
+        TensorHessianParams& h = P->th[ks.first];
+        const DevDerived& d = derived[ks.second].dev;
+        h.K[0] = d.noise_std * std::sqrt((double)N);
+        h.K[1] = gopf_double_of(d.seed);
+        h.K[2] = gopf_double_of(0ull);
     }
     for (const auto& kv : user_terms) {
         const UserTerm& u = kv.second;

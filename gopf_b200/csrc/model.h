@@ -92,6 +92,10 @@ public:
     std::vector<std::vector<SourceSpec>> sources;  // Model.AllSources (model.go:125, 161)
     std::vector<int> source_spectrum;              // per equation: work spectrum of its sources, -1 if none
     int n_work_spectra = 0;
+    // WhiteNoise fields that enter an equation as a plain explicit term are generated directly in
+    // k-space (TK_WHITE_NOISE_K, step_program.h) instead of being transformed every step.  Off by default.
+    bool kspace_noise = false;
+    std::vector<std::pair<int, int>> knoise_slots;  // (parameter slot, derived index) assigned by Init
     bool initialised = false;
     int attached_solvers = 0;  // solvers compiled from this model (their programs do not follow later edits)
 
@@ -121,6 +125,7 @@ public:
     void fill_program(DevKProgram* P, double dt, int rank) const;
 
 private:
+    int knoise_base_ = 0;
     void update_derived_fields(const std::string& eq);  // model.go:165-195
     DevTerm concrete_term(const parser::SubStringDelimiter& t) const;  // rhsBuilder.go:125-190
     void apply_prefixes(DevTerm* t, const std::vector<std::string>& prefixes) const;  // rhsBuilder.go:199-242

@@ -165,8 +165,24 @@ void Solver::drop_graph() {
     graph_steps_ = 0;
 }
 
+// true when some term draws white noise at the k-point (TK_WHITE_NOISE_K, step_program.h)
+bool program_has_knoise(const DevKProgram& P) {
+    for (int i = 0; i < P.n_fields; ++i)
+        for (int j = 0; j < P.eq[i].n_rhs; ++j)
+            if (P.eq[i].rhs[j].kind == TK_WHITE_NOISE_K) return true;
+    return false;
+}
+
+// the step counter of the k-space noise stream lives in the program (TensorHessianParams::K[2])
+static void stamp_noise_step(DevKProgram* P, unsigned long long step) {
+    for (int i = 0; i < P->n_fields; ++i)
+        for (int j = 0; j < P->eq[i].n_rhs; ++j)
+            if (P->eq[i].rhs[j].kind == TK_WHITE_NOISE_K) P->th[P->eq[i].rhs[j].param].K[2] = gopf_double_of(step);
+}
+
 bool Solver::graph_applicable() const {
     if (graph_disabled_ || !fused_ || profiling_ || stepper_ != StepperKind::Euler || !w_valid_) return false;
+    if (has_knoise_) return false;  // the step counter is part of the kernel arguments
     if (plan_->N > (size_t)1 << 20) return false;
     const int k = m_->derived[fused_derived_].dev.kind;
     return k == DK_MONOMIAL || k == DK_RPN;  // noise / table fields take the step number as a kernel argument
@@ -358,6 +374,16 @@ void Solver::rebuild_program() {
     prog_.filter = d_filter_;
     prog_.filter_n = filter_n_;
     for (int i = 0; i < GOPF_MAX_SPECIAL; ++i) prog_.lp_multiplier[i] = d_lp_state_ ? d_lp_state_ + 3 * i : nullptr;
+    has_knoise_ = program_has_knoise(prog_);
+#ifndef GOPF_KNOISE
+    if (has_knoise_)
+        throw Error("solver: the model asks for k-space noise (gopf_model_set_kspace_noise) but this library's device "
+                    "code was built without -DGOPF_KNOISE");
+#endif
+    // the pairing of k and -k follows the Freq components, which match the transform's layout only
+    // for 2-D and cubic 3-D grids (fft_plan.h freq_axis_consistent)
+    if (has_knoise_ && !plan_->freq_axis_consistent())
+        throw Error("solver: k-space noise needs a 2-D or cubic 3-D grid");
     fused_prog_ = prog_;
     if (fused_) finalize_single_field_program(&fused_prog_, (int)m_->fields.size());
     prog_dirty_ = false;
@@ -841,7 +867,7 @@ void Solver::launch_update(const DevKProgram& P) {
 // program bytes (they hold the filter / multiplier addresses too) and on which fields have a
 // tabulated implicit factor; any change recompiles.  false: not specialised.
 bool Solver::ensure_jit_program(const DevKProgram& P, unsigned tab_mask) {
-    if (!jit_on_) return false;
+    if (!jit_on_ || has_knoise_) return false;  // the noise step counter would change the image every step
     std::string key(reinterpret_cast<const char*>(&P), sizeof(P));
     key.push_back((char)tab_mask);
     if (key != jit_kupdate_key_) {
@@ -1064,6 +1090,7 @@ void Solver::step(int nsteps) {
     if (fused_ && stepper_ == StepperKind::Euler && nsteps > GRAPH_STEPS) {
         // the first step runs eagerly (it also produces W when it is not valid yet and sets every
         // kernel's attributes); whole blocks of GRAPH_STEPS steps are then replayed from the graph
+        if (has_knoise_) stamp_noise_step(&fused_prog_, (unsigned long long)steps_taken_);
         euler_step_fused();
         current_step_++;
         steps_taken_++;
@@ -1080,6 +1107,10 @@ void Solver::step(int nsteps) {
         }
     }
     for (int i = done; i < nsteps; ++i) {
+        if (has_knoise_) {
+            stamp_noise_step(&prog_, (unsigned long long)steps_taken_);
+            stamp_noise_step(&fused_prog_, (unsigned long long)steps_taken_);
+        }
         if (stepper_ == StepperKind::RK4) {
             rk4_step();  // Step does not advance CurrentStep (rk4.go:130-135)
         } else if (stepper_ == StepperKind::SDD) {

@@ -59,6 +59,8 @@ struct KernelTimer {  // CUDA-event timing of one kernel class, accumulated over
     long long launches = 0;
 };
 
+bool program_has_knoise(const DevKProgram& P);
+
 class Solver {
 public:
     Solver(Model* m, int rank, const int* n, double dt, int device);
@@ -161,6 +163,7 @@ private:
     DevKProgram prog_;
     DevKProgram fused_prog_;
     bool prog_dirty_ = true;
+    bool has_knoise_ = false;  // some term draws white noise at the k-point (model.h kspace_noise)
 
     // CUDA-graph replay of the fused step on small grids (launch-bound: 2-4 kernels of a few us)
     cudaGraphExec_t graph_exec_ = nullptr;

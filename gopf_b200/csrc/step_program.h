@@ -46,7 +46,8 @@ enum TermKind {
     TK_PAIR_CORR = 2,      // coef * (-A C2(2 pi |f|)) [* brick] * L^lap    pairCorrelationTerm.go:37-51,96-110
     TK_CONS_NOISE = 3,     // coef * sum_c 2i sin(pi f_c) xi_c * L^lap      noise.go:60-78
     TK_VOLUME_LP = 4,      // coef * lambda * [brick] * L^lap               volumeConserving.go:19-29
-    TK_TENSOR_HESSIAN = 5  // coef * (-4 pi^2 sum_ij K_ij f_i f_j) * L^lap  tensorialHessian.go:38-63
+    TK_TENSOR_HESSIAN = 5, // coef * (-4 pi^2 sum_ij K_ij f_i f_j) * L^lap  tensorialHessian.go:38-63
+    TK_WHITE_NOISE_K = 6   // coef * xi^(k) * L^lap: the spectrum of WhiteNoise (noise.go:20-23) generated in k-space
 };
 
 struct DevTerm {
@@ -78,7 +79,21 @@ struct PairCorrParams {
 struct TensorHessianParams {
     double K[9];  // row-major d x d (d = 3 when 9 coefficients were given, else 2; tensorialHessian.go:65-71)
     int d, pad;
+    // A TK_WHITE_NOISE_K term borrows a slot of this array (no layout change for the other kernels):
+    // K[0] = std * sqrt(N), K[1] = bits of the 64-bit seed, K[2] = bits of the step counter, which the
+    // solver stamps before every step.
 };
+
+__host__ __device__ inline unsigned long long gopf_bits_of(double v) {
+    union { double d; unsigned long long u; } c;
+    c.d = v;
+    return c.u;
+}
+__host__ __device__ inline double gopf_double_of(unsigned long long u) {
+    union { double d; unsigned long long u; } c;
+    c.u = u;
+    return c.d;
+}
 
 struct ConsNoiseParams {
     int dim;
@@ -165,6 +180,10 @@ __device__ __forceinline__ double filter_eval(const double* __restrict__ tab, in
     return y0 + (x - x0) * dy / dx;
 }
 
+#ifdef GOPF_KNOISE
+__device__ __forceinline__ cplx knoise_value(double amp, unsigned long long seed, unsigned long long step, const KPoint& kp);
+#endif
+
 // One RHS / denominator term at one k-point.  `get(brick)` returns the current
 // spectrum value of that brick at this k-point.
 template <class Get>
@@ -209,6 +228,13 @@ __device__ __forceinline__ cplx eval_term(const DevKProgram& P, const DevTerm& t
             val = mk(acc, 0.0);
             break;
         }
+#ifdef GOPF_KNOISE
+        case TK_WHITE_NOISE_K: {
+            const TensorHessianParams& h = P.th[t.param];
+            val = knoise_value(h.K[0], gopf_bits_of(h.K[1]), gopf_bits_of(h.K[2]), kp);
+            break;
+        }
+#endif
         case TK_VOLUME_LP: {
             const double lam = *GOPF_LP(P, t.param);
             val = get(t.brick) * lam;
@@ -320,6 +346,46 @@ __device__ __forceinline__ double philox_normal(unsigned long long seed, unsigne
     const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
     return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
+
+#ifdef GOPF_KNOISE
+// The spectrum of white noise generated where it is used.  For xi(x) iid N(0, s^2) on N nodes
+// (pf/noise.go:20-23), xi^(k) = sum_x xi(x) e^{-ikx} is complex Gaussian with E|xi^|^2 = N s^2,
+// xi^(-k) = conj xi^(k), and real on the modes that are their own conjugate (every component 0 or
+// Nyquist).  Both members of a pair {k, -k} draw from the Philox stream of the pair's canonical
+// member, found from the frequency components alone (first component that is neither 0 nor +-1/2
+// positive), so the generic, fused and slab-sharded kernels produce the same field.  The reference's
+// stream (Go math/rand) is unpinned: parity is statistical, as for the real-space generator.
+// amp = s * sqrt(N).
+__device__ __forceinline__ cplx knoise_value(double amp, unsigned long long seed, unsigned long long step, const KPoint& kp) {
+    int sgn = 0;
+    for (int c = 0; c < 3; ++c) {
+        const double f = kp.f[c];
+        const int s = (f == 0.0 || fabs(f) == 0.5) ? 0 : (f > 0.0 ? 1 : -1);
+        if (sgn == 0) sgn = s;
+    }
+    // canonical components on a 2^-30 lattice (f = i/n to 1 ulp on either member; n <= 2^20)
+    uint32_t c[4], k[2];
+    for (int a = 0; a < 3; ++a) {
+        const double f = kp.f[a];
+        const double g = fabs(f) == 0.5 ? 0.5 : (sgn < 0 ? -f : f);
+        c[a] = (uint32_t)(long long)(rint(g * 1073741824.0) + 1073741824.0);
+    }
+    c[3] = (uint32_t)step;
+    k[0] = (uint32_t)seed;
+    k[1] = (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32);
+    for (int r = 0; r < 10; ++r) philox_round(c, k);
+    const unsigned long long a = ((unsigned long long)c[0] << 32) | c[1];
+    const unsigned long long b = ((unsigned long long)c[2] << 32) | c[3];
+    const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);  // (0,1)
+    const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    const double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    if (sgn == 0) return mk(amp * r * cs, 0.0);
+    const double h = amp * 0.70710678118654752440 * r;
+    return mk(h * cs, sgn > 0 ? h * sn : -(h * sn));
+}
+#endif
 
 // Value of one derived field at one node.  `fld(j)` returns field j's real-space value.
 template <class Fld>

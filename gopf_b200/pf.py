@@ -101,6 +101,11 @@ class SpectralViscosity:
                                                             ctypes.c_double(self.DissipationThreshold), int(self.Power)))
 
 
+def HasKSpaceNoise() -> bool:
+    """True when libgopfcuda's device code was built with -DGOPF_KNOISE (Model.SetKSpaceNoise usable on the GPU)."""
+    return bool(lib().gopf_has_kspace_noise())
+
+
 class NegativeValuePenalty:
     """pf.NegativeValuePenalty (pf/negative_value_penalty.go:5-38).  ``Evaluate`` is what the
     reference passes to RegisterFunction; here it is the equivalent device expression:
@@ -476,6 +481,11 @@ class Model:
         else:
             raise GopfError("RegisterFunction: arbitrary closures cannot run on the device; pass an expression "
                             "string (see include/gopf_cuda.h) or WhiteNoise(...).Generate")
+
+    def SetKSpaceNoise(self, on: bool = True):
+        """Draw the spectrum of plain explicit WhiteNoise terms at the k-point instead of transforming a
+        real-space noise field every step (include/gopf_cuda.h: gopf_model_set_kspace_noise)."""
+        check(lib().gopf_model_set_kspace_noise(self._h, 1 if on else 0))
 
     def FunctionSource(self, name: str, kernel: bool = False) -> str:
         """C source the registered function `name` compiles to (kernel=True: the CUDA unit for NVRTC)."""

@@ -95,6 +95,15 @@ int gopf_model_kupdate_source(gopf_model* m, int rank, const int* n, double dt, 
                               int filter_n, uint64_t lp_addr, char* buf, int64_t len, int64_t* needed);
 int gopf_model_kupdate_compile(gopf_model* m, int rank, const int* n, double dt, unsigned tab_mask, uint64_t filter_addr,
                                int filter_n, uint64_t lp_addr, int64_t* cubin_bytes);
+/* WhiteNoise fields (pf/noise.go:20-23) that enter an equation as a plain explicit term: draw their
+ * spectrum directly at each k-point (Hermitian, E|xi^|^2 = N * 2 * Strength) instead of generating the
+ * field in real space and transforming it every step -- one transform less per step; a model with one
+ * field, one nonlinearity and such a noise term then takes the fused kernels.  The reference's random
+ * stream is unpinned, parity is statistical either way.  Off by default; needs a library whose device
+ * code was built with -DGOPF_KNOISE (gopf_solver_create fails otherwise).  Call before gopf_solver_create. */
+int gopf_model_set_kspace_noise(gopf_model* m, int on);
+/* 1 when the device code of this library carries the k-space noise generator (-DGOPF_KNOISE), else 0 */
+int gopf_has_kspace_noise(void);
 /* Raw images of what the model compiles to: the k-space program (struct DevKProgram of
  * gopf_b200/csrc/step_program.h, device pointers NULL) and derived field `index` (struct DevDerived;
  * index counts derived fields in registration order, spectrum index = number of fields + index).

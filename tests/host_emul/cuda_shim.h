@@ -38,10 +38,16 @@ template <class T>
 static inline T __ldg(const T* p) {
     return *p;
 }
+static inline void sincospi(double x, double* s, double* c);
 // cos(pi x) with the argument reduced exactly first, like the device function
 static inline double cospi(double x) {
     double r = fmod(fabs(x), 2.0);  // exact
     if (r > 1.0) r = 2.0 - r;       // cos is even and 2-periodic in x
     if (r == 0.5) return 0.0;
     return r < 0.5 ? cos(M_PI * r) : -cos(M_PI * (1.0 - r));
+}
+static inline double sinpi(double x) { return cospi(x - 0.5); }
+static inline void sincospi(double x, double* s, double* c) {
+    *s = sinpi(x);
+    *c = cospi(x);
 }

@@ -1,6 +1,6 @@
 // Test infrastructure: the device evaluators of the general path compiled for the host
 // (see cuda_shim.h).  Built by tests/test_host_emulation_cpu.py with
-//   g++ -O1 -ffp-contract=off -shared -fPIC -I gopf_b200/csrc tests/host_emul/emul.cpp
+//   g++ -O1 -ffp-contract=off -DGOPF_KNOISE -shared -fPIC -I gopf_b200/csrc tests/host_emul/emul.cpp
 #include "cuda_shim.h"
 
 #include "kupdate.cuh"
@@ -84,6 +84,14 @@ void emul_rk4_point(const void* program, const double* filter, int filter_n, con
     const DevKProgram P = load_program(program, filter, filter_n, lp0, lp1);
     rk4_point_all(P, mode, fdt, load_spectra(field), load_spectra(initial), load_spectra(final_), load_spectra(kf),
                   geom(rank, d0, d1, d2), n);
+}
+
+// Solver's stamp_noise_step (solver.cu): the step counter of the k-space noise stream lives in the program
+void emul_stamp_noise_step(void* program, unsigned long long step) {
+    DevKProgram* P = reinterpret_cast<DevKProgram*>(program);
+    for (int i = 0; i < P->n_fields; ++i)
+        for (int j = 0; j < P->eq[i].n_rhs; ++j)
+            if (P->eq[i].rhs[j].kind == TK_WHITE_NOISE_K) P->th[P->eq[i].rhs[j].param].K[2] = gopf_double_of(step);
 }
 
 // eval_derived (pf/model.go:237-241) at every node: fields = GOPF_MAX_FIELDS pointers to real-space
