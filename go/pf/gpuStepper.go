@@ -57,6 +57,11 @@ type GPUStepper struct {
 // them back on the host once per right-hand-side evaluation through gopfSourceTrampoline.
 var gpuSourceFuncs []TimeDepSource
 
+// GPUKSpaceNoise asks NewGPUStepper to draw the spectrum of plain explicit WhiteNoise terms at the
+// k-point (gopf_model_set_kspace_noise) instead of transforming a real-space noise field every step.
+// The library must have been built with -DGOPF_KNOISE (C.gopf_has_kspace_noise() == 1).
+var GPUKSpaceNoise = false
+
 //export gopfSourceTrampoline
 func gopfSourceTrampoline(t C.double, user unsafe.Pointer) C.double {
 	return C.double(gpuSourceFuncs[int(uintptr(user))-1](float64(t)))
@@ -202,6 +207,9 @@ func NewGPUStepper(m *Model, domainSize []int, dt float64, scheme string, exprs 
 	dims := make([]C.int, len(domainSize))
 	for i, v := range domainSize {
 		dims[i] = C.int(v)
+	}
+	if GPUKSpaceNoise {
+		gpuCheck(C.gopf_model_set_kspace_noise(st.model, 1))
 	}
 	gpuCheck(C.gopf_solver_create(st.model, C.int(len(dims)), &dims[0], C.double(dt), -1, &st.solver))
 	cs := cstr(scheme)
