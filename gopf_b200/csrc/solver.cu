@@ -557,6 +557,7 @@ void Solver::derived_pointwise(int d, cplx* out, unsigned long long step_no, cud
     const long long n = (long long)plan_->N;
     if (jit_on_ && dd.kind == DK_RPN) {
         if (jit_derived_.size() != m_->derived.size()) {
+            for (jit::Kernel* k : jit_derived_) jit::unload(k);
             jit_derived_.assign(m_->derived.size(), nullptr);
             jit_tried_.assign(m_->derived.size(), 0);
         }
