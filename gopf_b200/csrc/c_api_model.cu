@@ -86,6 +86,31 @@ int gopf_model_function_source(gopf_model* m, const char* name, int kernel, char
     GOPF_API_END
 }
 
+int gopf_model_function_pass_source(gopf_model* m, const char* name, int line_length, char* buf, int64_t len, int64_t* needed) {
+    GOPF_API_BEGIN
+    const DevDerived& D = registered_function(m, name);
+    const std::string src = jit::derived_pass_source(D, line_length, nullptr);
+    if (needed) *needed = (int64_t)src.size() + 1;
+    if (buf) {
+        if (len < (int64_t)src.size() + 1) throw Error("gopf_model_function_pass_source: buffer too small");
+        std::memcpy(buf, src.c_str(), src.size() + 1);
+    }
+    GOPF_API_END
+}
+
+int gopf_model_function_pass_compile(gopf_model* m, const char* name, int line_length, int64_t* cubin_bytes, char* lowered_name,
+                                     int lowered_len) {
+    GOPF_API_BEGIN
+    const DevDerived& D = registered_function(m, name);
+    std::vector<char> cubin;
+    std::string log, name_expr, lowered;
+    const std::string src = jit::derived_pass_source(D, line_length, &name_expr);
+    if (!jit::compile_cubin(src, &cubin, &log, &name_expr, &lowered)) throw Error("jit: " + log);
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    if (lowered_name) copy_name(lowered, lowered_name, lowered_len);
+    GOPF_API_END
+}
+
 int gopf_model_function_compile(gopf_model* m, const char* name, int64_t* cubin_bytes) {
     GOPF_API_BEGIN
     const DevDerived& D = registered_function(m, name);
@@ -722,6 +747,13 @@ int gopf_solver_set_jit(gopf_solver* s, int on) {
     GOPF_API_BEGIN
     if (!s) throw Error("solver is NULL");
     s->s->set_jit(on != 0);
+    GOPF_API_END
+}
+
+int gopf_solver_set_jit_inpass(gopf_solver* s, int on) {
+    GOPF_API_BEGIN
+    if (!s) throw Error("solver is NULL");
+    s->s->set_jit_inpass(on != 0);
     GOPF_API_END
 }
 

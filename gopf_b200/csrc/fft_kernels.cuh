@@ -241,6 +241,12 @@ __device__ __forceinline__ void pass_load_line(const PassIO& io, cplx (&v)[E], A
         for (int m = 0; m < E; ++m) w[m] = tab[at(m)];
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = mk(v[m].x * w[m], v[m].y * w[m]);
+#ifdef GOPF_JIT_LOAD_LINE
+    } else if (io.load_kind == LK_DERIVED) {
+        // run-time specialisation (jit.cu): the registered function as straight-line code on
+        // register-resident cells, all loads of a batch in flight like the plain case
+        GOPF_JIT_LOAD_LINE(io, v, at)
+#endif
     } else {
 #pragma unroll 1
         for (int m = 0; m < E; ++m) sm[sat(m)] = pass_load_slow(io, at(m));
@@ -464,6 +470,16 @@ cudaError_t launch_contig_n(const PassGeom& g, const PassIO& io, const cplx* tw,
     return cudaGetLastError();
 }
 
+// launch shape of k_pass_contig<N> for A lines (the run-time specialised copy of the kernel is launched
+// through the driver API with the same shape, jit.cu)
+template <int N>
+inline void contig_config_n(long long A, unsigned* grid, unsigned* block, size_t* smem) {
+    constexpr int T = ContigCfg<N>::T, LINES = ContigCfg<N>::LINES;
+    *smem = (size_t)LayoutPadded<N>::elems(N, LINES) * sizeof(cplx);
+    *grid = (unsigned)((A + LINES - 1) / LINES);
+    *block = (unsigned)(T * LINES);
+}
+
 template <int N>
 cudaError_t launch_pass_n(const PassGeom& g, int tx_want, const PassIO& io, const cplx* tw, cudaStream_t s) {
     if (g.B == 1) return launch_contig_n<N>(g, io, tw, s);
@@ -478,5 +494,7 @@ inline bool fast_length(int n) { return is_pow2(n) && n >= 2 && n <= 4096; }
 // One pass along g.axis (power-of-two length 2..4096).  Defined in pass_launch.cu; the
 // instantiations are spread over pass_inst_*.cu so they compile in parallel.
 cudaError_t launch_pass(const PassGeom& g, int tx_want, const PassIO& io, const cplx* tw, cudaStream_t s);
+// pass_launch.cu: contig_config_n for a run-time N; false when N is not a fast length
+bool contig_launch_config(int N, long long A, unsigned* grid, unsigned* block, size_t* smem);
 
 }  // namespace gopf

@@ -44,9 +44,9 @@ const char* kPrelude =
 
 }  // namespace
 
-std::string expression_source(const DevDerived& D, unsigned* used_mask) {
+std::string expression_source(const DevDerived& D, unsigned* used_mask, unsigned* imag_mask) {
     if (D.kind != DK_RPN) throw Error("jit: not a registered-function program");
-    unsigned mask = 0;
+    unsigned mask = 0, imask = 0;
     std::string body;
     std::vector<int> st;
     int next = 0;
@@ -80,6 +80,7 @@ std::string expression_source(const DevDerived& D, unsigned* used_mask) {
                 const int f = (int)a;
                 if (f < 0 || f >= GOPF_MAX_FIELDS) throw Error("jit: field index out of range");
                 mask |= 1u << f;
+                if (D.op[i] == OP_FIELD_IM) imask |= 1u << f;
                 push(std::string(D.op[i] == OP_FIELD_RE ? "r" : "i") + std::to_string(f));
                 break;
             }
@@ -147,6 +148,47 @@ std::string expression_source(const DevDerived& D, unsigned* used_mask) {
     // eval_derived returns the top of the stack, 0 for an empty program
     src += "    return " + (st.empty() ? std::string("0.0") : tmp(st.back())) + ";\n}\n";
     if (used_mask) *used_mask = mask;
+    if (imag_mask) *imag_mask = imask;
+    return src;
+}
+
+std::string derived_pass_source(const DevDerived& D, int N, std::string* name_expr) {
+    unsigned mask = 0, imask = 0;
+    std::string src = "#define GOPF_FN static __device__ __forceinline__\n" + expression_source(D, &mask, &imask);
+    src +=
+        "namespace gopf {\n"
+        "struct PassIO;\n"
+        "template <int E, class At>\n"
+        "__device__ __forceinline__ void gopf_jit_load_line(const PassIO& io, double2 (&v)[E], At at);\n"
+        "}\n"
+        "#define GOPF_JIT_LOAD_LINE(io, v, at) gopf_jit_load_line(io, v, at);\n"
+        "#include \"fft_kernels.cuh\"\n"
+        "namespace gopf {\n"
+        // batches of at most 8 cells bound the registers the loads hold while they are in flight
+        "template <int E, class At>\n"
+        "__device__ __forceinline__ void gopf_jit_load_line(const PassIO& io, double2 (&v)[E], At at) {\n"
+        "    constexpr int H = E > 8 ? 8 : E;\n"
+        "#pragma unroll\n"
+        "    for (int m0 = 0; m0 < E; m0 += H) {\n";
+    std::string args;
+    for (int f = 0; f < GOPF_MAX_FIELDS; ++f) {
+        const bool used = (mask >> f) & 1u, im = (imask >> f) & 1u;
+        if (used && im) {
+            src += strf("        double2 c%d[H];\n#pragma unroll\n        for (int j = 0; j < H; ++j) c%d[j] = io.R.r[%d][at(m0 + j)];\n", f, f, f);
+            args += strf("%sc%d[j].x, c%d[j].y", f ? ", " : "", f, f);
+        } else if (used) {
+            src += strf("        const double* p%d = reinterpret_cast<const double*>(io.R.r[%d]);\n        double r%d[H];\n", f, f, f);
+            src += strf("#pragma unroll\n        for (int j = 0; j < H; ++j) r%d[j] = p%d[2 * at(m0 + j)];\n", f, f);
+            args += strf("%sr%d[j], 0.0", f ? ", " : "", f);
+        } else {
+            args += strf("%s0.0, 0.0", f ? ", " : "");
+        }
+    }
+    src += "#pragma unroll\n        for (int j = 0; j < H; ++j) v[m0 + j] = mk(gopf_expr(" + args + "), 0.0);\n";
+    src += "    }\n}\n";
+    src += strf("template __global__ void k_pass_contig<%d>(const PassGeom g, const __grid_constant__ PassIO io, const cplx* __restrict__ tw);\n", N);
+    src += "}  // namespace gopf\n";
+    if (name_expr) *name_expr = strf("gopf::k_pass_contig<%d>", N);
     return src;
 }
 
@@ -252,6 +294,8 @@ struct Nvrtc {
     int (*GetProgramLogSize)(void*, size_t*) = nullptr;
     int (*GetProgramLog)(void*, char*) = nullptr;
     int (*DestroyProgram)(void**) = nullptr;
+    int (*AddNameExpression)(void*, const char*) = nullptr;
+    int (*GetLoweredName)(void*, const char*, const char**) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     std::string why;
 };
@@ -287,6 +331,8 @@ Nvrtc* nvrtc() {
                         sym(lib.h, "nvrtcGetProgramLogSize", &lib.GetProgramLogSize, &lib.why) &&
                         sym(lib.h, "nvrtcGetProgramLog", &lib.GetProgramLog, &lib.why) &&
                         sym(lib.h, "nvrtcDestroyProgram", &lib.DestroyProgram, &lib.why) &&
+                        sym(lib.h, "nvrtcAddNameExpression", &lib.AddNameExpression, &lib.why) &&
+                        sym(lib.h, "nvrtcGetLoweredName", &lib.GetLoweredName, &lib.why) &&
                         sym(lib.h, "nvrtcGetErrorString", &lib.GetErrorString, &lib.why);
         if (!ok) lib.h = nullptr;
     });
@@ -295,22 +341,29 @@ Nvrtc* nvrtc() {
 
 }  // namespace
 
-bool compile_cubin(const std::string& source, std::vector<char>* cubin, std::string* log) {
+bool compile_cubin(const std::string& source, std::vector<char>* cubin, std::string* log, const std::string* name_expr,
+                   std::string* lowered) {
     Nvrtc* rt = nvrtc();
     if (!rt->h) {
         if (log) *log = "NVRTC unavailable: " + rt->why;
         return false;
     }
     void* prog = nullptr;
-    const char* headers[] = {embed_cplx_cuh, embed_step_program_h, embed_kupdate_cuh};
-    const char* names[] = {"cplx.cuh", "step_program.h", "kupdate.cuh"};
-    int rc = rt->CreateProgram(&prog, source.c_str(), "gopf_jit.cu", 3, headers, names);
+    const char* headers[] = {embed_cplx_cuh, embed_step_program_h, embed_kupdate_cuh, embed_fft_engine_cuh, embed_fft_kernels_cuh};
+    const char* names[] = {"cplx.cuh", "step_program.h", "kupdate.cuh", "fft_engine.cuh", "fft_kernels.cuh"};
+    int rc = rt->CreateProgram(&prog, source.c_str(), "gopf_jit.cu", 5, headers, names);
     if (rc != 0) {
         if (log) *log = std::string("nvrtcCreateProgram: ") + rt->GetErrorString(rc);
         return false;
     }
-    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
-    rc = rt->CompileProgram(prog, 3, opts);
+    if (name_expr && (rc = rt->AddNameExpression(prog, name_expr->c_str())) != 0) {
+        if (log) *log = std::string("nvrtcAddNameExpression: ") + rt->GetErrorString(rc);
+        rt->DestroyProgram(&prog);
+        return false;
+    }
+    // -default-device: the host-side inline helpers of the embedded headers are never called here
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
+    rc = rt->CompileProgram(prog, 4, opts);
     std::string text;
     size_t log_size = 0;
     if (rt->GetProgramLogSize(prog, &log_size) == 0 && log_size > 1) {
@@ -327,6 +380,12 @@ bool compile_cubin(const std::string& source, std::vector<char>* cubin, std::str
             ok = rt->GetCUBIN(prog, cubin->data()) == 0;
         }
         if (!ok) text += "\nnvrtcGetCUBIN failed";
+        if (ok && name_expr && lowered) {
+            const char* low = nullptr;
+            ok = rt->GetLoweredName(prog, name_expr->c_str(), &low) == 0 && low;
+            if (ok) *lowered = low;
+            else text += "\nnvrtcGetLoweredName failed";
+        }
     }
     rt->DestroyProgram(&prog);
     if (log) *log = text;
@@ -357,6 +416,7 @@ struct Driver {
     int (*LaunchKernel)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**,
                         void**) = nullptr;
     int (*GetErrorString)(int, const char**) = nullptr;
+    int (*FuncSetAttribute)(void*, int, int) = nullptr;
     std::string why;
 };
 
@@ -374,7 +434,8 @@ Driver* driver() {
                         sym(lib.h, "cuModuleGetFunction", &lib.ModuleGetFunction, &lib.why) &&
                         sym(lib.h, "cuModuleUnload", &lib.ModuleUnload, &lib.why) &&
                         sym(lib.h, "cuLaunchKernel", &lib.LaunchKernel, &lib.why) &&
-                        sym(lib.h, "cuGetErrorString", &lib.GetErrorString, &lib.why);
+                        sym(lib.h, "cuGetErrorString", &lib.GetErrorString, &lib.why) &&
+                        sym(lib.h, "cuFuncSetAttribute", &lib.FuncSetAttribute, &lib.why);
         if (!ok) lib.h = nullptr;
     });
     return &lib;
@@ -391,6 +452,7 @@ std::string driver_error(Driver* d, const char* what, int rc) {
 struct Kernel {
     void* module = nullptr;
     void* function = nullptr;
+    size_t smem_opted = 0;  // dynamic shared memory the function has been opted in for
 };
 
 Kernel* load(const std::vector<char>& cubin, const char* entry, std::string* log) {
@@ -428,13 +490,22 @@ void unload(Kernel* k) {
     delete k;
 }
 
-bool launch(Kernel* k, unsigned grid, unsigned block, void** args, cudaStream_t stream, std::string* log) {
+bool launch(Kernel* k, unsigned grid, unsigned block, void** args, cudaStream_t stream, std::string* log, size_t smem) {
     Driver* d = driver();
     if (!k || !d->h) {
         if (log) *log = "jit kernel not loaded";
         return false;
     }
-    const int rc = d->LaunchKernel(k->function, grid, 1, 1, block, 1, 1, 0, (void*)stream, args, nullptr);
+    if (smem > 48 * 1024 && smem > k->smem_opted) {
+        const int CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8;
+        const int rc = d->FuncSetAttribute(k->function, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem);
+        if (rc != 0) {
+            if (log) *log = driver_error(d, "cuFuncSetAttribute", rc);
+            return false;
+        }
+        k->smem_opted = smem;
+    }
+    const int rc = d->LaunchKernel(k->function, grid, 1, 1, block, 1, 1, (unsigned)smem, (void*)stream, args, nullptr);
     if (rc != 0) {
         if (log) *log = driver_error(d, "cuLaunchKernel", rc);
         return false;
@@ -444,6 +515,11 @@ bool launch(Kernel* k, unsigned grid, unsigned block, void** args, cudaStream_t 
 
 bool enabled() {
     const char* e = std::getenv("GOPF_JIT");
+    return e && e[0] == '1';
+}
+
+bool inpass_enabled() {
+    const char* e = std::getenv("GOPF_JIT_INPASS");
     return e && e[0] == '1';
 }
 

@@ -29,10 +29,17 @@ namespace jit {
 //   static inline double gopf_expr(double r0, double i0, ..., double r3, double i3)
 // r_f / i_f = real / imaginary part of field f at the cell.  `used_mask` gets bit f set when field f
 // is read.  Throws on a malformed program.
-std::string expression_source(const DevDerived& D, unsigned* used_mask);
+std::string expression_source(const DevDerived& D, unsigned* used_mask, unsigned* imag_mask = nullptr);
 
 // Full translation unit: gopf_expr + extern "C" __global__ gopf_jit_derived(f0..f3, out, n)
 std::string derived_kernel_source(const DevDerived& D, unsigned* used_mask);
+
+// The first forward pass of a registered function's transform with the function evaluated in its
+// load (fft_kernels.cuh pass_load_line, hook GOPF_JIT_LOAD_LINE): the library's own k_pass_contig<N>
+// recompiled with a generated loader, so the function costs no pointwise kernel and no 32-B round
+// trip of its values.  *name_expr receives the C++ name of the kernel instance for
+// nvrtcGetLoweredName.
+std::string derived_pass_source(const DevDerived& D, int N, std::string* name_expr);
 
 // Translation unit of the specialised k-space kernels: extern "C" __global__
 // gopf_jit_kupdate(SpectraPtrs sp, ImplicitTab tab), gopf_jit_rk4_rhs(SpectraPtrs sp, SpectraPtrs kout),
@@ -42,15 +49,18 @@ std::string kupdate_kernel_source(const DevKProgram& P, const FreqGeom& fg, long
 
 // NVRTC: CUDA C -> sm_100a cubin.  Returns false (with the log) when NVRTC is unavailable or the
 // source does not compile.  Needs no GPU.
-bool compile_cubin(const std::string& source, std::vector<char>* cubin, std::string* log);
+// name_expr / lowered: optional C++ name of a kernel template instance and its mangled name in the image.
+bool compile_cubin(const std::string& source, std::vector<char>* cubin, std::string* log, const std::string* name_expr = nullptr,
+                   std::string* lowered = nullptr);
 
 struct Kernel;  // a loaded module + function
 // load on the current device (the CUDA runtime's primary context must be current); NULL on failure
 Kernel* load(const std::vector<char>& cubin, const char* entry, std::string* log);
 void unload(Kernel* k);
-// launch with a 1-D grid; false on failure
-bool launch(Kernel* k, unsigned grid, unsigned block, void** args, cudaStream_t stream, std::string* log);
+// launch with a 1-D grid; false on failure.  smem = dynamic shared memory in bytes (opted in above 48 KB)
+bool launch(Kernel* k, unsigned grid, unsigned block, void** args, cudaStream_t stream, std::string* log, size_t smem = 0);
 
+bool inpass_enabled();  // GOPF_JIT_INPASS=1: also evaluate registered functions inside their first forward pass
 bool enabled();  // GOPF_JIT=1 in the environment switches the specialisation on for new solvers
 
 }  // namespace jit

@@ -29,4 +29,13 @@ cudaError_t launch_pass(const PassGeom& g, int tx_want, const PassIO& io, const 
     }
 }
 
+bool contig_launch_config(int N, long long A, unsigned* grid, unsigned* block, size_t* smem) {
+    switch (N) {
+#define X(n) case n: contig_config_n<n>(A, grid, block, smem); return true;
+        X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)
+#undef X
+        default: return false;
+    }
+}
+
 }  // namespace gopf

@@ -90,6 +90,7 @@ Solver::Solver(Model* m, int rank, const int* n, double dt, int device) : m_(m),
         throw Error(strf("solver: rank must be 2 or 3 (got %d); FFTWWrapper.Freq indexes res[1] (fftWrap.go:61)", rank));
     m_->init();  // NewSolver calls m.Init() (solver.go:42)
     jit_on_ = jit::enabled();
+    jit_inpass_ = jit::inpass_enabled();
     plan_.reset(new FftPlan(rank, n, device));
     for (const HostField& f : m_->fields)  // solver.go:55-60
         if (f.n != plan_->N) throw Error("solver: Inconsistent domain size and number of grid points");
@@ -135,6 +136,7 @@ Solver::~Solver() {
     for (int i = 0; i < GOPF_MAX_SPECTRA; ++i)
         if (d_table_[i]) cudaFree(d_table_[i]);
     for (jit::Kernel* k : jit_derived_) jit::unload(k);
+    for (jit::Kernel* k : jit_pass_) jit::unload(k);
     jit::unload(jit_kupdate_);
     jit::unload(jit_rk4_rhs_);
     jit::unload(jit_rk4_point_);
@@ -592,6 +594,8 @@ int Solver::jit_kernels() const {
     int c = jit_kupdate_ ? 1 : 0;
     for (const jit::Kernel* k : jit_derived_)
         if (k) c++;
+    for (const jit::Kernel* k : jit_pass_)
+        if (k) c++;
     return c;
 }
 
@@ -617,9 +621,14 @@ void Solver::forward_derived(int d) {
     // Interpreted derived fields (registered functions, noise) are instruction-bound inside a pass
     // (one CTA holds few warps; measured 0.76 TB/s at 512^3): evaluate them in a pointwise kernel
     // at full occupancy and transform the result with plain passes (measured: see DESIGN.md 4.4).
+    // With GOPF_JIT_INPASS a registered function gets its own copy of the contiguous pass with the
+    // function compiled into the load (jit.h), which needs neither.
     const DevDerived& dd = m_->derived[d].dev;
     const bool in_pass = dd.kind == DK_MONOMIAL || dd.kind == DK_TABLE;
-    if (!in_pass) {
+    jit::Kernel* jit_pass = nullptr;
+    if (!in_pass && jit_on_ && jit_inpass_ && dd.kind == DK_RPN && plan_->geom(first_axis).B == 1)
+        jit_pass = jit_pass_kernel(d, plan_->geom(first_axis).N);
+    if (!in_pass && !jit_pass) {
         const int F0 = (int)m_->fields.size();
         const int id = tick("derived_pointwise", 16.0 * (double)plan_->N * (F0 + 1));
         derived_pointwise(d, out, step_no, s);
@@ -629,17 +638,53 @@ void Solver::forward_derived(int d) {
         if (plan_->extent(ax) <= 1) continue;
         const PassGeom g = plan_->geom(ax);
         PassIO io = plain_io(out, out, false, 1.0);
-        if (ax == first_axis && in_pass) {
+        const bool fused_load = ax == first_axis && (in_pass || jit_pass);
+        if (fused_load) {
             io.load_kind = LK_DERIVED;
             io.D = m_->derived[d].dev;
             io.R = R_;
             io.step = step_no;
         }
-        const int id = tick(ax == first_axis && in_pass ? "pass_forward_derived" : "pass_forward", cell);
-        cudaError_t e = launch_pass(g, plan_->tx_want, io, plan_->twiddle(ax), s);
+        const int id = tick(fused_load ? "pass_forward_derived" : "pass_forward", cell);
+        if (fused_load && jit_pass) {
+            unsigned grid = 0, block = 0;
+            size_t smem = 0;
+            if (!contig_launch_config(g.N, g.A, &grid, &block, &smem)) throw Error("jit pass: unsupported line length");
+            PassGeom gl = g;
+            gl.pf_tiles = 0;
+            const cplx* tw = plan_->twiddle(ax);
+            void* args[] = {&gl, &io, &tw};
+            std::string log;
+            if (!jit::launch(jit_pass, grid, block, args, s, &log, smem))
+                throw Error("jit launch of the forward pass of derived '" + m_->derived[d].name + "': " + log);
+        } else {
+            cudaError_t e = launch_pass(g, plan_->tx_want, io, plan_->twiddle(ax), s);
+            if (e != cudaSuccess) throw Error(strf("derived forward pass axis %d: %s", ax, cudaGetErrorString(e)));
+        }
         tock(id);
-        if (e != cudaSuccess) throw Error(strf("derived forward pass axis %d: %s", ax, cudaGetErrorString(e)));
     }
+}
+
+// k_pass_contig<N> with registered function d compiled into its load; NULL: not available
+jit::Kernel* Solver::jit_pass_kernel(int d, int N) {
+    if (jit_pass_.size() != m_->derived.size()) {
+        for (jit::Kernel* k : jit_pass_) jit::unload(k);
+        jit_pass_.assign(m_->derived.size(), nullptr);
+        jit_pass_tried_.assign(m_->derived.size(), 0);
+    }
+    if (!jit_pass_tried_[d]) {
+        jit_pass_tried_[d] = 1;
+        std::string log, name_expr, lowered;
+        std::vector<char> cubin;
+        try {
+            const std::string src = jit::derived_pass_source(m_->derived[d].dev, N, &name_expr);
+            if (jit::compile_cubin(src, &cubin, &log, &name_expr, &lowered)) jit_pass_[d] = jit::load(cubin, lowered.c_str(), &log);
+        } catch (const std::exception& e) {
+            log = e.what();
+        }
+        if (!jit_pass_[d]) jit_log_ += "forward pass of derived '" + m_->derived[d].name + "': " + log + "\n";
+    }
+    return jit_pass_[d];
 }
 
 void Solver::eval_real_fields() {

@@ -117,6 +117,7 @@ public:
     // run-time specialisation (jit.h): switch, and how many kernels (registered functions, the
     // k-space update) currently run as compiled images
     void set_jit(bool on) { jit_on_ = on; }
+    void set_jit_inpass(bool on) { jit_inpass_ = on; }
     int jit_kernels() const;
     const std::string& jit_log() const { return jit_log_; }
     long long residual_evaluations() const { return ie_residual_evals_; }
@@ -177,6 +178,11 @@ private:
     // entry keeps the interpreter kernel for that derived field
     std::vector<jit::Kernel*> jit_derived_;
     std::vector<char> jit_tried_;
+    // ... or compiled into the load of their first forward pass (GOPF_JIT_INPASS)
+    std::vector<jit::Kernel*> jit_pass_;
+    std::vector<char> jit_pass_tried_;
+    bool jit_inpass_ = false;
+    jit::Kernel* jit_pass_kernel(int d, int N);
     bool jit_on_ = false;
     std::string jit_log_;
     void derived_pointwise(int d, cplx* out, unsigned long long step_no, cudaStream_t s);

@@ -496,6 +496,21 @@ class Model:
         check(lib().gopf_model_function_source(self._h, _s(name), 1 if kernel else 0, buf, need, None))
         return buf.value.decode("utf-8")
 
+    def FunctionPassSource(self, name: str, line_length: int) -> str:
+        """CUDA unit of the forward pass with the registered function compiled into its load."""
+        need = ctypes.c_int64(0)
+        check(lib().gopf_model_function_pass_source(self._h, _s(name), int(line_length), None, ctypes.c_int64(0), ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        check(lib().gopf_model_function_pass_source(self._h, _s(name), int(line_length), buf, need, None))
+        return buf.value.decode("utf-8")
+
+    def FunctionPassCompile(self, name: str, line_length: int):
+        """NVRTC-compile it for sm_100a (needs no GPU); returns (cubin size, mangled kernel name)."""
+        n = ctypes.c_int64(0)
+        low = ctypes.create_string_buffer(512)
+        check(lib().gopf_model_function_pass_compile(self._h, _s(name), int(line_length), ctypes.byref(n), low, 512))
+        return n.value, low.value.decode()
+
     def FunctionCompile(self, name: str) -> int:
         """NVRTC-compile the function's kernel for sm_100a (needs no GPU); returns the cubin size."""
         n = ctypes.c_int64(0)
@@ -918,6 +933,10 @@ class Solver:
         """Compile registered functions with NVRTC into straight-line kernels at first use
         (default: the GOPF_JIT environment variable)."""
         check(lib().gopf_solver_set_jit(self._h, 1 if on else 0))
+
+    def SetJitInPass(self, on: bool = True):
+        """With SetJit: registered functions compiled into the load of their first forward pass."""
+        check(lib().gopf_solver_set_jit_inpass(self._h, 1 if on else 0))
 
     def JitKernels(self) -> int:
         n = ctypes.c_int(0)

@@ -82,6 +82,11 @@ int gopf_model_create(gopf_model** out);
  * translation unit handed to NVRTC (kernel = 1).  *needed = bytes including the terminator; buf
  * may be NULL to query.  Host only, no GPU. */
 int gopf_model_function_source(gopf_model* m, const char* name, int kernel, char* buf, int64_t len, int64_t* needed);
+/* The same for the forward pass with the function in its load (gopf_solver_set_jit_inpass) at line
+ * length `line_length`; the compile also reports the mangled name of the kernel instance. */
+int gopf_model_function_pass_source(gopf_model* m, const char* name, int line_length, char* buf, int64_t len, int64_t* needed);
+int gopf_model_function_pass_compile(gopf_model* m, const char* name, int line_length, int64_t* cubin_bytes, char* lowered_name,
+                                     int lowered_len);
 /* NVRTC-compile that translation unit for sm_100a; *cubin_bytes = size of the image.  No GPU needed. */
 int gopf_model_function_compile(gopf_model* m, const char* name, int64_t* cubin_bytes);
 /* The CUDA translation unit the k-space update of this model (pf/euler.go:27-39) is specialised to
@@ -270,6 +275,10 @@ int gopf_solver_force_generic(gopf_solver* s, int on);
  * created; gopf_solver_set_jit overrides that.  A function that fails to compile keeps the
  * interpreter kernel (both are device paths); gopf_solver_jit_log tells why. */
 int gopf_solver_set_jit(gopf_solver* s, int on);
+/* With the specialisation on, also compile each registered function into the load of the first
+ * forward pass of its transform (a copy of the library's contiguous-axis pass kernel with a generated
+ * loader): no pointwise kernel, no round trip of the function values.  Off unless GOPF_JIT_INPASS=1. */
+int gopf_solver_set_jit_inpass(gopf_solver* s, int on);
 /* number of derived fields currently evaluated by compiled kernels */
 int gopf_solver_jit_kernels(gopf_solver* s, int* count);
 int gopf_solver_jit_log(gopf_solver* s, char* buf, int len);

@@ -56,7 +56,8 @@ def run(kind, G, jit, steps):
             avg = k["total_ms"] / k["launches"]
             kernels[k["kernel"]] = {"avg_ms": round(avg, 4), "per_step": k["launches"] / steps,
                                     "gbs": round(k["bytes_per_launch"] / (avg * 1e-3) / 1e9, 1)}
-    info = {"workload": kind, "grid": G, "jit": bool(jit), "jit_kernels": s.JitKernels(), "jit_log": s.JitLog(),
+    info = {"workload": kind, "grid": G, "jit": bool(jit), "jit_inpass": bool(jit) and os.environ.get("GOPF_JIT_INPASS") == "1",
+            "jit_kernels": s.JitKernels(), "jit_log": s.JitLog(),
             "ms_per_step_profiled": round(wall_ms, 3), "kernels": kernels}
     s.close()
     return out, info

@@ -4,6 +4,7 @@
 #
 #   gpurun --timeout 900 -- 'bash scripts/round2_gpu_checks.sh suite'
 #   gpurun --timeout 900 -- 'bash scripts/round2_gpu_checks.sh jit'
+#   gpurun --timeout 900 -- 'bash scripts/round2_gpu_checks.sh inpass'
 #   gpurun --timeout 900 -- 'bash scripts/round2_gpu_checks.sh knoise'
 set -u
 mkdir -p gpurun_out
@@ -30,6 +31,13 @@ jit)
     GOPF_JIT_DUMP=gpurun_out/jit_dump ncu --set full --clock-control none --import-source on \
         -k regex:gopf_jit -c 6 -o gpurun_out/jit_kernels python scripts/jit_check.py 256 1 > gpurun_out/ncu_jit.log 2>&1
     tail -2 gpurun_out/jit_check_512.log
+    ;;
+inpass)
+    # 2b. registered functions compiled into the load of their first forward pass (GOPF_JIT_INPASS)
+    GOPF_TEST_INPASS=1 python -m pytest tests/test_zz_jit_gpu.py -q -k forward_pass > gpurun_out/inpass_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/inpass_pytest.log
+    GOPF_JIT_INPASS=1 python scripts/jit_check.py 256 5 > gpurun_out/jit_check_inpass_256.log 2>&1
+    GOPF_JIT_INPASS=1 python scripts/jit_check.py 512 5 > gpurun_out/jit_check_inpass_512.log 2>&1
+    tail -3 gpurun_out/inpass_pytest.log; tail -2 gpurun_out/jit_check_inpass_256.log
     ;;
 knoise)
     # 3. white noise drawn in k-space: rebuild the device code with the generator, check that the fast-form

@@ -178,6 +178,31 @@ def test_registered_function_kernels_compile_for_sm100a(tmp_path, monkeypatch):
             assert stack == 0 and regs <= 32, (cubin.name, regs, stack)  # 2048 resident threads per SM
 
 
+@needs_nvrtc
+@pytest.mark.parametrize("line_length", [64, 256, 1024])
+def test_forward_pass_with_the_function_in_its_load_compiles(line_length, tmp_path, monkeypatch):
+    """GOPF_JIT_INPASS: the library's own k_pass_contig<N>, recompiled by NVRTC from the embedded headers with a
+    generated loader.  The image must keep the library kernel's frame (no additional spills)."""
+    monkeypatch.setenv("GOPF_JIT_DUMP", str(tmp_path))
+    m = _model()
+    m.RegisterFunction("DERIV_PHASE_ORDER", workloads.DERIV_PHASE_EXPR)
+    m.RegisterFunction("WITH_IMAG", "re(conc)*im(phase) + exp(0.1*phase)")
+    src = m.FunctionPassSource("DERIV_PHASE_ORDER", line_length)
+    assert '#include "fft_kernels.cuh"' in src and "gopf_jit_load_line" in src and f"k_pass_contig<{line_length}>" in src
+    assert "p1[2 * at(m0 + j)]" in src  # real parts only when the function reads nothing else
+    assert "c1[j] = io.R.r[1][at(m0 + j)]" in m.FunctionPassSource("WITH_IMAG", line_length)
+    for name in ("DERIV_PHASE_ORDER", "WITH_IMAG"):
+        size, lowered = m.FunctionPassCompile(name, line_length)
+        assert size > 10000 and lowered.startswith("_ZN4gopf13k_pass_contigILi%dEEE" % line_length)
+    if shutil.which("cuobjdump"):
+        lib_kernel = subprocess.run(["cuobjdump", "-res-usage", os.path.join(os.path.dirname(gpf.__file__), "lib", "libgopfcuda.so")],
+                                    check=True, capture_output=True, text=True).stdout
+        ref = re.search(rf"k_pass_contigILi{line_length}EEE\S*:\s+REG:(\d+) STACK:(\d+)", lib_kernel)
+        for cubin in sorted(tmp_path.glob("*.cubin")):
+            regs, stack = _resource_usage(str(cubin))
+            assert stack <= int(ref.group(2)) and regs <= 128, (cubin.name, regs, stack, ref.groups())
+
+
 class _NoSolver:
     class Stepper:
         @staticmethod

@@ -72,6 +72,25 @@ def test_specialised_and_interpreted_kernels_agree_step_by_step():
     assert abs(out[1][2] - out[0][2]) <= 1e-9
 
 
+@pytest.mark.skipif(os.environ.get("GOPF_TEST_INPASS") != "1",
+                    reason="the in-pass specialisation has not run on a GPU yet (scripts/round2_gpu_checks.sh inpass)")
+@pytest.mark.parametrize("dims", [[32, 32], [16, 16, 16], [64, 64, 64]], ids=lambda d: "x".join(map(str, d)))
+def test_precipitate_functions_compiled_into_the_forward_pass(dims):
+    out = []
+    for inpass in (False, True):
+        m, conc, phase, s, vol = workloads.build_precipitate(gpf, gpf, gel, dims, expressions=True)
+        s.SetJit(True)
+        s.SetJitInPass(inpass)
+        s.Solve(2, 5)
+        assert s.JitKernels() == 4, s.JitLog()  # three functions (pointwise or in-pass) + the k-space update
+        out.append((conc.Data.copy(), phase.Data.copy(), s.LPMultiplier(0)))
+    assert rel_l2(out[1][0], out[0][0]) <= 1e-13 and rel_l2(out[1][1], out[0][1]) <= 1e-13
+    assert abs(out[1][2] - out[0][2]) <= 1e-9
+    if dims != [64, 64, 64]:
+        g = load(f"precipitate_{'x'.join(map(str, dims))}.npz")
+        assert rel_l2(out[1][0], g["conc"]) <= TOL and rel_l2(out[1][1], g["phase"]) <= TOL
+
+
 # ---- white noise drawn in k-space (Model.SetKSpaceNoise; device code behind -DGOPF_KNOISE) ---------------------
 @pytest.mark.skipif(not gpf.HasKSpaceNoise(), reason="libgopfcuda's device code was built without -DGOPF_KNOISE")
 @pytest.mark.parametrize("dims", [[64, 64], [32, 32, 32]], ids=lambda d: "x".join(map(str, d)))
