@@ -182,7 +182,7 @@ def test_registered_function_kernels_compile_for_sm100a(tmp_path, monkeypatch):
 @pytest.mark.parametrize("line_length", [64, 256, 1024])
 def test_forward_pass_with_the_function_in_its_load_compiles(line_length, tmp_path, monkeypatch):
     """GOPF_JIT_INPASS: the library's own k_pass_contig<N>, recompiled by NVRTC from the embedded headers with a
-    generated loader.  The image must keep the library kernel's frame (no additional spills)."""
+    generated loader.  The image must keep the library kernel's frame (no spills of the register-resident line)."""
     monkeypatch.setenv("GOPF_JIT_DUMP", str(tmp_path))
     m = _model()
     m.RegisterFunction("DERIV_PHASE_ORDER", workloads.DERIV_PHASE_EXPR)
