@@ -120,10 +120,11 @@ def pfc_initial(n_nodes: int, seed: int = PFC_SEED, mean_density: float = 0.0) -
     return out
 
 
-def build_pfc(pf, terms, dims, *, noise=None, filt_order=5, pinned: bool = False, noise_seed: int = 7):
+def build_pfc(pf, terms, dims, *, noise=None, filt_order=5, pinned: bool = False, noise_seed: int = 7, kspace_noise: bool = False):
     """Phase-field crystal: implicit pair-correlation term (two-peak set, main.go:63-72), mixed
     ideal-mixture term (main.go:75-83), optional white noise (``noise`` = "device": the device
     Philox stream through WhiteNoise.Generate; None: no noise) and Vandeven(filt_order) filter.
+    ``kspace_noise``: Model.SetKSpaceNoise (needs a library built with -DGOPF_KNOISE).
     Returns (model, density, solver)."""
     import math
     n = int(np.prod(dims))
@@ -149,6 +150,8 @@ def build_pfc(pf, terms, dims, *, noise=None, filt_order=5, pinned: bool = False
         m.RegisterFunction("NOISE", noise)
         eq += " + NOISE"
     m.AddEquation(eq)
+    if kspace_noise:  # draw the noise spectrum at the k-point (this package only)
+        m.SetKSpaceNoise(True)
     solver = pf.NewSolver(m, dims, PFC_DT)
     if filt_order is not None:
         solver.Stepper.SetFilter(terms.NewVandeven(filt_order))
