@@ -56,6 +56,11 @@ struct PassGeom {
     long long pf_tiles;
 };
 
+// GOPF_HOST_EMUL: tests/host_emul compiles this header with g++ and runs the kernels on the host (one OS
+// thread per CUDA thread); it sets the macro to skip what only exists on the device or in the CUDA runtime.
+#ifdef GOPF_HOST_EMUL
+inline void prefetch_l2(const void*) {}
+#else
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // resident CTAs of a launch = prefetch distance (host)
@@ -73,6 +78,7 @@ inline long long prefetch_distance(Kern kern, int threads, size_t smem) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess || nb < 1) return 0;
     return (long long)nb * sms;
 }
+#endif  // GOPF_HOST_EMUL
 
 __device__ __forceinline__ cplx* peer_row(const PeerOut& p, long long a, int j, long long b) {
     return p.base[j >> p.log] + (p.block_off + a * p.a_stride + (long long)(j & p.mask) * p.row_stride + b);
@@ -417,6 +423,7 @@ inline int pick_tx(int N, long long B, int want, bool peer = false) {
     return tx;
 }
 
+#ifndef GOPF_HOST_EMUL
 template <int N, int TX>
 cudaError_t launch_strided_n_tx(const PassGeom& g, const PassIO& io, const cplx* tw, cudaStream_t s) {
     constexpr int T = PlanFor<N>::T;
@@ -470,6 +477,8 @@ cudaError_t launch_contig_n(const PassGeom& g, const PassIO& io, const cplx* tw,
     return cudaGetLastError();
 }
 
+#endif  // GOPF_HOST_EMUL
+
 // launch shape of k_pass_contig<N> for A lines (the run-time specialised copy of the kernel is launched
 // through the driver API with the same shape, jit.cu)
 template <int N>
@@ -480,6 +489,7 @@ inline void contig_config_n(long long A, unsigned* grid, unsigned* block, size_t
     *block = (unsigned)(T * LINES);
 }
 
+#ifndef GOPF_HOST_EMUL
 template <int N>
 cudaError_t launch_pass_n(const PassGeom& g, int tx_want, const PassIO& io, const cplx* tw, cudaStream_t s) {
     if (g.B == 1) return launch_contig_n<N>(g, io, tw, s);
@@ -488,12 +498,16 @@ cudaError_t launch_pass_n(const PassGeom& g, int tx_want, const PassIO& io, cons
     return launch_strided_n<N>(g, tx, io, tw, s);
 }
 
+#endif  // GOPF_HOST_EMUL
+
 inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 inline bool fast_length(int n) { return is_pow2(n) && n >= 2 && n <= 4096; }
 
 // One pass along g.axis (power-of-two length 2..4096).  Defined in pass_launch.cu; the
 // instantiations are spread over pass_inst_*.cu so they compile in parallel.
+#ifndef GOPF_HOST_EMUL
 cudaError_t launch_pass(const PassGeom& g, int tx_want, const PassIO& io, const cplx* tw, cudaStream_t s);
+#endif
 // pass_launch.cu: contig_config_n for a run-time N; false when N is not a fast length
 bool contig_launch_config(int N, long long A, unsigned* grid, unsigned* block, size_t* smem);
 

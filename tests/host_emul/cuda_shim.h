@@ -31,7 +31,45 @@ static inline double2 make_double2(double x, double y) {
 struct emul_dim3 {
     unsigned x, y, z;
 };
+#ifndef GOPF_EMUL_THREADS
+// pointwise evaluators: one "thread" in a 1 x 1 grid
 static const emul_dim3 gridDim = {1, 1, 1}, blockDim = {1, 1, 1}, blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0};
+#else
+// kernels with shared memory and barriers (the FFT passes): one OS thread per CUDA thread of a block, blocks
+// one after the other; emul_launch below drives them
+#include <pthread.h>
+
+#include <thread>
+#include <vector>
+#define GOPF_HOST_EMUL 1
+static thread_local emul_dim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0};
+static emul_dim3 gridDim = {1, 1, 1}, blockDim = {1, 1, 1};
+static pthread_barrier_t emul_block_barrier;
+static inline void __syncthreads() { pthread_barrier_wait(&emul_block_barrier); }
+static inline void __syncwarp() { pthread_barrier_wait(&emul_block_barrier); }  // every thread of the block reaches it too
+#define __shared__
+#define __align__(n) __attribute__((aligned(n)))
+namespace gopf {
+alignas(16) unsigned char gopf_smem_raw[232448];  // the kernels' `extern __shared__` array (227 KB)
+}
+template <class Kernel, class... Args>
+static void emul_launch(Kernel kernel, unsigned grid, unsigned block, Args... args) {
+    gridDim.x = grid;
+    blockDim.x = block;
+    for (unsigned b = 0; b < grid; ++b) {
+        pthread_barrier_init(&emul_block_barrier, nullptr, block);
+        std::vector<std::thread> threads;
+        for (unsigned t = 0; t < block; ++t)
+            threads.emplace_back([=]() {
+                threadIdx.x = t;
+                blockIdx.x = b;
+                kernel(args...);
+            });
+        for (std::thread& th : threads) th.join();
+        pthread_barrier_destroy(&emul_block_barrier);
+    }
+}
+#endif
 
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
 template <class T>

@@ -35,7 +35,7 @@ def emul(tmp_path_factory):
         pytest.skip("g++ not available")
     so = tmp_path_factory.mktemp("emul") / "emul.so"
     # -DGOPF_KNOISE: the k-space noise generator, which the library's device build does not carry yet
-    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-w", "-DGOPF_KNOISE", "-shared", "-fPIC", "-I",
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-w", "-DGOPF_KNOISE", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I",
                     os.path.join(ROOT, "gopf_b200", "csrc"), "-o", str(so), os.path.join(ROOT, "tests", "host_emul", "emul.cpp")],
                    check=True)
     dll = ctypes.CDLL(str(so))
@@ -540,7 +540,7 @@ class SpecialisedEmulatedSolver(EmulatedSolver):
             stem = os.path.join(self.build_dir, f"unit_{SpecialisedEmulatedSolver.serial}")
             with open(stem + ".cpp", "w") as f:
                 f.write('#include "cuda_shim.h"\n' + src)
-            subprocess.run(["g++", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-I", os.path.join(ROOT, "gopf_b200", "csrc"),
+            subprocess.run(["g++", "-O1", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I", os.path.join(ROOT, "gopf_b200", "csrc"),
                             "-I", os.path.join(ROOT, "tests", "host_emul"), "-o", stem + ".so", stem + ".cpp"], check=True)
             unit = ctypes.CDLL(stem + ".so")
             self._kernel = unit.gopf_jit_kupdate
