@@ -188,6 +188,21 @@ int gopf_model_program_image(gopf_model* m, int rank, double dt, void* buf, int6
     GOPF_API_END
 }
 
+int gopf_model_fused_program_image(gopf_model* m, int rank, double dt, void* buf, int64_t len, int64_t* needed, int* derived_index) {
+    GOPF_API_BEGIN
+    if (!m) throw Error("model is NULL");
+    if (rank != 2 && rank != 3) throw Error("rank must be 2 or 3");
+    m->m.init();
+    const int d = single_field_derived_index(m->m);
+    if (d < 0) throw Error("model: not a single-field model with one nonlinearity (the fused kernels do not apply)");
+    DevKProgram P;
+    m->m.fill_program(&P, dt, rank);
+    finalize_single_field_program(&P, (int)m->m.fields.size());
+    copy_image(&P, sizeof(P), buf, len, needed);
+    if (derived_index) *derived_index = d;
+    GOPF_API_END
+}
+
 int gopf_model_derived_image(gopf_model* m, int index, void* buf, int64_t len, int64_t* needed, int* used) {
     GOPF_API_BEGIN
     if (!m) throw Error("model is NULL");

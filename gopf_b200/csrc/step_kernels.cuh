@@ -29,6 +29,22 @@ struct FreqTabs {
     int off1;  // slab-sharded k-space: this rank's first k1 (0 on a single GPU)
 };
 
+// 16-byte asynchronous global -> shared copies (cp.async.cg).  tests/host_emul (GOPF_HOST_EMUL) runs these
+// kernels on the host, where the "shared address" is an offset into the block's buffer and the copy is immediate.
+#ifdef GOPF_HOST_EMUL
+inline unsigned smem_address(const void* p) { return (unsigned)(reinterpret_cast<const unsigned char*>(p) - gopf_smem_raw); }
+inline void cp_async16(unsigned dst, const void* src) { memcpy(gopf_smem_raw + dst, src, 16); }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
+#else
+__device__ __forceinline__ unsigned smem_address(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+#endif
+
 // ---- fused real-space kernel (contiguous axis) ------------------------------------
 // MODE 0: inverse + /N + g + forward (steady state)
 // MODE 1: inverse + /N, store real field only
@@ -128,24 +144,24 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
         if (LATE) {
             // the line is live in registers here: walk the rows with two running addresses in a
             // rolled loop instead of materialising E address pairs
-            const unsigned sbase = (unsigned)__cvta_generic_to_shared(sS);
+            const unsigned sbase = smem_address(sS);
             const cplx* src = S + base + (size_t)t * strideB;
             const size_t src_step = (size_t)T * strideB;
 #pragma unroll 1
             for (int m = 0; m < E; ++m) {
                 const unsigned dst = sbase + (unsigned)(Lay::at(t + T * m, l) * (int)sizeof(cplx));
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+                cp_async16(dst, src);
                 src += src_step;
             }
         } else {
 #pragma unroll
             for (int m = 0; m < E; ++m) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(sS + Lay::at(t + T * m, l));
+                const unsigned dst = smem_address(sS + Lay::at(t + T * m, l));
                 const cplx* src = S + base + (size_t)(t + T * m) * strideB;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+                cp_async16(dst, src);
             }
         }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        cp_async_commit();
     };
     if (!LATE) prefetch_spectrum();
     cplx v[E];
@@ -172,7 +188,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
     } else {
         line_fft<N, Lay, SyncCta>(v, t, l, sm, tw);
     }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    cp_async_wait_all();
     if (LATE || P.fast) {  // LATE is launched for fast-form programs only (fused_launch.h)
         const double s2 = fa * fa + fb * fb;
 #pragma unroll

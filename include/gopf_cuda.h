@@ -117,6 +117,10 @@ int gopf_has_kspace_noise(void);
  * Both call Model.Init.  Host only. */
 int gopf_model_program_image(gopf_model* m, int rank, double dt, void* buf, int64_t len, int64_t* needed);
 int gopf_model_derived_image(gopf_model* m, int index, void* buf, int64_t len, int64_t* needed, int* used);
+/* The program as the fused single-field kernels take it (spectrum 0 = the field, 1 = its one derived field,
+ * real-polynomial fast form when it applies; solver.cu finalize_single_field_program, no filter set) and the
+ * index of that derived field.  Fails when the model is not of that shape. */
+int gopf_model_fused_program_image(gopf_model* m, int rank, double dt, void* buf, int64_t len, int64_t* needed, int* derived_index);
 /* pf.NewField + Model.AddField (pf/model.go:44-57, 141-144).  host_c128 is the
  * caller-owned Field.Data backing array of n_nodes complex128; it is read by
  * gopf_solver_upload/propagate and written by gopf_solver_download/propagate,
