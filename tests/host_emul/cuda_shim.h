@@ -45,8 +45,14 @@ static const emul_dim3 gridDim = {1, 1, 1}, blockDim = {1, 1, 1}, blockIdx = {0,
 static thread_local emul_dim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0};
 static emul_dim3 gridDim = {1, 1, 1}, blockDim = {1, 1, 1};
 static pthread_barrier_t emul_block_barrier;
+static pthread_barrier_t emul_warp_barrier[32];  // one per warp of the block: __syncwarp orders that warp only
+#ifdef GOPF_EMUL_NO_BARRIERS  // self-test of the sanitizer runs: without the barriers the races must be reported
+static inline void __syncthreads() {}
+static inline void __syncwarp() {}
+#else
 static inline void __syncthreads() { pthread_barrier_wait(&emul_block_barrier); }
-static inline void __syncwarp() { pthread_barrier_wait(&emul_block_barrier); }  // every thread of the block reaches it too
+static inline void __syncwarp() { pthread_barrier_wait(&emul_warp_barrier[threadIdx.x / 32]); }
+#endif
 #define __shared__
 #define __align__(n) __attribute__((aligned(n)))
 namespace gopf {
@@ -58,6 +64,8 @@ static void emul_launch(Kernel kernel, unsigned grid, unsigned block, Args... ar
     blockDim.x = block;
     for (unsigned b = 0; b < grid; ++b) {
         pthread_barrier_init(&emul_block_barrier, nullptr, block);
+        const unsigned warps = (block + 31) / 32;
+        for (unsigned w = 0; w < warps; ++w) pthread_barrier_init(&emul_warp_barrier[w], nullptr, w + 1 < warps ? 32 : block - 32 * w);
         std::vector<std::thread> threads;
         for (unsigned t = 0; t < block; ++t)
             threads.emplace_back([=]() {
@@ -67,6 +75,7 @@ static void emul_launch(Kernel kernel, unsigned grid, unsigned block, Args... ar
             });
         for (std::thread& th : threads) th.join();
         pthread_barrier_destroy(&emul_block_barrier);
+        for (unsigned w = 0; w < warps; ++w) pthread_barrier_destroy(&emul_warp_barrier[w]);
     }
 }
 #endif
