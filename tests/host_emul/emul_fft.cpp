@@ -71,6 +71,10 @@ static int dispatch(const PassGeom& g, const PassIO& io, int tx) {
         case 64: return run_pass<64>(g, io, tx);
         case 128: return run_pass<128>(g, io, tx);
         case 256: return run_pass<256>(g, io, tx);
+        case 512: return run_pass<512>(g, io, tx);
+        case 1024: return run_pass<1024>(g, io, tx);
+        case 2048: return run_pass<2048>(g, io, tx);
+        case 4096: return run_pass<4096>(g, io, tx);
         default: return 1;
     }
 }

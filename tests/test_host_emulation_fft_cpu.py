@@ -66,6 +66,20 @@ def test_contiguous_pass_is_the_dft(fft, n):
     assert rel(_pass(fft, x, 2, True, scale=1.0 / n), np.fft.ifft(x, axis=2)) < 4e-16 * np.log2(n) + 1e-16
 
 
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+def test_long_lines(fft, n):
+    """The line lengths of cfg 3 (1024^3) and beyond: three radix stages, the instantiations the device tests only
+    reach on the largest grids."""
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((1, 2, n)) + 1j * rng.standard_normal((1, 2, n))
+    assert rel(_pass(fft, x, 2, False), np.fft.fft(x, axis=2)) < 1e-14
+    assert rel(_pass(fft, x, 2, True, scale=1.0 / n), np.fft.ifft(x, axis=2)) < 1e-14
+    if n <= 2048:  # strided: one tile of n x 2 cells
+        y = rng.standard_normal((n, 1, 2)) + 1j * rng.standard_normal((n, 1, 2))
+        assert rel(_pass(fft, y, 0, False, tx=2), np.fft.fft(y, axis=0)) < 1e-14
+        assert rel(_pass(fft, y, 0, True, tx=2), np.fft.ifft(y, axis=0) * n) < 1e-14
+
+
 @pytest.mark.parametrize("tx", [2, 4, 8])
 @pytest.mark.parametrize("shape,axis", [((1, 32, 16), 1), ((16, 2, 8), 0), ((8, 64, 8), 1), ((128, 1, 8), 0)],
                          ids=["mid32", "slow16", "mid64", "slow128"])
