@@ -180,11 +180,30 @@ WORKLOADS = {
                     "name": "strain-single-precipitate-3d-{G}^3-khachaturyan-elasticity-volume-constraint"},
     "pfc": {"contract_bytes": 192.0, "ref_bytes": 480.0, "default_grid": 512,
             "name": "pfc-3d-{G}^3-pair-correlation-white-noise-vandeven"},
+    # SURVEY.md 8d, cfg 2 variant: + SquaredGradient as an explicit term: T_min = 2 + 4 = 6 transforms in 3-D
+    # (reference 3 + 6 = 9)
+    "ch_sqgrad": {"contract_bytes": 576.0, "ref_bytes": 864.0, "default_grid": 256,
+                  "name": "cahn-hilliard-3d-{G}^3-semi-implicit-euler-plus-squared-gradient"},
 }
 
 
 def build_workload(kind, pf, terms, elasticity, dims, pinned, device_noise=True):
     from gopf_b200 import workloads
+    if kind == "ch_sqgrad":
+        from gopf_b200 import synthetic
+        n = int(np.prod(dims))
+        m = pf.NewModel()
+        if pinned:
+            f = pf.NewField("conc", n, None, pinned=True)
+            f.Data[:] = 0.1 * synthetic.cahn_hilliard_initial(n, 5)
+        else:
+            f = pf.NewField("conc", n, 0.1 * synthetic.cahn_hilliard_initial(n, 5))
+        m.AddScalar(pf.NewScalar("gamma", synthetic.CAHN_HILLIARD_GAMMA))
+        m.AddScalar(pf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
+        m.AddField(f)
+        m.RegisterExplicitTerm("GRAD_SQ", terms.NewSquareGradient("conc", dims), None)
+        m.AddEquation(synthetic.CAHN_HILLIARD_EQUATION + " + GRAD_SQ")
+        return m, pf.NewSolver(m, dims, 0.05)
     if kind == "precipitate":
         m, conc, phase, solver, _ = workloads.build_precipitate(pf, terms, elasticity, dims, expressions=pf.__name__.startswith("gopf_b200"),
                                                                pinned=pinned)
@@ -456,7 +475,7 @@ def main():
                     help="N = 1: skip the extra 1024^3 single-GPU measurement (strong-scaling base of the sharded arm)")
     ap.add_argument("--no-jit", action="store_true",
                     help="general workloads: interpreter kernels instead of the NVRTC-specialised ones")
-    ap.add_argument("--workload", default="ch", choices=["ch", "precipitate", "pfc"],
+    ap.add_argument("--workload", default="ch", choices=["ch", "precipitate", "pfc", "ch_sqgrad"],
                     help="ch: Cahn-Hilliard (BASELINE.json configs 1-3, the metric's workload); precipitate: cfg 4; pfc: cfg 5")
     ap.add_argument("--exchange", default="peer", choices=["peer", "dma", "nccl"],
                     help="sharded runs: peer stores fused into the passes, copy-engine copies pipelined under the "
