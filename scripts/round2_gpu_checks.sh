@@ -23,7 +23,7 @@ jit)
     #    events; then one ncu pass over the specialised kernels (their cubins and sources are dumped for
     #    --import-source)
     python scripts/jit_check.py 512 5 > gpurun_out/jit_check_512.log 2>&1
-    for w in precipitate pfc; do
+    for w in precipitate pfc ch_sqgrad; do
         python bench.py --workload $w --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_${w}_jit.json 2> gpurun_out/bench_${w}_jit.err
         python bench.py --workload $w --steps 20 --warmup 5 --no-cpu-baseline --no-jit > gpurun_out/bench_${w}_nojit.json 2> gpurun_out/bench_${w}_nojit.err
     done
