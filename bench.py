@@ -235,6 +235,10 @@ def run_general_workload(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     solver.SetStream(stream.cuda_stream)
+    if args.stepper == "rk4":
+        solver.SetStepper("rk4")
+    elif args.stepper == "implicit_euler":  # configs[1] names this stepper; one step = one Newton-Krylov solve
+        solver.Stepper = gpf.ImplicitEuler(solver.Dt)
     # registered functions and the k-space update as NVRTC images (profiles/r1d_jit_notes.md)
     solver.SetJit(not args.no_jit)
     solver.Upload()
@@ -289,7 +293,7 @@ def run_general_workload(args):
     line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": W["name"].format(G=G), "grid": dims, "stepper": "euler",
+            "config": {"workload": W["name"].format(G=G), "grid": dims, "stepper": args.stepper,
                        "cache": f"arrays of {16 * n / 2**20:.0f} MiB each exceed the 126 MB L2 (no flush needed)",
                        "path": "fused single-field kernels" if solver.IsFused else "general multi-field path",
                        "specialised_kernels": solver.JitKernels()},
@@ -473,6 +477,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scaling-base", dest="scaling_base", action="store_false",
                     help="N = 1: skip the extra 1024^3 single-GPU measurement (strong-scaling base of the sharded arm)")
+    ap.add_argument("--stepper", default="euler", choices=["euler", "rk4", "implicit_euler"],
+                    help="general workloads: time stepper (the default 3-D Cahn-Hilliard arm is semi-implicit Euler)")
     ap.add_argument("--no-jit", action="store_true",
                     help="general workloads: interpreter kernels instead of the NVRTC-specialised ones")
     ap.add_argument("--workload", default="ch", choices=["ch", "precipitate", "pfc", "ch_sqgrad"],
