@@ -493,6 +493,9 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "ch" and args.stepper != "euler":
+        raise SystemExit("bench.py: the 3-D Cahn-Hilliard arm is the semi-implicit Euler step of the metric; "
+                         "--stepper applies to --workload precipitate | pfc | ch_sqgrad")
     if args.workload != "ch":
         if max(args.gpus, world) > 1:
             raise SystemExit("bench.py: the sharded path covers the Cahn-Hilliard workload; cfg 4 / cfg 5 run on one GPU")
