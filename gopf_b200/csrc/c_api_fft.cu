@@ -1,5 +1,6 @@
 // C ABI, part 1: library info, pfutil index helpers and the transform-level
 // FFTWWrapper replacement.  Contract: include/gopf_cuda.h.
+#include "tma_launch.h"
 #include "../../include/gopf_cuda.h"
 #include "fft_plan.h"
 
@@ -14,6 +15,13 @@ extern "C" {
 const char* gopf_last_error(void) { return get_last_error(); }
 
 int gopf_abi_version(void) { return GOPF_ABI_VERSION; }
+
+int gopf_tma_launch_count(int reset, int64_t* launches) {
+    GOPF_API_BEGIN
+    if (!launches) throw Error("gopf_tma_launch_count: launches is NULL");
+    *launches = (int64_t)tma_launch_count(reset != 0);
+    GOPF_API_END
+}
 
 int gopf_device_count(int* count) {
     GOPF_API_BEGIN

@@ -216,7 +216,7 @@ void DistSolver::kspace_step_cols(const cplx* Tin, cplx* S, cplx* Tout, int k1_b
     ft.off1 = rank_ * m_;
     PassGeom g = make_geom(n_, m_, n_, 0);
     g.b0 = (long long)k1_begin * n_;
-    g.bcount = (long long)k1_count * n_;
+    g.bcount = g.bw = (long long)k1_count * n_;
     check(launch_fused_kspace(g, plan_->tx_want, Tin, Tout, S, prog_, ft, plan_->twiddle(0), stream()),
           "fused k-space kernel (columns)");
 }

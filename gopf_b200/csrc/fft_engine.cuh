@@ -275,6 +275,17 @@ __device__ __forceinline__ void line_fft(cplx (&v)[PlanFor<N>::E], int t, int l,
     if (P::NS > 2) fft_stage<N, (P::NS > 2 ? 2 : 0), Layout, Sync>(v, t, l, sm, tw);
 }
 
+// Stages S0 .. NS-1 of the same transform (S0 = 0: all of it).  Lets a kernel do something between two
+// stages (tma_kernels.cuh takes the shared spectrum buffer after the first exchange).
+template <int N, int S0, class Layout, class Sync>
+__device__ __forceinline__ void line_fft_from(cplx (&v)[PlanFor<N>::E], int t, int l, cplx* sm,
+                                              const cplx* __restrict__ tw) {
+    typedef PlanFor<N> P;
+    if (S0 <= 0) fft_stage<N, 0, Layout, Sync>(v, t, l, sm, tw);
+    if (S0 <= 1 && P::NS > 1) fft_stage<N, (P::NS > 1 ? 1 : 0), Layout, Sync>(v, t, l, sm, tw);
+    if (S0 <= 2 && P::NS > 2) fft_stage<N, (P::NS > 2 ? 2 : 0), Layout, Sync>(v, t, l, sm, tw);
+}
+
 // The same transform in two parts, for kernels that want the exchange buffer back early:
 // after line_fft_head every thread has passed the last barrier of the last exchange, so `sm`
 // is free while line_fft_tail (register-only butterflies of the last stage) runs.

@@ -45,7 +45,12 @@ struct PassGeom {
     RowMap in, out;  // strided kernels only
     long long node0; // reference node number of this array's first cell (slab offset when sharded)
     PeerOut peer;    // strided kernels only
-    long long b0, bcount;  // fused k-space kernel: columns [b0, b0 + bcount) of B (chunked launches)
+    // Column window (chunked launches): the pass covers `bcount` of the B columns, laid out as rows of `bw`
+    // consecutive columns starting at b0, one row every `bpitch` columns: window column w is column
+    // (w / bw) * bpitch + b0 + w % bw.  bw == bcount: one contiguous run [b0, b0 + bcount).  The slab-sharded
+    // k-space kernel uses rows = k1_local, bpitch = n2 and a k2 window, so that the inverse middle pass of that
+    // k2 window can start while the next window is still being exchanged (dist_solver.cu).
+    long long b0, bcount, bw, bpitch;
     // Next-wave L2 prefetch (plain axis passes): a CTA asks L2 for the input tile of CTA
     // blockIdx.x + pf_tiles (the one that takes its place on the SM, = resident CTAs of the launch),
     // so DRAM keeps streaming while this tile is in its compute phase and the next wave's loads hit
@@ -105,8 +110,18 @@ inline PassGeom make_geom(int n0, int n1, int n2, int axis) {
     g.peer = PeerOut{};
     g.b0 = 0;
     g.bcount = g.B;
+    g.bw = g.B;
+    g.bpitch = 0;
     g.pf_tiles = 0;
     return g;
+}
+
+// first column of tile `t` (TX columns wide, TX divides bw) of the column window
+__host__ __device__ __forceinline__ long long window_col(const PassGeom& g, long long t, int tx) {
+    const long long w = t * tx;
+    if (g.bw == g.bcount) return g.b0 + w;
+    const long long r = w / g.bw;
+    return r * g.bpitch + g.b0 + (w - r * g.bw);
 }
 
 struct RealPtrs {
@@ -299,9 +314,9 @@ __device__ __forceinline__ void pass_strided_tile(const PassGeom& g, const PassI
     constexpr int E = PlanFor<N>::E, T = PlanFor<N>::T;
     const int tid = threadIdx.x;
     const int l = tid % TX, t = tid / TX;
-    const long long tilesB = g.B / TX;
+    const long long tilesB = g.bcount / TX;
     const long long a = tile / tilesB;
-    const long long b = (tile - a * tilesB) * TX + l;
+    const long long b = window_col(g, tile - a * tilesB, TX) + l;
     cplx v[E];
     const size_t ibase = (size_t)a * g.in.a_stride + b, obase = (size_t)a * g.out.a_stride + b;
     auto at_in = [&](int m) -> size_t {
@@ -318,7 +333,7 @@ __device__ __forceinline__ void pass_strided_tile(const PassGeom& g, const PassI
         const long long tile2 = tile + g.pf_tiles;
         if (tile2 < g.A * tilesB) {
             const long long a2 = tile2 / tilesB;
-            const size_t ib2 = (size_t)a2 * g.in.a_stride + (size_t)((tile2 - a2 * tilesB) * TX + l);
+            const size_t ib2 = (size_t)a2 * g.in.a_stride + (size_t)(window_col(g, tile2 - a2 * tilesB, TX) + l);
 #pragma unroll
             for (int m = 0; m < E; ++m) {
                 const int j = t + T * m;
@@ -344,7 +359,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB(PlanFor<N>::T* TX
     extern __shared__ __align__(16) unsigned char gopf_smem_raw[];
     cplx* sm = reinterpret_cast<cplx*>(gopf_smem_raw);
     if (PEER) {
-        const long long tiles = g.A * (g.B / TX);
+        const long long tiles = g.A * (g.bcount / TX);
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) pass_strided_tile<N, TX, true>(g, io, tw, sm, tile);
     } else {
         pass_strided_tile<N, TX, false>(g, io, tw, sm, blockIdx.x);
@@ -433,7 +448,7 @@ cudaError_t launch_strided_n_tx(const PassGeom& g, const PassIO& io, const cplx*
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    long long tiles = g.A * (g.B / TX);
+    long long tiles = g.A * (g.bcount / TX);
     if (g.peer.n > 0 && g.peer.max_ctas > 0 && tiles > g.peer.max_ctas) tiles = g.peer.max_ctas;
     PassGeom gl = g;
     if (g.peer.n == 0) gl.pf_tiles = prefetch_distance(kern, T * TX, smem);
@@ -493,7 +508,8 @@ inline void contig_config_n(long long A, unsigned* grid, unsigned* block, size_t
 template <int N>
 cudaError_t launch_pass_n(const PassGeom& g, int tx_want, const PassIO& io, const cplx* tw, cudaStream_t s) {
     if (g.B == 1) return launch_contig_n<N>(g, io, tw, s);
-    const int tx = pick_tx(N, g.B, tx_want, g.peer.n > 0);
+    int tx = pick_tx(N, g.B, tx_want, g.peer.n > 0);
+    while (tx > 1 && (g.bw % tx) != 0) tx >>= 1;  // tiles must not straddle a row of the column window
     if (tx < 2) return cudaErrorInvalidValue;
     return launch_strided_n<N>(g, tx, io, tw, s);
 }

@@ -1,5 +1,6 @@
 // Dispatch of the fused single-field kernels to their per-length instantiations.
 #include "fused_launch.h"
+#include "tma_launch.h"
 
 #include <cstdlib>
 
@@ -31,6 +32,10 @@ bool fused_length_supported(int n) {
 
 cudaError_t launch_fused_kspace(const PassGeom& g, int tx_want, const cplx* W, cplx* Wout, cplx* S, const DevKProgram& P,
                                 const FreqTabs& ft, const cplx* tw, cudaStream_t s) {
+    {
+        const cudaError_t e = launch_fused_kspace_tma(g, W, Wout, S, P, ft, tw, s);
+        if (e != cudaErrorNotSupported) return e;
+    }
     switch (g.N) {
 #define X(v) case v: return fused_kspace_##v(g, tx_want, W, Wout, S, P, ft, tw, s);
         GOPF_FUSED_N(X)
@@ -41,6 +46,10 @@ cudaError_t launch_fused_kspace(const PassGeom& g, int tx_want, const cplx* W, c
 
 cudaError_t launch_fused_real(const PassGeom& g, int mode, cplx* W, cplx* real_out, const DevDerived& D, double inv_n,
                               unsigned long long step, const cplx* tw, cudaStream_t s) {
+    if (mode == 0 && real_out == nullptr) {
+        const cudaError_t e = launch_fused_real_tma(g, W, D, inv_n, step, tw, s);
+        if (e != cudaErrorNotSupported) return e;
+    }
     switch (g.N) {
 #define X(v) case v: return fused_real_##v(g, mode, W, real_out, D, inv_n, step, tw, s);
         GOPF_FUSED_N(X)

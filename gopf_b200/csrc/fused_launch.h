@@ -77,13 +77,13 @@ cudaError_t fused_kspace_n(const PassGeom& g, int tx_want, const cplx* W, cplx* 
     if (late) {
         tx = 16;
         while (tx > 8 && line_bytes * tx > 64 * 1024) tx >>= 1;
-        while (tx > 2 && (line_bytes * tx > 128 * 1024 || T * tx > 1024 || (g.bcount % tx) != 0)) tx >>= 1;
+        while (tx > 2 && (line_bytes * tx > 128 * 1024 || T * tx > 1024 || (g.bw % tx) != 0)) tx >>= 1;
     } else {
         tx = pick_tx(N, g.bcount, tx_want);
-        while (tx > 2 && line_bytes * tx * 2 > 128 * 1024) tx >>= 1;
+        while (tx > 2 && (line_bytes * tx * 2 > 128 * 1024 || (g.bw % tx) != 0)) tx >>= 1;
     }
     const int env_tx = env_int("GOPF_KSPACE_TX", 0);
-    if (env_tx > 0 && (g.bcount % env_tx) == 0) tx = env_tx;
+    if (env_tx > 0 && (g.bw % env_tx) == 0) tx = env_tx;
     return late ? fused_kspace_n_late<N, true>(g, tx, W, Wout, S, P, ft, tw, s)
                 : fused_kspace_n_late<N, false>(g, tx, W, Wout, S, P, ft, tw, s);
 }

@@ -513,9 +513,11 @@ bool launch(Kernel* k, unsigned grid, unsigned block, void** args, cudaStream_t 
     return true;
 }
 
+// On by default since round 2 (the whole device suite runs green with it); GOPF_JIT=0 keeps the
+// interpreter kernels.
 bool enabled() {
     const char* e = std::getenv("GOPF_JIT");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
 }
 
 bool inpass_enabled() {

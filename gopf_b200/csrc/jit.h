@@ -61,7 +61,7 @@ void unload(Kernel* k);
 bool launch(Kernel* k, unsigned grid, unsigned block, void** args, cudaStream_t stream, std::string* log, size_t smem = 0);
 
 bool inpass_enabled();  // GOPF_JIT_INPASS=1: also evaluate registered functions inside their first forward pass
-bool enabled();  // GOPF_JIT=1 in the environment switches the specialisation on for new solvers
+bool enabled();  // default on; GOPF_JIT=0 in the environment keeps the interpreter kernels for new solvers
 
 }  // namespace jit
 }  // namespace gopf

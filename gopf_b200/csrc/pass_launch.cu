@@ -1,5 +1,6 @@
 // Dispatch of one axis pass to the per-length instantiations (pass_inst_*.cu).
 #include "fft_kernels.cuh"
+#include "tma_launch.h"
 
 #include <cstdlib>
 
@@ -21,6 +22,11 @@ GOPF_DECL(512) GOPF_DECL(1024) GOPF_DECL(2048) GOPF_DECL(4096)
 #undef GOPF_DECL
 
 cudaError_t launch_pass(const PassGeom& g, int tx_want, const PassIO& io, const cplx* tw, cudaStream_t s) {
+    // long strided lines: the copy-engine-fed kernel (tma_kernels.cuh) when the shape is covered
+    {
+        const cudaError_t e = launch_pass_tma(g, io, tw, s);
+        if (e != cudaErrorNotSupported) return e;
+    }
     switch (g.N) {
 #define X(n) case n: return launch_pass_##n(g, tx_want, io, tw, s);
         X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096)

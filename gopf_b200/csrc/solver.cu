@@ -1123,7 +1123,10 @@ void Solver::rk4_step() {
     sync_and_rhs();
     point(0, dt_ / 6.0);
     point(2, dt_);                  // rk4.go:57-68
-    elastic_hooks();                // solver.go:74-82 (OnStepFinished after Stepper.Step)
+    // solver.go:74-82: OnStepFinished of every term after Stepper.Step, whatever the stepper.  The
+    // indicator spectrum of the 4th stage is still in S_, which is what the reference's bricks hold.
+    volume_lp_hooks();
+    elastic_hooks();
 }
 
 void Solver::step(int nsteps) {

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
     const long long tilesB = g.bcount / TX;
     const long long tile = blockIdx.x;
     const long long a = tile / tilesB;
-    const long long b = g.b0 + (tile - a * tilesB) * TX + l;
+    const long long b = window_col(g, tile - a * tilesB, TX) + l;
     const size_t base = (size_t)a * N * g.B + b;
     const size_t strideB = (size_t)g.B;
     // Each thread later reads back exactly the spectrum cells it copied, so cp.async.wait_group

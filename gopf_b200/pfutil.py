@@ -95,3 +95,10 @@ class FFTWWrapper:
 def NewFFTW(n, device: int = -1) -> FFTWWrapper:
     """pfutil.NewFFTW (pfutil/fftWrap.go:16-23)."""
     return FFTWWrapper(n, device)
+
+
+def TmaLaunchCount(reset: bool = False) -> int:
+    """Launches that took the copy-engine-fed long-line kernels since the last reset (diagnostics)."""
+    n = ctypes.c_int64(0)
+    check(lib().gopf_tma_launch_count(1 if reset else 0, ctypes.byref(n)))
+    return n.value

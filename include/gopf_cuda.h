@@ -41,6 +41,11 @@ const char* gopf_last_error(void);
 int gopf_abi_version(void);
 /* number of visible CUDA devices (0 and status != 0 when the driver is absent) */
 int gopf_device_count(int* count);
+/* Launches that took the copy-engine-fed (TMA, warp-specialised) line kernels since the last reset:
+ * the long-line variants of the axis passes and of the fused kernels behind gopf_fft_exec /
+ * gopf_solver_step (tma_kernels.cuh; GOPF_TMA=0 in the environment keeps the register-resident
+ * kernels).  Diagnostics for tests and the bench line; no reference counterpart. */
+int gopf_tma_launch_count(int reset, int64_t* launches);
 
 /* ---- pfutil index / k-table helpers (host side, integer-exact) ------------- */
 /* pfutil.NodeIdx (pfutil/indexPositionConversion.go:4-22); pos = [row, col(, depth)] */

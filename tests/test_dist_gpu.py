@@ -77,3 +77,39 @@ def test_sharded_cuda_matches_oracle(tmp_path, world, n, split, exchange):
     got = np.concatenate([np.load(tmp_path / f"slab{r}.npy") for r in range(world)])
     ref = _oracle(n, sum(split))
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-10
+
+
+def _single_gpu(n, nsteps):
+    """The same run on one GPU through the fused single-field kernels (the P = 1 member of SURVEY.md 8d's
+    "P-GPU vs 1-GPU" comparison)."""
+    from gopf_b200 import pf as gpf
+    total = n ** 3
+    m = gpf.NewModel()
+    f = gpf.NewField("conc", total, synthetic.cahn_hilliard_initial(total, 0))
+    m.AddScalar(gpf.NewScalar("gamma", synthetic.CAHN_HILLIARD_GAMMA))
+    m.AddScalar(gpf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
+    m.AddField(f)
+    m.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
+    s = gpf.NewSolver(m, [n, n, n], synthetic.CAHN_HILLIARD_DT)
+    assert s.IsFused
+    s.Upload()
+    s.StepDevice(nsteps)
+    s.Download()
+    out = f.Data.copy()
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("world,n,split", [(1, 256, (6, 4)), (2, 256, (10,)), (4, 256, (10,)), (8, 256, (10,)),
+                                           (2, 512, (4,)), (4, 512, (4,)), (8, 512, (4,))])
+def test_sharded_matches_single_gpu_at_benchmark_scale(tmp_path, world, n, split, exchange):
+    """P-GPU vs 1-GPU at 256^3 and 512^3, <= 1e-13 (same kernels, different tiling and
+    exchange; world = 1 runs every PEER / split-row-map instantiation of the 256-cell lines on any box)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(world, _free_port(), n, split, str(tmp_path), exchange), nprocs=world, join=True)
+    got = np.concatenate([np.load(tmp_path / f"slab{r}.npy") for r in range(world)])
+    ref = _single_gpu(n, sum(split))
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-13

@@ -127,3 +127,41 @@ def test_observers():
     s.Solve(1, 5)
     e = np.array([m.MixedTerms["IDEAL"].GetEnergy(), m.ImplicitTerms["EXCESS"].GetEnergy()])
     assert np.allclose(e, g["pfc_energy"], rtol=1e-10, atol=0.0)
+
+
+# ---- benchmark-scale fingerprints (tests/golden/make_golden_large.py) --------------
+def _fingerprint_check(got, g, k):
+    idx = g["indices"]
+    ref = g[f"after_{k}_samples"]
+    # relative L2 over 16 384 fixed cells: an unbiased estimate of the full-field figure
+    assert rel_l2(got[idx], ref) <= TOL
+    re = got.real
+    n = re.size
+    assert abs(float(np.sqrt(np.sum(re.astype(np.longdouble) ** 2))) - float(g[f"after_{k}_l2"])) <= 1e-11 * float(g[f"after_{k}_l2"])
+    assert abs(float(re.sum(dtype=np.longdouble)) - float(g[f"after_{k}_sum"])) <= 1e-9 * n ** 0.5
+    assert abs(float(np.max(np.abs(re))) - float(g[f"after_{k}_max_abs"])) <= 1e-10
+    assert float(np.max(np.abs(got.imag))) <= 1e-11
+
+
+@pytest.mark.parametrize("edge", [128, 256])
+def test_cahn_hilliard_benchmark_grid_100_steps_vs_oracle_fingerprint(edge):
+    """BASELINE.json configs[1] at its own size: the fused kernels (k_fused_kspace<256,16,LATE>,
+    k_fused_real<256>, k_pass_strided<256,*>) against the oracle's state after 10 and 100 steps
+    (pf/euler.go:16-47), through the fingerprint frozen by make_golden_large.py."""
+    g = load(f"ch_3d_{edge}_fingerprint.npz")
+    n = edge ** 3
+    m = gpf.NewModel()
+    f = gpf.NewField("conc", n, synthetic.cahn_hilliard_initial(n, 0))
+    m.AddScalar(gpf.NewScalar("gamma", synthetic.CAHN_HILLIARD_GAMMA))
+    m.AddScalar(gpf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
+    m.AddField(f)
+    m.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
+    s = gpf.NewSolver(m, [edge] * 3, synthetic.CAHN_HILLIARD_DT)
+    assert s.IsFused
+    s.Upload()
+    s.StepDevice(10)
+    s.Download()
+    _fingerprint_check(f.Data, g, 10)
+    s.StepDevice(90)   # device state untouched by the read-back
+    s.Download()
+    _fingerprint_check(f.Data, g, 100)

@@ -270,6 +270,9 @@ class EmulatedSolver:
             spectra = sync_and_rhs()
             point(*first, spectra)
             point(*second, spectra)
+        for slot, (fi, ii, dt) in enumerate(self.lp_terms):  # Solver::volume_lp_hooks (solver.go:74-82)
+            state = ctypes.cast(self.lp_state.ctypes.data + 24 * slot, DP)
+            self.dll.emul_volume_lp_update(state, spectra[fi].ctypes.data_as(DP), spectra[ii].ctypes.data_as(DP), ctypes.c_double(dt))
         self.steps_taken += 1
 
 
@@ -355,8 +358,9 @@ def test_rk4(T):
     T.test_rk4_cahn_hilliard_vs_oracle([16, 16, 16])
 
 
-def test_two_phase_functions_and_volume_constraint(T):
-    T.test_two_phase_functions_and_volume_constraint_vs_oracle()
+@pytest.mark.parametrize("stepper", ["euler", "rk4"])
+def test_two_phase_functions_and_volume_constraint(T, stepper):
+    T.test_two_phase_functions_and_volume_constraint_vs_oracle(stepper)
 
 
 def test_tabulated_and_literal_implicit_side_agree(emul, monkeypatch):
@@ -602,7 +606,8 @@ def test_specialised_rk4_and_volume_constraint_units_on_the_host(TS):
     TS.test_rk4_simple_model_and_implicit()
     TS.test_rk4_cahn_hilliard_vs_oracle([16, 16, 16])
     assert SpecialisedEmulatedSolver.calls > 100
-    TS.test_two_phase_functions_and_volume_constraint_vs_oracle()  # the multiplier's address as a literal
+    TS.test_two_phase_functions_and_volume_constraint_vs_oracle("euler")  # the multiplier's address as a literal
+    TS.test_two_phase_functions_and_volume_constraint_vs_oracle("rk4")
 
 
 def test_emulated_freq_is_the_reference_k_table(emul):

@@ -391,9 +391,11 @@ def test_conservative_noise_prescribed_currents_vs_oracle():
     assert rel_l2(outs[0], outs[1]) <= TOL
 
 
-def test_two_phase_functions_and_volume_constraint_vs_oracle():
+@pytest.mark.parametrize("stepper", ["euler", "rk4"])
+def test_two_phase_functions_and_volume_constraint_vs_oracle(stepper):
     # the non-elastic part of cfg 4 (examples/strain_single_precipitate/main.go:45-111):
-    # registered functions, kappa*LAP terms and the VolumeConservingLP constraint
+    # registered functions, kappa*LAP terms and the VolumeConservingLP constraint.  Under RK4 the
+    # OnStepFinished hooks still run after every Stepper.Step (pf/solver.go:70-84).
     M = 32
     dims = [M, M]
     n = M * M
@@ -431,6 +433,8 @@ def test_two_phase_functions_and_volume_constraint_vs_oracle():
         m.AddEquation("dconc/dt = CHEMICALPOT + kappa*LAP conc")
         m.AddEquation("dphase/dt = DERIV_PHASE_ORDER + kappa*LAP phase + CONSERVE_PREC_VOL")
         s = mod.NewSolver(m, dims, dt)
+        if stepper != "euler":
+            s.SetStepper(stepper)
         if mod is gpf:
             s.Upload()
             s.StepDevice(30)  # hooks run on the device between steps
@@ -474,6 +478,40 @@ def test_cahn_hilliard_256_cubed_properties():
     s.StepDevice(20)
     s.Download()
     assert rel_l2(f.Data, fused) < 1e-12
+
+
+@pytest.mark.parametrize("dims,steps", [([256, 256, 256], 10), ([512, 512, 512], 3), ([1024, 1024], 100), ([2048, 2048], 20),
+                                        ([1024, 256], 20)], ids=lambda v: "x".join(map(str, v)) if isinstance(v, list) else str(v))
+def test_cahn_hilliard_benchmark_scale_vs_oracle(dims, steps):
+    """the fused kernels at the sizes that are benchmarked, against the oracle itself
+    (pf/euler.go:16-47; scipy.fft with every host thread).  256^3 = BASELINE.json configs[1];
+    512^3 = the cfg 4 / cfg 5 line length; 1024^2 and 2048^2 run k_fused_kspace<1024|2048> and
+    k_fused_real<1024|2048>, the line kernels of the 1024^3 sharded arm (configs[2])."""
+    import os
+    n = opfutil.prod_int(dims)
+    init = synthetic.cahn_hilliard_initial(n, 0)
+    gm = gpf.NewModel()
+    gf = gpf.NewField("conc", n, init.copy())
+    gm.AddScalar(gpf.NewScalar("gamma", synthetic.CAHN_HILLIARD_GAMMA))
+    gm.AddScalar(gpf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
+    gm.AddField(gf)
+    gm.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
+    gs = gpf.NewSolver(gm, dims, synthetic.CAHN_HILLIARD_DT)
+    assert gs.IsFused
+    gs.Upload()
+    gs.StepDevice(steps)
+    gs.Download()
+    got = gf.Data.copy()
+    gs.close()
+    del gs, gm, gf
+    om = opf.NewModel()
+    of = opf.NewField("conc", n, init)
+    om.AddScalar(opf.NewScalar("gamma", synthetic.CAHN_HILLIARD_GAMMA))
+    om.AddScalar(opf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
+    om.AddField(of)
+    om.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
+    opf.NewSolver(om, dims, synthetic.CAHN_HILLIARD_DT, workers=os.cpu_count() or 1).Propagate(steps)
+    assert rel_l2(got, of.Data) <= TOL
 
 
 # ---- cfg 4: examples/strain_single_precipitate with HomogeneousModulusLinElast -----------

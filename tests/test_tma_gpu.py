@@ -1,0 +1,98 @@
+"""The copy-engine-fed (TMA, warp-specialised) long-line kernels of tma_kernels.cuh against the
+register-resident kernels they replace and against the oracle.
+
+They run the same Stockham engine on the same cells, so the results must be BITWISE those of the
+register-resident kernels (GOPF_TMA=0); the oracle comparison is the usual 1e-10 / 1e-13.  Reference
+semantics: pfutil/fftWrap.go:26-39 (transform), pf/euler.go:16-47 (step)."""
+import os
+
+import numpy as np
+import pytest
+
+from gopf_b200 import pf as gpf
+from gopf_b200 import pfutil as gpfutil
+from gopf_b200 import synthetic
+from oracle import pfutil as opfutil
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def tma_env():
+    keys = ("GOPF_TMA", "GOPF_TMA_MIN_N", "GOPF_TMA_L2", "GOPF_TMA_PASS", "GOPF_TMA_REAL", "GOPF_TMA_KSPACE")
+    saved = {k: os.environ.get(k) for k in keys}
+    yield os.environ
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+def _fft(dims, x, sign):
+    y = x.copy()
+    ft = gpfutil.NewFFTW(dims)
+    (ft.FFT if sign < 0 else ft.IFFT)(y)
+    ft.close()
+    return y
+
+
+@pytest.mark.parametrize("dims,min_n", [([1024, 4, 8], 1024), ([4, 1024, 8], 1024), ([2, 1024, 1024], 1024), ([1024, 1024], 1024),
+                                        ([512, 8, 8], 512), ([8, 512, 16], 512), ([512, 512], 512)],
+                         ids=lambda v: "x".join(map(str, v)) if isinstance(v, list) else f"min{v}")
+def test_strided_pass_bitwise_and_vs_oracle(tma_env, dims, min_n):
+    n = int(np.prod(dims))
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    tma_env["GOPF_TMA_MIN_N"] = str(min_n)
+    for sign in (-1, 1):
+        tma_env["GOPF_TMA"] = "1"
+        gpfutil.TmaLaunchCount(reset=True)
+        a = _fft(dims, x, sign)
+        assert gpfutil.TmaLaunchCount() > 0, "the copy-engine kernel did not run"
+        tma_env["GOPF_TMA"] = "0"
+        gpfutil.TmaLaunchCount(reset=True)
+        b = _fft(dims, x, sign)
+        assert gpfutil.TmaLaunchCount() == 0
+        assert np.array_equal(a, b)
+        ref = x.copy()
+        oft = opfutil.NewFFTW(dims)
+        (oft.FFT if sign < 0 else oft.IFFT)(ref)
+        assert np.linalg.norm(a - ref) / np.linalg.norm(ref) < 1e-13
+
+
+def _ch(dims, steps):
+    n = int(np.prod(dims))
+    m = gpf.NewModel()
+    f = gpf.NewField("conc", n, synthetic.cahn_hilliard_initial(n, 0))
+    m.AddScalar(gpf.NewScalar("gamma", synthetic.CAHN_HILLIARD_GAMMA))
+    m.AddScalar(gpf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
+    m.AddField(f)
+    m.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
+    s = gpf.NewSolver(m, dims, synthetic.CAHN_HILLIARD_DT)
+    assert s.IsFused
+    s.Upload()
+    s.StepDevice(steps)
+    s.Download()
+    out = f.Data.copy()
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("dims,min_n,steps", [([1024, 1024], 1024, 12), ([512, 512], 512, 12), ([512, 512, 512], 512, 3)],
+                         ids=lambda v: "x".join(map(str, v)) if isinstance(v, list) else str(v))
+@pytest.mark.parametrize("which", ["all", "pass", "real", "kspace"])
+def test_fused_step_bitwise(tma_env, dims, min_n, steps, which):
+    """Cahn-Hilliard through the fused kernels with the copy-engine variants switched on one at a time."""
+    if which == "pass" and len(dims) == 2:
+        pytest.skip("2-D has no plain middle pass")
+    tma_env["GOPF_TMA_MIN_N"] = str(min_n)
+    tma_env["GOPF_TMA"] = "0"
+    ref = _ch(dims, steps)
+    tma_env["GOPF_TMA"] = "1"
+    for k in ("pass", "real", "kspace"):
+        tma_env["GOPF_TMA_" + k.upper()] = "1" if which in ("all", k) else "0"
+    gpfutil.TmaLaunchCount(reset=True)
+    got = _ch(dims, steps)
+    assert gpfutil.TmaLaunchCount() > 0
+    assert np.array_equal(got, ref)
