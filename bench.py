@@ -41,12 +41,13 @@ DEFAULT_GRID = 1024               # every N (strong scaling); --grid 256 runs co
 PARITY_GRID, PARITY_STEPS = 256, 3
 
 
-def ch_config(G):
+def ch_config(G, n_gpus=1):
     """`config` of the metric's workload -- identical in the CUDA arm and the reference arm."""
     from gopf_b200 import synthetic
     return {"workload": f"cahn-hilliard-3d-{G}^3-semi-implicit-euler", "grid": [G, G, G], "dt": synthetic.CAHN_HILLIARD_DT,
             "equation": synthetic.CAHN_HILLIARD_EQUATION, "stepper": "euler",
-            "cache": f"arrays of {16 * G ** 3 / 2**20:.0f} MiB each exceed the 126 MB L2 (no flush needed)"}
+            "parallelism": "single-gpu" if n_gpus <= 1 else f"slab{n_gpus}",
+            "cache": f"per-GPU arrays of {16 * G ** 3 / max(1, n_gpus) / 2**20:.0f} MiB each exceed the 126 MB L2 (no flush needed)"}
 
 
 def lib_sha16():
@@ -185,6 +186,41 @@ def parity_single_gpu(dev):
             "seconds": round(time.perf_counter() - t0, 1)}
 
 
+def parity_sharded(world, rank, local, exchange, nchunks, comm_ctas):
+    """256^3, 3 steps, the slab-sharded CUDA path on `world` GPUs against the oracle (rank 0 compares)."""
+    import torch
+    import torch.distributed as tdist
+    from gopf_b200 import dist as gdist
+    from gopf_b200 import pf as gpf
+    from gopf_b200 import synthetic
+    t0 = time.perf_counter()
+    n = PARITY_GRID
+    cells = n ** 3 // world
+    model, f, _ = build_ch(gpf, n, cells=cells, offset=rank * cells)
+    s = gdist.ShardedSolver(model, n, synthetic.CAHN_HILLIARD_DT, device=local, exchange=exchange,
+                            nchunks=min(nchunks, max(1, n // world // 4)), comm_ctas=comm_ctas)
+    s.Upload()
+    s.StepDevice(PARITY_STEPS)
+    s.Download()
+    mine = torch.view_as_real(torch.from_numpy(f.Data).to(torch.device("cuda", local))).reshape(-1)
+    full = torch.empty(world * mine.numel(), dtype=mine.dtype, device=mine.device)
+    tdist.all_gather_into_tensor(full, mine)
+    used = s.exchange
+    s.close()
+    rec = None
+    if rank == 0:
+        got = torch.view_as_complex(full.reshape(-1, 2)).cpu().numpy()
+        ref = oracle_reference_field(n, PARITY_STEPS)
+        err = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        rec = {"rel_l2": err, "grid": n, "steps": PARITY_STEPS, "tolerance": 1e-10, "ok": bool(err <= 1e-10),
+               "against": "oracle restatement of pf/euler.go (scipy.fft), same seeded field", "n_gpus": world,
+               "exchange": used, "seconds": round(time.perf_counter() - t0, 1)}
+    del full, mine
+    torch.cuda.empty_cache()
+    tdist.barrier()
+    return rec
+
+
 def cpu_baseline(workers, budget_s):
     """Times the oracle on a bounded sample of the metric's workload: whole Euler steps of a 256^3
     grid (cells/s is size-normalised; a 1024^3 step is ~3 min on one core)."""
@@ -228,7 +264,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": ch_config(args.grid),
+        "dtype": "f64", "data": "synthetic", "config": ch_config(args.grid, args.gpus),
         "sample": {"grid": [sample] * 3, "is_full_grid": sample == args.grid, "what": desc},
         "cpu_baseline": {"value": value, "unit": METRIC, "cores": workers, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -268,6 +304,8 @@ def measure_ch(G, dev, warmup, steps, blocks=5, e2e=True):
     solver.StepDevice(warmup)
     torch.cuda.synchronize()
     solver.KernelLaunches(reset=True)
+    from gopf_b200 import pfutil as gpfutil
+    gpfutil.TmaLaunchCount(reset=True)
     sampler = ClockSampler(dev)
     sampler.start()
     time.sleep(0.25)
@@ -281,6 +319,7 @@ def measure_ch(G, dev, warmup, steps, blocks=5, e2e=True):
         torch.cuda.synchronize()
         block_ms.append(e0.elapsed_time(e1))
     launches = solver.KernelLaunches(reset=True) // blocks
+    tma_launches = gpfutil.TmaLaunchCount(reset=True) // blocks
     solver.ProfileBegin()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record(stream)
@@ -310,7 +349,7 @@ def measure_ch(G, dev, warmup, steps, blocks=5, e2e=True):
                                                                         "block_ms": [round(b, 4) for b in block_ms],
                                                                         "spread": (max(block_ms) - min(block_ms)) / ms,
                                                                         "value_from": "median block"},
-           "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
+           "clocks": clocks, "gpu_launches": launches, "tma_launches": tma_launches, "roofline": roofline}
     if e2e:
         # end to end through Solver.Propagate on host buffers: H2D 16 B/cell + forward FFT + step + inverse FFT + D2H
         e2e_steps = 3 if G >= 1024 else max(3, min(steps, 20))
@@ -496,6 +535,7 @@ def run_single_gpu(args):
         "ms_per_step": main_rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": ch_config(G),
         "detail": {"path": "fused single-field kernels", "lib_sha16": lib_sha16(),
+                   "copy_engine_kernel_launches_per_block": main_rec["tma_launches"],
                    "scaling_note": "the same 1024^3 grid runs at every N (strong scaling); cfg2 = BASELINE.json configs[1]"},
         "timed_blocks": main_rec["timed_blocks"], "clocks": main_rec["clocks"], "e2e": main_rec["e2e"],
         "gpu_launches": main_rec["gpu_launches"], "roofline": main_rec["roofline"],

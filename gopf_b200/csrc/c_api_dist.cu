@@ -119,6 +119,18 @@ int gopf_dist_peer_import(gopf_dist_solver* s, int which, int rank, const void* 
     GOPF_API_END
 }
 
+int gopf_dist_peer_unmap(gopf_dist_solver* s) {
+    GOPF_API_BEGIN
+    ds(s).peer_unmap();
+    GOPF_API_END
+}
+
+int gopf_dist_set_grid_cap(gopf_dist_solver* s, int ctas) {
+    GOPF_API_BEGIN
+    ds(s).set_grid_cap(ctas);
+    GOPF_API_END
+}
+
 int gopf_dist_peer_local(gopf_dist_solver* s, int which, void** dev_ptr) {
     GOPF_API_BEGIN
     if (!dev_ptr || (which != 0 && which != 1)) throw Error("gopf_dist_peer_local: bad argument");

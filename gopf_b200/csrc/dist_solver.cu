@@ -82,6 +82,16 @@ void DistSolver::peer_import(int which, int rank, const void* handle64) {
     (which == 0 ? X_ : Y_)[rank] = reinterpret_cast<cplx*>(p);
 }
 
+void DistSolver::peer_unmap() {
+    plan_->use_device();
+    for (int q = 0; q < GOPF_MAX_PEERS; ++q) {
+        if (q == rank_) continue;
+        if (X_[q]) cudaIpcCloseMemHandle(X_[q]);
+        if (Y_[q]) cudaIpcCloseMemHandle(Y_[q]);
+        X_[q] = Y_[q] = nullptr;
+    }
+}
+
 bool DistSolver::peer_ready() const {
     for (int q = 0; q < world_; ++q)
         if (!X_[q] || !Y_[q]) return false;
@@ -180,6 +190,7 @@ void DistSolver::inverse_mid_planes(const cplx* recv, cplx* W, int begin, int co
     plan_->use_device();
     PassGeom g = slab_axis1(true, false);
     g.A = count;
+    g.grid_cap = grid_cap_;
     check(launch_pass(g, plan_->tx_want,
                       plain_io(recv + (size_t)begin * m_ * n_, W + (size_t)begin * n_ * n_, true, 1.0), plan_->twiddle(1),
                       stream()),
@@ -189,6 +200,7 @@ void DistSolver::inverse_mid_planes(const cplx* recv, cplx* W, int begin, int co
 void DistSolver::real_step_planes(cplx* W, int begin, int count) {
     plan_->use_device();
     PassGeom g = make_geom(count, n_, n_, 2);
+    g.grid_cap = grid_cap_;
     g.node0 = ((long long)rank_ * m_ + begin) * n_ * n_;
     const double inv_n = 1.0 / ((double)n_ * n_ * n_);
     check(launch_fused_real(g, 0, W + (size_t)begin * n_ * n_, nullptr, m_model_->derived[derived_].dev, inv_n,

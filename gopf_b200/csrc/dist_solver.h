@@ -62,6 +62,11 @@ public:
     void peer_import(int which, int rank, const void* handle64);
     cplx* peer_local(int which) const { return which == 0 ? X_[rank_] : Y_[rank_]; }
     bool peer_ready() const;
+    // Close the mappings of the other ranks' buffers (the caller then runs a cross-rank barrier before any rank
+    // frees its own: an exported allocation must outlive its importers' mappings).
+    void peer_unmap();
+    // compute-stream persistent kernels launch at most `ctas` CTAs from now on (0: no cap); see PassGeom::grid_cap
+    void set_grid_cap(int ctas) { grid_cap_ = ctas < 0 ? 0 : ctas; }
     void inverse_start_peer(const cplx* S);   // S -> inverse axis 0 -> peers' X
     void forward_mid_peer(const cplx* W);     // W -> forward axis 1 -> peers' Y
     void kspace_step_peer(cplx* S);           // local Y, S -> S; inverse axis 0 of the new S -> peers' X
@@ -97,6 +102,7 @@ private:
     DevKProgram prog_;
     int derived_ = -1;
     long long steps_taken_ = 0, current_step_ = 0, launches_ = 0;
+    int grid_cap_ = 0;
     cplx* X_[GOPF_MAX_PEERS];  // [rank]: mapped receive buffers (own rank: owned allocation)
     cplx* Y_[GOPF_MAX_PEERS];
     PeerOut peer_out(cplx* const* bufs, bool kspace_rows) const;

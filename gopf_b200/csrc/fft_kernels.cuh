@@ -59,6 +59,10 @@ struct PassGeom {
     // slowest axis lost up to 30 % (scripts/tune_axis0.py: 512^3 2996 -> 2017 GB/s at TX 4) and the
     // fused kernels 15 %.  0: off.
     long long pf_tiles;
+    // Persistent kernels (tma_kernels.cuh) launch at most this many CTAs (0: one per SM).  The slab-sharded step
+    // sets it while an NVLink-bound pass is confined to a few SMs on the second stream, so that the statically
+    // partitioned tiles of the compute-stream kernel are not queued behind it.
+    int grid_cap;
 };
 
 // GOPF_HOST_EMUL: tests/host_emul compiles this header with g++ and runs the kernels on the host (one OS
@@ -113,6 +117,7 @@ inline PassGeom make_geom(int n0, int n1, int n2, int axis) {
     g.bw = g.B;
     g.bpitch = 0;
     g.pf_tiles = 0;
+    g.grid_cap = 0;
     return g;
 }
 

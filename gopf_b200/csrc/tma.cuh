@@ -103,8 +103,11 @@ __device__ __forceinline__ void group_sync(int id, int threads) {
 // is encoded over doubles (2 per cell) because there is no 16-byte element type.  l2_promotion: 0 none,
 // 1 64 B, 2 128 B, 3 256 B (the granularity at which L2 fills from DRAM: narrow row segments of adjacent
 // tiles then share one DRAM burst).
+// swizzle: 0 none, 1 32 B, 2 64 B, 3 128 B (16-byte chunks XOR-ed with shared-memory address bits 7..: the
+// inner box must not exceed the swizzle span).
 inline cudaError_t encode_c128_4d(CUtensorMap* out, const void* base, const unsigned long long dims[4],
-                                  const unsigned long long strides_cells[3], const unsigned box[4], int l2_promotion) {
+                                  const unsigned long long strides_cells[3], const unsigned box[4], int l2_promotion,
+                                  int swizzle = 0) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -125,8 +128,12 @@ inline cudaError_t encode_c128_4d(CUtensorMap* out, const void* base, const unsi
                                    : l2_promotion == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                    : l2_promotion == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                                        : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    const CUtensorMapSwizzle sw = swizzle == 3   ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
     const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void*>(base), gd, gs, bx, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 

@@ -27,7 +27,7 @@ int env_flag(const char* name, int fallback) {
 bool enabled(const char* which) { return env_flag("GOPF_TMA", 1) != 0 && env_flag(which, 1) != 0; }
 int min_n() { return env_flag("GOPF_TMA_MIN_N", 1024); }
 
-int sm_count() {
+int sm_count_raw() {
     static int sms[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -36,11 +36,17 @@ int sm_count() {
     return sms[dev] > 0 ? sms[dev] : 148;
 }
 
+long long grid_for(const PassGeom& g, long long tiles) {
+    long long cap = sm_count_raw();
+    if (g.grid_cap > 0 && g.grid_cap < cap) cap = g.grid_cap;
+    return std::min<long long>(tiles, cap);
+}
+
 // One tensor map + the row addressing the kernel needs for it.
 struct MapKey {
     const void* base;
     long long B, a_stride, row_stride, split_stride, A;
-    int N, split_log, tx, promo, dev;
+    int N, split_log, tx, promo, dev, swizzle;
     bool operator<(const MapKey& o) const { return std::memcmp(this, &o, sizeof(MapKey)) < 0; }
 };
 struct MapVal {
@@ -49,7 +55,8 @@ struct MapVal {
 };
 
 // rows j of a tile: address a*a_stride + (j >> split_log)*split_stride + (j & mask)*row_stride + b
-cudaError_t tensor_map_for(const void* base, long long B, const RowMap& rm, long long A, int N, int tx, MapVal* out) {
+cudaError_t tensor_map_for(const void* base, long long B, const RowMap& rm, long long A, int N, int tx, int swizzle,
+                           MapVal* out) {
     static std::map<MapKey, MapVal> cache;
     static std::mutex mu;
     MapKey key;
@@ -64,6 +71,7 @@ cudaError_t tensor_map_for(const void* base, long long B, const RowMap& rm, long
     key.split_log = rm.split_log;
     key.tx = tx;
     key.promo = env_flag("GOPF_TMA_L2", 3);
+    key.swizzle = swizzle;
     cudaGetDevice(&key.dev);
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
@@ -110,7 +118,7 @@ cudaError_t tensor_map_for(const void* base, long long B, const RowMap& rm, long
             val.rows.p_a = 1 + i;
         }
     }
-    cudaError_t e = tma::encode_c128_4d(&val.map, base, gd, gs, box, key.promo);
+    cudaError_t e = tma::encode_c128_4d(&val.map, base, gd, gs, box, key.promo, swizzle);
     if (e != cudaSuccess) return e;
     if (cache.size() > 256) cache.clear();
     cache[key] = val;
@@ -128,15 +136,15 @@ cudaError_t pass_tma_n(const PassGeom& g, const PassIO& io, const cplx* tw, cuda
     typedef TmaCfg<N, TX> C;
     if (g.bw % TX != 0 || g.bcount % TX != 0) return cudaErrorNotSupported;
     MapVal in, out;
-    cudaError_t e = tensor_map_for(io.in, g.B, g.in, g.A, N, TX, &in);
+    cudaError_t e = tensor_map_for(io.in, g.B, g.in, g.A, N, TX, C::SWIZZLE, &in);
     if (e != cudaSuccess) return cudaErrorNotSupported;
-    e = tensor_map_for(io.out, g.B, g.out, g.A, N, TX, &out);
+    e = tensor_map_for(io.out, g.B, g.out, g.A, N, TX, C::SWIZZLE, &out);
     if (e != cudaSuccess) return cudaErrorNotSupported;
     auto kern = k_pass_strided_tma<N, TX>;
     e = opt_in_smem(kern, C::smem_bytes());
     if (e != cudaSuccess) return e;
     const long long tiles = g.A * (g.bcount / TX);
-    const unsigned grid = (unsigned)std::min<long long>(tiles, sm_count());
+    const unsigned grid = (unsigned)grid_for(g, tiles);
     kern<<<grid, C::THREADS, C::smem_bytes(), s>>>(in.map, out.map, g, in.rows, out.rows, io.inv, io.scale, tw);
     g_tma_launches++;
     return cudaGetLastError();
@@ -146,12 +154,10 @@ template <int N>
 cudaError_t real_tma_n(const PassGeom& g, cplx* W, const DevDerived& D, double inv_n, unsigned long long step, const cplx* tw,
                        cudaStream_t s) {
     typedef TmaRealCfg<N> C;
-    if (g.A % C::LINES != 0) return cudaErrorNotSupported;
     auto kern = k_fused_real_tma<N>;
     cudaError_t e = opt_in_smem(kern, C::smem_bytes());
     if (e != cudaSuccess) return e;
-    const long long tiles = g.A / C::LINES;
-    const unsigned grid = (unsigned)std::min<long long>(tiles, sm_count());
+    const unsigned grid = (unsigned)grid_for(g, (g.A + C::WORKERS - 1) / C::WORKERS);
     kern<<<grid, C::THREADS, C::smem_bytes(), s>>>(W, g.A, g.node0, D, inv_n, step, tw);
     g_tma_launches++;
     return cudaGetLastError();
@@ -164,16 +170,16 @@ cudaError_t kspace_tma_n(const PassGeom& g, const cplx* W, cplx* Wout, cplx* S, 
     if (g.bw % TX != 0 || g.bcount % TX != 0) return cudaErrorNotSupported;
     const RowMap uni = uniform_rows((long long)N * g.B, g.B);
     MapVal win, wout, sp;
-    if (tensor_map_for(W, g.B, uni, g.A, N, TX, &win) != cudaSuccess) return cudaErrorNotSupported;
-    if (tensor_map_for(Wout, g.B, uni, g.A, N, TX, &wout) != cudaSuccess) return cudaErrorNotSupported;
-    if (tensor_map_for(S, g.B, uni, g.A, N, TX, &sp) != cudaSuccess) return cudaErrorNotSupported;
+    if (tensor_map_for(W, g.B, uni, g.A, N, TX, C::SWIZZLE, &win) != cudaSuccess) return cudaErrorNotSupported;
+    if (tensor_map_for(Wout, g.B, uni, g.A, N, TX, C::SWIZZLE, &wout) != cudaSuccess) return cudaErrorNotSupported;
+    if (tensor_map_for(S, g.B, uni, g.A, N, TX, C::SWIZZLE, &sp) != cudaSuccess) return cudaErrorNotSupported;
     auto kern = k_fused_kspace_tma<N, TX>;
-    const size_t smem = 3 * C::tile_bytes() + 128;
+    const size_t smem = C::STAGES * C::buf_bytes() + sizeof(TmaKCtl) + 128;
     cudaError_t e = opt_in_smem(kern, smem);
     if (e != cudaSuccess) return e;
     const long long tiles = g.A * (g.bcount / TX);
-    const unsigned grid = (unsigned)std::min<long long>(tiles, sm_count());
-    kern<<<grid, C::THREADS, smem, s>>>(win.map, wout.map, sp.map, g, win.rows, sp.rows, P, ft, tw);
+    const unsigned grid = (unsigned)grid_for(g, tiles);
+    kern<<<grid, C::THREADS, smem, s>>>(win.map, wout.map, sp.map, g, win.rows, wout.rows, sp.rows, P, ft, tw);
     g_tma_launches++;
     return cudaGetLastError();
 }
@@ -208,8 +214,7 @@ cudaError_t launch_fused_real_tma(const PassGeom& g, cplx* W, const DevDerived& 
 
 cudaError_t launch_fused_kspace_tma(const PassGeom& g, const cplx* W, cplx* Wout, cplx* S, const DevKProgram& P,
                                     const FreqTabs& ft, const cplx* tw, cudaStream_t s) {
-    if (!enabled("GOPF_TMA_KSPACE") || g.N < min_n() || !P.fast || g.peer.n > 0)
-        return cudaErrorNotSupported;
+    if (!enabled("GOPF_TMA_KSPACE") || g.N < min_n() || !P.fast || g.peer.n > 0) return cudaErrorNotSupported;
     switch (g.N) {
         case 512: return kspace_tma_n<512, 8>(g, W, Wout, S, P, ft, tw, s);
         case 1024: return kspace_tma_n<1024, 4>(g, W, Wout, S, P, ft, tw, s);

@@ -63,10 +63,13 @@ def run_steps_peer(phases, barrier, S, A, nsteps: int, x_valid: bool, slab: int 
             phases.real_step(A)              # inverse axis 2, /N, g(c), forward axis 2
             phases.forward_mid_peer(A)       # forward axis 1 -> every rank's Y
         else:
-            for b, c in parts:
+            for i, (b, c) in enumerate(parts):
+                # from the second chunk on the peer-storing pass of the previous chunk holds comm_ctas SMs
+                phases.set_grid_cap(comm_ctas if i > 0 else 0, reserve=True)
                 phases.inverse_mid_planes_x(A, b, c)
                 phases.real_step_planes(A, b, c)
                 phases.forward_mid_peer_planes(A, b, c, comm_ctas)
+            phases.set_grid_cap(0)
             phases.exchange_join()
         barrier()
         phases.kspace_step_peer(S)           # Y: forward axis 0, Euler update of S, inverse axis 0 -> every rank's X
@@ -169,6 +172,11 @@ class CudaPhases:
         cells = ctypes.c_int64(0)
         check(lib().gopf_dist_solver_local_cells(self._h, ctypes.byref(cells)))
         self.local_cells = cells.value
+        try:
+            import torch
+            self.sm_count = int(torch.cuda.get_device_properties(device).multi_processor_count)
+        except Exception:
+            self.sm_count = 148
 
     @staticmethod
     def _p(t):
@@ -260,6 +268,16 @@ class CudaPhases:
 
     def exchange_join(self):
         check(lib().gopf_dist_exchange_join(self._h))
+
+    def set_grid_cap(self, ctas: int, reserve: bool = False):
+        """Persistent compute-stream kernels launch at most ``ctas`` CTAs (0: one per SM); with ``reserve`` the
+        argument is the number of SMs to leave free instead."""
+        if reserve and ctas > 0:
+            ctas = max(1, self.sm_count - ctas)
+        check(lib().gopf_dist_set_grid_cap(self._h, int(ctas)))
+
+    def peer_unmap(self):
+        check(lib().gopf_dist_peer_unmap(self._h))
 
     def forward_mid_peer_planes(self, W, begin: int, count: int, max_ctas: int):
         check(lib().gopf_dist_forward_mid_peer_planes(self._h, self._p(W), int(begin), int(count), int(max_ctas)))
@@ -425,3 +443,17 @@ class ShardedSolver:
         self.Upload()
         self.StepDevice(nsteps)
         self.Download()
+
+    def close(self):
+        """Collective tear-down: every rank closes its mappings of the other ranks' receive buffers, a barrier,
+        then each rank frees its own (an exported allocation must outlive its importers' mappings)."""
+        if self.phases is None:
+            return
+        self.torch.cuda.synchronize(self.device)
+        if self.exchange in ("peer", "dma"):
+            self.phases.peer_unmap()
+            if self.world > 1:
+                self.tdist.barrier(group=self.group)
+        self.phases.close()
+        self.phases = None
+        self.S = self.A = self.B = None

@@ -30,7 +30,7 @@ class TimedPhases:
 
     def __getattr__(self, name):
         fn = getattr(self.p, name)
-        if name in ("advance", "get_time", "kernel_launches"):
+        if name in ("advance", "get_time", "kernel_launches", "set_grid_cap", "peer_unmap", "sm_count"):
             return fn
         return lambda *args: self._timed(name, fn, *args)
 
@@ -52,6 +52,7 @@ def run(args):
 
     from . import dist as gdist
     from . import pf as gpf
+    from . import pfutil as gpfutil
     from . import synthetic
     import bench as B  # ClockSampler, measured_hbm_peak
 
@@ -62,6 +63,11 @@ def run(args):
     tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.grid
     cells = n ** 3 // world
+    exchange = getattr(args, "exchange", "peer")
+    nchunks = getattr(args, "chunks", 8)
+    comm_ctas = getattr(args, "comm_ctas", 48)
+    # the same sharded CUDA path at 256^3 against the oracle, before anything is timed
+    parity = None if getattr(args, "no_parity", False) else B.parity_sharded(world, rank, local, exchange, nchunks, comm_ctas)
     model = gpf.NewModel()
     conc = gpf.NewField("conc", cells, None, pinned=True)
     synthetic.cahn_hilliard_initial(cells, 0, offset=rank * cells, out=conc.Data)
@@ -69,9 +75,6 @@ def run(args):
     model.AddScalar(gpf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
     model.AddField(conc)
     model.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
-    exchange = getattr(args, "exchange", "peer")
-    nchunks = getattr(args, "chunks", 8)
-    comm_ctas = getattr(args, "comm_ctas", 48)
     solver = gdist.ShardedSolver(model, n, synthetic.CAHN_HILLIARD_DT, device=local, exchange=exchange, nchunks=nchunks,
                                  comm_ctas=comm_ctas)
     exchange = solver.exchange  # what actually runs (peer mapping can fall back to nccl on every rank)
@@ -171,10 +174,10 @@ def run(args):
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"cahn-hilliard-3d-{n}^3-semi-implicit-euler-slab-sharded", "grid": [n, n, n],
-                       "dt": synthetic.CAHN_HILLIARD_DT, "equation": synthetic.CAHN_HILLIARD_EQUATION,
-                       "parallelism": f"slab{world}", "exchange": exch_desc,
-                       "cache": f"per-GPU arrays of {16 * cells / 2**20:.0f} MiB each exceed the 126 MB L2"},
+            "config": B.ch_config(n, world),
+            "detail": {"exchange": exch_desc, "chunks": nchunks, "comm_ctas": comm_ctas, "lib_sha16": B.lib_sha16(),
+                       "tma_launches": gpfutil.TmaLaunchCount()},
+            "parity": parity,
             "clocks": clocks,
             "e2e": {"value": total * e2e_steps / e2e_dt, "unit": METRIC, "h2d_bytes_per_step": 16 * total,
                     "d2h_bytes_per_step": 16 * total, "steps": e2e_steps,
@@ -189,5 +192,6 @@ def run(args):
                          "nvlink": nvlink},
         }
         print(json.dumps(line), flush=True)
+    solver.close()
     tdist.barrier()
     tdist.destroy_process_group()

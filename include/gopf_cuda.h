@@ -375,6 +375,14 @@ int gopf_dist_inverse_finish(gopf_dist_solver* s, void* w_c128, void* real_out_c
 int gopf_dist_peer_alloc(gopf_dist_solver* s);
 int gopf_dist_peer_export(gopf_dist_solver* s, int which, void* handle64);
 int gopf_dist_peer_import(gopf_dist_solver* s, int which, int rank, const void* handle64);
+/* Close this rank's mappings of the other ranks' buffers.  Tear-down order: every rank unmaps, a cross-rank
+ * barrier, then gopf_dist_solver_destroy frees the rank's own buffers (an exported allocation must outlive
+ * its importers' mappings). */
+int gopf_dist_peer_unmap(gopf_dist_solver* s);
+/* The persistent (copy-engine-fed) kernels of the chunked compute-stream phases launch at most `ctas` CTAs
+ * from now on (0: one per SM).  Set to SMs - max_ctas of forward_mid_peer_planes while that pass runs on the
+ * second stream, so the statically partitioned tiles are not queued behind it. */
+int gopf_dist_set_grid_cap(gopf_dist_solver* s, int ctas);
 int gopf_dist_peer_local(gopf_dist_solver* s, int which, void** dev_ptr);
 int gopf_dist_inverse_start_peer(gopf_dist_solver* s, const void* spectrum_c128);
 int gopf_dist_forward_mid_peer(gopf_dist_solver* s, const void* w_c128);

@@ -18,12 +18,10 @@ from gopf_b200 import synthetic  # noqa: E402
 BYTES = {"fused_kspace": 64.0, "fused_real": 32.0, "pass_inverse_mid": 32.0, "pass_forward_mid": 32.0}
 grids = [int(a) for a in sys.argv[1:]] or [1024]
 VARIANTS = [("register kernels", {"GOPF_TMA": "0"}),
-            ("tma all, L2 256B", {"GOPF_TMA": "1", "GOPF_TMA_L2": "3"}),
-            ("tma all, L2 128B", {"GOPF_TMA": "1", "GOPF_TMA_L2": "2"}),
-            ("tma all, L2 none", {"GOPF_TMA": "1", "GOPF_TMA_L2": "0"}),
-            ("tma pass only", {"GOPF_TMA": "1", "GOPF_TMA_L2": "3", "GOPF_TMA_REAL": "0", "GOPF_TMA_KSPACE": "0"}),
-            ("tma real only", {"GOPF_TMA": "1", "GOPF_TMA_L2": "3", "GOPF_TMA_PASS": "0", "GOPF_TMA_KSPACE": "0"}),
-            ("tma kspace only", {"GOPF_TMA": "1", "GOPF_TMA_L2": "3", "GOPF_TMA_PASS": "0", "GOPF_TMA_REAL": "0"})]
+            ("tma all", {"GOPF_TMA": "1"}),
+            ("tma pass only", {"GOPF_TMA": "1", "GOPF_TMA_REAL": "0", "GOPF_TMA_KSPACE": "0"}),
+            ("tma real only", {"GOPF_TMA": "1", "GOPF_TMA_PASS": "0", "GOPF_TMA_KSPACE": "0"}),
+            ("tma kspace only", {"GOPF_TMA": "1", "GOPF_TMA_PASS": "0", "GOPF_TMA_REAL": "0"})]
 KEYS = ("GOPF_TMA", "GOPF_TMA_L2", "GOPF_TMA_PASS", "GOPF_TMA_REAL", "GOPF_TMA_KSPACE")
 for G in grids:
     n = G ** 3

@@ -113,6 +113,9 @@ class NumpyPeerPhases(NumpyPhases):
         self.barriers += 1
         tdist.barrier()
 
+    def set_grid_cap(self, ctas, reserve=False):  # launch shaping only; nothing to emulate
+        self.grid_caps = getattr(self, "grid_caps", []) + [(ctas, reserve)]
+
     def inverse_start_peer(self, S):
         self.inverse_start(S, self._send)
         self._a2a(self.X, self._send)
