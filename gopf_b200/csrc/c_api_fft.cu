@@ -134,6 +134,45 @@ int gopf_fft_exec_axis_device(gopf_fft_plan* plan, const void* in, void* out, in
     GOPF_API_END
 }
 
+int gopf_fft_exec_rows_device(gopf_fft_plan* plan, const void* in, void* out, int sign, int axis, int64_t slabs, int64_t cols,
+                              const int64_t* in_map, const int64_t* out_map, int tile_cells, void* stream) {
+    GOPF_API_BEGIN
+    if (!plan || !in || !out || !in_map || !out_map) throw Error("gopf_fft_exec_rows_device: NULL argument");
+    FftPlan& p = *plan->p;
+    if (axis < 0 || axis > 2 || p.extent(axis) <= 1) throw Error("gopf_fft_exec_rows_device: bad axis");
+    if (!p.axis_fast(axis)) throw Error("gopf_fft_exec_rows_device: axis length has no fast kernel");
+    if (sign != -1 && sign != 1) throw Error("gopf_fft_exec_rows_device: sign must be -1 or +1");
+    if (slabs < 1 || cols < 2) throw Error("gopf_fft_exec_rows_device: need slabs >= 1 and cols >= 2");
+    p.use_device();
+    cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : p.stream;
+    PassGeom g = p.geom(axis);
+    g.axis = 1;  // a strided pass: the axis number only matters to the k-space kernels
+    g.A = slabs;
+    g.B = cols;
+    g.bcount = g.bw = cols;
+    auto to_map = [](const int64_t* m) {
+        RowMap r = uniform_rows(m[0], m[1]);
+        if (m[3] < 31) {
+            r.split_stride = m[2];
+            r.split_log = (int)m[3];
+            r.split_mask = (1 << r.split_log) - 1;
+        }
+        if (m[5] < 31) {
+            r.a_split_stride = m[4];
+            r.a_split_log = (int)m[5];
+            r.a_split_mask = (1 << r.a_split_log) - 1;
+        }
+        return r;
+    };
+    g.in = to_map(in_map);
+    g.out = to_map(out_map);
+    cudaError_t e = launch_pass(g, tile_cells > 0 ? tile_cells : p.tx_want,
+                                plain_io(reinterpret_cast<const cplx*>(in), reinterpret_cast<cplx*>(out), sign > 0, 1.0),
+                                p.twiddle(axis), s);
+    if (e != cudaSuccess) throw Error(strf("row pass failed: %s", cudaGetErrorString(e)));
+    GOPF_API_END
+}
+
 int gopf_fft_freq_device(gopf_fft_plan* plan, const int64_t* nodes, int64_t count, double* out) {
     GOPF_API_BEGIN
     if (!plan || !nodes || !out) throw Error("gopf_fft_freq_device: NULL argument");

@@ -744,6 +744,14 @@ int gopf_solver_get_time(gopf_solver* s, double* t) {
     GOPF_API_END
 }
 
+int gopf_solver_blocked_layout(gopf_solver* s, int* block_log, int* active) {
+    GOPF_API_BEGIN
+    if (!s || !block_log || !active) throw Error("gopf_solver_blocked_layout: NULL argument");
+    *block_log = s->s->blocked_log();
+    *active = s->s->blocked_now() ? 1 : 0;
+    GOPF_API_END
+}
+
 int gopf_solver_is_fused(gopf_solver* s, int* fused) {
     GOPF_API_BEGIN
     if (!s || !fused) throw Error("NULL argument");

@@ -172,6 +172,7 @@ void Solver::charge_transport_terms() {
 
 // ChargeTransport.Current(density, N, false) on the device-resident spectrum of the term's field
 void Solver::charge_current(const std::string& name, double* host_out) {
+    leave_blocked();
     if (!on_device_) throw Error("solver: nothing on the device (upload first)");
     if (!host_out) throw Error("charge_current: host_out is NULL");
     auto it = m_->user_terms.find(name);
@@ -311,6 +312,7 @@ void Solver::observe(const cplx* a, const cplx* b, int mode, const double* q, do
 // IdealMixtureTerm.GetEnergy (pairCorrelationTerm.go:185-193) / PairCorrlationTerm.GetEnergy (:58-84)
 // of the registered term `name` on the device-resident state
 double Solver::term_energy(const std::string& name) {
+    leave_blocked();
     if (!on_device_) throw Error("solver: nothing on the device (upload first)");
     auto it = m_->user_terms.find(name);
     if (it == m_->user_terms.end()) throw Error("GetEnergy: '" + name + "' is not a registered term");
@@ -345,6 +347,7 @@ double Solver::term_energy(const std::string& name) {
 // Uint8IO.SaveFields payload of one field (pf/fileIO.go:29-44, pf/util.go:108-117): minimum and
 // maximum of the real part, then the real part scaled to 0..255 -- 1 byte per cell over PCIe
 void Solver::download_uint8(int field, unsigned char* host_out, double* mn_out, double* mx_out) {
+    leave_blocked();
     if (!on_device_) throw Error("solver: nothing on the device to download");
     if (field < 0 || field >= (int)m_->fields.size()) throw Error("download_uint8: field index out of range");
     if (!host_out) throw Error("download_uint8: host_out is NULL");

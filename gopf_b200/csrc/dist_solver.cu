@@ -175,6 +175,9 @@ RowMap DistSolver::split_map() const {
     r.split_stride = (long long)m_ * m_ * n_;
     r.split_log = ilog2(m_);
     r.split_mask = m_ - 1;
+    r.a_split_stride = 0;
+    r.a_split_log = 31;
+    r.a_split_mask = 0x7fffffff;
     return r;
 }
 

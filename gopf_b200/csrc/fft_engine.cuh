@@ -181,17 +181,31 @@ struct SyncWarp {
 // passes are limited by the load/store queues, not by the fp64 pipe (ncu: fp64 pipe 24 % busy,
 // lg_throttle + mio_throttle stalls dominate at 1024-point lines), so trading loads for DFMAs pays.
 // Each product costs about 1.5 ulp of the unit-modulus twiddle, far inside the 1e-10 tolerance.
-template <int R>
+// Where the twiddle table lives.  TwGlobal: global memory through the read-only path (L1-resident when the
+// kernel leaves L1 some room).  TwShared: a copy in shared memory for the kernels whose tile buffers take the
+// whole unified L1 / shared array (tma_kernels.cuh: with 209 KB of buffers the table fell out of L1 and every
+// twiddle became an L2 round trip, long_scoreboard 12 cycles per issue).  Entry j sits at j + (j >> 3), so the
+// four loads of a radix-16 butterfly (strides 1, 2, 4, 8 over eight consecutive threads) are bank-conflict free.
+struct TwGlobal {
+    static __device__ __forceinline__ cplx ld(const cplx* __restrict__ tw, int j) { return ld_tab(tw + j); }
+};
+struct TwShared {
+    static constexpr int elems(int n) { return n + n / 8; }
+    static __device__ __forceinline__ int at(int j) { return j + (j >> 3); }
+    static __device__ __forceinline__ cplx ld(const cplx* tw, int j) { return tw[at(j)]; }
+};
+
+template <int R, class Tw>
 __device__ __forceinline__ void twiddle_mul(cplx (&a)[R], const cplx* __restrict__ tw, int bh) {
     if (R == 2) {
-        a[1] = a[1] * ld_tab(tw + bh);
+        a[1] = a[1] * Tw::ld(tw, bh);
     } else if (R == 4) {
-        const cplx w1 = ld_tab(tw + bh), w2 = ld_tab(tw + 2 * bh);
+        const cplx w1 = Tw::ld(tw, bh), w2 = Tw::ld(tw, 2 * bh);
         a[1] = a[1] * w1;
         a[2] = a[2] * w2;
         a[3] = a[3] * (w1 * w2);
     } else if (R == 8) {
-        const cplx w1 = ld_tab(tw + bh), w2 = ld_tab(tw + 2 * bh), w4 = ld_tab(tw + 4 * bh);
+        const cplx w1 = Tw::ld(tw, bh), w2 = Tw::ld(tw, 2 * bh), w4 = Tw::ld(tw, 4 * bh);
         const cplx w3 = w1 * w2;
         a[1] = a[1] * w1;
         a[2] = a[2] * w2;
@@ -201,7 +215,7 @@ __device__ __forceinline__ void twiddle_mul(cplx (&a)[R], const cplx* __restrict
         a[6] = a[6] * (w4 * w2);
         a[7] = a[7] * (w4 * w3);
     } else {  // 16
-        const cplx w1 = ld_tab(tw + bh), w2 = ld_tab(tw + 2 * bh), w4 = ld_tab(tw + 4 * bh), w8 = ld_tab(tw + 8 * bh);
+        const cplx w1 = Tw::ld(tw, bh), w2 = Tw::ld(tw, 2 * bh), w4 = Tw::ld(tw, 4 * bh), w8 = Tw::ld(tw, 8 * bh);
         const cplx w3 = w1 * w2;
         a[1] = a[1] * w1;
         a[2] = a[2] * w2;
@@ -231,7 +245,7 @@ __device__ __forceinline__ void twiddle_mul(cplx (&a)[R], const cplx* __restrict
 }
 
 // ---- one stage -------------------------------------------------------------------
-template <int N, int S, class Layout, class Sync>
+template <int N, int S, class Layout, class Sync, class Tw = TwGlobal>
 __device__ __forceinline__ void fft_stage(cplx (&v)[PlanFor<N>::E], int t, int l, cplx* sm,
                                           const cplx* __restrict__ tw) {
     typedef PlanFor<N> P;
@@ -250,7 +264,7 @@ __device__ __forceinline__ void fft_stage(cplx (&v)[PlanFor<N>::E], int t, int l
             const int b = t + T * i;
             const int bl = b & (L - 1);
             const int bh = b - bl;  // (b div L) * L
-            twiddle_mul<R>(a, tw, bh);
+            twiddle_mul<R, Tw>(a, tw, bh);
             const int base = bl + (bh * R);
 #pragma unroll
             for (int k = 0; k < R; ++k) sm[Layout::at(base + L * k, l)] = a[k];
@@ -266,13 +280,13 @@ __device__ __forceinline__ void fft_stage(cplx (&v)[PlanFor<N>::E], int t, int l
 
 // Forward DFT of one line.  v[m] <-> position t + T*m on entry and on exit.
 // sm: the CTA's exchange buffer (unused when NS == 1).  tw: W_N^j = exp(-2 pi i j / N).
-template <int N, class Layout, class Sync>
+template <int N, class Layout, class Sync, class Tw = TwGlobal>
 __device__ __forceinline__ void line_fft(cplx (&v)[PlanFor<N>::E], int t, int l, cplx* sm,
                                          const cplx* __restrict__ tw) {
     typedef PlanFor<N> P;
-    fft_stage<N, 0, Layout, Sync>(v, t, l, sm, tw);
-    if (P::NS > 1) fft_stage<N, (P::NS > 1 ? 1 : 0), Layout, Sync>(v, t, l, sm, tw);
-    if (P::NS > 2) fft_stage<N, (P::NS > 2 ? 2 : 0), Layout, Sync>(v, t, l, sm, tw);
+    fft_stage<N, 0, Layout, Sync, Tw>(v, t, l, sm, tw);
+    if (P::NS > 1) fft_stage<N, (P::NS > 1 ? 1 : 0), Layout, Sync, Tw>(v, t, l, sm, tw);
+    if (P::NS > 2) fft_stage<N, (P::NS > 2 ? 2 : 0), Layout, Sync, Tw>(v, t, l, sm, tw);
 }
 
 // Stages S0 .. NS-1 of the same transform (S0 = 0: all of it).  Lets a kernel do something between two

@@ -18,10 +18,22 @@ namespace gopf {
 // Uniform arrays use split_log = 31 (no split).  The slab-sharded transform reads the
 // all-to-all receive buffer / writes the send buffer through a split map, so the
 // pack/unpack of the transpose costs no pass of its own (dist_solver.cu).
+// The slab index splits the same way (a_split_*): slab a sits at
+//   (a >> a_split_log)*a_split_stride + (a & a_split_mask)*a_stride,
+// which is how the blocked k-space layout of large 3-D grids ([n0/2^s][n1][2^s][n2], solver.cu) looks to the
+// middle-axis passes (slab = axis-0 index, split into block and position in block).
 struct RowMap {
     long long a_stride, row_stride, split_stride;
     int split_log, split_mask;
+    long long a_split_stride = 0;
+    int a_split_log = 31, a_split_mask = 0x7fffffff;
 };
+__host__ __device__ __forceinline__ long long slab_off(const RowMap& r, long long a) {
+    return (a >> r.a_split_log) * r.a_split_stride + (a & r.a_split_mask) * r.a_stride;
+}
+__host__ __device__ __forceinline__ long long row_off(const RowMap& r, int j) {
+    return (long long)(j >> r.split_log) * r.split_stride + (long long)(j & r.split_mask) * r.row_stride;
+}
 
 // Peer-store output of the slab-sharded transform: row j of tile (a, b) belongs to rank
 // q = j >> log and is written straight into rank q's receive buffer over NVLink,
@@ -37,9 +49,12 @@ struct PeerOut {
     int max_ctas;  // > 0: launch at most this many (persistent) CTAs
 };
 
+// PassGeom::axis of the fused k-space kernel on the blocked layout: lines run along axis 0, but the tiles are
+// numbered (slab = axis-1 index, column = axis-2 index) instead of (slab 0, column = n2*i1 + i2)
+#define GOPF_AXIS0_BY_PLANE 3
 struct PassGeom {
     int n0, n1, n2;  // extents in FFTW order (2-D: n0 == 1; 1-D: n0 == n1 == 1)
-    int axis;        // 0, 1 or 2
+    int axis;        // 0, 1 or 2 (GOPF_AXIS0_BY_PLANE: see above)
     long long A, B;  // outer count / inner stride for this axis
     int N;           // n[axis]
     RowMap in, out;  // strided kernels only
@@ -100,6 +115,9 @@ inline RowMap uniform_rows(long long a_stride, long long row_stride) {
     r.split_stride = 0;
     r.split_log = 31;
     r.split_mask = 0x7fffffff;
+    r.a_split_stride = 0;
+    r.a_split_log = 31;
+    r.a_split_mask = 0x7fffffff;
     return r;
 }
 
@@ -323,7 +341,7 @@ __device__ __forceinline__ void pass_strided_tile(const PassGeom& g, const PassI
     const long long a = tile / tilesB;
     const long long b = window_col(g, tile - a * tilesB, TX) + l;
     cplx v[E];
-    const size_t ibase = (size_t)a * g.in.a_stride + b, obase = (size_t)a * g.out.a_stride + b;
+    const size_t ibase = (size_t)slab_off(g.in, a) + b, obase = (size_t)slab_off(g.out, a) + b;
     auto at_in = [&](int m) -> size_t {
         const int j = t + T * m;
         return ibase + (size_t)(j >> g.in.split_log) * g.in.split_stride + (size_t)(j & g.in.split_mask) * g.in.row_stride;
@@ -338,7 +356,7 @@ __device__ __forceinline__ void pass_strided_tile(const PassGeom& g, const PassI
         const long long tile2 = tile + g.pf_tiles;
         if (tile2 < g.A * tilesB) {
             const long long a2 = tile2 / tilesB;
-            const size_t ib2 = (size_t)a2 * g.in.a_stride + (size_t)(window_col(g, tile2 - a2 * tilesB, TX) + l);
+            const size_t ib2 = (size_t)slab_off(g.in, a2) + (size_t)(window_col(g, tile2 - a2 * tilesB, TX) + l);
 #pragma unroll
             for (int m = 0; m < E; ++m) {
                 const int j = t + T * m;

@@ -134,7 +134,14 @@ void Model::register_white_noise(const std::string& name, double strength, unsig
     std::memset(&d.dev, 0, sizeof(d.dev));
     d.dev.kind = DK_WHITE_NOISE;
     d.dev.noise_std = std::sqrt(2.0 * strength);  // noise.go:21
-    d.dev.seed = seed;
+    // The reference draws every WhiteNoise instance from the shared math/rand stream, so two noise fields are
+    // independent.  The Philox key is (seed, step, node): mix in the instance number (0 for the first, so a
+    // model with one noise field keeps its stream) or two fields registered with the same seed -- the Python
+    // mirror's default -- would be identical at every node and step.
+    unsigned long long instance = 0;
+    for (const DerivedSpec& o : derived)
+        if (o.origin == DerivedOrigin::WhiteNoise) instance++;
+    d.dev.seed = seed ^ (0x9E3779B97F4A7C15ULL * instance);
     d.source = "white_noise";
     d.used = false;
     derived.push_back(d);

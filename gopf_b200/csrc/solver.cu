@@ -35,6 +35,20 @@ __global__ void k_real_part(const cplx* __restrict__ in, double* __restrict__ ou
     }
 }
 
+// row-major [n0][n1][n2] <-> blocked [n0 >> s][n1][1 << s][n2] (solver.h): whole n2-lines move, 16 B per thread
+__global__ void __launch_bounds__(256)
+    k_relayout_blocked(const cplx* __restrict__ in, cplx* __restrict__ out, int n1, int n2, int s, int to_blocked, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long line = i / n2;
+        const int i2 = (int)(i - line * n2);
+        const long long i0 = line / n1;
+        const int i1 = (int)(line - i0 * n1);
+        const long long j = ((((i0 >> s) * n1 + i1) << s) + (i0 & ((1 << s) - 1))) * n2 + i2;
+        if (to_blocked) out[j] = in[i];
+        else out[i] = in[j];
+    }
+}
+
 __global__ void k_scale(cplx* a, double s, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         a[i] = mk(a[i].x * s, a[i].y * s);
@@ -114,6 +128,7 @@ Solver::~Solver() {
     drop_graph();
     for (int i = 0; i < GOPF_MAX_SPECTRA; ++i)
         if (S_.s[i]) cudaFree(S_.s[i]);
+    if (W2_) cudaFree(W2_);
     for (int i = 0; i < GOPF_MAX_FIELDS; ++i) {
         if (Rw_[i]) cudaFree(Rw_[i]);
         if (rk_initial_[i]) cudaFree(rk_initial_[i]);
@@ -183,7 +198,7 @@ static void stamp_noise_step(DevKProgram* P, unsigned long long step) {
 }
 
 bool Solver::graph_applicable() const {
-    if (graph_disabled_ || !fused_ || profiling_ || stepper_ != StepperKind::Euler || !w_valid_) return false;
+    if (graph_disabled_ || !fused_ || profiling_ || stepper_ != StepperKind::Euler || !w_valid_ || blocked_) return false;
     if (has_knoise_) return false;  // the step counter is part of the kernel arguments
     if (plan_->N > (size_t)1 << 20) return false;
     const int k = m_->derived[fused_derived_].dev.kind;
@@ -225,6 +240,7 @@ void Solver::synchronize() {
 }
 
 void Solver::set_stepper(const std::string& name) {
+    leave_blocked();
     if (name == "euler") stepper_ = StepperKind::Euler;
     else if (name == "rk4") stepper_ = StepperKind::RK4;
     // not a SetStepper name in the reference: there the user assigns solver.Stepper = &pf.ImplicitEuler{...}
@@ -241,6 +257,7 @@ void Solver::set_stepper(const std::string& name) {
 }
 
 void Solver::force_generic(bool on) {
+    leave_blocked();
     allow_fused_ = !on;
     decide_path();
 }
@@ -263,6 +280,8 @@ void Solver::set_filter(const double* table, int n) {
 
 // which derived fields are transformed, and whether the single-field fused path applies
 void Solver::decide_path() {
+    leave_blocked();
+    block_log_ = -1;
     fused_ = false;
     fused_derived_ = -1;
     w_valid_ = false;
@@ -954,6 +973,7 @@ bool Solver::launch_update_jit(const DevKProgram& P, const ImplicitTab& tab) {
 
 // ---- host synchronisation ------------------------------------------------------------
 void Solver::upload() {
+    blocked_ = false;  // the spectra are rewritten, row-major
     ensure_buffers();
     rebuild_program();
     cudaStream_t s = stream();
@@ -969,6 +989,8 @@ void Solver::upload() {
 
 void Solver::download() {
     if (!on_device_) throw Error("solver: nothing on the device to download");
+    plan_->use_device();
+    leave_blocked();
     cudaStream_t s = stream();
     const int F = (int)m_->fields.size();
     for (int i = 0; i < F; ++i) {
@@ -983,6 +1005,7 @@ void Solver::download_real(int field, double* host_out, bool big_endian) {
     if (field < 0 || field >= (int)m_->fields.size()) throw Error("download_real: field index out of range");
     if (!host_out) throw Error("download_real: host_out is NULL");
     plan_->use_device();
+    leave_blocked();
     ensure_buffers();
     cudaStream_t s = stream();
     const long long n = (long long)plan_->N;
@@ -1017,23 +1040,101 @@ void Solver::euler_update_generic() {
     launch_update(prog_);                                    // euler.go:27-39
 }
 
+// ---- blocked k-space layout (solver.h) -------------------------------------------------
+// GOPF_BLOCKED: 0 never, 1 whenever the shape allows, unset: 3-D grids whose axis-0 row stride reaches 8 MB and
+// whose axis-0 / axis-1 lines the copy-engine kernels cover (measured on B200, scripts/tune_blocked.py, 1024^3:
+// axis-0 pass 2973 GB/s row-major -> 6060 GB/s blocked s = 7; middle-axis passes converting on the fly 6064 /
+// 6217 GB/s against 6206 GB/s row-major to row-major).  GOPF_BLOCK_LOG overrides s.
+int Solver::blocked_log() const {
+    if (!fused_ || stepper_ != StepperKind::Euler || plan_->rank != 3) return 0;
+    const int n0 = plan_->n0, n1 = plan_->n1, n2 = plan_->n2;
+    if ((n0 & (n0 - 1)) != 0 || n0 < 16) return 0;
+    const int mode = env_int("GOPF_BLOCKED", -1);
+    if (mode == 0) return 0;
+    const bool tma_ok = env_int("GOPF_TMA", 1) != 0 && n0 >= env_int("GOPF_TMA_MIN_N", 1024) &&
+                        n1 >= env_int("GOPF_TMA_MIN_N", 1024) && (n0 == 512 || n0 == 1024) && (n1 == 512 || n1 == 1024);
+    if (mode < 0 && (!tma_ok || (long long)n1 * n2 * (long long)sizeof(cplx) < (8LL << 20))) return 0;
+    int s = env_int("GOPF_BLOCK_LOG", 7);
+    while (s > 1 && (n0 >> s) < 2) --s;
+    return s < 1 ? 0 : s;
+}
+
+PassGeom Solver::blocked_axis0_geom() const {
+    const int s = block_log_;
+    PassGeom g = plan_->geom(0);
+    g.axis = GOPF_AXIS0_BY_PLANE;
+    g.A = plan_->n1;
+    g.B = plan_->n2;
+    g.bcount = g.bw = g.B;
+    RowMap r = uniform_rows((long long)plan_->n2 << s, plan_->n2);
+    r.split_stride = ((long long)plan_->n1 * plan_->n2) << s;
+    r.split_log = s;
+    r.split_mask = (1 << s) - 1;
+    g.in = g.out = r;
+    return g;
+}
+
+PassGeom Solver::blocked_axis1_geom(bool in_blocked, bool out_blocked) const {
+    const int s = block_log_;
+    PassGeom g = plan_->geom(1);
+    RowMap r = uniform_rows(plan_->n2, (long long)plan_->n2 << s);  // slab = axis-0 index (split), row = axis-1 index
+    r.a_split_stride = ((long long)plan_->n1 * plan_->n2) << s;
+    r.a_split_log = s;
+    r.a_split_mask = (1 << s) - 1;
+    if (in_blocked) g.in = r;
+    if (out_blocked) g.out = r;
+    return g;
+}
+
+void Solver::enter_blocked() {
+    if (blocked_) return;
+    cudaStream_t s = stream();
+    const long long n = (long long)plan_->N;
+    if (!W2_) GOPF_CUDA(cudaMalloc(&W2_, sizeof(cplx) * n));
+    k_relayout_blocked<<<grid_for(n), 256, 0, s>>>(S_.s[0], W2_, plan_->n1, plan_->n2, block_log_, 1, n);
+    GOPF_CUDA(cudaGetLastError());
+    launches_++;
+    std::swap(S_.s[0], W2_);
+    blocked_ = true;
+    w_valid_ = false;
+}
+
+void Solver::leave_blocked() {
+    if (!blocked_) return;
+    plan_->use_device();
+    cudaStream_t s = stream();
+    const long long n = (long long)plan_->N;
+    // W2_ holds the first inverse pass of the current spectrum at this point (w_valid_) or nothing of value:
+    // either way it is recomputed by the next fused step
+    k_relayout_blocked<<<grid_for(n), 256, 0, s>>>(S_.s[0], W2_, plan_->n1, plan_->n2, block_log_, 0, n);
+    GOPF_CUDA(cudaGetLastError());
+    launches_++;
+    std::swap(S_.s[0], W2_);
+    blocked_ = false;
+    w_valid_ = false;
+}
+
 void Solver::euler_step_fused() {
     cudaStream_t s = stream();
     const double n = (double)plan_->N;
     const int slow = plan_->rank == 3 ? 0 : 1;  // slowest active axis
-    const PassGeom gs = plan_->geom(slow);
+    if (block_log_ < 0) block_log_ = blocked_log();
+    const bool blk = block_log_ > 0;
+    if (blk) enter_blocked();
+    const PassGeom gs = blk ? blocked_axis0_geom() : plan_->geom(slow);
+    cplx* Wk = blk ? W2_ : W_;  // the work array on the k-space side of the middle-axis passes
     if (!w_valid_) {
         // first inverse pass of the current spectrum: S -> W
         const int id = tick("pass_inverse", 32.0 * n);
-        cudaError_t e = launch_pass(gs, plan_->tx_want, plain_io(S_.s[0], W_, true, 1.0), plan_->twiddle(slow), s);
+        cudaError_t e = launch_pass(gs, plan_->tx_want, plain_io(S_.s[0], Wk, true, 1.0), plan_->twiddle(slow), s);
         tock(id);
         if (e != cudaSuccess) throw Error(strf("fused: first inverse pass: %s", cudaGetErrorString(e)));
         w_valid_ = true;
     }
     if (plan_->rank == 3) {
-        const PassGeom g1 = plan_->geom(1);
+        const PassGeom g1 = blk ? blocked_axis1_geom(true, false) : plan_->geom(1);
         const int id = tick("pass_inverse_mid", 32.0 * n);
-        cudaError_t e = launch_pass(g1, plan_->tx_want, plain_io(W_, W_, true, 1.0), plan_->twiddle(1), s);
+        cudaError_t e = launch_pass(g1, plan_->tx_want, plain_io(Wk, W_, true, 1.0), plan_->twiddle(1), s);
         tock(id);
         if (e != cudaSuccess) throw Error(strf("fused: middle inverse pass: %s", cudaGetErrorString(e)));
     }
@@ -1046,15 +1147,15 @@ void Solver::euler_step_fused() {
         if (e != cudaSuccess) throw Error(strf("fused: real-space kernel: %s", cudaGetErrorString(e)));
     }
     if (plan_->rank == 3) {
-        const PassGeom g1 = plan_->geom(1);
+        const PassGeom g1 = blk ? blocked_axis1_geom(false, true) : plan_->geom(1);
         const int id = tick("pass_forward_mid", 32.0 * n);
-        cudaError_t e = launch_pass(g1, plan_->tx_want, plain_io(W_, W_, false, 1.0), plan_->twiddle(1), s);
+        cudaError_t e = launch_pass(g1, plan_->tx_want, plain_io(W_, Wk, false, 1.0), plan_->twiddle(1), s);
         tock(id);
         if (e != cudaSuccess) throw Error(strf("fused: middle forward pass: %s", cudaGetErrorString(e)));
     }
     {
         const int id = tick("fused_kspace", 64.0 * n);
-        cudaError_t e = launch_fused_kspace(gs, plan_->tx_want, W_, W_, S_.s[0], fused_prog_, freq_tabs(),
+        cudaError_t e = launch_fused_kspace(gs, plan_->tx_want, Wk, Wk, S_.s[0], fused_prog_, freq_tabs(),
                                             plan_->twiddle(slow), s);
         tock(id);
         if (e != cudaSuccess) throw Error(strf("fused: k-space kernel: %s", cudaGetErrorString(e)));
@@ -1135,6 +1236,15 @@ void Solver::step(int nsteps) {
     plan_->use_device();
     ensure_buffers();
     rebuild_program();
+    if (!(fused_ && stepper_ == StepperKind::Euler)) leave_blocked();
+    {
+        // the layout choice follows the environment from one step() call to the next (tuning scripts, tests)
+        const int want = blocked_log();
+        if (want != block_log_) {
+            leave_blocked();
+            block_log_ = want;
+        }
+    }
     int done = 0;
     if (fused_ && stepper_ == StepperKind::Euler && nsteps > GRAPH_STEPS) {
         // the first step runs eagerly (it also produces W when it is not valid yet and sets every

@@ -100,7 +100,14 @@ public:
     void reset_launch_count() { launches_ = 0; }
     void set_profiling(bool on);
     const std::vector<KernelTimer>& collect_profile();
-    cplx* spectrum(int i) { return S_.s[i]; }
+    cplx* spectrum(int i) {
+        leave_blocked();
+        return S_.s[i];
+    }
+    // Blocked k-space layout of the fused path on large 3-D grids (solver.cu): 0 = off,
+    // s > 0 = on with blocks of 2^s axis-0 positions.  blocked_now(): the field spectrum currently sits in it.
+    int blocked_log() const;
+    bool blocked_now() const { return blocked_; }
     FftPlan& plan() { return *plan_; }
     void synchronize();
     void force_generic(bool on);
@@ -140,6 +147,22 @@ private:
     RealPtrs R_;               // real-space fields (generic path)
     cplx* Rw_[GOPF_MAX_FIELDS];
     cplx* W_ = nullptr;        // fused work array
+    // Blocked k-space layout (large 3-D grids, fused path).  Lines along axis 0 of a row-major [n0][n1][n2]
+    // array have a row stride of n1*n2 cells: at 1024^3 every one of the 1024 rows of a tile sits in its own
+    // 2-MB page 16 MB from the next, and the copy engine reads such tiles at 3.0 TB/s against 6.2 TB/s for the
+    // 16-KB stride of the middle axis (scripts/tune_blocked.py).  So while fused steps run, the field spectrum
+    // S and the work array between the middle-axis passes and the k-space kernel (W2_) are kept as
+    // [n0 / 2^s][n1][2^s][n2]: 2^s consecutive axis-0 positions of one (i1, *) line are n2 cells apart.  The
+    // k-space kernel then reads tiles made of n0/2^s runs of 2^s rows at the short stride (6.1 TB/s at s = 7),
+    // and the middle-axis passes convert on the fly (row-major on the real-space side, blocked on the k-space
+    // side) at no extra traffic.  Everything else sees the row-major S: leave_blocked() converts back.
+    cplx* W2_ = nullptr;
+    bool blocked_ = false;
+    int block_log_ = -1;  // decided at first use (-1: not yet)
+    void enter_blocked();
+    void leave_blocked();
+    PassGeom blocked_axis0_geom() const;           // lines along axis 0 of a blocked array, tiles by (i1, i2)
+    PassGeom blocked_axis1_geom(bool in_blocked, bool out_blocked) const;
     double* d_real_out_ = nullptr;  // staging for download_real
     double* d_filter_ = nullptr;
     int filter_n_ = 0;

@@ -136,8 +136,10 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
     const long long tile = blockIdx.x;
     const long long a = tile / tilesB;
     const long long b = window_col(g, tile - a * tilesB, TX) + l;
-    const size_t base = (size_t)a * N * g.B + b;
-    const size_t strideB = (size_t)g.B;
+    // W and S share the input row map, Wout the output one (uniform [A][N][B] unless the launch says otherwise:
+    // blocked k-space layout, solver.cu)
+    const size_t base = (size_t)slab_off(g.in, a) + b, obase = (size_t)slab_off(g.out, a) + b;
+    auto roff = [&](int j) -> size_t { return (size_t)row_off(g.in, j); };
     // Each thread later reads back exactly the spectrum cells it copied, so cp.async.wait_group
     // is the only synchronisation the copy needs.
     auto prefetch_spectrum = [&]() {
@@ -145,19 +147,17 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
             // the line is live in registers here: walk the rows with two running addresses in a
             // rolled loop instead of materialising E address pairs
             const unsigned sbase = smem_address(sS);
-            const cplx* src = S + base + (size_t)t * strideB;
-            const size_t src_step = (size_t)T * strideB;
+            const cplx* src = S + base;
 #pragma unroll 1
             for (int m = 0; m < E; ++m) {
                 const unsigned dst = sbase + (unsigned)(Lay::at(t + T * m, l) * (int)sizeof(cplx));
-                cp_async16(dst, src);
-                src += src_step;
+                cp_async16(dst, src + roff(t + T * m));
             }
         } else {
 #pragma unroll
             for (int m = 0; m < E; ++m) {
                 const unsigned dst = smem_address(sS + Lay::at(t + T * m, l));
-                const cplx* src = S + base + (size_t)(t + T * m) * strideB;
+                const cplx* src = S + base + roff(t + T * m);
                 cp_async16(dst, src);
             }
         }
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
     if (!LATE) prefetch_spectrum();
     cplx v[E];
 #pragma unroll
-    for (int m = 0; m < E; ++m) v[m] = W[base + (size_t)(t + T * m) * strideB];
+    for (int m = 0; m < E; ++m) v[m] = W[base + roff(t + T * m)];
 
     // Reference Freq components [row, col, depth] = FFTW axes [1, 2, 0] (fftWrap.go:42-74).
     // Two of them are fixed along this thread's line, the third runs with j.
@@ -175,6 +175,10 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
     if (g.axis == 0) {
         fa = ft.f1[ft.off1 + (int)(b / g.n2)];
         fb = ft.f2[(int)(b % g.n2)];
+        fline = ft.f0;
+    } else if (g.axis == GOPF_AXIS0_BY_PLANE) {  // lines along axis 0, slab = axis-1 index, column = axis-2 index
+        fa = ft.f1[ft.off1 + (int)a];
+        fb = ft.f2[(int)b];
         fline = ft.f0;
     } else {  // axis 1
         fa = ft.f2[(int)b];
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
             const int j = t + T * m;
             const double fl = fline[j];
             const cplx cur = fast_update(P, fma(fl, fl, s2), sS[Lay::at(j, l)], v[m]);
-            S[base + (size_t)j * strideB] = cur;
+            S[base + roff(j)] = cur;
             v[m] = cswap(cur);
         }
         if (LATE) __syncthreads();  // spectrum cells were read from the exchange tile
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
             const KPoint kp = (g.axis == 0) ? make_kpoint(fa, fb, fl) : make_kpoint(fl, fa, fb);  // row, col, depth
             const cplx old = sS[pos], nl = sm[pos];
             const cplx cur = euler_update(P, 0, kp, old, [&](int bi) -> cplx { return bi == 0 ? old : nl; });
-            S[base + (size_t)j * strideB] = cur;
+            S[base + roff(j)] = cur;
             sm[pos] = cswap(cur);
         }
 #pragma unroll
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
         for (int m = 0; m < E; ++m) *peer_row(g.peer, a, t + T * m, b) = cswap(v[m]);
     } else {
 #pragma unroll
-        for (int m = 0; m < E; ++m) Wout[base + (size_t)(t + T * m) * strideB] = cswap(v[m]);
+        for (int m = 0; m < E; ++m) Wout[obase + (size_t)row_off(g.out, t + T * m)] = cswap(v[m]);
     }
 }
 

@@ -71,6 +71,25 @@ __device__ __forceinline__ void prefetch_4d(const CUtensorMap* map, int c0, int 
                  "r"(c3)
                  : "memory");
 }
+// rank 5 (the blocked k-space layout: column, row_low, row_high, slab_low, slab_high)
+__device__ __forceinline__ void load_5d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                        uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void store_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];\n" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];\n" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
 __device__ __forceinline__ void prefetch_descriptor(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(map) : "memory");
 }
@@ -98,16 +117,17 @@ __device__ __forceinline__ void group_sync(int id, int threads) {
 }
 #endif  // __CUDACC__
 
-// ---- host: rank-4 fp64 tensor map over a complex128 array ------------------------------------------------
+// ---- host: fp64 tensor map (rank 2..5) over a complex128 array ------------------------------------------------
 // dims / strides in complex cells (innermost first; stride[0] is implicitly 1 cell), box in cells.  The map
 // is encoded over doubles (2 per cell) because there is no 16-byte element type.  l2_promotion: 0 none,
 // 1 64 B, 2 128 B, 3 256 B (the granularity at which L2 fills from DRAM: narrow row segments of adjacent
 // tiles then share one DRAM burst).
 // swizzle: 0 none, 1 32 B, 2 64 B, 3 128 B (16-byte chunks XOR-ed with shared-memory address bits 7..: the
 // inner box must not exceed the swizzle span).
-inline cudaError_t encode_c128_4d(CUtensorMap* out, const void* base, const unsigned long long dims[4],
-                                  const unsigned long long strides_cells[3], const unsigned box[4], int l2_promotion,
-                                  int swizzle = 0) {
+inline cudaError_t encode_c128(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
+                               const unsigned long long* strides_cells, const unsigned* box, int l2_promotion,
+                               int swizzle = 0) {
+    if (rank < 2 || rank > 5) return cudaErrorInvalidValue;
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -120,10 +140,13 @@ inline cudaError_t encode_c128_4d(CUtensorMap* out, const void* base, const unsi
         if (!p || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
         fn = reinterpret_cast<EncodeFn>(p);
     }
-    cuuint64_t gd[4] = {dims[0] * 2, dims[1], dims[2], dims[3]};
-    cuuint64_t gs[3] = {strides_cells[0] * 16, strides_cells[1] * 16, strides_cells[2] * 16};
-    cuuint32_t bx[4] = {box[0] * 2, box[1], box[2], box[3]};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < rank; ++i) {
+        gd[i] = i == 0 ? dims[0] * 2 : dims[i];
+        bx[i] = i == 0 ? box[0] * 2 : box[i];
+        if (i > 0) gs[i - 1] = strides_cells[i - 1] * 16;
+    }
     CUtensorMapL2promotion promo = l2_promotion == 3   ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
                                    : l2_promotion == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                    : l2_promotion == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
@@ -132,7 +155,7 @@ inline cudaError_t encode_c128_4d(CUtensorMap* out, const void* base, const unsi
                                   : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
                                   : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_32B
                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
-    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void*>(base), gd, gs, bx, es,
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }

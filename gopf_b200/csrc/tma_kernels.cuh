@@ -20,8 +20,9 @@
 //
 // Strided tiles land as [row][TX] through a tensor map with the 64-B / 128-B shared-memory swizzle, so the
 // line-major reads (eight consecutive rows of one column per quarter-warp) are bank-conflict free.  The tensor
-// maps are rank 4 over doubles: (2*column, row_low, row_high, slab); row_high serves the split row addressing
-// of the slab-sharded layouts (RowMap in fft_kernels.cuh).
+// maps are rank 5 over doubles: (2*column, row_low, row_high, slab_low, slab_high), outer dimensions in
+// ascending stride order; row_high serves the split row addressing of the slab-sharded layouts, the slab split
+// the blocked k-space layout of large grids (RowMap in fft_kernels.cuh).
 #pragma once
 #include "fft_kernels.cuh"
 #include "step_kernels.cuh"
@@ -49,35 +50,36 @@ struct SyncLine {
 // The three outer tensor dimensions (row_low, row_high, slab) are encoded in ascending stride order; p_lo, p_hi,
 // p_a give the coordinate slot (1..3) of each.
 struct TmaRows {
-    int log, mask;
-    int box_rows;  // rows per bulk copy (<= 256, divides the low row dimension)
-    int p_lo, p_hi, p_a;
+    int log, mask;    // row j -> (j & mask, j >> log)
+    int alog, amask;  // slab a -> (a & amask, a >> alog)
+    int box_rows;     // rows per bulk copy (<= 256, divides the low row dimension)
+    int p_lo, p_hi, p_a, p_ahi;
 };
 
 struct TmaCoord {
-    int c[4];
+    int c[5];
 };
 __device__ __forceinline__ TmaCoord tma_coord(const TmaRows& R, int c0, int row, int a) {
     const int lo = row & R.mask, hi = row >> R.log;
+    const int alo = a & R.amask, ahi = a >> R.alog;
     TmaCoord q;  // selects, not indexed stores: the coordinates stay in registers
     q.c[0] = c0;
-    q.c[1] = R.p_lo == 1 ? lo : (R.p_hi == 1 ? hi : a);
-    q.c[2] = R.p_lo == 2 ? lo : (R.p_hi == 2 ? hi : a);
-    q.c[3] = R.p_lo == 3 ? lo : (R.p_hi == 3 ? hi : a);
+#pragma unroll
+    for (int i = 1; i < 5; ++i) q.c[i] = R.p_lo == i ? lo : (R.p_hi == i ? hi : (R.p_a == i ? alo : ahi));
     return q;
 }
 __device__ __forceinline__ void tma_load_rows(void* dst, const CUtensorMap* map, const TmaRows& R, int c0, int row, int a,
                                               uint64_t* bar) {
     const TmaCoord q = tma_coord(R, c0, row, a);
-    tma::load_4d(dst, map, q.c[0], q.c[1], q.c[2], q.c[3], bar);
+    tma::load_5d(dst, map, q.c[0], q.c[1], q.c[2], q.c[3], q.c[4], bar);
 }
 __device__ __forceinline__ void tma_store_rows(const CUtensorMap* map, const TmaRows& R, int c0, int row, int a, const void* src) {
     const TmaCoord q = tma_coord(R, c0, row, a);
-    tma::store_4d(map, q.c[0], q.c[1], q.c[2], q.c[3], src);
+    tma::store_5d(map, q.c[0], q.c[1], q.c[2], q.c[3], q.c[4], src);
 }
 __device__ __forceinline__ void tma_prefetch_rows(const CUtensorMap* map, const TmaRows& R, int c0, int row, int a) {
     const TmaCoord q = tma_coord(R, c0, row, a);
-    tma::prefetch_4d(map, q.c[0], q.c[1], q.c[2], q.c[3]);
+    tma::prefetch_5d(map, q.c[0], q.c[1], q.c[2], q.c[3], q.c[4]);
 }
 
 // control block behind the buffers
@@ -85,6 +87,12 @@ __device__ __forceinline__ void tma_prefetch_rows(const CUtensorMap* map, const 
 struct TmaCtl {
     unsigned long long full[GOPF_TMA_MAX_STAGES];  // per stage: the bytes have landed
     volatile unsigned issued[GOPF_TMA_MAX_STAGES];  // per stage: loads issued so far (guards the parity wait, see tma_wait_tile)
+    volatile long long tile[GOPF_TMA_MAX_STAGES];   // per stage: the tile that was claimed for it (-1: no tiles left)
+};
+
+struct TmaKCtl {
+    TmaCtl ring;
+    unsigned long long sfull[2];  // per group: the spectrum tile has landed
 };
 
 // The workers interleave on the ring, so a worker can reach stage s for its use u before the worker that
@@ -116,42 +124,55 @@ struct TmaCfg {
     };
     static constexpr size_t tile_bytes() { return (size_t)CELLS * sizeof(cplx); }
     static constexpr size_t buf_bytes() { return (size_t)PADDED * sizeof(cplx); }
-    static constexpr size_t smem_bytes() { return STAGES * buf_bytes() + sizeof(TmaCtl) + 128; }
+    static constexpr size_t tw_bytes() { return (size_t)TwShared::elems(N) * sizeof(cplx); }
+    static constexpr size_t smem_bytes() { return STAGES * buf_bytes() + tw_bytes() + sizeof(TmaKCtl) + 128; }
     // cell (row, line) of the landed / outgoing tile (hardware swizzle: 16-B chunk index ^= address bits 7..)
     static __device__ __forceinline__ int sw(int row, int l) { return row * TX + (l ^ ((row >> ROW_SHIFT) & (TX - 1))); }
 };
 
+// Tiles are handed out in order through a global counter (`next_tile`, zeroed before the launch), not by a
+// static stride: persistent CTAs drift apart, and with a static partition the 64-B row segments in flight at
+// any instant end up planes apart -- measured 5.6 TB/s at 55 tiles per CTA falling to 2.8 TB/s at 1771
+// (1024^3).  With in-order claims the ~450 tiles in flight stay within two planes, like the hardware's own
+// block scheduler does for a non-persistent grid.  A claim is made one tile ahead of its use, so the atomic's
+// round trip is off the critical path.
 template <int N, int TX>
 __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
     k_pass_strided_tma(const __grid_constant__ CUtensorMap tin, const __grid_constant__ CUtensorMap tout,
                        const __grid_constant__ PassGeom g, TmaRows rin, TmaRows rout, int inv, double scale,
-                       const cplx* __restrict__ tw) {
+                       const cplx* __restrict__ tw, unsigned* __restrict__ next_tile) {
     typedef TmaCfg<N, TX> C;
     typedef LayoutPadded<N> Lay;
     constexpr int E = C::E, T = C::T, GT = C::GT, STAGES = C::STAGES;
     extern __shared__ __align__(1024) unsigned char gopf_smem_raw[];
-    TmaCtl* ctl = reinterpret_cast<TmaCtl*>(gopf_smem_raw + STAGES * C::buf_bytes());
+    cplx* twsm = reinterpret_cast<cplx*>(gopf_smem_raw + STAGES * C::buf_bytes());
+    TmaCtl* ctl = reinterpret_cast<TmaCtl*>(gopf_smem_raw + STAGES * C::buf_bytes() + C::tw_bytes());
     const int tid = threadIdx.x;
     const int grp = tid / GT, gtid = tid - grp * GT;
     const int l = gtid / T, t = gtid - l * T;
     const long long tilesB = g.bcount / TX, tiles = g.A * tilesB;
-    const long long first = blockIdx.x, hop = gridDim.x;
-    const long long mine = first < tiles ? (tiles - first + hop - 1) / hop : 0;  // tiles of this CTA
+    for (int j = tid; j < N; j += C::THREADS) twsm[TwShared::at(j)] = tw[j];
 
     auto buffer = [&](int s) -> cplx* { return reinterpret_cast<cplx*>(gopf_smem_raw + (size_t)s * C::buf_bytes()); };
-    auto tile_coords = [&](long long k, int* c0, int* c3) {
-        const long long tile = first + k * hop;
+    auto tile_coords = [&](long long tile, int* c0, int* c3) {
         const long long a = tile / tilesB;
         *c0 = (int)(2 * window_col(g, tile - a * tilesB, TX));
         *c3 = (int)a;
     };
-    auto issue_load = [&](long long k) {  // one thread
+    // one thread: stage k % STAGES receives `tile` (or the end marker when the claim ran past the last tile)
+    auto issue_load = [&](long long k, long long tile) {
         const int s = (int)(k % STAGES);
-        int c0, c3;
-        tile_coords(k, &c0, &c3);
         uint64_t* bar = reinterpret_cast<uint64_t*>(&ctl->full[s]);
-        tma::mbar_arrive_expect_tx(bar, (unsigned)C::tile_bytes());
-        for (int r = 0; r < N; r += rin.box_rows) tma_load_rows(buffer(s) + (size_t)r * TX, &tin, rin, c0, r, c3, bar);
+        if (tile < tiles) {
+            int c0, c3;
+            tile_coords(tile, &c0, &c3);
+            ctl->tile[s] = tile;
+            tma::mbar_arrive_expect_tx(bar, (unsigned)C::tile_bytes());
+            for (int r = 0; r < N; r += rin.box_rows) tma_load_rows(buffer(s) + (size_t)r * TX, &tin, rin, c0, r, c3, bar);
+        } else {
+            ctl->tile[s] = -1;
+            tma::mbar_arrive(bar);
+        }
         __threadfence_block();
         ctl->issued[s] = ctl->issued[s] + 1;
     };
@@ -167,12 +188,20 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
     }
     __syncthreads();
     if (tid == 0)
-        for (long long k = 0; k < mine && k < STAGES; ++k) issue_load(k);
+        for (int k = 0; k < STAGES; ++k) issue_load(k, (long long)atomicAdd(next_tile, 1u));
 
-    for (long long k = grp; k < mine; k += C::GROUPS) {
+    for (long long k = grp;; k += C::GROUPS) {
         const int s = (int)(k % STAGES);
         cplx* buf = buffer(s);
         tma_wait_tile(ctl, s, (unsigned)(k / STAGES));
+        const long long tile = ctl->tile[s];
+        if (tile < 0) {
+            // no tiles left: pass the end marker on to the stage the other group will wait for, then leave
+            if (gtid == 0) issue_load(k + STAGES, tiles);
+            break;
+        }
+        long long claimed = 0;
+        if (gtid == 0) claimed = (long long)atomicAdd(next_tile, 1u);  // for stage reuse k + STAGES; consumed after the store
         cplx v[E];
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = buf[C::sw(t + T * m, l)];
@@ -182,7 +211,7 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
         }
         // tile-wide: the padded exchange regions of the lines overlay the landed tile
         tma::group_sync(9 + grp, GT);
-        line_fft<N, Lay, SyncLine<T> >(v, t, l, buf, tw);
+        line_fft<N, Lay, SyncLine<T>, TwShared>(v, t, l, buf, twsm);
         tma::group_sync(9 + grp, GT);  // every line has read its last exchange: the outgoing tile may overwrite them
         if (inv) {
 #pragma unroll
@@ -195,11 +224,11 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
         tma::group_sync(9 + grp, GT);
         if (gtid == 0) {
             int c0, c3;
-            tile_coords(k, &c0, &c3);
+            tile_coords(tile, &c0, &c3);
             for (int r = 0; r < N; r += rout.box_rows) tma_store_rows(&tout, rout, c0, r, c3, buf + (size_t)r * TX);
             tma::store_commit();
             tma::store_wait_read();  // the copy engine has read the buffer: refill it for the other group
-            if (k + STAGES < mine) issue_load(k + STAGES);
+            issue_load(k + STAGES, claimed);
         }
         __syncwarp();
     }
@@ -213,43 +242,47 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
 // in place (pf/euler.go:28-38) -> the new spectrum leaves by bulk store -> inverse FFT of it (exchanges again)
 // -> the first inverse pass of the next step leaves as W.  Traffic 64 B per cell, no thread touches global memory
 // except for the k-tables.
-struct TmaKCtl {
-    TmaCtl ring;
-    unsigned long long sfull[2];  // per group: the spectrum tile has landed
-};
 
 template <int N, int TX>
 __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
     k_fused_kspace_tma(const __grid_constant__ CUtensorMap tw_in, const __grid_constant__ CUtensorMap tw_out,
                        const __grid_constant__ CUtensorMap ts, const __grid_constant__ PassGeom g, TmaRows rin, TmaRows rout,
-                       TmaRows rs, const __grid_constant__ DevKProgram P, FreqTabs ft, const cplx* __restrict__ tw) {
+                       TmaRows rs, const __grid_constant__ DevKProgram P, FreqTabs ft, const cplx* __restrict__ tw,
+                       unsigned* __restrict__ next_tile) {
     typedef TmaCfg<N, TX> C;
     typedef LayoutPadded<N> Lay;
     constexpr int E = C::E, T = C::T, GT = C::GT, STAGES = C::STAGES;
     extern __shared__ __align__(1024) unsigned char gopf_smem_raw[];
-    TmaKCtl* kctl = reinterpret_cast<TmaKCtl*>(gopf_smem_raw + STAGES * C::buf_bytes());
+    cplx* twsm = reinterpret_cast<cplx*>(gopf_smem_raw + STAGES * C::buf_bytes());
+    TmaKCtl* kctl = reinterpret_cast<TmaKCtl*>(gopf_smem_raw + STAGES * C::buf_bytes() + C::tw_bytes());
     TmaCtl* ctl = &kctl->ring;
+    for (int j = threadIdx.x; j < N; j += C::THREADS) twsm[TwShared::at(j)] = tw[j];
     const int tid = threadIdx.x;
     const int grp = tid / GT, gtid = tid - grp * GT;
     const int l = gtid / T, t = gtid - l * T;
     uint64_t* sfull = reinterpret_cast<uint64_t*>(&kctl->sfull[grp]);
     const long long tilesB = g.bcount / TX, tiles = g.A * tilesB;
-    const long long first = blockIdx.x, hop = gridDim.x;
-    const long long mine = first < tiles ? (tiles - first + hop - 1) / hop : 0;
 
     auto buffer = [&](int s) -> cplx* { return reinterpret_cast<cplx*>(gopf_smem_raw + (size_t)s * C::buf_bytes()); };
-    auto tile_col = [&](long long k, long long* a) -> long long {
-        const long long tile = first + k * hop;
+    auto tile_col = [&](long long tile, long long* a) -> long long {
         *a = tile / tilesB;
         return window_col(g, tile - *a * tilesB, TX);
     };
-    auto issue_load = [&](long long k) {  // one thread
+    auto issue_load = [&](long long k, long long tile) {  // one thread
         const int s = (int)(k % STAGES);
-        long long a;
-        const int c0 = (int)(2 * tile_col(k, &a));
         uint64_t* bar = reinterpret_cast<uint64_t*>(&ctl->full[s]);
-        tma::mbar_arrive_expect_tx(bar, (unsigned)C::tile_bytes());
-        for (int r = 0; r < N; r += rin.box_rows) tma_load_rows(buffer(s) + (size_t)r * TX, &tw_in, rin, c0, r, (int)a, bar);
+        if (tile < tiles) {
+            long long a;
+            const int c0 = (int)(2 * tile_col(tile, &a));
+            ctl->tile[s] = tile;
+            tma::mbar_arrive_expect_tx(bar, (unsigned)C::tile_bytes());
+            for (int r = 0; r < N; r += rin.box_rows) tma_load_rows(buffer(s) + (size_t)r * TX, &tw_in, rin, c0, r, (int)a, bar);
+            // the tile's spectrum rows into L2 while it waits its turn and runs its forward FFT
+            for (int r = 0; r < N; r += rs.box_rows) tma_prefetch_rows(&ts, rs, c0, r, (int)a);
+        } else {
+            ctl->tile[s] = -1;
+            tma::mbar_arrive(bar);
+        }
         __threadfence_block();
         ctl->issued[s] = ctl->issued[s] + 1;
     };
@@ -268,24 +301,29 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
     }
     __syncthreads();
     if (tid == 0)
-        for (long long k = 0; k < mine && k < STAGES; ++k) issue_load(k);
+        for (int k = 0; k < STAGES; ++k) issue_load(k, (long long)atomicAdd(next_tile, 1u));
 
     unsigned use = 0;  // tiles this group has processed (phase of its sfull barrier)
-    for (long long k = grp; k < mine; k += C::GROUPS, ++use) {
+    for (long long k = grp;; k += C::GROUPS, ++use) {
         const int s = (int)(k % STAGES);
         cplx* buf = buffer(s);
+        tma_wait_tile(ctl, s, (unsigned)(k / STAGES));
+        const long long tile = ctl->tile[s];
+        if (tile < 0) {
+            if (gtid == 0) issue_load(k + STAGES, tiles);
+            break;
+        }
+        long long claimed = 0;
+        if (gtid == 0) claimed = (long long)atomicAdd(next_tile, 1u);
         long long a;
-        const long long bcol = tile_col(k, &a);
+        const long long bcol = tile_col(tile, &a);
         const long long b = bcol + l;
         const int c0 = (int)(2 * bcol);
-        if (gtid == 0)  // this tile's spectrum rows into L2 while the forward FFT runs
-            for (int r = 0; r < N; r += rs.box_rows) tma_prefetch_rows(&ts, rs, c0, r, (int)a);
-        tma_wait_tile(ctl, s, (unsigned)(k / STAGES));
         cplx v[E];
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = buf[C::sw(t + T * m, l)];
         tma::group_sync(9 + grp, GT);
-        line_fft<N, Lay, SyncLine<T> >(v, t, l, buf, tw);
+        line_fft<N, Lay, SyncLine<T>, TwShared>(v, t, l, buf, twsm);
         tma::group_sync(9 + grp, GT);  // every line has read its last exchange: the spectrum tile may land
         if (gtid == 0) {
             tma::mbar_arrive_expect_tx(sfull, (unsigned)C::tile_bytes());
@@ -297,6 +335,10 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
         if (g.axis == 0) {
             fa = ft.f1[ft.off1 + (int)(b / g.n2)];
             fb = ft.f2[(int)(b % g.n2)];
+            fline = ft.f0;
+        } else if (g.axis == GOPF_AXIS0_BY_PLANE) {
+            fa = ft.f1[ft.off1 + (int)a];
+            fb = ft.f2[(int)b];
             fline = ft.f0;
         } else {  // axis 1
             fa = ft.f2[(int)b];
@@ -322,7 +364,7 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
             tma::store_wait_read();  // the new spectrum has left the buffer: it becomes the exchange tile again
         }
         tma::group_sync(9 + grp, GT);
-        line_fft<N, Lay, SyncLine<T> >(v, t, l, buf, tw);
+        line_fft<N, Lay, SyncLine<T>, TwShared>(v, t, l, buf, twsm);
         tma::group_sync(9 + grp, GT);
 #pragma unroll
         for (int m = 0; m < E; ++m) buf[C::sw(t + T * m, l)] = cswap(v[m]);
@@ -332,7 +374,7 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
             for (int r = 0; r < N; r += rout.box_rows) tma_store_rows(&tw_out, rout, c0, r, (int)a, buf + (size_t)r * TX);
             tma::store_commit();
             tma::store_wait_read();
-            if (k + STAGES < mine) issue_load(k + STAGES);
+            issue_load(k + STAGES, claimed);
         }
         __syncwarp();
     }
@@ -352,11 +394,12 @@ struct TmaRealCfg {
         THREADS = 512,
         WORKERS = THREADS / T,
         LS = N + N / 16,
-        STAGES_RAW = (int)((220 * 1024) / (LS * 16)),
+        STAGES_RAW = (int)((206 * 1024) / (LS * 16)),
         STAGES = STAGES_RAW > GOPF_TMA_MAX_STAGES ? GOPF_TMA_MAX_STAGES : STAGES_RAW
     };
     static constexpr size_t buf_bytes() { return (size_t)LS * sizeof(cplx); }
-    static constexpr size_t smem_bytes() { return STAGES * buf_bytes() + sizeof(TmaCtl) + 128; }
+    static constexpr size_t tw_bytes() { return (size_t)TwShared::elems(N) * sizeof(cplx); }
+    static constexpr size_t smem_bytes() { return STAGES * buf_bytes() + tw_bytes() + sizeof(TmaCtl) + 128; }
 };
 
 // inverse, /N, g(c), forward, in place on W (MODE 0 of k_fused_real)
@@ -371,9 +414,11 @@ __global__ void __launch_bounds__(TmaRealCfg<N>::THREADS, 1)
         static __device__ __forceinline__ int at(int pos, int) { return pos + (pos >> 4); }
     };
     extern __shared__ __align__(128) unsigned char gopf_smem_raw[];
-    TmaCtl* ctl = reinterpret_cast<TmaCtl*>(gopf_smem_raw + STAGES * C::buf_bytes());
+    cplx* twsm = reinterpret_cast<cplx*>(gopf_smem_raw + STAGES * C::buf_bytes());
+    TmaCtl* ctl = reinterpret_cast<TmaCtl*>(gopf_smem_raw + STAGES * C::buf_bytes() + C::tw_bytes());
     const int tid = threadIdx.x;
     const int worker = tid / T, p = tid - worker * T;
+    for (int j = tid; j < N; j += C::THREADS) twsm[TwShared::at(j)] = tw[j];
     const long long first = blockIdx.x, hop = gridDim.x;
     const long long mine = first < lines ? (lines - first + hop - 1) / hop : 0;  // lines of this CTA
     constexpr unsigned LINE_BYTES = (unsigned)(N * sizeof(cplx));
@@ -406,7 +451,7 @@ __global__ void __launch_bounds__(TmaRealCfg<N>::THREADS, 1)
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = cswap(buf[p + T * m]);
         SyncLine<T>::run();  // the line is in registers: its buffer becomes the exchange region
-        line_fft<N, Lay, SyncLine<T> >(v, p, 0, buf, tw);
+        line_fft<N, Lay, SyncLine<T>, TwShared>(v, p, 0, buf, twsm);
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = mk(v[m].y * inv_n, v[m].x * inv_n);  // swap back, /N
         if (derived_is_fast(D)) {
@@ -427,7 +472,7 @@ __global__ void __launch_bounds__(TmaRealCfg<N>::THREADS, 1)
             for (int m = 0; m < E; ++m) v[m] = buf[Lay::at(p + T * m, 0)];
             SyncLine<T>::run();
         }
-        line_fft<N, Lay, SyncLine<T> >(v, p, 0, buf, tw);
+        line_fft<N, Lay, SyncLine<T>, TwShared>(v, p, 0, buf, twsm);
 #pragma unroll
         for (int m = 0; m < E; ++m) buf[p + T * m] = v[m];
         tma::fence_proxy_async();

@@ -45,8 +45,8 @@ long long grid_for(const PassGeom& g, long long tiles) {
 // One tensor map + the row addressing the kernel needs for it.
 struct MapKey {
     const void* base;
-    long long B, a_stride, row_stride, split_stride, A;
-    int N, split_log, tx, promo, dev, swizzle;
+    long long B, a_stride, row_stride, split_stride, a_split_stride, A;
+    int N, split_log, a_split_log, tx, promo, dev, swizzle;
     bool operator<(const MapKey& o) const { return std::memcmp(this, &o, sizeof(MapKey)) < 0; }
 };
 struct MapVal {
@@ -69,6 +69,8 @@ cudaError_t tensor_map_for(const void* base, long long B, const RowMap& rm, long
     key.A = A;
     key.N = N;
     key.split_log = rm.split_log;
+    key.a_split_stride = rm.a_split_stride;
+    key.a_split_log = rm.a_split_log;
     key.tx = tx;
     key.promo = env_flag("GOPF_TMA_L2", 3);
     key.swizzle = swizzle;
@@ -82,14 +84,18 @@ cudaError_t tensor_map_for(const void* base, long long B, const RowMap& rm, long
     const long long rows_lo = rm.split_log >= 30 ? N : std::min<long long>(N, 1LL << rm.split_log);
     const long long rows_hi = N / rows_lo;
     if (rows_lo * rows_hi != N) return cudaErrorNotSupported;
+    const long long a_lo = rm.a_split_log >= 30 ? A : std::min<long long>(A, 1LL << rm.a_split_log);
+    const long long a_hi = A / a_lo;
+    if (a_lo * a_hi != A) return cudaErrorNotSupported;
     // outer dimensions in ascending stride order; extent-1 dimensions go last with a stride that keeps the
     // sequence monotonic (their stride is never used)
     struct Dim {
         long long extent, stride;
-        int who;  // 0 row_low, 1 row_high, 2 slab
+        int who;  // 0 row_low, 1 row_high, 2 slab_low, 3 slab_high
     };
     std::vector<Dim> real_dims, unit_dims;
-    const Dim cand[3] = {{rows_lo, rm.row_stride, 0}, {rows_hi, rm.split_stride, 1}, {A, rm.a_stride, 2}};
+    const Dim cand[4] = {{rows_lo, rm.row_stride, 0}, {rows_hi, rm.split_stride, 1}, {a_lo, rm.a_stride, 2},
+                         {a_hi, rm.a_split_stride, 3}};
     for (const Dim& d : cand) (d.extent > 1 ? real_dims : unit_dims).push_back(d);
     std::sort(real_dims.begin(), real_dims.end(), [](const Dim& x, const Dim& y) { return x.stride < y.stride; });
     std::vector<Dim> dims = real_dims;
@@ -102,10 +108,12 @@ cudaError_t tensor_map_for(const void* base, long long B, const RowMap& rm, long
     std::memset(&val, 0, sizeof(val));
     val.rows.log = rm.split_log >= 30 ? 31 : rm.split_log;
     val.rows.mask = rm.split_log >= 30 ? 0x7fffffff : (int)(rows_lo - 1);
+    val.rows.alog = rm.a_split_log >= 30 ? 31 : rm.a_split_log;
+    val.rows.amask = rm.a_split_log >= 30 ? 0x7fffffff : (int)(a_lo - 1);
     val.rows.box_rows = (int)std::min<long long>(256, rows_lo);
-    unsigned long long gd[4] = {(unsigned long long)B, 1, 1, 1}, gs[3] = {0, 0, 0};
-    unsigned box[4] = {(unsigned)tx, 1, 1, 1};
-    for (int i = 0; i < 3; ++i) {
+    unsigned long long gd[5] = {(unsigned long long)B, 1, 1, 1, 1}, gs[4] = {0, 0, 0, 0};
+    unsigned box[5] = {(unsigned)tx, 1, 1, 1, 1};
+    for (int i = 0; i < 4; ++i) {
         gd[1 + i] = (unsigned long long)dims[i].extent;
         gs[i] = (unsigned long long)dims[i].stride;
         if (gs[i] == 0 || gs[i] >= (1ULL << 36)) return cudaErrorNotSupported;  // bytes < 2^40
@@ -114,15 +122,44 @@ cudaError_t tensor_map_for(const void* base, long long B, const RowMap& rm, long
             box[1 + i] = (unsigned)val.rows.box_rows;
         } else if (dims[i].who == 1) {
             val.rows.p_hi = 1 + i;
-        } else {
+        } else if (dims[i].who == 2) {
             val.rows.p_a = 1 + i;
+        } else {
+            val.rows.p_ahi = 1 + i;
         }
     }
-    cudaError_t e = tma::encode_c128_4d(&val.map, base, gd, gs, box, key.promo, swizzle);
+    cudaError_t e = tma::encode_c128(&val.map, base, 5, gd, gs, box, key.promo, swizzle);
     if (e != cudaSuccess) return e;
     if (cache.size() > 256) cache.clear();
     cache[key] = val;
     *out = val;
+    return cudaSuccess;
+}
+
+// Tile counter of one launch of a dynamically scheduled kernel: a slot of a per-device pool, zeroed on the
+// launch's stream just before the kernel.  Slots rotate, so kernels running concurrently on different streams
+// never share one (a slot comes round again 4096 launches later).
+cudaError_t fresh_counter(cudaStream_t s, unsigned** out) {
+    constexpr int SLOTS = 4096;
+    static unsigned* pool[64] = {nullptr};
+    static std::atomic<unsigned> next{0};
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!pool[dev]) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!pool[dev]) {
+            unsigned* p = nullptr;
+            cudaError_t e = cudaMalloc(&p, SLOTS * sizeof(unsigned));
+            if (e != cudaSuccess) return e;
+            pool[dev] = p;
+        }
+    }
+    unsigned* c = pool[dev] + (next++ % SLOTS);
+    cudaError_t e = cudaMemsetAsync(c, 0, sizeof(unsigned), s);
+    if (e != cudaSuccess) return e;
+    *out = c;
     return cudaSuccess;
 }
 
@@ -145,7 +182,10 @@ cudaError_t pass_tma_n(const PassGeom& g, const PassIO& io, const cplx* tw, cuda
     if (e != cudaSuccess) return e;
     const long long tiles = g.A * (g.bcount / TX);
     const unsigned grid = (unsigned)grid_for(g, tiles);
-    kern<<<grid, C::THREADS, C::smem_bytes(), s>>>(in.map, out.map, g, in.rows, out.rows, io.inv, io.scale, tw);
+    unsigned* ctr = nullptr;
+    e = fresh_counter(s, &ctr);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, C::THREADS, C::smem_bytes(), s>>>(in.map, out.map, g, in.rows, out.rows, io.inv, io.scale, tw, ctr);
     g_tma_launches++;
     return cudaGetLastError();
 }
@@ -168,18 +208,20 @@ cudaError_t kspace_tma_n(const PassGeom& g, const cplx* W, cplx* Wout, cplx* S, 
                          const cplx* tw, cudaStream_t s) {
     typedef TmaCfg<N, TX> C;
     if (g.bw % TX != 0 || g.bcount % TX != 0) return cudaErrorNotSupported;
-    const RowMap uni = uniform_rows((long long)N * g.B, g.B);
     MapVal win, wout, sp;
-    if (tensor_map_for(W, g.B, uni, g.A, N, TX, C::SWIZZLE, &win) != cudaSuccess) return cudaErrorNotSupported;
-    if (tensor_map_for(Wout, g.B, uni, g.A, N, TX, C::SWIZZLE, &wout) != cudaSuccess) return cudaErrorNotSupported;
-    if (tensor_map_for(S, g.B, uni, g.A, N, TX, C::SWIZZLE, &sp) != cudaSuccess) return cudaErrorNotSupported;
+    if (tensor_map_for(W, g.B, g.in, g.A, N, TX, C::SWIZZLE, &win) != cudaSuccess) return cudaErrorNotSupported;
+    if (tensor_map_for(Wout, g.B, g.out, g.A, N, TX, C::SWIZZLE, &wout) != cudaSuccess) return cudaErrorNotSupported;
+    if (tensor_map_for(S, g.B, g.in, g.A, N, TX, C::SWIZZLE, &sp) != cudaSuccess) return cudaErrorNotSupported;
     auto kern = k_fused_kspace_tma<N, TX>;
-    const size_t smem = C::STAGES * C::buf_bytes() + sizeof(TmaKCtl) + 128;
+    const size_t smem = C::smem_bytes();
     cudaError_t e = opt_in_smem(kern, smem);
     if (e != cudaSuccess) return e;
     const long long tiles = g.A * (g.bcount / TX);
     const unsigned grid = (unsigned)grid_for(g, tiles);
-    kern<<<grid, C::THREADS, smem, s>>>(win.map, wout.map, sp.map, g, win.rows, wout.rows, sp.rows, P, ft, tw);
+    unsigned* ctr = nullptr;
+    e = fresh_counter(s, &ctr);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, C::THREADS, smem, s>>>(win.map, wout.map, sp.map, g, win.rows, wout.rows, sp.rows, P, ft, tw, ctr);
     g_tma_launches++;
     return cudaGetLastError();
 }

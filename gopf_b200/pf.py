@@ -920,6 +920,12 @@ class Solver:
         data = np.ascontiguousarray(filt.Data, dtype=np.float64)
         check(lib().gopf_solver_set_filter(self._h, data.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), data.shape[0]))
 
+    def BlockedLayout(self):
+        """(s, active): blocked k-space layout of the fused path on large 3-D grids (s = 0: row-major)."""
+        s, a = ctypes.c_int(0), ctypes.c_int(0)
+        check(lib().gopf_solver_blocked_layout(self._h, ctypes.byref(s), ctypes.byref(a)))
+        return s.value, bool(a.value)
+
     @property
     def IsFused(self) -> bool:
         f = ctypes.c_int(0)

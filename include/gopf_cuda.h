@@ -70,6 +70,14 @@ int gopf_fft_exec_device(gopf_fft_plan* plan, void* dev_inout_c128, int sign, vo
  * equal in; tile_cells = strided-tile width in cells (0: plan default).  Kernel tuning and tests. */
 int gopf_fft_exec_axis_device(gopf_fft_plan* plan, const void* dev_in_c128, void* dev_out_c128, int sign, int axis,
                               int tile_cells, void* stream);
+/* One strided line pass with explicit tile geometry (layout experiments, tests of the blocked k-space layout):
+ * `slabs` x `cols` lines of the plan's extent along `axis`; cell (a, j, b) sits at element offset
+ *   (a >> map[5]) * map[4] + (a & ((1 << map[5]) - 1)) * map[0] + (j >> map[3]) * map[2] + (j & ((1 << map[3]) - 1)) * map[1] + b
+ * with map = {slab_stride, row_stride, row_split_stride, row_split_log (>= 31: none), slab_split_stride,
+ * slab_split_log (>= 31: none)}, separately for input and output. */
+int gopf_fft_exec_rows_device(gopf_fft_plan* plan, const void* dev_in_c128, void* dev_out_c128, int sign, int axis,
+                              int64_t slabs, int64_t cols, const int64_t* in_map, const int64_t* out_map, int tile_cells,
+                              void* stream);
 /* Freq(i) for `count` node numbers evaluated ON THE DEVICE by the same code the
  * k-space kernels use (bit-exactness check of the device k-table). */
 int gopf_fft_freq_device(gopf_fft_plan* plan, const int64_t* nodes, int64_t count, double* out);
@@ -275,6 +283,11 @@ int gopf_solver_download(gopf_solver* s);
 int gopf_solver_synchronize(gopf_solver* s);
 /* TimeStepper.GetTime (pf/euler.go:50-52, pf/rk4.go:143-145) */
 int gopf_solver_get_time(gopf_solver* s, double* t);
+/* Blocked k-space layout of the fused path on large 3-D grids: *block_log = s when fused steps keep
+ * the spectrum as [n0 / 2^s][n1][2^s][n2] between host synchronisations (0: row-major throughout), *active = 1
+ * while the device spectrum currently sits in that layout.  Diagnostics and tests; every entry point that
+ * exposes the spectrum converts back first. */
+int gopf_solver_blocked_layout(gopf_solver* s, int* block_log, int* active);
 /* 1 when the single-field fused kernels are in use, 0 for the general path */
 int gopf_solver_is_fused(gopf_solver* s, int* fused);
 int gopf_solver_force_generic(gopf_solver* s, int on);

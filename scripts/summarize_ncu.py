@@ -2,6 +2,8 @@
 
   python scripts/summarize_ncu.py launches gpurun_out/r1_launches_bench.csv profiles/r1_launches_bench.md
   python scripts/summarize_ncu.py full gpurun_out/r1_prof_step.ncu-rep profiles/r1_ncu_full_step.md
+  python scripts/summarize_ncu.py traffic gpurun_out/r2_prof_1024.ncu-rep 1024 [more.ncu-rep grid ...]
+      -> profiles/ncu_traffic.json: dram bytes per launch by kernel class and grid (read by bench.py's roofline.traffic)
 """
 import collections
 import csv
@@ -71,5 +73,52 @@ def full(src, dst):
                     f.write(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |\n")
 
 
+def kernel_class(name, order):
+    """bench.py's kernel classes (Solver::tick names) from the demangled kernel name and launch order."""
+    if "k_fused_kspace" in name:
+        return "fused_kspace"
+    if "k_fused_real" in name:
+        return "fused_real"
+    if "k_pass_strided" in name:
+        # inside the fused step the middle passes alternate inverse, forward
+        return "pass_inverse_mid" if order % 2 == 0 else "pass_forward_mid"
+    return None
+
+
+def traffic(args):
+    import json
+    import os
+    entries = []
+    for src, grid in zip(args[0::2], args[1::2]):
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        hdr, units = rows[0], rows[1]
+        idx = {h: i for i, h in enumerate(hdr)}
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        acc = collections.OrderedDict()
+        n_strided = 0
+        for r in rows[2:]:
+            name = r[idx["Kernel Name"]]
+            cls = kernel_class(name, n_strided)
+            if "k_pass_strided" in name:
+                n_strided += 1
+            if cls is None:
+                continue
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(r[idx[k]].replace(",", "")) * scale.get(units[idx[k]], 1.0)
+            acc.setdefault((cls, name.split("(")[0]), []).append(tot)
+        for (cls, name), v in acc.items():
+            entries.append({"kernel": cls, "grid": int(grid), "dram_bytes": sum(v) / len(v), "launches": len(v),
+                            "kernel_name": name, "source": os.path.basename(src)})
+    dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    json.dump({"what": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full --clock-control none)",
+               "entries": entries}, open(dst, "w"), indent=1)
+    print(dst, len(entries), "entries")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2:])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -17,12 +17,17 @@ from gopf_b200 import synthetic  # noqa: E402
 
 BYTES = {"fused_kspace": 64.0, "fused_real": 32.0, "pass_inverse_mid": 32.0, "pass_forward_mid": 32.0}
 grids = [int(a) for a in sys.argv[1:]] or [1024]
-VARIANTS = [("register kernels", {"GOPF_TMA": "0"}),
-            ("tma all", {"GOPF_TMA": "1"}),
-            ("tma pass only", {"GOPF_TMA": "1", "GOPF_TMA_REAL": "0", "GOPF_TMA_KSPACE": "0"}),
-            ("tma real only", {"GOPF_TMA": "1", "GOPF_TMA_PASS": "0", "GOPF_TMA_KSPACE": "0"}),
-            ("tma kspace only", {"GOPF_TMA": "1", "GOPF_TMA_PASS": "0", "GOPF_TMA_REAL": "0"})]
-KEYS = ("GOPF_TMA", "GOPF_TMA_L2", "GOPF_TMA_PASS", "GOPF_TMA_REAL", "GOPF_TMA_KSPACE")
+VARIANTS = [("register kernels", {"GOPF_TMA": "0", "GOPF_BLOCKED": "0"}),
+            ("register kernels, blocked s=7", {"GOPF_TMA": "0", "GOPF_BLOCKED": "1"}),
+            ("tma all, blocked s=7", {"GOPF_TMA": "1", "GOPF_BLOCKED": "1"}),
+            ("tma all, blocked s=6", {"GOPF_TMA": "1", "GOPF_BLOCKED": "1", "GOPF_BLOCK_LOG": "6"}),
+            ("tma all, blocked s=8", {"GOPF_TMA": "1", "GOPF_BLOCKED": "1", "GOPF_BLOCK_LOG": "8"}),
+            ("tma pass+real, register kspace, blocked s=7", {"GOPF_TMA": "1", "GOPF_BLOCKED": "1", "GOPF_TMA_KSPACE": "0"}),
+            ("tma pass+real, register kspace, row-major", {"GOPF_TMA": "1", "GOPF_BLOCKED": "0", "GOPF_TMA_KSPACE": "0"}),
+            ("tma all, row-major", {"GOPF_TMA": "1", "GOPF_BLOCKED": "0"})]
+if os.environ.get("TUNE_VARIANTS"):
+    VARIANTS = [v for v in VARIANTS if any(w in v[0] for w in os.environ["TUNE_VARIANTS"].split(";"))]
+KEYS = ("GOPF_TMA", "GOPF_TMA_L2", "GOPF_TMA_PASS", "GOPF_TMA_REAL", "GOPF_TMA_KSPACE", "GOPF_BLOCKED", "GOPF_BLOCK_LOG")
 for G in grids:
     n = G ** 3
     os.environ["GOPF_TMA_MIN_N"] = str(min(G, 1024))
@@ -66,7 +71,6 @@ for G in grids:
             print(json.dumps(rec), flush=True)
         except Exception as exc:
             print(json.dumps({"grid": G, "variant": name, "error": str(exc)[:300]}), flush=True)
-            break
     solver.close()
     del solver, model, conc
     torch.cuda.empty_cache()

@@ -337,6 +337,10 @@ def test_white_noise_statistics(T):
     T.test_white_noise_statistics()
 
 
+def test_two_white_noise_fields_are_independent(T):
+    T.test_two_white_noise_fields_are_independent()
+
+
 def test_conservative_noise(T):
     T.test_conservative_noise_properties()
     T.test_conservative_noise_prescribed_currents_vs_oracle()

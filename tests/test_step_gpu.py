@@ -340,6 +340,26 @@ def test_white_noise_statistics():
     assert abs(np.corrcoef(first, inc)[0, 1]) < 0.01  # fresh draws every step
 
 
+def test_two_white_noise_fields_are_independent():
+    # the reference draws every WhiteNoise from the shared math/rand stream (pf/noise.go:20-23): two noise
+    # fields registered with the same (default) seed must not be the same field
+    N = 256
+    m = gpf.NewModel()
+    a = gpf.NewField("a", N * N)
+    b = gpf.NewField("b", N * N)
+    m.AddField(a)
+    m.AddField(b)
+    m.RegisterFunction("NOISE_A", gpf.WhiteNoise(0.5).Generate)
+    m.RegisterFunction("NOISE_B", gpf.WhiteNoise(0.5).Generate)
+    m.AddEquation("da/dt = NOISE_A")
+    m.AddEquation("db/dt = NOISE_B")
+    s = gpf.NewSolver(m, [N, N], 1.0)
+    s.Propagate(1)
+    x, y = a.Data.real, b.Data.real
+    assert abs(np.std(x, ddof=1) - 1.0) < 0.02 and abs(np.std(y, ddof=1) - 1.0) < 0.02
+    assert abs(np.corrcoef(x, y)[0, 1]) < 0.02
+
+
 def test_conservative_noise_properties():
     # pf/noise_test.go:50-94: field stays real and its integral stays zero
     N = 16
