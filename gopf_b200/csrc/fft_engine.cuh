@@ -245,9 +245,16 @@ __device__ __forceinline__ void twiddle_mul(cplx (&a)[R], const cplx* __restrict
 }
 
 // ---- one stage -------------------------------------------------------------------
-template <int N, int S, class Layout, class Sync, class Tw = TwGlobal>
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// `pre` runs once, after the first butterfly of the stage and before its first exchange write: a kernel whose
+// exchange buffer is still busy (a bulk store reading it, other lines still reading the landed tile) puts the
+// wait there, behind the register-only arithmetic, instead of in front of the transform (tma_kernels.cuh).
+template <int N, int S, class Layout, class Sync, class Tw = TwGlobal, class Pre = NoHook>
 __device__ __forceinline__ void fft_stage(cplx (&v)[PlanFor<N>::E], int t, int l, cplx* sm,
-                                          const cplx* __restrict__ tw) {
+                                          const cplx* __restrict__ tw, Pre pre = Pre()) {
     typedef PlanFor<N> P;
     typedef StageInfo<N, S> SI;
     constexpr int E = P::E, T = P::T, R = SI::R, L = SI::L, Q = E / R;
@@ -265,6 +272,7 @@ __device__ __forceinline__ void fft_stage(cplx (&v)[PlanFor<N>::E], int t, int l
             const int bl = b & (L - 1);
             const int bh = b - bl;  // (b div L) * L
             twiddle_mul<R, Tw>(a, tw, bh);
+            if (i == 0) pre();
             const int base = bl + (bh * R);
 #pragma unroll
             for (int k = 0; k < R; ++k) sm[Layout::at(base + L * k, l)] = a[k];
@@ -303,17 +311,25 @@ __device__ __forceinline__ void line_fft_from(cplx (&v)[PlanFor<N>::E], int t, i
 // The same transform in two parts, for kernels that want the exchange buffer back early:
 // after line_fft_head every thread has passed the last barrier of the last exchange, so `sm`
 // is free while line_fft_tail (register-only butterflies of the last stage) runs.
-template <int N, class Layout, class Sync>
+template <int N, class Layout, class Sync, class Tw = TwGlobal, class Pre = NoHook>
 __device__ __forceinline__ void line_fft_head(cplx (&v)[PlanFor<N>::E], int t, int l, cplx* sm,
-                                              const cplx* __restrict__ tw) {
+                                              const cplx* __restrict__ tw, Pre pre = Pre()) {
     typedef PlanFor<N> P;
-    if (P::NS > 1) fft_stage<N, 0, Layout, Sync>(v, t, l, sm, tw);
-    if (P::NS > 2) fft_stage<N, (P::NS > 2 ? 1 : 0), Layout, Sync>(v, t, l, sm, tw);
+    if (P::NS > 1) fft_stage<N, 0, Layout, Sync, Tw, Pre>(v, t, l, sm, tw, pre);
+    if (P::NS > 2) fft_stage<N, (P::NS > 2 ? 1 : 0), Layout, Sync, Tw>(v, t, l, sm, tw);
 }
-template <int N, class Layout, class Sync>
+template <int N, class Layout, class Sync, class Tw = TwGlobal>
 __device__ __forceinline__ void line_fft_tail(cplx (&v)[PlanFor<N>::E], int t, int l, cplx* sm,
                                               const cplx* __restrict__ tw) {
-    fft_stage<N, PlanFor<N>::NS - 1, Layout, Sync>(v, t, l, sm, tw);
+    fft_stage<N, PlanFor<N>::NS - 1, Layout, Sync, Tw>(v, t, l, sm, tw);
+}
+// whole transform with the hook of its first stage (NS >= 2)
+template <int N, class Layout, class Sync, class Tw, class Pre>
+__device__ __forceinline__ void line_fft_pre(cplx (&v)[PlanFor<N>::E], int t, int l, cplx* sm,
+                                             const cplx* __restrict__ tw, Pre pre) {
+    static_assert(PlanFor<N>::NS >= 2, "line_fft_pre: single-stage plans never touch the exchange buffer");
+    line_fft_head<N, Layout, Sync, Tw, Pre>(v, t, l, sm, tw, pre);
+    line_fft_tail<N, Layout, Sync, Tw>(v, t, l, sm, tw);
 }
 
 }  // namespace gopf

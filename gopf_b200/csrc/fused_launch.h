@@ -24,7 +24,11 @@ cudaError_t fused_kspace_n_tx(const PassGeom& g, const cplx* W, cplx* Wout, cplx
     constexpr int T = PlanFor<N>::T;
     // exchange tile, plus (early prefetch only) the spectrum tile
     const size_t smem = (size_t)N * TX * sizeof(cplx) * (LATE ? 1 : 2);
-    auto kern = g.peer.n > 0 ? k_fused_kspace<N, TX, true, LATE> : k_fused_kspace<N, TX, false, LATE>;
+    const bool split = g.in.split_log < 31 || g.in.a_split_log < 31 || g.out.split_log < 31 || g.out.a_split_log < 31 ||
+                       g.axis == GOPF_AXIS0_BY_PLANE;
+    if (split && g.peer.n > 0) return cudaErrorNotSupported;
+    auto kern = split ? k_fused_kspace<N, TX, false, LATE, true>
+                      : (g.peer.n > 0 ? k_fused_kspace<N, TX, true, LATE, false> : k_fused_kspace<N, TX, false, LATE, false>);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -121,7 +121,10 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
 // LATE = true: the spectrum tile lands in the exchange tile itself once the forward FFT has made
 //   its last exchange (its latency hides behind the last register-only butterfly stage and the
 //   other resident CTAs); 1 tile of shared memory, so long lines keep wide tiles / two CTAs per SM.
-template <int N, int TX, bool PEER, bool LATE>
+// SPLIT: W / S / Wout are addressed through the row maps of the launch (blocked k-space layout, solver.cu);
+//   otherwise they are plain [A][N][B] arrays and a row is one multiply away (the maps cost ~10 % more
+//   instructions, measured 5073 -> 4643 GB/s at 256^3, so the uniform case keeps its own instantiation).
+template <int N, int TX, bool PEER, bool LATE, bool SPLIT = false>
 __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* TX, (LATE ? 1 : 2) * N * TX * 16))
     k_fused_kspace(const __grid_constant__ PassGeom g, const cplx* W, cplx* Wout, cplx* __restrict__ S,
                    const __grid_constant__ DevKProgram P, FreqTabs ft, const cplx* __restrict__ tw) {
@@ -138,8 +141,11 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
     const long long b = window_col(g, tile - a * tilesB, TX) + l;
     // W and S share the input row map, Wout the output one (uniform [A][N][B] unless the launch says otherwise:
     // blocked k-space layout, solver.cu)
-    const size_t base = (size_t)slab_off(g.in, a) + b, obase = (size_t)slab_off(g.out, a) + b;
-    auto roff = [&](int j) -> size_t { return (size_t)row_off(g.in, j); };
+    const size_t base = SPLIT ? (size_t)slab_off(g.in, a) + b : (size_t)a * N * g.B + b;
+    const size_t obase = SPLIT ? (size_t)slab_off(g.out, a) + b : base;
+    const size_t strideB = (size_t)g.B;
+    auto roff = [&](int j) -> size_t { return SPLIT ? (size_t)row_off(g.in, j) : (size_t)j * strideB; };
+    auto roff_out = [&](int j) -> size_t { return SPLIT ? (size_t)row_off(g.out, j) : (size_t)j * strideB; };
     // Each thread later reads back exactly the spectrum cells it copied, so cp.async.wait_group
     // is the only synchronisation the copy needs.
     auto prefetch_spectrum = [&]() {
@@ -147,11 +153,22 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
             // the line is live in registers here: walk the rows with two running addresses in a
             // rolled loop instead of materialising E address pairs
             const unsigned sbase = smem_address(sS);
-            const cplx* src = S + base;
+            if (SPLIT) {
+                const cplx* src = S + base;
 #pragma unroll 1
-            for (int m = 0; m < E; ++m) {
-                const unsigned dst = sbase + (unsigned)(Lay::at(t + T * m, l) * (int)sizeof(cplx));
-                cp_async16(dst, src + roff(t + T * m));
+                for (int m = 0; m < E; ++m) {
+                    const unsigned dst = sbase + (unsigned)(Lay::at(t + T * m, l) * (int)sizeof(cplx));
+                    cp_async16(dst, src + roff(t + T * m));
+                }
+            } else {
+                const cplx* src = S + base + (size_t)t * strideB;
+                const size_t src_step = (size_t)T * strideB;
+#pragma unroll 1
+                for (int m = 0; m < E; ++m) {
+                    const unsigned dst = sbase + (unsigned)(Lay::at(t + T * m, l) * (int)sizeof(cplx));
+                    cp_async16(dst, src);
+                    src += src_step;
+                }
             }
         } else {
 #pragma unroll
@@ -213,7 +230,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
             const int j = t + T * m;
             const int pos = Lay::at(j, l);
             const double fl = fline[j];
-            const KPoint kp = (g.axis == 0) ? make_kpoint(fa, fb, fl) : make_kpoint(fl, fa, fb);  // row, col, depth
+            const KPoint kp = (g.axis != 1) ? make_kpoint(fa, fb, fl) : make_kpoint(fl, fa, fb);  // row, col, depth
             const cplx old = sS[pos], nl = sm[pos];
             const cplx cur = euler_update(P, 0, kp, old, [&](int bi) -> cplx { return bi == 0 ? old : nl; });
             S[base + roff(j)] = cur;
@@ -229,7 +246,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
         for (int m = 0; m < E; ++m) *peer_row(g.peer, a, t + T * m, b) = cswap(v[m]);
     } else {
 #pragma unroll
-        for (int m = 0; m < E; ++m) Wout[obase + (size_t)row_off(g.out, t + T * m)] = cswap(v[m]);
+        for (int m = 0; m < E; ++m) Wout[obase + roff_out(t + T * m)] = cswap(v[m]);
     }
 }
 

@@ -13,6 +13,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace gopf {
 namespace tma {
@@ -48,8 +49,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    return t;
+}
+// A wait that never completes would hang the device until the driver's watchdog (or the caller's patience) ends
+// it.  Every spin loop of these kernels therefore gives up after GOPF_TMA_WAIT_LIMIT_NS (4 s: four orders of
+// magnitude above any legitimate wait), reports where, and traps: the launch fails with an error instead.
+#define GOPF_TMA_WAIT_LIMIT_NS 4000000000ULL
+__device__ __noinline__ void wait_timed_out(int where, unsigned a, unsigned b) {
+    printf("gopf: copy-engine kernel wait %d timed out (block %d thread %d, %u %u)\n", where, (int)blockIdx.x, (int)threadIdx.x, a, b);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity, int where = 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > GOPF_TMA_WAIT_LIMIT_NS) wait_timed_out(where, parity, spins);
     }
 }
 

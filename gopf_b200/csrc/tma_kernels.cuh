@@ -92,16 +92,22 @@ struct TmaCtl {
 
 struct TmaKCtl {
     TmaCtl ring;
-    unsigned long long sfull[2];  // per group: the spectrum tile has landed
+    unsigned long long sfull[4];  // per group: the spectrum tile has landed
 };
 
 // The workers interleave on the ring, so a worker can reach stage s for its use u before the worker that
 // held the stage last has even issued that load; a bare parity wait would then pass on the phase of use u-2.
 // The issue counter closes that window.
 __device__ __forceinline__ void tma_wait_tile(TmaCtl* ctl, int stage, unsigned use) {
-    while (ctl->issued[stage] <= use) {
+    if (ctl->issued[stage] <= use) {
+        const unsigned long long t0 = tma::global_timer_ns();
+        unsigned spins = 0;
+        while (ctl->issued[stage] <= use) {
+            if ((++spins & 1023u) == 0 && tma::global_timer_ns() - t0 > GOPF_TMA_WAIT_LIMIT_NS)
+                tma::wait_timed_out(1, (unsigned)stage, use);
+        }
     }
-    tma::mbar_wait(reinterpret_cast<uint64_t*>(&ctl->full[stage]), use & 1u);
+    tma::mbar_wait(reinterpret_cast<uint64_t*>(&ctl->full[stage]), use & 1u, 2);
 }
 
 // ---- strided axis pass: out = FFT(in) along rows, TX adjacent lines per tile ---------------------------
@@ -139,7 +145,8 @@ struct TmaCfg {
 template <int N, int TX>
 __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
     k_pass_strided_tma(const __grid_constant__ CUtensorMap tin, const __grid_constant__ CUtensorMap tout,
-                       const __grid_constant__ PassGeom g, TmaRows rin, TmaRows rout, int inv, double scale,
+                       const __grid_constant__ PassGeom g, const __grid_constant__ TmaRows rin, const __grid_constant__ TmaRows rout, int inv,
+                       double scale,
                        const cplx* __restrict__ tw, unsigned* __restrict__ next_tile) {
     typedef TmaCfg<N, TX> C;
     typedef LayoutPadded<N> Lay;
@@ -196,7 +203,11 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
         tma_wait_tile(ctl, s, (unsigned)(k / STAGES));
         const long long tile = ctl->tile[s];
         if (tile < 0) {
-            // no tiles left: pass the end marker on to the stage the other group will wait for, then leave
+            // No tiles left: pass the end marker on to the stage the other group will wait for, then leave.  The
+            // marker re-arms THIS stage's barrier and completes its next phase at once, so every warp of the group
+            // must have passed its wait on the current phase first: a warp arriving late would find the barrier
+            // two phases on, its parity test would fail for ever (seen as a rare hang on small 2-D grids).
+            tma::group_sync(9 + grp, GT);
             if (gtid == 0) issue_load(k + STAGES, tiles);
             break;
         }
@@ -209,9 +220,9 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
 #pragma unroll
             for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
         }
-        // tile-wide: the padded exchange regions of the lines overlay the landed tile
-        tma::group_sync(9 + grp, GT);
-        line_fft<N, Lay, SyncLine<T>, TwShared>(v, t, l, buf, twsm);
+        // tile-wide, but only before the first exchange WRITE (the padded exchange regions of the lines overlay
+        // the landed tile): the first butterflies run while the slower warps of the group still read
+        line_fft_pre<N, Lay, SyncLine<T>, TwShared>(v, t, l, buf, twsm, [&]() { tma::group_sync(9 + grp, GT); });
         tma::group_sync(9 + grp, GT);  // every line has read its last exchange: the outgoing tile may overwrite them
         if (inv) {
 #pragma unroll
@@ -246,8 +257,9 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
 template <int N, int TX>
 __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
     k_fused_kspace_tma(const __grid_constant__ CUtensorMap tw_in, const __grid_constant__ CUtensorMap tw_out,
-                       const __grid_constant__ CUtensorMap ts, const __grid_constant__ PassGeom g, TmaRows rin, TmaRows rout,
-                       TmaRows rs, const __grid_constant__ DevKProgram P, FreqTabs ft, const cplx* __restrict__ tw,
+                       const __grid_constant__ CUtensorMap ts, const __grid_constant__ PassGeom g,
+                       const __grid_constant__ TmaRows rin, const __grid_constant__ TmaRows rout,
+                       const __grid_constant__ TmaRows rs, const __grid_constant__ DevKProgram P, FreqTabs ft, const cplx* __restrict__ tw,
                        unsigned* __restrict__ next_tile) {
     typedef TmaCfg<N, TX> C;
     typedef LayoutPadded<N> Lay;
@@ -292,8 +304,7 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
             tma::mbar_init(reinterpret_cast<uint64_t*>(&ctl->full[s]), 1);
             ctl->issued[s] = 0;
         }
-        tma::mbar_init(reinterpret_cast<uint64_t*>(&kctl->sfull[0]), 1);
-        tma::mbar_init(reinterpret_cast<uint64_t*>(&kctl->sfull[1]), 1);
+        for (int q = 0; q < C::GROUPS; ++q) tma::mbar_init(reinterpret_cast<uint64_t*>(&kctl->sfull[q]), 1);
         tma::fence_barrier_init();
         tma::prefetch_descriptor(&tw_in);
         tma::prefetch_descriptor(&tw_out);
@@ -310,6 +321,7 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
         tma_wait_tile(ctl, s, (unsigned)(k / STAGES));
         const long long tile = ctl->tile[s];
         if (tile < 0) {
+            tma::group_sync(9 + grp, GT);  // see k_pass_strided_tma
             if (gtid == 0) issue_load(k + STAGES, tiles);
             break;
         }
@@ -322,13 +334,13 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
         cplx v[E];
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = buf[C::sw(t + T * m, l)];
-        tma::group_sync(9 + grp, GT);
-        line_fft<N, Lay, SyncLine<T>, TwShared>(v, t, l, buf, twsm);
-        tma::group_sync(9 + grp, GT);  // every line has read its last exchange: the spectrum tile may land
+        line_fft_head<N, Lay, SyncLine<T>, TwShared>(v, t, l, buf, twsm, [&]() { tma::group_sync(9 + grp, GT); });
+        tma::group_sync(9 + grp, GT);  // every line has read its last exchange: the spectrum tile may land ...
         if (gtid == 0) {
             tma::mbar_arrive_expect_tx(sfull, (unsigned)C::tile_bytes());
             for (int r = 0; r < N; r += rs.box_rows) tma_load_rows(buf + (size_t)r * TX, &ts, rs, c0, r, (int)a, sfull);
         }
+        line_fft_tail<N, Lay, SyncLine<T>, TwShared>(v, t, l, buf, twsm);  // ... under the register-only last stage
         // Reference Freq components [row, col, depth] = FFTW axes [1, 2, 0] (fftWrap.go:42-74).
         double fa, fb;
         const double* fline;
@@ -346,7 +358,7 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
             fline = ft.f1;
         }
         const double s2 = fa * fa + fb * fb;
-        tma::mbar_wait(sfull, use & 1u);
+        tma::mbar_wait(sfull, use & 1u, 3);
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int j = t + T * m;
@@ -361,10 +373,13 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
         if (gtid == 0) {
             for (int r = 0; r < N; r += rs.box_rows) tma_store_rows(&ts, rs, c0, r, (int)a, buf + (size_t)r * TX);
             tma::store_commit();
-            tma::store_wait_read();  // the new spectrum has left the buffer: it becomes the exchange tile again
         }
-        tma::group_sync(9 + grp, GT);
-        line_fft<N, Lay, SyncLine<T>, TwShared>(v, t, l, buf, twsm);
+        // the buffer becomes the exchange tile again once the copy engine has read the new spectrum out of it:
+        // that wait sits behind the first butterflies of the inverse transform
+        line_fft_pre<N, Lay, SyncLine<T>, TwShared>(v, t, l, buf, twsm, [&]() {
+            if (gtid == 0) tma::store_wait_read();
+            tma::group_sync(9 + grp, GT);
+        });
         tma::group_sync(9 + grp, GT);
 #pragma unroll
         for (int m = 0; m < E; ++m) buf[C::sw(t + T * m, l)] = cswap(v[m]);

@@ -42,16 +42,21 @@ for G in grids:
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     solver.SetStream(stream.cuda_stream)
+    print("grid", G, "upload", file=sys.stderr, flush=True)
     solver.Upload()
+    torch.cuda.synchronize()
+    print("  uploaded", file=sys.stderr, flush=True)
     steps = 10 if G >= 1024 else 30
     for name, env in VARIANTS:
         for k in KEYS:
             os.environ.pop(k, None)
         os.environ.update(env)
         try:
+            print("variant", name, file=sys.stderr, flush=True)
             gpfutil.TmaLaunchCount(reset=True)
             solver.StepDevice(3)
             torch.cuda.synchronize()
+            print("  warm", file=sys.stderr, flush=True)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             solver.StepDevice(steps)
