@@ -752,6 +752,13 @@ int gopf_solver_blocked_layout(gopf_solver* s, int* block_log, int* active) {
     GOPF_API_END
 }
 
+int gopf_solver_fused_form(gopf_solver* s, int* form, int* derived_form) {
+    GOPF_API_BEGIN
+    if (!s || !form || !derived_form) throw Error("gopf_solver_fused_form: NULL argument");
+    s->s->fused_form(form, derived_form);
+    GOPF_API_END
+}
+
 int gopf_solver_is_fused(gopf_solver* s, int* fused) {
     GOPF_API_BEGIN
     if (!s || !fused) throw Error("NULL argument");

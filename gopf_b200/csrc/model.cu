@@ -363,6 +363,77 @@ struct ExprCompiler {
 };
 }  // namespace
 
+// A registered function that is a real polynomial (degree <= GOPF_MAX_POLY) of re(field 0) alone -- the PFC
+// ideal-mixture nonlinearity 3 a v^2 + 4 b v^3 (pf/pairCorrelationTerm.go:144-156), Landau and interpolation
+// polynomials -- gets its coefficients recorded next to the program, so that the fused real-space kernels can
+// evaluate it by Horner on register-resident cells (step_program.h derived_poly).  The program itself stays:
+// every other path keeps interpreting (or compiling) it.
+static void detect_polynomial(DevDerived* D) {
+    typedef std::vector<double> Poly;
+    D->poly_deg = -1;
+    for (int i = 0; i <= GOPF_MAX_POLY; ++i) D->poly[i] = 0.0;
+    auto mul = [](const Poly& a, const Poly& b) {
+        Poly r(a.size() + b.size() - 1, 0.0);
+        for (size_t i = 0; i < a.size(); ++i)
+            for (size_t j = 0; j < b.size(); ++j) r[i + j] += a[i] * b[j];
+        return r;
+    };
+    auto lin = [](double ca, const Poly& a, double cb, const Poly& b) {
+        Poly r(std::max(a.size(), b.size()), 0.0);
+        for (size_t i = 0; i < a.size(); ++i) r[i] += ca * a[i];
+        for (size_t i = 0; i < b.size(); ++i) r[i] += cb * b[i];
+        return r;
+    };
+    std::vector<Poly> st;
+    for (int i = 0; i < D->n_ops; ++i) {
+        const double arg = D->arg[i];
+        switch (D->op[i]) {
+            case OP_CONST: st.push_back(Poly{arg}); break;
+            case OP_FIELD_RE:
+                if ((int)arg != 0) return;
+                st.push_back(Poly{0.0, 1.0});
+                break;
+            case OP_ADD: case OP_SUB: case OP_MUL: {
+                if (st.size() < 2) return;
+                const Poly b = st.back();
+                st.pop_back();
+                const Poly a = st.back();
+                st.pop_back();
+                st.push_back(D->op[i] == OP_MUL ? mul(a, b) : lin(1.0, a, D->op[i] == OP_ADD ? 1.0 : -1.0, b));
+                break;
+            }
+            case OP_NEG:
+                if (st.empty()) return;
+                for (double& c : st.back()) c = -c;
+                break;
+            case OP_POWI: {
+                if (st.empty() || arg < 0 || arg > GOPF_MAX_POLY || arg != std::floor(arg)) return;
+                Poly r{1.0};
+                for (int k = 0; k < (int)arg; ++k) r = mul(r, st.back());
+                st.back() = r;
+                break;
+            }
+            case OP_H: case OP_DH: case OP_LANDAU: case OP_DLANDAU: {
+                if (st.empty()) return;
+                const Poly x = st.back(), x2 = mul(x, x), x3 = mul(x2, x), x4 = mul(x2, x2);
+                if (D->op[i] == OP_H) st.back() = lin(3.0, x2, -2.0, x3);
+                else if (D->op[i] == OP_DH) st.back() = lin(6.0, x, -6.0, x2);
+                else if (D->op[i] == OP_LANDAU) st.back() = lin(1.0, lin(1.0, x2, -2.0, x3), 1.0, x4);
+                else st.back() = lin(1.0, lin(2.0, x, -6.0, x2), 4.0, x3);
+                break;
+            }
+            default: return;  // division, transcendental functions, imaginary parts
+        }
+        if (!st.empty() && st.back().size() > 4 * (GOPF_MAX_POLY + 1)) return;
+    }
+    if (st.size() != 1) return;
+    Poly r = st.back();
+    while (r.size() > 1 && r.back() == 0.0) r.pop_back();
+    if ((int)r.size() > GOPF_MAX_POLY + 1) return;
+    for (size_t i = 0; i < r.size(); ++i) D->poly[i] = r[i];
+    D->poly_deg = (int)r.size() - 1;
+}
+
 DevDerived Model::compile_expression(const std::string& expr) const {
     DevDerived D;
     std::memset(&D, 0, sizeof(D));
@@ -382,6 +453,7 @@ DevDerived Model::compile_expression(const std::string& expr) const {
         maxsp = std::max(maxsp, sp);
     }
     if (sp != 1 || maxsp > GOPF_RPN_STACK) throw Error("function expression '" + expr + "' is too deeply nested");
+    detect_polynomial(&D);
     return D;
 }
 

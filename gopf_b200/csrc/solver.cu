@@ -19,6 +19,24 @@ __global__ void __launch_bounds__(256)
     implicit_table_all(P, i, out, fg, n);
 }
 
+// filter / (1 - dt*den) of the single-field program, real part (finalize_single_field_program admits only real,
+// time-independent implicit terms to the tabulated form)
+__global__ void __launch_bounds__(256)
+    k_fused_dtab(const __grid_constant__ DevKProgram P, double* out, FreqGeom fg, long long n) {
+    const bool small = n < (1LL << 31);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        double f[3] = {0.0, 0.0, 0.0};
+        ref_freq_fast(fg, idx, small, f);
+        const KPoint kp = make_kpoint(f[0], f[1], f[2]);
+        const DevEquation& q = P.eq[0];
+        cplx den = mk(0.0, 0.0);
+        for (int j = 0; j < q.n_den; ++j) den += eval_term(P, q.den[j], kp, [&](int) -> cplx { return mk(1.0, 0.0); });
+        cplx r = cdiv(mk(1.0, 0.0), mk(1.0 - P.dt * den.x, -P.dt * den.y));
+        if (P.filter) r = mk(r.x * filter_eval(P.filter, P.filter_n, kp.frad * 2.0 / GOPF_PI), 0.0);
+        out[idx] = r.x;
+    }
+}
+
 // real part of every cell; big-endian byte order on request (encoding/binary.BigEndian in
 // pf/fileIO.go:85-95 SaveFloat64)
 __global__ void k_real_part(const cplx* __restrict__ in, double* __restrict__ out, int big_endian, long long n) {
@@ -129,6 +147,7 @@ Solver::~Solver() {
     for (int i = 0; i < GOPF_MAX_SPECTRA; ++i)
         if (S_.s[i]) cudaFree(S_.s[i]);
     if (W2_) cudaFree(W2_);
+    if (fused_dtab_) cudaFree(fused_dtab_);
     for (int i = 0; i < GOPF_MAX_FIELDS; ++i) {
         if (Rw_[i]) cudaFree(Rw_[i]);
         if (rk_initial_[i]) cudaFree(rk_initial_[i]);
@@ -406,7 +425,18 @@ void Solver::rebuild_program() {
     if (has_knoise_ && !plan_->freq_axis_consistent())
         throw Error("solver: k-space noise needs a 2-D or cubic 3-D grid");
     fused_prog_ = prog_;
-    if (fused_) finalize_single_field_program(&fused_prog_, (int)m_->fields.size());
+    if (fused_) {
+        finalize_single_field_program(&fused_prog_, (int)m_->fields.size(), env_int("GOPF_FUSED_TABLE", 1) != 0);
+        if (fused_prog_.fast == 2) {
+            // tabulated form: filter / (1 - dt*den) for every k-point, in the spectrum's (row-major) order
+            const long long n = (long long)plan_->N;
+            if (!fused_dtab_) GOPF_CUDA(cudaMalloc(&fused_dtab_, sizeof(double) * n));
+            k_fused_dtab<<<grid_for(n), 256, 0, stream()>>>(fused_prog_, fused_dtab_, plan_->freq_geom(), n);
+            GOPF_CUDA(cudaGetLastError());
+            launches_++;
+            fused_prog_.dtab = fused_dtab_;
+        }
+    }
     prog_dirty_ = false;
     implicit_tab_dirty_ = true;
 }
@@ -414,21 +444,32 @@ void Solver::rebuild_program() {
 // Program as seen by the fused single-field kernels: spectrum 0 = the field, 1 = the derived
 // field; plus the real-polynomial fast form when every term is a monomial with a real
 // coefficient, degree <= 4, no self term on the explicit side and no filter.
-void finalize_single_field_program(DevKProgram* prog, int n_fields) {
+void finalize_single_field_program(DevKProgram* prog, int n_fields, bool allow_table) {
     DevKProgram& P = *prog;
     DevEquation& q = P.eq[0];
     for (int j = 0; j < q.n_rhs; ++j)
         if (q.rhs[j].brick >= n_fields) q.rhs[j].brick = 1;
     for (int j = 0; j < q.n_den; ++j)
         if (q.den[j].brick >= n_fields) q.den[j].brick = 1;
-    bool fast = true;
-    for (int i = 0; i <= GOPF_MAX_POLY; ++i) P.p_nl[i] = P.p_self[i] = P.q[i] = 0.0;
+    bool rhs_poly = true, den_poly = true, den_real = true;
+    double p_noise[GOPF_MAX_POLY + 1];
+    for (int i = 0; i <= GOPF_MAX_POLY; ++i) P.p_nl[i] = P.p_self[i] = P.q[i] = p_noise[i] = 0.0;
     P.deg_nl = 0;
     P.deg_self = -1;
     P.deg_q = 0;
-    for (int j = 0; j < q.n_rhs && fast; ++j) {
+    P.noise_param = -1;
+    P.dtab = nullptr;
+    int n_noise = 0, deg_noise = 0;
+    for (int j = 0; j < q.n_rhs && rhs_poly; ++j) {
         const DevTerm& t = q.rhs[j];
-        if (t.kind != TK_MONOMIAL || !negligible_imag(t) || t.lap > GOPF_MAX_POLY || t.brick < 0) { fast = false; break; }
+        if (t.kind == TK_WHITE_NOISE_K && negligible_imag(t) && t.lap <= GOPF_MAX_POLY) {
+            n_noise++;
+            P.noise_param = t.param;
+            p_noise[t.lap] += t.cre;
+            if (t.lap > deg_noise) deg_noise = t.lap;
+            continue;
+        }
+        if (t.kind != TK_MONOMIAL || !negligible_imag(t) || t.lap > GOPF_MAX_POLY || t.brick < 0) { rhs_poly = false; break; }
         if (t.brick == 1) {
             P.p_nl[t.lap] += t.cre;
             if (t.lap > P.deg_nl) P.deg_nl = t.lap;
@@ -437,17 +478,27 @@ void finalize_single_field_program(DevKProgram* prog, int n_fields) {
             if (t.lap > P.deg_self) P.deg_self = t.lap;
         }
     }
-    for (int j = 0; j < q.n_den && fast; ++j) {
+    for (int j = 0; j < q.n_den; ++j) {
         const DevTerm& t = q.den[j];
-        if (t.kind != TK_MONOMIAL || !negligible_imag(t) || t.lap > GOPF_MAX_POLY || t.brick >= 0) { fast = false; break; }
+        // real-valued, time-independent multipliers (step_program.h eval_term)
+        const bool real_kind = (t.kind == TK_MONOMIAL || t.kind == TK_PAIR_CORR || t.kind == TK_SPECTRAL_VISC ||
+                                t.kind == TK_TENSOR_HESSIAN) && t.brick < 0 && negligible_imag(t);
+        if (!real_kind) den_real = false;
+        if (t.kind != TK_MONOMIAL || !negligible_imag(t) || t.lap > GOPF_MAX_POLY || t.brick >= 0) { den_poly = false; continue; }
         P.q[t.lap] += t.cre;
         if (t.lap > P.deg_q) P.deg_q = t.lap;
     }
-    if (P.deg_nl > 4 || P.deg_q > 4 || P.deg_self >= 0 || P.filter != nullptr) fast = false;
-    P.fast = fast ? 1 : 0;
+    const bool fast1 = rhs_poly && den_poly && n_noise == 0 && P.deg_nl <= 4 && P.deg_q <= 4 && P.deg_self < 0 &&
+                       P.filter == nullptr;
+    const bool fast2 = !fast1 && allow_table && rhs_poly && den_real && n_noise <= 1 && P.deg_nl <= 4 && P.deg_self <= 4 &&
+                       deg_noise <= 4;
+    P.fast = fast1 ? 1 : (fast2 ? 2 : 0);
+    if (!fast2) P.noise_param = -1;
     for (int i = 0; i < 5; ++i) {
         P.fa[i] = P.dt * P.p_nl[i];
         P.fq[i] = (i == 0 ? 1.0 : 0.0) - P.dt * P.q[i];
+        P.fself[i] = (i == 0 ? 1.0 : 0.0) + P.dt * P.p_self[i];
+        P.fnz[i] = P.dt * p_noise[i];
     }
 }
 
@@ -464,6 +515,17 @@ int single_field_derived_index(const Model& m) {
         if (kv.second.kind == UserTermKind::VolumeConservingLP || kv.second.kind == UserTermKind::ConservativeNoise)
             return -1;
     return used;
+}
+
+void Solver::fused_form(int* form, int* derived_form) {
+    *form = *derived_form = 0;
+    if (!fused_) return;
+    plan_->use_device();
+    rebuild_program();
+    *form = fused_prog_.fast;
+    const DevDerived& D = m_->derived[fused_derived_].dev;
+    if (D.kind == DK_MONOMIAL && D.n_factors == 1 && D.ipower[0] >= 0 && D.ipower[0] <= 15) *derived_form = 1;
+    else if (D.kind == DK_RPN && D.poly_deg >= 0) *derived_form = 2;
 }
 
 FreqTabs Solver::freq_tabs() const {
@@ -1047,6 +1109,7 @@ void Solver::euler_update_generic() {
 // 6217 GB/s against 6206 GB/s row-major to row-major).  GOPF_BLOCK_LOG overrides s.
 int Solver::blocked_log() const {
     if (!fused_ || stepper_ != StepperKind::Euler || plan_->rank != 3) return 0;
+    if (fused_prog_.fast == 2) return 0;  // the table of the tabulated form is kept row-major
     const int n0 = plan_->n0, n1 = plan_->n1, n2 = plan_->n2;
     if ((n0 & (n0 - 1)) != 0 || n0 < 16) return 0;
     const int mode = env_int("GOPF_BLOCKED", -1);

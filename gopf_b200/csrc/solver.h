@@ -48,7 +48,8 @@ struct SddState {
 };
 
 // shared by Solver and DistSolver (solver.cu)
-void finalize_single_field_program(DevKProgram* prog, int n_fields);
+// allow_table: admit the tabulated form (DevKProgram::fast == 2); the caller then owns and fills P.dtab
+void finalize_single_field_program(DevKProgram* prog, int n_fields, bool allow_table = false);
 int single_field_derived_index(const Model& m);
 
 struct KernelTimer {  // CUDA-event timing of one kernel class, accumulated over launches
@@ -96,6 +97,7 @@ public:
     double sdd_get(const std::string& key);
     void sdd_get_orientation(double* host_out);
     bool fused() const { return fused_; }
+    void fused_form(int* form, int* derived_form);
     long long kernel_launches() const { return launches_; }
     void reset_launch_count() { launches_ = 0; }
     void set_profiling(bool on);
@@ -157,6 +159,7 @@ private:
     // and the middle-axis passes convert on the fly (row-major on the real-space side, blocked on the k-space
     // side) at no extra traffic.  Everything else sees the row-major S: leave_blocked() converts back.
     cplx* W2_ = nullptr;
+    double* fused_dtab_ = nullptr;  // tabulated single-field form: filter / (1 - dt*den) per k-point
     bool blocked_ = false;
     int block_log_ = -1;  // decided at first use (-1: not yet)
     void enter_blocked();

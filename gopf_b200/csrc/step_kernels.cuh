@@ -82,10 +82,13 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
 #pragma unroll
         for (int m = 0; m < E; ++m) real_out[base + p + T * m] = v[m];
     }
-    if (derived_is_fast(D)) {
+    if (derived_is_monomial_fast(D)) {
         const int pw = D.ipower[0];
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = derived_fast(pw, v[m]);
+    } else if (derived_is_poly_fast(D)) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = derived_poly(D, v[m]);
     } else {
         // general derived field: cells staged in shared memory, interpreter in a rolled loop
 #pragma unroll
@@ -212,13 +215,28 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
     cp_async_wait_all();
     if (LATE || P.fast) {  // LATE is launched for fast-form programs only (fused_launch.h)
         const double s2 = fa * fa + fb * fb;
+        if (P.fast == 2) {
+            // tabulated form: one real per k-point read next to the spectrum cell (8 more bytes per cell)
+            const double* __restrict__ dtab = P.dtab;
 #pragma unroll
-        for (int m = 0; m < E; ++m) {
-            const int j = t + T * m;
-            const double fl = fline[j];
-            const cplx cur = fast_update(P, fma(fl, fl, s2), sS[Lay::at(j, l)], v[m]);
-            S[base + roff(j)] = cur;
-            v[m] = cswap(cur);
+            for (int m = 0; m < E; ++m) {
+                const int j = t + T * m;
+                const double fl = fline[j];
+                const double dk = dtab[base + roff(j)];
+                const cplx cur = (g.axis != 1) ? tab_update(P, fma(fl, fl, s2), fa, fb, fl, dk, sS[Lay::at(j, l)], v[m])
+                                               : tab_update(P, fma(fl, fl, s2), fl, fa, fb, dk, sS[Lay::at(j, l)], v[m]);
+                S[base + roff(j)] = cur;
+                v[m] = cswap(cur);
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int j = t + T * m;
+                const double fl = fline[j];
+                const cplx cur = fast_update(P, fma(fl, fl, s2), sS[Lay::at(j, l)], v[m]);
+                S[base + roff(j)] = cur;
+                v[m] = cswap(cur);
+            }
         }
         if (LATE) __syncthreads();  // spectrum cells were read from the exchange tile
     } else {

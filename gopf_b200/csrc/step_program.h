@@ -114,9 +114,16 @@ struct DevKProgram {
     // Single-field fast form (fused kernels): when every term of eq[0] is a monomial with a
     // real coefficient the update collapses to polynomials in L = -(2 pi |f|)^2:
     //   c^ <- (c^ + dt*(p_nl(L)*g^ + p_self(L)*c^)) / (1 - dt*q(L))
+    // fast == 2, the tabulated form: the explicit side is still polynomial (plus at most one k-space white-noise
+    // term), the implicit side and the modal filter are arbitrary but real and time-independent, tabulated once:
+    //   c^ <- (b(L)*c^ + a(L)*g^ + n(L)*xi^(k)) * dtab[k],   dtab = filter / (1 - dt*den),  b = 1 + dt*p_self
+    // (phase-field crystal: pair-correlation + ideal-mixture terms, Vandeven filter, white noise: cfg 5).
     int fast, deg_nl, deg_self, deg_q;
     double p_nl[GOPF_MAX_POLY + 1], p_self[GOPF_MAX_POLY + 1], q[GOPF_MAX_POLY + 1];
     double fa[5], fq[5];  // fast form folded with dt: fa = dt*p_nl, fq = 1 - dt*q (degree <= 4)
+    double fself[5], fnz[5];  // tabulated form: 1 + dt*p_self, dt * (noise coefficient) * L^lap
+    int noise_param, pad2;    // tabulated form: P.th slot of the white-noise term (-1: none)
+    const double* dtab;       // tabulated form: one real per k-point, same order as the spectrum
 };
 
 // ---- k-point ---------------------------------------------------------------------
@@ -300,6 +307,10 @@ struct DevDerived {
     const double* table;      // DK_TABLE: prescribed real values, row (step mod table_steps)
     long long table_steps;
     long long table_n;
+    // DK_RPN whose expression is a real polynomial of re(field 0) alone (model.cu detects it): the fused
+    // real-space kernels evaluate it by Horner on the register-resident line instead of interpreting the program
+    int poly_deg, pad3;       // -1: not a polynomial
+    double poly[GOPF_MAX_POLY + 1];
 };
 
 // Go cmplx.Pow(x, p) for real p (math/cmplx/pow.go), polar form
@@ -442,8 +453,19 @@ __device__ __forceinline__ cplx eval_derived(const DevDerived& D, Fld fld, unsig
 // branch-free and stay in registers; every other case goes through the general evaluators
 // above in a ROLLED loop over cells staged in shared memory (see step_kernels.cuh), so the
 // interpreter is instantiated once and never forces the register-resident line to spill.
-__device__ __forceinline__ bool derived_is_fast(const DevDerived& D) {
+__device__ __forceinline__ bool derived_is_monomial_fast(const DevDerived& D) {
     return D.kind == DK_MONOMIAL && D.n_factors == 1 && D.ipower[0] >= 0 && D.ipower[0] <= 15;
+}
+__device__ __forceinline__ bool derived_is_poly_fast(const DevDerived& D) { return D.kind == DK_RPN && D.poly_deg >= 0; }
+__device__ __forceinline__ bool derived_is_fast(const DevDerived& D) {
+    return derived_is_monomial_fast(D) || derived_is_poly_fast(D);
+}
+// real polynomial of the real part (registered functions like 3 a v^2 + 4 b v^3 of the PFC ideal-mixture term)
+__device__ __forceinline__ cplx derived_poly(const DevDerived& D, cplx c) {
+    double r = D.poly[GOPF_MAX_POLY];
+#pragma unroll
+    for (int i = GOPF_MAX_POLY - 1; i >= 0; --i) r = fma(r, c.x, D.poly[i]);
+    return mk(r, 0.0);
 }
 
 // c^p by square-and-multiply (p <= 15): c^3 = c * (c * c)
@@ -470,6 +492,24 @@ __device__ __forceinline__ cplx fast_update(const DevKProgram& P, double frad2, 
     const double d = fma(fma(fma(fma(P.fq[4], L, P.fq[3]), L, P.fq[2]), L, P.fq[1]), L, P.fq[0]);
     const double inv = 1.0 / d;
     return mk(fma(a, nl.x, cur.x) * inv, fma(a, nl.y, cur.y) * inv);
+}
+
+// Tabulated form (DevKProgram::fast == 2).  `dk` = P.dtab at this k-point; kp only feeds the noise generator.
+__device__ __forceinline__ cplx tab_update(const DevKProgram& P, double frad2, double f0, double f1, double f2, double dk,
+                                           cplx cur, cplx nl) {
+    const double L = -(4.0 * GOPF_PI * GOPF_PI) * frad2;
+    const double a = fma(fma(fma(fma(P.fa[4], L, P.fa[3]), L, P.fa[2]), L, P.fa[1]), L, P.fa[0]);
+    const double b = fma(fma(fma(fma(P.fself[4], L, P.fself[3]), L, P.fself[2]), L, P.fself[1]), L, P.fself[0]);
+    cplx num = mk(fma(a, nl.x, b * cur.x), fma(a, nl.y, b * cur.y));
+#ifdef GOPF_KNOISE
+    if (P.noise_param >= 0) {
+        const TensorHessianParams& h = P.th[P.noise_param];
+        const cplx xi = knoise_value(h.K[0], gopf_bits_of(h.K[1]), gopf_bits_of(h.K[2]), make_kpoint(f0, f1, f2));
+        const double c = fma(fma(fma(fma(P.fnz[4], L, P.fnz[3]), L, P.fnz[2]), L, P.fnz[1]), L, P.fnz[0]);
+        num = mk(fma(c, xi.x, num.x), fma(c, xi.y, num.y));
+    }
+#endif
+    return mk(num.x * dk, num.y * dk);
 }
 
 }  // namespace gopf

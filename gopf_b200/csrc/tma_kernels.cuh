@@ -469,10 +469,13 @@ __global__ void __launch_bounds__(TmaRealCfg<N>::THREADS, 1)
         line_fft<N, Lay, SyncLine<T>, TwShared>(v, p, 0, buf, twsm);
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = mk(v[m].y * inv_n, v[m].x * inv_n);  // swap back, /N
-        if (derived_is_fast(D)) {
+        if (derived_is_monomial_fast(D)) {
             const int pw = D.ipower[0];
 #pragma unroll
             for (int m = 0; m < E; ++m) v[m] = derived_fast(pw, v[m]);
+        } else if (derived_is_poly_fast(D)) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = derived_poly(D, v[m]);
         } else {
             const size_t base = (size_t)(first + i * hop) * N;
 #pragma unroll

@@ -256,7 +256,7 @@ cudaError_t launch_fused_real_tma(const PassGeom& g, cplx* W, const DevDerived& 
 
 cudaError_t launch_fused_kspace_tma(const PassGeom& g, const cplx* W, cplx* Wout, cplx* S, const DevKProgram& P,
                                     const FreqTabs& ft, const cplx* tw, cudaStream_t s) {
-    if (!enabled("GOPF_TMA_KSPACE") || g.N < min_n() || !P.fast || g.peer.n > 0) return cudaErrorNotSupported;
+    if (!enabled("GOPF_TMA_KSPACE") || g.N < min_n() || P.fast != 1 || g.peer.n > 0) return cudaErrorNotSupported;
     switch (g.N) {
         case 512: return kspace_tma_n<512, 8>(g, W, Wout, S, P, ft, tw, s);
         case 1024: return kspace_tma_n<1024, 4>(g, W, Wout, S, P, ft, tw, s);

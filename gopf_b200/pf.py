@@ -926,6 +926,13 @@ class Solver:
         check(lib().gopf_solver_blocked_layout(self._h, ctypes.byref(s), ctypes.byref(a)))
         return s.value, bool(a.value)
 
+    def FusedForm(self):
+        """(form, derived_form) of the fused single-field kernels: form 0 interpreter / 1 polynomial / 2 tabulated;
+        derived_form 0 interpreter / 1 integer power / 2 real polynomial (include/gopf_cuda.h)."""
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        check(lib().gopf_solver_fused_form(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     @property
     def IsFused(self) -> bool:
         f = ctypes.c_int(0)

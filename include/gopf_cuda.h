@@ -288,6 +288,11 @@ int gopf_solver_get_time(gopf_solver* s, double* t);
  * while the device spectrum currently sits in that layout.  Diagnostics and tests; every entry point that
  * exposes the spectrum converts back first. */
 int gopf_solver_blocked_layout(gopf_solver* s, int* block_log, int* active);
+/* How the fused single-field kernels evaluate the model (diagnostics, tests).  *form: 0 = not fused or the term
+ * interpreter, 1 = polynomial form (every term a monomial with a real coefficient), 2 = tabulated form (polynomial
+ * explicit side, optional k-space white noise; implicit side and modal filter tabulated once per k-point).
+ * *derived_form: 0 = interpreter, 1 = integer power of the field, 2 = real polynomial of re(field). */
+int gopf_solver_fused_form(gopf_solver* s, int* form, int* derived_form);
 /* 1 when the single-field fused kernels are in use, 0 for the general path */
 int gopf_solver_is_fused(gopf_solver* s, int* fused);
 int gopf_solver_force_generic(gopf_solver* s, int on);

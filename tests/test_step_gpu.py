@@ -290,6 +290,32 @@ def test_pfc_pair_correlation_ideal_mixture_vs_oracle(lap):
     assert rel_l2(gf.Data, of.Data) <= TOL
 
 
+@pytest.mark.parametrize("dims", [[64, 64], [32, 32, 32]], ids=lambda d: "x".join(map(str, d)))
+@pytest.mark.parametrize("knoise", [False, True], ids=["nonoise", "knoise"])
+def test_pfc_tabulated_fused_form_vs_general_path_and_oracle(dims, knoise):
+    """cfg 5 on the fused kernels: implicit pair-correlation + ideal-mixture terms and the Vandeven filter tabulated
+    once per k-point, the ideal-mixture polynomial evaluated by Horner, white noise drawn at the k-point.  The
+    general path interprets the same program and draws the same Philox stream, so the two must agree to rounding;
+    without noise the oracle (pf/euler.go:16-47, pf/pairCorrelationTerm.go:37-51, pf/vandeven.go:30-40) pins both."""
+    from gopf_b200 import workloads
+    if knoise and not gpf.HasKSpaceNoise():
+        pytest.skip("library built without -DGOPF_KNOISE")
+    kw = dict(noise="device" if knoise else None, filt_order=5, kspace_noise=knoise)
+    m, f, s = workloads.build_pfc(gpf, gpf, dims, **kw)
+    assert s.IsFused and s.FusedForm() == (2, 2)
+    s.Solve(2, 5)
+    fused = f.Data.copy()
+    m2, f2, s2 = workloads.build_pfc(gpf, gpf, dims, **kw)
+    s2.ForceGeneric(True)
+    assert not s2.IsFused
+    s2.Solve(2, 5)
+    assert rel_l2(fused, f2.Data) <= 1e-11
+    if not knoise:
+        om, of, osolver = workloads.build_pfc(opf, oterms, dims, noise=None, filt_order=5)
+        osolver.Solve(2, 5)
+        assert rel_l2(fused, of.Data) <= TOL
+
+
 def test_pfc_with_vandeven_filter_and_prescribed_noise_vs_oracle():
     # cfg 5 additions (SURVEY 8d): white noise injected from a shared array, Vandeven(5)
     dims = [32, 32, 32]
