@@ -26,9 +26,14 @@ cudaError_t fused_kspace_n_tx(const PassGeom& g, const cplx* W, cplx* Wout, cplx
     const size_t smem = (size_t)N * TX * sizeof(cplx) * (LATE ? 1 : 2);
     const bool split = g.in.split_log < 31 || g.in.a_split_log < 31 || g.out.split_log < 31 || g.out.a_split_log < 31 ||
                        g.axis == GOPF_AXIS0_BY_PLANE;
-    if (split && g.peer.n > 0) return cudaErrorNotSupported;
-    auto kern = split ? k_fused_kspace<N, TX, false, LATE, true>
-                      : (g.peer.n > 0 ? k_fused_kspace<N, TX, true, LATE, false> : k_fused_kspace<N, TX, false, LATE, false>);
+    const bool tab = P.fast == 2;
+    if ((split || tab) && g.peer.n > 0) return cudaErrorNotSupported;
+    if (split && tab) return cudaErrorNotSupported;
+    if (tab && !LATE) return cudaErrorNotSupported;
+    auto kern = split ? k_fused_kspace<N, TX, false, LATE, GOPF_KMODE_SPLIT>
+                : tab ? k_fused_kspace<N, TX, false, true, GOPF_KMODE_TAB>
+                      : (g.peer.n > 0 ? k_fused_kspace<N, TX, true, LATE, GOPF_KMODE_PLAIN>
+                                      : k_fused_kspace<N, TX, false, LATE, GOPF_KMODE_PLAIN>);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -76,7 +81,7 @@ cudaError_t fused_kspace_n(const PassGeom& g, int tx_want, const cplx* W, cplx* 
     constexpr int T = PlanFor<N>::T;
     bool late = P.fast != 0;
     const int env_late = env_int("GOPF_KSPACE_LATE", -1);
-    if (env_late >= 0) late = P.fast && env_late != 0;
+    if (env_late >= 0) late = P.fast && (env_late != 0 || P.fast == 2);
     int tx;
     if (late) {
         tx = 16;

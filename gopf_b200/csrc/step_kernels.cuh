@@ -127,7 +127,13 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
 // SPLIT: W / S / Wout are addressed through the row maps of the launch (blocked k-space layout, solver.cu);
 //   otherwise they are plain [A][N][B] arrays and a row is one multiply away (the maps cost ~10 % more
 //   instructions, measured 5073 -> 4643 GB/s at 256^3, so the uniform case keeps its own instantiation).
-template <int N, int TX, bool PEER, bool LATE, bool SPLIT = false>
+// TAB: the tabulated single-field form (DevKProgram::fast == 2) instead of the polynomial one; its own
+//   instantiation because the noise generator and the extra polynomials cost the plain kernels registers
+//   (256-length kernel: 5073 -> 3730 GB/s when both forms shared one kernel).
+#define GOPF_KMODE_PLAIN 0
+#define GOPF_KMODE_SPLIT 1
+#define GOPF_KMODE_TAB 2
+template <int N, int TX, bool PEER, bool LATE, int MODE = GOPF_KMODE_PLAIN>
 __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* TX, (LATE ? 1 : 2) * N * TX * 16))
     k_fused_kspace(const __grid_constant__ PassGeom g, const cplx* W, cplx* Wout, cplx* __restrict__ S,
                    const __grid_constant__ DevKProgram P, FreqTabs ft, const cplx* __restrict__ tw) {
@@ -135,6 +141,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
     cplx* sm = reinterpret_cast<cplx*>(gopf_smem_raw);
     cplx* sS = LATE ? sm : sm + N * TX;
     constexpr int E = PlanFor<N>::E, T = PlanFor<N>::T;
+    constexpr bool SPLIT = MODE == GOPF_KMODE_SPLIT, TAB = MODE == GOPF_KMODE_TAB;
     typedef LayoutInterleaved<TX> Lay;
     const int tid = threadIdx.x;
     const int l = tid % TX, t = tid / TX;
@@ -215,16 +222,30 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
     cp_async_wait_all();
     if (LATE || P.fast) {  // LATE is launched for fast-form programs only (fused_launch.h)
         const double s2 = fa * fa + fb * fb;
-        if (P.fast == 2) {
-            // tabulated form: one real per k-point read next to the spectrum cell (8 more bytes per cell)
+        if (TAB) {
+            // Tabulated form: one real per k-point read next to the spectrum cell (8 more bytes per cell).  The
+            // noise term is folded into the staged spectrum cell first, in a ROLLED loop: sixteen inlined copies
+            // of the Philox / Box-Muller chain next to the register-resident line spill (532 bytes measured).
             const double* __restrict__ dtab = P.dtab;
+#ifdef GOPF_KNOISE
+            if (P.noise_param >= 0) {
+#pragma unroll 1
+                for (int m = 0; m < E; ++m) {
+                    const int j = t + T * m;
+                    const double fl = fline[j];
+                    const int pos = Lay::at(j, l);
+                    sS[pos] = (g.axis != 1) ? tab_self_and_noise(P, fma(fl, fl, s2), fa, fb, fl, sS[pos])
+                                            : tab_self_and_noise(P, fma(fl, fl, s2), fl, fa, fb, sS[pos]);
+                }
+            }
+#endif
+            const bool folded = P.noise_param >= 0;
 #pragma unroll
             for (int m = 0; m < E; ++m) {
                 const int j = t + T * m;
                 const double fl = fline[j];
                 const double dk = dtab[base + roff(j)];
-                const cplx cur = (g.axis != 1) ? tab_update(P, fma(fl, fl, s2), fa, fb, fl, dk, sS[Lay::at(j, l)], v[m])
-                                               : tab_update(P, fma(fl, fl, s2), fl, fa, fb, dk, sS[Lay::at(j, l)], v[m]);
+                const cplx cur = tab_update(P, fma(fl, fl, s2), dk, sS[Lay::at(j, l)], v[m], folded);
                 S[base + roff(j)] = cur;
                 v[m] = cswap(cur);
             }

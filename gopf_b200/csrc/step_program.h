@@ -494,22 +494,31 @@ __device__ __forceinline__ cplx fast_update(const DevKProgram& P, double frad2, 
     return mk(fma(a, nl.x, cur.x) * inv, fma(a, nl.y, cur.y) * inv);
 }
 
-// Tabulated form (DevKProgram::fast == 2).  `dk` = P.dtab at this k-point; kp only feeds the noise generator.
-__device__ __forceinline__ cplx tab_update(const DevKProgram& P, double frad2, double f0, double f1, double f2, double dk,
-                                           cplx cur, cplx nl) {
+// Tabulated form (DevKProgram::fast == 2):  c^ <- (b(L)*c^ + a(L)*g^ + n(L)*xi^(k)) * dk,  dk = P.dtab at this k-point.
+// tab_self_and_noise gives b*c^ + n*xi^ (the part a kernel folds into its staged spectrum cell in a rolled loop);
+// tab_update finishes: `folded` says cur already is that sum.
+__device__ __forceinline__ double tab_poly(const double (&c)[5], double L) {
+    return fma(fma(fma(fma(c[4], L, c[3]), L, c[2]), L, c[1]), L, c[0]);
+}
+__device__ __forceinline__ cplx tab_self_and_noise(const DevKProgram& P, double frad2, double f0, double f1, double f2, cplx cur) {
     const double L = -(4.0 * GOPF_PI * GOPF_PI) * frad2;
-    const double a = fma(fma(fma(fma(P.fa[4], L, P.fa[3]), L, P.fa[2]), L, P.fa[1]), L, P.fa[0]);
-    const double b = fma(fma(fma(fma(P.fself[4], L, P.fself[3]), L, P.fself[2]), L, P.fself[1]), L, P.fself[0]);
-    cplx num = mk(fma(a, nl.x, b * cur.x), fma(a, nl.y, b * cur.y));
+    const double b = tab_poly(P.fself, L);
+    cplx r = mk(b * cur.x, b * cur.y);
 #ifdef GOPF_KNOISE
     if (P.noise_param >= 0) {
         const TensorHessianParams& h = P.th[P.noise_param];
         const cplx xi = knoise_value(h.K[0], gopf_bits_of(h.K[1]), gopf_bits_of(h.K[2]), make_kpoint(f0, f1, f2));
-        const double c = fma(fma(fma(fma(P.fnz[4], L, P.fnz[3]), L, P.fnz[2]), L, P.fnz[1]), L, P.fnz[0]);
-        num = mk(fma(c, xi.x, num.x), fma(c, xi.y, num.y));
+        const double c = tab_poly(P.fnz, L);
+        r = mk(fma(c, xi.x, r.x), fma(c, xi.y, r.y));
     }
 #endif
-    return mk(num.x * dk, num.y * dk);
+    return r;
+}
+__device__ __forceinline__ cplx tab_update(const DevKProgram& P, double frad2, double dk, cplx cur, cplx nl, bool folded) {
+    const double L = -(4.0 * GOPF_PI * GOPF_PI) * frad2;
+    const double a = tab_poly(P.fa, L);
+    const double b = folded ? 1.0 : tab_poly(P.fself, L);
+    return mk(fma(a, nl.x, b * cur.x) * dk, fma(a, nl.y, b * cur.y) * dk);
 }
 
 }  // namespace gopf
