@@ -160,7 +160,12 @@ enum LoadKind {
     LK_SUM_SQUARES = 3,  // sum_d g_d[idx]^2 (squareGradientTerm.go:53-62, summed before the transform)
     LK_ELAST_H = 4,      // H(re phi[idx]), phi = g[0]                       (homoLinElast.go:53-57)
     LK_ELAST_R = 5,      // H'(phi) * in[idx] - aux * H(phi) * H'(phi)        (homoLinElast.go:64-97, by linearity)
-    LK_MUL_TABLE = 6     // rtab[idx] * in[idx]: tabulated real k-space multiplier (elastic.cuh M(k))
+    LK_MUL_TABLE = 6,    // rtab[idx] * in[idx]: tabulated real k-space multiplier (elastic.cuh M(k))
+    // LK_GRADIENT applied in the pass that runs ALONG the component's axis: the multiplier i 2 pi f_comp depends on
+    // the row of the line only (rtab = that axis' Freq table, FftPlan::freq_axis), and it commutes with the
+    // transforms along the other axes, so it need not sit in the first pass of the inverse transform.  No index
+    // decomposition per cell (LK_GRADIENT: two 64-bit divisions, 0.41 instead of 0.09 ms per 256^3 pass).
+    LK_GRADIENT_LINE = 7
 };
 
 struct PassIO {
@@ -245,12 +250,42 @@ __device__ __forceinline__ cplx pass_load_slow(const PassIO& io, size_t idx) {
 // Every other load kind evaluates its interpreter in a ROLLED loop whose results are staged
 // in the thread's own shared-memory cells (`sat(m)`), so the interpreter is instantiated once
 // and the register-resident line never spills.
-template <int E, class At, class SAt>
-__device__ __forceinline__ void pass_load_line(const PassIO& io, cplx (&v)[E], At at, cplx* sm, SAt sat) {
+// `row(m)` is the position of slot m along the line.
+template <int E, class At, class SAt, class Row>
+__device__ __forceinline__ void pass_load_line(const PassIO& io, cplx (&v)[E], At at, cplx* sm, SAt sat, Row row) {
     if (io.load_kind == LK_PLAIN) {
         const cplx* __restrict__ in = io.in;
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = in[at(m)];
+    } else if (io.load_kind == LK_GRADIENT_LINE) {
+        const cplx* __restrict__ in = io.in;
+        const double* __restrict__ ftab = io.rtab;
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = in[at(m)];
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            double fd = ftab[row(m)];
+            if (fabs(fd - 0.5) < 1e-10) fd = 0.0;  // squareGradientTerm.go:45-50
+            const double w = 2.0 * GOPF_PI * fd;
+            v[m] = mk(-v[m].y * w, v[m].x * w);
+        }
+    } else if (io.load_kind == LK_SUM_SQUARES) {
+        // two or three loads per cell, all in flight (the rolled loop below serialises them)
+        const cplx* __restrict__ g0 = io.g[0];
+        const cplx* __restrict__ g1 = io.g[1];
+        const cplx* __restrict__ g2 = io.g[2];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = g0[at(m)];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = v[m] * v[m];
+        for (int d = 1; d < io.dim; ++d) {
+            const cplx* __restrict__ gd = d == 1 ? g1 : g2;
+            cplx u[E];
+#pragma unroll
+            for (int m = 0; m < E; ++m) u[m] = gd[at(m)];
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] += u[m] * u[m];
+        }
     } else if (io.load_kind == LK_ELAST_H) {
         // simple arithmetic on one or two loads per cell: keep every load of the thread in flight
         // like the plain case (the rolled loop below serialises them: 1.3 vs 1.0 ms per 512^3 pass)
@@ -351,7 +386,8 @@ __device__ __forceinline__ void pass_strided_tile(const PassGeom& g, const PassI
         return obase + (size_t)(j >> g.out.split_log) * g.out.split_stride +
                (size_t)(j & g.out.split_mask) * g.out.row_stride;
     };
-    pass_load_line<E>(io, v, at_in, sm, [&](int m) -> int { return LayoutInterleaved<TX>::at(t + T * m, l); });
+    pass_load_line<E>(io, v, at_in, sm, [&](int m) -> int { return LayoutInterleaved<TX>::at(t + T * m, l); },
+                      [&](int m) -> int { return t + T * m; });
     if (!PEER && g.pf_tiles > 0 && io.load_kind == LK_PLAIN) {
         const long long tile2 = tile + g.pf_tiles;
         if (tile2 < g.A * tilesB) {
@@ -413,7 +449,8 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
     const size_t base = (size_t)line * N;
     cplx v[E];
     auto at = [&](int m) -> size_t { return base + p + T * m; };
-    pass_load_line<E>(io, v, at, sm, [&](int m) -> int { return LayoutPadded<N>::at(p + T * m, l); });
+    pass_load_line<E>(io, v, at, sm, [&](int m) -> int { return LayoutPadded<N>::at(p + T * m, l); },
+                      [&](int m) -> int { return p + T * m; });
     if (g.pf_tiles > 0 && io.load_kind == LK_PLAIN) {
         const long long line2 = line + g.pf_tiles * LINES;
         if (line2 < g.A) {

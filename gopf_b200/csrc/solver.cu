@@ -804,7 +804,13 @@ void Solver::squared_gradient_terms() {
                 if (plan_->extent(ax) <= 1) continue;
                 const PassGeom g = plan_->geom(ax);
                 PassIO io = plain_io(first ? S_.s[fi] : sg_tmp_[d], sg_tmp_[d], true, ax == last_axis ? inv_n : 1.0);
-                if (first) {
+                if (plan_->freq_axis_consistent()) {
+                    // the multiplier of component d sits in the pass along that component's axis (LK_GRADIENT_LINE)
+                    if (ax == plan_->axis_of_component(d)) {
+                        io.load_kind = LK_GRADIENT_LINE;
+                        io.rtab = plan_->freq_axis(ax);
+                    }
+                } else if (first) {
                     io.load_kind = LK_GRADIENT;
                     io.fg = plan_->freq_geom();
                     io.comp = d;

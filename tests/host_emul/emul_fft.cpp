@@ -101,6 +101,40 @@ int emul_fft_pass_derived(int n0, int n1, int n2, const void* derived, const dou
     return dispatch(g, io, 0);
 }
 
+// SquaredGradient loads (pf/squareGradientTerm.go:38-65).  emul_fft_pass_gradient: one inverse pass along `axis`
+// with the multiplier i 2 pi f_comp in its load -- per node from FFTWWrapper.Freq (LK_GRADIENT, line_table == NULL)
+// or from the axis' own Freq table (LK_GRADIENT_LINE; only valid when `axis` carries component `comp`).
+int emul_fft_pass_gradient(int n0, int n1, int n2, int axis, int rank, int d0, int d1, int d2, int comp,
+                           const double* line_table, const double* in, double* out, int tx) {
+    const PassGeom g = make_geom(n0, n1, n2, axis);
+    PassIO io = plain_io(reinterpret_cast<const cplx*>(in), reinterpret_cast<cplx*>(out), true, 1.0);
+    if (line_table) {
+        io.load_kind = LK_GRADIENT_LINE;
+        io.rtab = line_table;
+    } else {
+        io.load_kind = LK_GRADIENT;
+        io.fg.rank = rank;
+        io.fg.d0 = d0;
+        io.fg.d1 = d1;
+        io.fg.d2 = d2;
+        io.comp = comp;
+    }
+    return dispatch(g, io, tx);
+}
+
+// forward pass along `axis` of sum_d g_d^2 (LK_SUM_SQUARES)
+int emul_fft_pass_sum_squares(int n0, int n1, int n2, int axis, int dim, const double* g0, const double* g1, const double* g2,
+                              double* out, int tx) {
+    const PassGeom g = make_geom(n0, n1, n2, axis);
+    PassIO io = plain_io(reinterpret_cast<cplx*>(out), reinterpret_cast<cplx*>(out), false, 1.0);
+    io.load_kind = LK_SUM_SQUARES;
+    io.dim = dim;
+    io.g[0] = reinterpret_cast<const cplx*>(g0);
+    io.g[1] = reinterpret_cast<const cplx*>(g1);
+    io.g[2] = reinterpret_cast<const cplx*>(g2 ? g2 : g1);
+    return dispatch(g, io, tx);
+}
+
 int emul_fft_has_jit_loader(void) {
 #ifdef GOPF_JIT_LOAD_LINE
     return 1;

@@ -175,3 +175,65 @@ def test_forward_pass_with_the_generated_loader_on_the_host(name, tmp_path):
     # plain loads of the same unit are untouched by the hook
     x = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
     assert rel(_pass(dll, x, 2, False), np.fft.fft(x, axis=2)) < 1e-15
+
+
+# ---- SquaredGradient loads (pf/squareGradientTerm.go:38-65) ----------------------------------------------------------
+def _wrap_freq(n):
+    f = np.arange(n) / float(n)
+    f[f > 0.5] -= 1.0
+    return f
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 16), (8, 8, 8), (16, 16, 16)], ids=["2d", "3d-8", "3d-16"])
+def test_gradient_multiplier_in_the_pass_along_its_axis_is_the_per_node_form(fft, shape):
+    """The inverse transform of i 2 pi f_c u^ (Nyquist zeroed): the multiplier applied per node in the FIRST pass
+    (LK_GRADIENT, literal FFTWWrapper.Freq) against the multiplier from the axis table applied in the pass ALONG the
+    component's axis (LK_GRADIENT_LINE), and both against numpy."""
+    n0, n1, n2 = shape
+    rank = 2 if n0 == 1 else 3
+    dims = [n1, n2] if rank == 2 else [n0, n1, n2]
+    axes = [a for a in (0, 1, 2) if shape[a] > 1]
+    rng = np.random.default_rng(8)
+    u = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+    axis_of_component = {0: 1, 1: 2, 2: 0}  # FftPlan::axis_of_component
+    for comp in range(rank):
+        ax_c = axis_of_component[comp]
+        f = _wrap_freq(shape[ax_c])
+        f[np.abs(f - 0.5) < 1e-10] = 0.0
+        bshape = [1, 1, 1]
+        bshape[ax_c] = shape[ax_c]
+        want = np.fft.ifftn(u * (2j * np.pi * f.reshape(bshape)), axes=axes) * np.prod([shape[a] for a in axes])
+        results = []
+        for line in (False, True):
+            x = np.array(u, dtype=np.complex128, order="C")
+            for i, ax in enumerate(axes):
+                out = np.empty_like(x)
+                tx = 0 if ax == 2 else 2
+                if line and ax == ax_c:
+                    tab = np.ascontiguousarray(_wrap_freq(shape[ax]))
+                    rc = fft.emul_fft_pass_gradient(n0, n1, n2, ax, rank, 0, 0, 0, comp, tab.ctypes.data_as(DP), x.ctypes.data_as(DP),
+                                                    out.ctypes.data_as(DP), tx)
+                elif not line and i == 0:
+                    d = dims + [1] * (3 - len(dims))
+                    rc = fft.emul_fft_pass_gradient(n0, n1, n2, ax, rank, d[0], d[1], d[2], comp, None, x.ctypes.data_as(DP),
+                                                    out.ctypes.data_as(DP), tx)
+                else:
+                    rc = fft.emul_fft_pass(n0, n1, n2, ax, 1, ctypes.c_double(1.0), x.ctypes.data_as(DP), out.ctypes.data_as(DP), tx)
+                assert rc == 0, rc
+                x = out
+            results.append(x)
+        assert rel(results[0], want) < 1e-13, comp
+        assert rel(results[1], want) < 1e-13, comp
+        assert rel(results[1], results[0]) < 1e-13, comp
+
+
+@pytest.mark.parametrize("shape,dim", [((1, 6, 16), 2), ((4, 4, 16), 3)], ids=["2d", "3d"])
+def test_sum_of_squares_in_the_forward_pass_load(fft, shape, dim):
+    n0, n1, n2 = shape
+    rng = np.random.default_rng(9)
+    g = [np.ascontiguousarray(rng.normal(size=shape) + 1j * rng.normal(size=shape)) for _ in range(dim)]
+    out = np.zeros(shape, dtype=np.complex128)
+    rc = fft.emul_fft_pass_sum_squares(n0, n1, n2, 2, dim, g[0].ctypes.data_as(DP), g[1].ctypes.data_as(DP),
+                                       g[2].ctypes.data_as(DP) if dim > 2 else None, out.ctypes.data_as(DP), 0)
+    assert rc == 0, rc
+    assert rel(out, np.fft.fft(sum(x * x for x in g), axis=2)) < 1e-14
