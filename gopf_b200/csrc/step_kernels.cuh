@@ -20,6 +20,23 @@
 #include "step_program.h"
 
 namespace gopf {
+// Freq of position j = t + T*m along a line of power-of-two length N (every fused length is one): wrap(j / N) of
+// FFTWWrapper.Freq (pfutil/fftWrap.go:57-74) is exact in binary floating point, so it is computed instead of read
+// from the axis table -- one DADD per cell instead of a dependent global load (the k-space kernels sat on
+// long_scoreboard stalls for these: 5.2 per issue at 256^3, profiles/r1c_ncu_full_step.md).  For unrolled m the
+// wrap test is a compile-time constant except at j = N/2 + t.
+template <int N, int T>
+struct LineFreq {
+    double f0;
+    int t;
+    __device__ __forceinline__ explicit LineFreq(int t_) : f0((double)t_ * (1.0 / N)), t(t_) {}
+    __device__ __forceinline__ double at(int m) const {
+        const double f = f0 + (double)(T * m) * (1.0 / N);
+        const bool wrap = T * m > N / 2 ? true : (T * m + (T - 1) <= N / 2 ? false : t + T * m > N / 2);
+        return wrap ? f - 1.0 : f;
+    }
+};
+
 
 struct FreqTabs {
     const double* f0;  // per normalised FFTW axis 0, 1, 2: wrap(idx / n), fftWrap.go:57-74
@@ -196,22 +213,19 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
     for (int m = 0; m < E; ++m) v[m] = W[base + roff(t + T * m)];
 
     // Reference Freq components [row, col, depth] = FFTW axes [1, 2, 0] (fftWrap.go:42-74).
-    // Two of them are fixed along this thread's line, the third runs with j.
+    // Two of them are fixed along this thread's line, the third runs with j (LineFreq).
     double fa, fb;        // the two fixed components
-    const double* fline;  // table of the running component
     if (g.axis == 0) {
         fa = ft.f1[ft.off1 + (int)(b / g.n2)];
         fb = ft.f2[(int)(b % g.n2)];
-        fline = ft.f0;
     } else if (g.axis == GOPF_AXIS0_BY_PLANE) {  // lines along axis 0, slab = axis-1 index, column = axis-2 index
         fa = ft.f1[ft.off1 + (int)a];
         fb = ft.f2[(int)b];
-        fline = ft.f0;
     } else {  // axis 1
         fa = ft.f2[(int)b];
         fb = ft.rank > 2 ? ft.f0[(int)a] : 0.0;
-        fline = ft.f1;
     }
+    const LineFreq<N, T> lf(t);
     if (LATE) {
         line_fft_head<N, Lay, SyncCta>(v, t, l, sm, tw);
         prefetch_spectrum();  // the exchange tile is free from here until the next transform's first exchange
@@ -229,13 +243,15 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
             const double* __restrict__ dtab = P.dtab;
 #ifdef GOPF_KNOISE
             if (P.noise_param >= 0) {
+                const KnComp ca = knoise_comp(fa), cb = knoise_comp(fb);  // fixed along the line
 #pragma unroll 1
                 for (int m = 0; m < E; ++m) {
                     const int j = t + T * m;
-                    const double fl = fline[j];
+                    const double fl = lf.at(m);
+                    const KnComp cl = knoise_comp_index<N>(j > N / 2 ? j - N : j);
                     const int pos = Lay::at(j, l);
-                    sS[pos] = (g.axis != 1) ? tab_self_and_noise(P, fma(fl, fl, s2), fa, fb, fl, sS[pos])
-                                            : tab_self_and_noise(P, fma(fl, fl, s2), fl, fa, fb, sS[pos]);
+                    sS[pos] = (g.axis != 1) ? tab_self_and_noise(P, fma(fl, fl, s2), ca, cb, cl, sS[pos])
+                                            : tab_self_and_noise(P, fma(fl, fl, s2), cl, ca, cb, sS[pos]);
                 }
             }
 #endif
@@ -243,7 +259,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
 #pragma unroll
             for (int m = 0; m < E; ++m) {
                 const int j = t + T * m;
-                const double fl = fline[j];
+                const double fl = lf.at(m);
                 const double dk = dtab[base + roff(j)];
                 const cplx cur = tab_update(P, fma(fl, fl, s2), dk, sS[Lay::at(j, l)], v[m], folded);
                 S[base + roff(j)] = cur;
@@ -253,7 +269,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
 #pragma unroll
             for (int m = 0; m < E; ++m) {
                 const int j = t + T * m;
-                const double fl = fline[j];
+                const double fl = lf.at(m);
                 const cplx cur = fast_update(P, fma(fl, fl, s2), sS[Lay::at(j, l)], v[m]);
                 S[base + roff(j)] = cur;
                 v[m] = cswap(cur);
@@ -268,7 +284,7 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
         for (int m = 0; m < E; ++m) {
             const int j = t + T * m;
             const int pos = Lay::at(j, l);
-            const double fl = fline[j];
+            const double fl = lf.at(m);
             const KPoint kp = (g.axis != 1) ? make_kpoint(fa, fb, fl) : make_kpoint(fl, fa, fb);  // row, col, depth
             const cplx old = sS[pos], nl = sm[pos];
             const cplx cur = euler_update(P, 0, kp, old, [&](int bi) -> cplx { return bi == 0 ? old : nl; });

@@ -379,29 +379,50 @@ __device__ __forceinline__ double philox_normal(unsigned long long seed, unsigne
 // positive), so the generic, fused and slab-sharded kernels produce the same field.  The reference's
 // stream (Go math/rand) is unpinned: parity is statistical, as for the real-space generator.
 // amp = s * sqrt(N).
-__device__ __forceinline__ cplx knoise_value(double amp, unsigned long long seed, unsigned long long step, const KPoint& kp) {
-    int sgn = 0;
-    for (int c = 0; c < 3; ++c) {
-        const double f = kp.f[c];
-        const int s = (f == 0.0 || fabs(f) == 0.5) ? 0 : (f > 0.0 ? 1 : -1);
-        if (sgn == 0) sgn = s;
-    }
-    // canonical components on a 2^-30 lattice (f = i/n to 1 ulp on either member; n <= 2^20)
+// One frequency component as the generator sees it: its sign class and its coordinate on a 2^-30 lattice for
+// either orientation of the pair (f = i/n to 1 ulp on either member; n <= 2^20).  Depends on one component only,
+// so the fused kernels build the two line-constant components once per line and the running one from the integer
+// position (knoise_comp_index; bit-identical for power-of-two extents).
+struct KnComp {
+    int s;              // 0: the component is its own negative (0 or +-1/2); +-1: its sign
+    uint32_t pos, neg;  // lattice coordinate when the pair's canonical member is k / -k
+};
+__device__ __forceinline__ KnComp knoise_comp(double f) {
+    KnComp c;
+    const bool nyq = fabs(f) == 0.5;
+    c.s = (f == 0.0 || nyq) ? 0 : (f > 0.0 ? 1 : -1);
+    const double g = nyq ? 0.5 : f;
+    c.pos = (uint32_t)(long long)(rint(g * 1073741824.0) + 1073741824.0);
+    c.neg = nyq ? c.pos : (uint32_t)(long long)(rint(-g * 1073741824.0) + 1073741824.0);
+    return c;
+}
+// component i/N, i in (-N/2, N/2], N a power of two <= 2^20: i * 2^30 / N is an integer
+template <int N>
+__device__ __forceinline__ KnComp knoise_comp_index(int i) {
+    KnComp c;
+    const bool nyq = i == N / 2 || i == -(N / 2);
+    c.s = (i == 0 || nyq) ? 0 : (i > 0 ? 1 : -1);
+    const int g = (nyq ? N / 2 : i) * (int)(1073741824LL / N);
+    c.pos = (uint32_t)(1073741824 + g);
+    c.neg = nyq ? c.pos : (uint32_t)(1073741824 - g);
+    return c;
+}
+// the draw at the k-point whose components (reference order row, col, depth) are x0, x1, x2
+__device__ __forceinline__ cplx knoise_draw(double amp, unsigned long long seed, unsigned long long step, const KnComp& x0,
+                                            const KnComp& x1, const KnComp& x2) {
+    const int sgn = x0.s != 0 ? x0.s : (x1.s != 0 ? x1.s : x2.s);  // first component that is neither 0 nor +-1/2
     uint32_t c[4], k[2];
-    for (int a = 0; a < 3; ++a) {
-        const double f = kp.f[a];
-        const double g = fabs(f) == 0.5 ? 0.5 : (sgn < 0 ? -f : f);
-        c[a] = (uint32_t)(long long)(rint(g * 1073741824.0) + 1073741824.0);
-    }
+    c[0] = sgn < 0 ? x0.neg : x0.pos;
+    c[1] = sgn < 0 ? x1.neg : x1.pos;
+    c[2] = sgn < 0 ? x2.neg : x2.pos;
     c[3] = (uint32_t)step;
     k[0] = (uint32_t)seed;
     k[1] = (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32);
     for (int r = 0; r < 10; ++r) philox_round(c, k);
     // Box-Muller in single precision on the special-function unit: the draw is a random variate, so 2^-21
     // relative accuracy is statistically invisible, and the double-precision log / sincospi cost more fp64
-    // instructions than both FFTs of the k-space kernel together (512^3 PFC step: 4.37 ms of 6.73 in this
-    // kernel, fp64 pipe bound).  u1 = (c0 + 1/2) 2^-32 in (0, 1]: radius up to 6.7 sigma; angle = c2 as a
-    // signed 32-bit fraction of pi in [-pi, pi).
+    // instructions than both FFTs of the k-space kernel together.  u1 = (c0 + 1/2) 2^-32 in (0, 1]: radius up
+    // to 6.7 sigma; angle = c2 as a signed 32-bit fraction of pi in [-pi, pi).
     const float u1 = ((float)c[0] + 0.5f) * 2.3283064365386963e-10f;
     const float ang = (float)(int)c[2] * 1.4629180792671596e-9f;  // pi * 2^-31
     float snf, csf;
@@ -411,6 +432,9 @@ __device__ __forceinline__ cplx knoise_value(double amp, unsigned long long seed
     if (sgn == 0) return mk(amp * r * cs, 0.0);
     const double h = amp * 0.70710678118654752440 * r;
     return mk(h * cs, sgn > 0 ? h * sn : -(h * sn));
+}
+__device__ __forceinline__ cplx knoise_value(double amp, unsigned long long seed, unsigned long long step, const KPoint& kp) {
+    return knoise_draw(amp, seed, step, knoise_comp(kp.f[0]), knoise_comp(kp.f[1]), knoise_comp(kp.f[2]));
 }
 #endif
 
@@ -516,20 +540,17 @@ __device__ __forceinline__ cplx fast_update(const DevKProgram& P, double frad2, 
 __device__ __forceinline__ double tab_poly(const double (&c)[5], double L) {
     return fma(fma(fma(fma(c[4], L, c[3]), L, c[2]), L, c[1]), L, c[0]);
 }
-__device__ __forceinline__ cplx tab_self_and_noise(const DevKProgram& P, double frad2, double f0, double f1, double f2, cplx cur) {
+#ifdef GOPF_KNOISE
+__device__ __forceinline__ cplx tab_self_and_noise(const DevKProgram& P, double frad2, const KnComp& x0, const KnComp& x1,
+                                                   const KnComp& x2, cplx cur) {
     const double L = -(4.0 * GOPF_PI * GOPF_PI) * frad2;
     const double b = tab_poly(P.fself, L);
-    cplx r = mk(b * cur.x, b * cur.y);
-#ifdef GOPF_KNOISE
-    if (P.noise_param >= 0) {
-        const TensorHessianParams& h = P.th[P.noise_param];
-        const cplx xi = knoise_value(h.K[0], gopf_bits_of(h.K[1]), gopf_bits_of(h.K[2]), make_kpoint(f0, f1, f2));
-        const double c = tab_poly(P.fnz, L);
-        r = mk(fma(c, xi.x, r.x), fma(c, xi.y, r.y));
-    }
-#endif
-    return r;
+    const TensorHessianParams& h = P.th[P.noise_param];
+    const cplx xi = knoise_draw(h.K[0], gopf_bits_of(h.K[1]), gopf_bits_of(h.K[2]), x0, x1, x2);
+    const double c = tab_poly(P.fnz, L);
+    return mk(fma(c, xi.x, b * cur.x), fma(c, xi.y, b * cur.y));
 }
+#endif
 __device__ __forceinline__ cplx tab_update(const DevKProgram& P, double frad2, double dk, cplx cur, cplx nl, bool folded) {
     const double L = -(4.0 * GOPF_PI * GOPF_PI) * frad2;
     const double a = tab_poly(P.fa, L);

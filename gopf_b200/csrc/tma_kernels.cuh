@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
             tma::mbar_arrive_expect_tx(bar, (unsigned)C::tile_bytes());
             for (int r = 0; r < N; r += rin.box_rows) tma_load_rows(buffer(s) + (size_t)r * TX, &tw_in, rin, c0, r, (int)a, bar);
             // the tile's spectrum rows into L2 while it waits its turn and runs its forward FFT
-            for (int r = 0; r < N; r += rs.box_rows) tma_prefetch_rows(&ts, rs, c0, r, (int)a);
+            if (g.pf_tiles == 0)
+                for (int r = 0; r < N; r += rs.box_rows) tma_prefetch_rows(&ts, rs, c0, r, (int)a);
         } else {
             ctl->tile[s] = -1;
             tma::mbar_arrive(bar);
@@ -314,6 +315,8 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
     if (tid == 0)
         for (int k = 0; k < STAGES; ++k) issue_load(k, (long long)atomicAdd(next_tile, 1u));
 
+    const LineFreq<N, T> lf(t);
+    const int spf = (int)g.pf_tiles;  // when the spectrum tile is asked into L2: 0 at load issue, 1 at compute start, 2 never
     unsigned use = 0;  // tiles this group has processed (phase of its sfull barrier)
     for (long long k = grp;; k += C::GROUPS, ++use) {
         const int s = (int)(k % STAGES);
@@ -331,6 +334,8 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
         const long long bcol = tile_col(tile, &a);
         const long long b = bcol + l;
         const int c0 = (int)(2 * bcol);
+        if (spf == 1 && gtid == 0)
+            for (int r = 0; r < N; r += rs.box_rows) tma_prefetch_rows(&ts, rs, c0, r, (int)a);
         cplx v[E];
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = buf[C::sw(t + T * m, l)];
@@ -343,26 +348,22 @@ __global__ void __launch_bounds__(TmaCfg<N, TX>::THREADS, 1)
         line_fft_tail<N, Lay, SyncLine<T>, TwShared>(v, t, l, buf, twsm);  // ... under the register-only last stage
         // Reference Freq components [row, col, depth] = FFTW axes [1, 2, 0] (fftWrap.go:42-74).
         double fa, fb;
-        const double* fline;
         if (g.axis == 0) {
             fa = ft.f1[ft.off1 + (int)(b / g.n2)];
             fb = ft.f2[(int)(b % g.n2)];
-            fline = ft.f0;
         } else if (g.axis == GOPF_AXIS0_BY_PLANE) {
             fa = ft.f1[ft.off1 + (int)a];
             fb = ft.f2[(int)b];
-            fline = ft.f0;
         } else {  // axis 1
             fa = ft.f2[(int)b];
             fb = ft.rank > 2 ? ft.f0[(int)a] : 0.0;
-            fline = ft.f1;
         }
         const double s2 = fa * fa + fb * fb;
         tma::mbar_wait(sfull, use & 1u, 3);
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int j = t + T * m;
-            const double fl = fline[j];
+            const double fl = lf.at(m);
             const int pos = C::sw(j, l);
             const cplx cur = fast_update(P, fma(fl, fl, s2), buf[pos], v[m]);
             buf[pos] = cur;  // each thread rewrites exactly the cells it read

@@ -221,7 +221,9 @@ cudaError_t kspace_tma_n(const PassGeom& g, const cplx* W, cplx* Wout, cplx* S, 
     unsigned* ctr = nullptr;
     e = fresh_counter(s, &ctr);
     if (e != cudaSuccess) return e;
-    kern<<<grid, C::THREADS, smem, s>>>(win.map, wout.map, sp.map, g, win.rows, wout.rows, sp.rows, P, ft, tw, ctr);
+    PassGeom gk = g;
+    gk.pf_tiles = env_flag("GOPF_TMA_SPF", 2);  // spectrum-tile L2 prefetch: 0 at load issue, 1 at compute start, 2 never (1024^3: 16.15 / 15.03 / 14.94 ms)
+    kern<<<grid, C::THREADS, smem, s>>>(win.map, wout.map, sp.map, gk, win.rows, wout.rows, sp.rows, P, ft, tw, ctr);
     g_tma_launches++;
     return cudaGetLastError();
 }

@@ -13,7 +13,7 @@ r = d["roofline"]
 print(f"headline {d['config']['workload']}: {d['ms_per_step']:.3f} ms/step {d['value'] / 1e9:.2f} G/s  clocks {d['clocks']['sm_mhz']} {d['clocks']['reasons']}")
 print(f"  roofline {r['kernel']} {r['achieved']:.0f} GB/s frac {r['frac']:.3f} traffic {r.get('traffic')}; step model frac {r['step_model']['frac']:.3f}")
 print("  " + kern(r))
-print(f"  e2e {d['e2e']['ms_per_step']:.1f} ms/step {d['e2e']['value'] / 1e9:.3f} G/s; cpu {d.get('cpu_baseline', {}).get('value', 0) / 1e6:.2f} M/s; parity {d.get('parity', {}).get('rel_l2')}")
+print(f"  e2e {d['e2e'].get('ms_per_step', 0):.1f} ms/step {d['e2e']['value'] / 1e9:.3f} G/s; cpu {d.get('cpu_baseline', {}).get('value', 0) / 1e6:.2f} M/s; parity {d.get('parity', {}).get('rel_l2')}")
 if "cfg2" in d:
     c = d["cfg2"]
     print(f"cfg2: {c['ms_per_step']:.4f} ms/step {c['value'] / 1e9:.2f} G/s frac {c['roofline']['frac']:.3f}; {kern(c['roofline'])}")
