@@ -371,6 +371,10 @@ void Solver::implicit_euler_step() {
         GOPF_CUDA(cudaGetLastError());
         launches_ += 2;
     }
+    if (!ie_converged_) {  // the update of the last iteration may have converged: look once more before reporting
+        ie_residual(x, fx);
+        ie_converged_ = ie_max_abs(fx) < nk_.tol;
+    }
     // vec2fields(res.X): the persistent spectrum of the new fields
     for (int i = 0; i < F; ++i) {
         k_real_to_cplx<<<ie_grid(n), 256, 0, s>>>(x + (size_t)i * n, S_.s[i], n);

@@ -27,7 +27,7 @@ struct NewtonKrylovOptions {
     int maxiter = 50;
     double step_size = 1e-3;
     double tol = 1e-7;
-    int stencil = 2;       // central-difference points for J v: 2, 4 or 6 (the reference default is 6)
+    int stencil = 6;       // central-difference points for J v: 2, 4 or 6 (DefaultNonLinSolver: 6, implicitEuler.go:226)
     int restart = 30;      // GMRES restart length
     double inner_tol = 1e-4;
     int max_restarts = 4;

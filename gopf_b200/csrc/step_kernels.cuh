@@ -208,6 +208,14 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* 
         cp_async_commit();
     };
     if (!LATE) prefetch_spectrum();
+    if (TAB) {
+        // the tabulated factors of this tile into L2 now: they are read after both the forward transform and the
+        // noise loop, and a DRAM round trip there is exposed (ncu, 512^3 cfg 5: a third of the kernel's stall
+        // samples sat on the multiplies that consume them)
+        const double* __restrict__ dtab = P.dtab;
+#pragma unroll 4
+        for (int m = 0; m < E; ++m) prefetch_l2(dtab + base + roff(t + T * m));
+    }
     cplx v[E];
 #pragma unroll
     for (int m = 0; m < E; ++m) v[m] = W[base + roff(t + T * m)];

@@ -67,6 +67,14 @@ class Field:
             self.Data = data
         self.Name = name
 
+    # The C model keeps the host pointer of the array registered by Model.AddField for its lifetime (pf.Field.Data
+    # is a Go slice header there).  Rebinding Data afterwards would leave the library with a dangling pointer, so
+    # it is refused: write into the array (f.Data[:] = ...) instead.
+    def __setattr__(self, key, value):
+        if key == "Data" and getattr(self, "_registered", False):
+            raise GopfError("Field.Data is registered with a model: assign into it (f.Data[:] = ...) instead of rebinding it")
+        object.__setattr__(self, key, value)
+
     def Get(self, i):
         return self.Data[i]
 
@@ -447,6 +455,7 @@ class Model:
         self.Equations: List[str] = []
         self._solvers = []
         self._sources: List["Source"] = []  # keeps the ctypes callbacks alive
+        self._host_buffers: list = []       # registered Field.Data arrays (+ pin owners): the C model holds their pointers
         self.ImplicitTerms, self.ExplicitTerms, self.MixedTerms = {}, {}, {}  # model.go:120-123
 
     def AddField(self, f: Field):
@@ -454,6 +463,9 @@ class Model:
                                          f.Data.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
         self.Fields.append(f)
         self.Bricks[f.Name] = f
+        # the registered buffer (and the owner of a pinned allocation) must outlive the C model
+        self._host_buffers.append((f.Data, getattr(f, "_pin", None)))
+        object.__setattr__(f, "_registered", True)
 
     def AddScalar(self, s: Scalar):
         check(lib().gopf_model_add_scalar(self._h, _s(s.Name), ctypes.c_double(s.Value.real), ctypes.c_double(s.Value.imag)))
@@ -650,7 +662,7 @@ class NewtonKrylov:
     """Settings of the non-linear solve inside ImplicitEuler (nonlin.NewtonKrylov in the reference,
     pf/implicitEuler.go:221-229)."""
 
-    def __init__(self, Maxiter=50, StepSize=1e-3, Tol=1e-7, Stencil=2, Restart=30, InnerTol=1e-4, MaxRestarts=4):
+    def __init__(self, Maxiter=50, StepSize=1e-3, Tol=1e-7, Stencil=6, Restart=30, InnerTol=1e-4, MaxRestarts=4):
         self.Maxiter, self.StepSize, self.Tol, self.Stencil = Maxiter, StepSize, Tol, Stencil
         self.Restart, self.InnerTol, self.MaxRestarts = Restart, InnerTol, MaxRestarts
 

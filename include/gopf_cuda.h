@@ -261,8 +261,8 @@ int gopf_solver_set_stepper(gopf_solver* s, const char* name);
  * gopf_solver_set_stepper(s, "implicit_euler").  The non-linear solve is a Jacobian-free
  * Newton-Krylov iteration on the device (gopf_b200/csrc/implicit_euler.cu); the reference
  * delegates it to third-party modules that are not in its tree, so trajectories agree with it to
- * the solver tolerance only.  Defaults = DefaultNonLinSolver (implicitEuler.go:221-229)
- * except Stencil (2 instead of 6 residual evaluations per Jacobian-vector product). */
+ * the solver tolerance only.  Defaults = DefaultNonLinSolver (implicitEuler.go:221-229:
+ * Maxiter 50, StepSize 1e-3, Tol 1e-7, Stencil 6); GMRES restarts after `restart` vectors. */
 int gopf_solver_set_newton_krylov(gopf_solver* s, int maxiter, double step_size, double tol, int stencil, int restart,
                                   double inner_tol, int max_restarts);
 /* after a step: res.Converged of the last solve (the reference logs a warning when false,

@@ -753,7 +753,7 @@ class NewtonKrylov:
     Two converged runs agree to the solver tolerance, not to 1e-10.
     """
 
-    def __init__(self, Maxiter=50, StepSize=1e-3, Tol=1e-7, Stencil=2, Restart=30, InnerTol=1e-4, MaxRestarts=4):
+    def __init__(self, Maxiter=50, StepSize=1e-3, Tol=1e-7, Stencil=6, Restart=30, InnerTol=1e-4, MaxRestarts=4):
         self.Maxiter, self.StepSize, self.Tol, self.Stencil = Maxiter, StepSize, Tol, Stencil
         self.Restart, self.InnerTol, self.MaxRestarts = Restart, InnerTol, MaxRestarts
         self.residual_evaluations = 0

@@ -141,3 +141,20 @@ def test_hessian_with_model_term_counts():
     m.Init()
     rhs = m.RHS
     assert len(rhs[0].Terms) == 0 and len(rhs[0].Denum) == 1
+
+
+def test_registered_field_data_cannot_be_rebound():
+    """The C model holds the host pointer of a registered field (pf.Field.Data, pf/model.go:16-22): rebinding the
+    Python attribute would leave it dangling, so it is refused; writing into the array is the supported way."""
+    import numpy as np
+    import pytest
+    from gopf_b200 import pf as gpf
+    from gopf_b200._lib import GopfError
+    f = gpf.NewField("c", 16, np.zeros(16, dtype=np.complex128))
+    f.Data = np.ones(16, dtype=np.complex128)  # free to rebind before registration
+    m = gpf.NewModel()
+    m.AddField(f)
+    with pytest.raises(GopfError):
+        f.Data = np.zeros(16, dtype=np.complex128)
+    f.Data[:] = 2.0
+    assert m._host_buffers[0][0] is f.Data
