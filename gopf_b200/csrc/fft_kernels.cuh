@@ -320,6 +320,15 @@ __device__ __forceinline__ void pass_load_line(const PassIO& io, cplx (&v)[E], A
         for (int m = 0; m < E; ++m) w[m] = tab[at(m)];
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = mk(v[m].x * w[m], v[m].y * w[m]);
+    } else if (io.load_kind == LK_DERIVED && derived_is_monomial_fast(io.D)) {
+        // field^p, p a small integer (pf/model.go:237-241): square-and-multiply on register-resident cells, all
+        // loads in flight (the interpreter loop below ran this pass at 2.1 TB/s, 256^3)
+        const cplx* __restrict__ in = io.R.r[io.D.field[0]];
+        const int pw = io.D.ipower[0];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = in[at(m)];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = derived_fast(pw, v[m]);
 #ifdef GOPF_JIT_LOAD_LINE
     } else if (io.load_kind == LK_DERIVED) {
         // run-time specialisation (jit.cu): the registered function as straight-line code on

@@ -304,7 +304,7 @@ int gopf_solver_force_generic(gopf_solver* s, int on);
 int gopf_solver_set_jit(gopf_solver* s, int on);
 /* With the specialisation on, also compile each registered function into the load of the first
  * forward pass of its transform (a copy of the library's contiguous-axis pass kernel with a generated
- * loader): no pointwise kernel, no round trip of the function values.  Off unless GOPF_JIT_INPASS=1. */
+ * loader): no pointwise kernel, no round trip of the function values.  On by default; GOPF_JIT_INPASS=0 switches it off. */
 int gopf_solver_set_jit_inpass(gopf_solver* s, int on);
 /* number of derived fields currently evaluated by compiled kernels */
 int gopf_solver_jit_kernels(gopf_solver* s, int* count);

@@ -72,8 +72,6 @@ def test_specialised_and_interpreted_kernels_agree_step_by_step():
     assert abs(out[1][2] - out[0][2]) <= 1e-9
 
 
-@pytest.mark.skipif(os.environ.get("GOPF_TEST_INPASS") != "1",
-                    reason="the in-pass specialisation has not run on a GPU yet (scripts/round2_gpu_checks.sh inpass)")
 @pytest.mark.parametrize("dims", [[32, 32], [16, 16, 16], [64, 64, 64]], ids=lambda d: "x".join(map(str, d)))
 def test_precipitate_functions_compiled_into_the_forward_pass(dims):
     out = []
