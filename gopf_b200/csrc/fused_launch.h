@@ -23,8 +23,8 @@ cudaError_t fused_kspace_n_tx(const PassGeom& g, const cplx* W, cplx* Wout, cplx
                               const FreqTabs& ft, const cplx* tw, cudaStream_t s) {
     constexpr int T = PlanFor<N>::T;
     const bool tab = P.fast == 2;
-    // exchange tile, plus the spectrum tile (early prefetch) or the parking tile of the tabulated form's noise loop
-    const size_t smem = (size_t)N * TX * sizeof(cplx) * ((LATE && !tab) ? 1 : 2);
+    // exchange tile, plus (early prefetch only) the spectrum tile
+    const size_t smem = (size_t)N * TX * sizeof(cplx) * (LATE ? 1 : 2);
     const bool split = g.in.split_log < 31 || g.in.a_split_log < 31 || g.out.split_log < 31 || g.out.a_split_log < 31 ||
                        g.axis == GOPF_AXIS0_BY_PLANE;
     if ((split || tab) && g.peer.n > 0) return cudaErrorNotSupported;
@@ -84,10 +84,9 @@ cudaError_t fused_kspace_n(const PassGeom& g, int tx_want, const cplx* W, cplx* 
     if (env_late >= 0) late = P.fast && (env_late != 0 || P.fast == 2);
     int tx;
     if (late) {
-        const size_t tiles_per_cta = P.fast == 2 ? 2 : 1;  // the tabulated form parks the line in a second tile
         tx = 16;
-        while (tx > (P.fast == 2 ? 4 : 8) && line_bytes * tx * tiles_per_cta > 64 * 1024) tx >>= 1;
-        while (tx > 2 && (line_bytes * tx * tiles_per_cta > 128 * 1024 || T * tx > 1024 || (g.bw % tx) != 0)) tx >>= 1;
+        while (tx > 8 && line_bytes * tx > 64 * 1024) tx >>= 1;
+        while (tx > 2 && (line_bytes * tx > 128 * 1024 || T * tx > 1024 || (g.bw % tx) != 0)) tx >>= 1;
     } else {
         tx = pick_tx(N, g.bcount, tx_want);
         while (tx > 2 && (line_bytes * tx * 2 > 128 * 1024 || (g.bw % tx) != 0)) tx >>= 1;

@@ -426,11 +426,7 @@ void Solver::rebuild_program() {
         throw Error("solver: k-space noise needs a 2-D or cubic 3-D grid");
     fused_prog_ = prog_;
     if (fused_) {
-        // the tabulated form's k-space kernel holds two shared-memory tiles of at least two lines of the slowest
-        // active axis (step_kernels.cuh): 4096-cell lines do not fit and keep the term interpreter
-        const int slowest = plan_->n0 > 1 ? plan_->n0 : plan_->n1;
-        finalize_single_field_program(&fused_prog_, (int)m_->fields.size(),
-                                      env_int("GOPF_FUSED_TABLE", 1) != 0 && slowest <= 2048);
+        finalize_single_field_program(&fused_prog_, (int)m_->fields.size(), env_int("GOPF_FUSED_TABLE", 1) != 0);
         if (fused_prog_.fast == 2) {
             // tabulated form: filter / (1 - dt*den) for every k-point, in the spectrum's (row-major) order
             const long long n = (long long)plan_->N;

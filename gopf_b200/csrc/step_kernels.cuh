@@ -151,8 +151,7 @@ __global__ void __launch_bounds__(ContigCfg<N>::T* ContigCfg<N>::LINES, GOPF_MIN
 #define GOPF_KMODE_SPLIT 1
 #define GOPF_KMODE_TAB 2
 template <int N, int TX, bool PEER, bool LATE, int MODE = GOPF_KMODE_PLAIN>
-__global__ void __launch_bounds__(PlanFor<N>::T* TX,
-                                  GOPF_MINB_K(PlanFor<N>::T* TX, ((LATE && MODE != GOPF_KMODE_TAB) ? 1 : 2) * N * TX * 16))
+__global__ void __launch_bounds__(PlanFor<N>::T* TX, GOPF_MINB_K(PlanFor<N>::T* TX, (LATE ? 1 : 2) * N * TX * 16))
     k_fused_kspace(const __grid_constant__ PassGeom g, const cplx* W, cplx* Wout, cplx* __restrict__ S,
                    const __grid_constant__ DevKProgram P, FreqTabs ft, const cplx* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char gopf_smem_raw[];
@@ -253,12 +252,6 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX,
 #ifdef GOPF_KNOISE
             if (P.noise_param >= 0) {
                 const KnComp ca = knoise_comp(fa), cb = knoise_comp(fb);  // fixed along the line
-                // The transformed line waits in the kernel's second shared-memory tile while the generator runs: left
-                // in registers it is spilled (200 bytes per thread, 100 KB per SM next to 128 KB of tiles: the spill
-                // set fell out of L1 and 83 % of the update loop's stall samples were reloads, ncu 512^3 cfg 5).
-                cplx* sV = sm + N * TX;
-#pragma unroll
-                for (int m = 0; m < E; ++m) sV[Lay::at(t + T * m, l)] = v[m];
 #pragma unroll 1
                 for (int m = 0; m < E; ++m) {
                     const int j = t + T * m;
@@ -268,8 +261,6 @@ __global__ void __launch_bounds__(PlanFor<N>::T* TX,
                     sS[pos] = (g.axis != 1) ? tab_self_and_noise(P, fma(fl, fl, s2), ca, cb, cl, sS[pos])
                                             : tab_self_and_noise(P, fma(fl, fl, s2), cl, ca, cb, sS[pos]);
                 }
-#pragma unroll
-                for (int m = 0; m < E; ++m) v[m] = sV[Lay::at(t + T * m, l)];  // own cells: no barrier
             }
 #endif
             const bool folded = P.noise_param >= 0;
