@@ -74,6 +74,29 @@ class FFTWWrapper:
                                          out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
         return out
 
+    # ---- gradient-based catalog terms at operator level (include/gopf_cuda.h) ----------------------------------
+    def GradientCalculate(self, indata: np.ndarray, out: np.ndarray, comp: int, keep_nyquist: bool = False) -> np.ndarray:
+        """GradientCalculator{FT: self, Comp, KeepNyquist}.Calculate(indata, out) (pf/gradientCalculator.go:19-31)."""
+        check(lib().gopf_gradient_calculate(self._h, _c128_ptr(indata), _c128_ptr(out), int(comp), 1 if keep_nyquist else 0))
+        return out
+
+    def AdvectionConstruct(self, field: np.ndarray, velocity, out: np.ndarray, transformed: bool = False) -> np.ndarray:
+        """-sum_d v_d GRAD_d(field): Advection.PrepareModel's derived field negated by Construct (pf/advection.go:50-96)."""
+        vs = [np.ascontiguousarray(v, dtype=np.complex128) for v in velocity]
+        arr = (ctypes.POINTER(ctypes.c_double) * len(vs))(*[_c128_ptr(v) for v in vs])
+        check(lib().gopf_advection_construct(self._h, _c128_ptr(field), arr, len(vs), _c128_ptr(out), 1 if transformed else 0))
+        return out
+
+    def DivGradConstruct(self, field: np.ndarray, func_values: np.ndarray, out: np.ndarray) -> np.ndarray:
+        """DivGrad.Construct over PrepareModel's derived fields (pf/gradientCalculator.go:72-108)."""
+        check(lib().gopf_div_grad_construct(self._h, _c128_ptr(field), _c128_ptr(func_values), _c128_ptr(out)))
+        return out
+
+    def WeightedLaplacianConstruct(self, field_hat: np.ndarray, prefactor_hat: np.ndarray, out: np.ndarray) -> np.ndarray:
+        """WeightedLaplacian.Construct (pf/gradientCalculator.go:131-172); both inputs are spectra."""
+        check(lib().gopf_weighted_laplacian_construct(self._h, _c128_ptr(field_hat), _c128_ptr(prefactor_hat), _c128_ptr(out)))
+        return out
+
     def ConjugateNode(self, i: int) -> int:
         out = ctypes.c_int64(0)
         check(lib().gopf_conjugate_node(len(self.Dimensions), int_array(self.Dimensions), ctypes.c_int64(i),

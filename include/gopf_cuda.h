@@ -83,6 +83,36 @@ int gopf_fft_exec_rows_device(gopf_fft_plan* plan, const void* dev_in_c128, void
 int gopf_fft_freq_device(gopf_fft_plan* plan, const int64_t* nodes, int64_t count, double* out);
 int gopf_fft_plan_destroy(gopf_fft_plan* plan);
 
+/* ---- gradient-based catalog terms at operator level ----------------------------------------
+ * GradientCalculator, DivGrad, WeightedLaplacian (pf/gradientCalculator.go:10-172) and Advection
+ * (pf/advection.go:17-98).  As shipped the reference cannot register these with a model (their
+ * OnStepFinished(t) lacks the `bricks` argument of pf.PureTerm, pf/userDefinedTerm.go:35); they are used by
+ * calling PrepareModel / Construct by hand, and these calls are that surface on a transform plan.  Arrays are
+ * N complex128 (N = product of the plan's dimensions); the *_device forms take device pointers on the plan's
+ * device and a stream (NULL: the plan's), the others host pointers (Field.Data / DerivedField.Data).
+ *
+ * gopf_gradient_calculate: GradientCalculator{FT, Comp, KeepNyquist}.Calculate(in, out)
+ *   (gradientCalculator.go:19-31): out = IFFT(i 2 pi f_comp FFT(in)) / N, f = +1/2 zeroed unless keep_nyquist.
+ * gopf_advection_construct: Advection{Field, VelocityFields}: what Construct's closure leaves in `field`
+ *   (advection.go:87-94) after the derived fields of PrepareModel (:50-85) are up to date:
+ *   -sum_d velocity[d] * GRAD_d(field), in real space (transformed = 0, as the reference's test reads it) or
+ *   forward-transformed (transformed = 1, as a step sees derived fields).  n_velocity must equal the rank.
+ * gopf_div_grad_construct: DivGrad{Field, F}.Construct (gradientCalculator.go:96-108) with the derived fields of
+ *   PrepareModel (:72-93): sum_d i 2 pi f_d FFT(func_values * GRAD_d(field)); func_values = F(i, bricks) per node.
+ * gopf_weighted_laplacian_construct: WeightedLaplacian.Construct (gradientCalculator.go:131-172):
+ *   FFT( IFFT(L field_hat)/N * IFFT(prefactor_hat)/N ), L = -(2 pi |f|)^2; both inputs are spectra. */
+int gopf_gradient_calculate(gopf_fft_plan* plan, const double* in, double* out, int comp, int keep_nyquist);
+int gopf_gradient_calculate_device(gopf_fft_plan* plan, const void* in, void* out, int comp, int keep_nyquist, void* stream);
+int gopf_advection_construct(gopf_fft_plan* plan, const double* field, const double* const* velocity, int n_velocity,
+                             double* out, int transformed);
+int gopf_advection_construct_device(gopf_fft_plan* plan, const void* field, const void* const* velocity, int n_velocity,
+                                    void* out, int transformed, void* stream);
+int gopf_div_grad_construct(gopf_fft_plan* plan, const double* field, const double* func_values, double* out);
+int gopf_div_grad_construct_device(gopf_fft_plan* plan, const void* field, const void* func_values, void* out, void* stream);
+int gopf_weighted_laplacian_construct(gopf_fft_plan* plan, const double* field_hat, const double* prefactor_hat, double* out);
+int gopf_weighted_laplacian_construct_device(gopf_fft_plan* plan, const void* field_hat, const void* prefactor_hat, void* out,
+                                             void* stream);
+
 /* ---- step level: pf.Model ---------------------------------------------------
  * The model records what the Go API calls describe and compiles it, at
  * gopf_model_init / gopf_solver_create, into device programs.  Arbitrary Go

@@ -591,6 +591,34 @@ class DivGrad:
         pass
 
 
+class WeightedLaplacian:
+    """pf/gradientCalculator.go:114-172: F(c) LAP field.  Field and PreFactor name bricks that hold SPECTRA when the
+    closure runs (inside a step every field and derived field is transformed, euler.go:18-26)."""
+
+    def __init__(self, Field: str, PreFactor: str, FT):
+        self.Field, self.PreFactor, self.FT = Field, PreFactor, FT
+
+    def Construct(self, bricks):
+        def fn(freq, t, field: np.ndarray):
+            n = field.shape[0]
+            idx = np.arange(n)
+            field[:] = bricks[self.Field].Get(idx)
+            f = as_frequency(freq).table(n)
+            field *= -(2.0 * math.pi * np.sqrt(np.sum(f * f, axis=1))) ** 2  # LaplacianN{Power: 1}.Eval, diffOp.go:25-30
+            self.FT.IFFT(field)
+            field /= float(n)
+            work = np.array(bricks[self.PreFactor].Get(idx), dtype=np.complex128)
+            self.FT.IFFT(work)
+            work /= float(n)
+            field *= work
+            self.FT.FFT(field)
+
+        return fn
+
+    def OnStepFinished(self, t, bricks=None):
+        pass
+
+
 class Advection:
     """pf/advection.go:10-96: -(v . grad field) through gradient derived fields."""
 

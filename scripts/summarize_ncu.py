@@ -58,8 +58,16 @@ def launches(src, dst):
         f.write("```\n")
 
 
+def raw_page(src):
+    """The raw page of a capture as CSV text: exported here from a .ncu-rep, or read as is when the GPU-side script
+    already exported it (the reports of the 1024^3 kernels exceed what gpurun copies back)."""
+    if src.endswith(".csv"):
+        return open(src).read()
+    return subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+
+
 def full(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = raw_page(src)
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -90,7 +98,7 @@ def traffic(args):
     import os
     entries = []
     for src, grid in zip(args[0::2], args[1::2]):
-        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        out = raw_page(src)
         rows = list(csv.reader(out.splitlines()))
         hdr, units = rows[0], rows[1]
         idx = {h: i for i, h in enumerate(hdr)}

@@ -1,7 +1,7 @@
 """Oracle restatements of the remaining catalog terms (GradientCalculator,
-DivGrad, Advection, Source, NegativeValuePenalty) pinned to the reference's own tests.  These have
-no device implementation yet; the oracle goes first so that one can be checked against it.
-No GPU needed."""
+DivGrad, WeightedLaplacian, Advection, Source, NegativeValuePenalty) pinned to the reference's own tests.
+The device side of the gradient-based ones is gopf_b200/csrc/gradient_terms.cu, checked against these
+restatements in tests/test_terms_gradient_gpu.py.  No GPU needed."""
 import math
 
 import numpy as np
@@ -54,6 +54,26 @@ def test_div_grad():
     ok = (np.abs(re - want) < 1e-3) | (np.abs(re - want) < want * 1e-3)
     assert np.all(ok)
     assert np.max(np.abs(res.imag)) < 1e-10
+
+
+def test_weighted_laplacian():
+    # pf/gradientCalculator_test.go:150-196: sin(2 pi x) LAP cos(2 pi x) on 16 x 16
+    N = 16
+    i = np.arange(N * N)
+    x = (i // N) / float(N)  # pfutil.Pos(...)[0]
+    two_pi = 2.0 * math.pi
+    prefactor = pf.NewField("prefactor", N * N, np.sin(two_pi * x).astype(np.complex128))
+    field = pf.NewField("field", N * N, np.cos(two_pi * x).astype(np.complex128))
+    expect = -two_pi ** 2 * np.sin(two_pi * x) * np.cos(two_pi * x) / float(N * N)
+    ft = pfutil.NewFFTW([N, N])
+    ft.FFT(field.Data)
+    ft.FFT(prefactor.Data)
+    wl = terms.WeightedLaplacian("field", "prefactor", ft)
+    result = np.zeros(N * N, dtype=np.complex128)
+    wl.Construct({"prefactor": prefactor, "field": field})(ft.Freq, 0.0, result)
+    ft.IFFT(result)
+    result /= float(N * N)
+    assert np.max(np.abs(result - expect)) < 1e-10
 
 
 def _gauss(N):
