@@ -78,3 +78,28 @@ func (fw *FFTWWrapper) ConjugateNode(i int) int {
 	check(C.gopf_conjugate_node(C.int(len(dims)), &dims[0], C.int64_t(i), &out))
 	return int(out)
 }
+
+// GradientCalculate is pf.GradientCalculator{FT: fw, Comp: comp, KeepNyquist: keepNyquist}.Calculate(indata, data)
+// (pf/gradientCalculator.go:19-31) on the device: data = IFFT(i 2 pi f_comp FFT(indata)) / N.
+func (fw *FFTWWrapper) GradientCalculate(indata []complex128, data []complex128, comp int, keepNyquist bool) {
+	keep := C.int(0)
+	if keepNyquist {
+		keep = 1
+	}
+	check(C.gopf_gradient_calculate(fw.plan, (*C.double)(unsafe.Pointer(&indata[0])), (*C.double)(unsafe.Pointer(&data[0])),
+		C.int(comp), keep))
+}
+
+// DivGradConstruct is what pf.DivGrad{Field, F}.Construct's closure leaves in `out` once the derived fields of
+// PrepareModel hold F * grad field (pf/gradientCalculator.go:72-108); funcValues[i] = F(i, bricks).
+func (fw *FFTWWrapper) DivGradConstruct(field []complex128, funcValues []complex128, out []complex128) {
+	check(C.gopf_div_grad_construct(fw.plan, (*C.double)(unsafe.Pointer(&field[0])), (*C.double)(unsafe.Pointer(&funcValues[0])),
+		(*C.double)(unsafe.Pointer(&out[0]))))
+}
+
+// WeightedLaplacianConstruct is pf.WeightedLaplacian.Construct's closure (pf/gradientCalculator.go:131-172); both
+// inputs are spectra.
+func (fw *FFTWWrapper) WeightedLaplacianConstruct(fieldHat []complex128, prefactorHat []complex128, out []complex128) {
+	check(C.gopf_weighted_laplacian_construct(fw.plan, (*C.double)(unsafe.Pointer(&fieldHat[0])),
+		(*C.double)(unsafe.Pointer(&prefactorHat[0])), (*C.double)(unsafe.Pointer(&out[0]))))
+}
