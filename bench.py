@@ -559,6 +559,16 @@ def run_single_gpu(args):
                 recs.append(measure_workload(kind, WORKLOADS[kind]["default_grid"], dev, 3, 10))
             except Exception as exc:
                 recs.append({"workload": kind, "error": str(exc)[:300]})
+        # BASELINE.json configs[1] as worded: ImplicitEuler (Newton-Krylov on the device) + SquareGradientTerm at
+        # 256^3.  One step = one non-linear solve = many right-hand-side evaluations, so the contract fraction of
+        # the Euler step does not apply: the record is the time per step and the launches behind it.
+        try:
+            r = measure_workload("ch_sqgrad", WORKLOADS["ch_sqgrad"]["default_grid"], dev, 1, 2, stepper="implicit_euler")
+            r["workload"] += " (stepper: ImplicitEuler, DefaultNonLinSolver settings)"
+            r["roofline"]["step_model"]["note"] = "fraction of the Euler step's contract; not meaningful for a Newton-Krylov solve"
+            recs.append(r)
+        except Exception as exc:
+            recs.append({"workload": "ch_sqgrad/implicit_euler", "error": str(exc)[:300]})
         line["workloads"] = recs
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(1, args.cpu_budget)
@@ -588,7 +598,7 @@ def main():
                     help="sharded runs: peer stores fused into the passes, copy-engine copies pipelined under the "
                          "kernels, or NCCL all-to-all")
     ap.add_argument("--chunks", type=int, default=8, help="sharded runs: plane / column chunks the exchange is pipelined in")
-    ap.add_argument("--comm-ctas", type=int, default=48,
+    ap.add_argument("--comm-ctas", type=int, default=0,
                     help="--exchange peer: SMs given to the NVLink-bound peer-storing pass while it overlaps the next chunk")
     args = ap.parse_args()
     if args.warmup < 3:
