@@ -37,8 +37,43 @@ DistSolver::DistSolver(Model* m, int n, int world, int rank, double dt, int devi
     for (int i = 0; i < GOPF_MAX_PEERS; ++i) X_[i] = Y_[i] = nullptr;
 }
 
+// max |Im x| over an array (upload: is this rank's slab real?)
+static __global__ void k_slab_max_abs_imag(const cplx* __restrict__ x, long long n, double* out) {
+    double m = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmax(m, fabs(x[i].y));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0)  // non-negative doubles order like their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
+}
+
+void DistSolver::check_real(const cplx* W) {
+    if (!d_imag_max_) GOPF_CUDA(cudaMalloc(&d_imag_max_, sizeof(double)));
+    if (!h_imag_max_) GOPF_CUDA(cudaMallocHost(&h_imag_max_, sizeof(double)));
+    cudaStream_t s = stream();
+    GOPF_CUDA(cudaMemsetAsync(d_imag_max_, 0, sizeof(double), s));
+    const long long n = (long long)local_cells();
+    k_slab_max_abs_imag<<<148 * 8, 256, 0, s>>>(W, n, d_imag_max_);
+    GOPF_CUDA(cudaGetLastError());
+    GOPF_CUDA(cudaMemcpyAsync(h_imag_max_, d_imag_max_, sizeof(double), cudaMemcpyDeviceToHost, s));
+    real_check_pending_ = true;
+    launches_++;
+}
+
+// Each rank decides for its own slab: both kernels are valid for real data, so the ranks need not agree.
+int DistSolver::real_pairs() {
+    if (real_check_pending_) {
+        GOPF_CUDA(cudaStreamSynchronize(stream()));
+        field_real_ = *h_imag_max_ == 0.0;
+        real_check_pending_ = false;
+    }
+    return (field_real_ && prog_.fast == 1) ? 1 : 0;
+}
+
 DistSolver::~DistSolver() {
     cudaSetDevice(plan_->device);
+    if (d_imag_max_) cudaFree(d_imag_max_);
+    if (h_imag_max_) cudaFreeHost(h_imag_max_);
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
     if (ev_compute_) cudaEventDestroy(ev_compute_);
     if (ev_copy_) cudaEventDestroy(ev_copy_);
@@ -137,6 +172,7 @@ void DistSolver::forward_mid_peer(const cplx* W) {
 
 void DistSolver::forward_local_peer(cplx* W) {
     plan_->use_device();
+    check_real(W);
     check(launch_pass(make_geom(m_, n_, n_, 2), plan_->tx_want, plain_io(W, W, false, 1.0), plan_->twiddle(2), stream()),
           "forward axis 2");
     forward_mid_peer(W);
@@ -204,6 +240,7 @@ void DistSolver::real_step_planes(cplx* W, int begin, int count) {
     plan_->use_device();
     PassGeom g = make_geom(count, n_, n_, 2);
     g.grid_cap = grid_cap_;
+    g.real_pairs = real_pairs();
     g.node0 = ((long long)rank_ * m_ + begin) * n_ * n_;
     const double inv_n = 1.0 / ((double)n_ * n_ * n_);
     check(launch_fused_real(g, 0, W + (size_t)begin * n_ * n_, nullptr, m_model_->derived[derived_].dev, inv_n,
@@ -293,6 +330,7 @@ void DistSolver::exchange_join() {
 
 void DistSolver::forward_local(cplx* W, cplx* send) {
     plan_->use_device();
+    check_real(W);
     check(launch_pass(make_geom(m_, n_, n_, 2), plan_->tx_want, plain_io(W, W, false, 1.0), plan_->twiddle(2), stream()),
           "forward axis 2");
     forward_mid(W, send);
@@ -326,6 +364,7 @@ void DistSolver::real_step(cplx* W) {
     plan_->use_device();
     PassGeom g = make_geom(m_, n_, n_, 2);
     g.node0 = (long long)rank_ * m_ * n_ * n_;
+    g.real_pairs = real_pairs();
     const double inv_n = 1.0 / ((double)n_ * n_ * n_);
     check(launch_fused_real(g, 0, W, nullptr, m_model_->derived[derived_].dev, inv_n, (unsigned long long)steps_taken_,
                             plan_->twiddle(2), stream()),

@@ -103,6 +103,13 @@ private:
     int derived_ = -1;
     long long steps_taken_ = 0, current_step_ = 0, launches_ = 0;
     int grid_cap_ = 0;
+    // the uploaded slab had no imaginary part (checked on the device in forward_local*): the real-space kernel may
+    // pair lines (PassGeom::real_pairs, tma_kernels.cuh); the answer is collected at the first real-space step
+    bool field_real_ = false, real_check_pending_ = false;
+    double* d_imag_max_ = nullptr;
+    double* h_imag_max_ = nullptr;
+    void check_real(const cplx* W);
+    int real_pairs();
     cplx* X_[GOPF_MAX_PEERS];  // [rank]: mapped receive buffers (own rank: owned allocation)
     cplx* Y_[GOPF_MAX_PEERS];
     PeerOut peer_out(cplx* const* bufs, bool kspace_rows) const;

@@ -78,6 +78,10 @@ struct PassGeom {
     // sets it while an NVLink-bound pass is confined to a few SMs on the second stream, so that the statically
     // partitioned tiles of the compute-stream kernel are not queued behind it.
     int grid_cap;
+    // The caller vouches that the field is REAL in real space (its spectrum Hermitian, every term keeps it so):
+    // the copy-engine real-space kernel may then carry two lines through one complex transform each way
+    // (k_fused_real_pair_tma, tma_kernels.cuh).  0: lines are general complex data.
+    int real_pairs;
 };
 
 // GOPF_HOST_EMUL: tests/host_emul compiles this header with g++ and runs the kernels on the host (one OS
@@ -136,6 +140,7 @@ inline PassGeom make_geom(int n0, int n1, int n2, int axis) {
     g.bpitch = 0;
     g.pf_tiles = 0;
     g.grid_cap = 0;
+    g.real_pairs = 0;
     return g;
 }
 

@@ -180,6 +180,8 @@ Solver::~Solver() {
     if (d_real_out_) cudaFree(d_real_out_);
     if (d_filter_) cudaFree(d_filter_);
     if (d_lp_state_) cudaFree(d_lp_state_);
+    if (d_imag_max_) cudaFree(d_imag_max_);
+    if (h_imag_max_) cudaFreeHost(h_imag_max_);
     for (KernelTimer& t : timers_)
         for (auto& ev : t.events) {
             cudaEventDestroy(ev.first);
@@ -1040,6 +1042,25 @@ bool Solver::launch_update_jit(const DevKProgram& P, const ImplicitTab& tab) {
 }
 
 // ---- host synchronisation ------------------------------------------------------------
+// max |Im x| over an array (upload: is the field real?)
+__global__ void k_max_abs_imag(const cplx* __restrict__ x, long long n, double* out) {
+    double m = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmax(m, fabs(x[i].y));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // non-negative doubles order like their bit patterns
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
+}
+
+void Solver::resolve_real_check() {
+    if (!real_check_pending_) return;
+    GOPF_CUDA(cudaStreamSynchronize(stream()));
+    const bool now_real = *h_imag_max_ == 0.0;
+    if (now_real != field_real_) drop_graph();  // a captured step holds the kernel choice
+    field_real_ = now_real;
+    real_check_pending_ = false;
+}
+
 void Solver::upload() {
     blocked_ = false;  // the spectra are rewritten, row-major
     ensure_buffers();
@@ -1049,6 +1070,18 @@ void Solver::upload() {
     for (int i = 0; i < F; ++i) {
         if (!m_->fields[i].host) throw Error("solver: field '" + m_->fields[i].name + "' has no host array");
         GOPF_CUDA(cudaMemcpyAsync(S_.s[i], m_->fields[i].host, sizeof(cplx) * plan_->N, cudaMemcpyHostToDevice, s));
+        if (fused_ && i == 0) {
+            // is the field real?  One read of the array on the device (a host scan would cost more than the copy);
+            // the answer is collected at the next step (resolve_real_check)
+            if (!d_imag_max_) GOPF_CUDA(cudaMalloc(&d_imag_max_, sizeof(double)));
+            if (!h_imag_max_) GOPF_CUDA(cudaMallocHost(&h_imag_max_, sizeof(double)));
+            GOPF_CUDA(cudaMemsetAsync(d_imag_max_, 0, sizeof(double), s));
+            k_max_abs_imag<<<grid_for((long long)plan_->N), 256, 0, s>>>(S_.s[i], (long long)plan_->N, d_imag_max_);
+            GOPF_CUDA(cudaGetLastError());
+            GOPF_CUDA(cudaMemcpyAsync(h_imag_max_, d_imag_max_, sizeof(double), cudaMemcpyDeviceToHost, s));
+            real_check_pending_ = true;
+            launches_++;
+        }
         plan_->exec_device(S_.s[i], -1, s);  // euler.go:19-21
     }
     on_device_ = true;
@@ -1208,7 +1241,10 @@ void Solver::euler_step_fused() {
         if (e != cudaSuccess) throw Error(strf("fused: middle inverse pass: %s", cudaGetErrorString(e)));
     }
     {
-        const PassGeom g2 = plan_->geom(2);
+        PassGeom g2 = plan_->geom(2);
+        // real field + real fast-form program (real polynomial multipliers, no noise): the real-space kernel may
+        // carry two lines per complex transform (tma_kernels.cuh)
+        g2.real_pairs = (field_real_ && fused_prog_.fast == 1 && !has_knoise_) ? 1 : 0;
         const int id = tick("fused_real", 32.0 * n);
         cudaError_t e = launch_fused_real(g2, 0, W_, nullptr, m_->derived[fused_derived_].dev, 1.0 / n,
                                           (unsigned long long)steps_taken_, plan_->twiddle(2), s);
@@ -1314,6 +1350,7 @@ void Solver::step(int nsteps) {
             block_log_ = want;
         }
     }
+    resolve_real_check();
     int done = 0;
     if (fused_ && stepper_ == StepperKind::Euler && nsteps > GRAPH_STEPS) {
         // the first step runs eagerly (it also produces W when it is not valid yet and sets every

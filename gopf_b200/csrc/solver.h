@@ -142,6 +142,12 @@ private:
     bool on_device_ = false;
     bool fused_ = false, allow_fused_ = true;
     bool w_valid_ = false;  // fused path: W holds the first inverse pass of the current spectrum
+    // fused path: the uploaded field had no imaginary part (checked on the device at upload); with a real fast-form
+    // program the real-space kernel may then pair lines (PassGeom::real_pairs)
+    bool field_real_ = false, real_check_pending_ = false;
+    double* d_imag_max_ = nullptr;
+    double* h_imag_max_ = nullptr;  // page-locked
+    void resolve_real_check();
     int fused_derived_ = -1;
     long long launches_ = 0;
 

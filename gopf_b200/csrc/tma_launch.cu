@@ -203,6 +203,20 @@ cudaError_t real_tma_n(const PassGeom& g, cplx* W, const DevDerived& D, double i
     return cudaGetLastError();
 }
 
+// real fields: two lines per complex transform (k_fused_real_pair_tma)
+template <int N>
+cudaError_t real_pair_tma_n(const PassGeom& g, cplx* W, const DevDerived& D, double inv_n, const cplx* tw, cudaStream_t s) {
+    typedef TmaRealPairCfg<N> C;
+    auto kern = k_fused_real_pair_tma<N>;
+    cudaError_t e = opt_in_smem(kern, C::smem_bytes());
+    if (e != cudaSuccess) return e;
+    const long long pairs = g.A / 2;
+    const unsigned grid = (unsigned)grid_for(g, (pairs + C::WORKERS - 1) / C::WORKERS);
+    kern<<<grid, C::THREADS, C::smem_bytes(), s>>>(W, pairs, D, inv_n, tw);
+    g_tma_launches++;
+    return cudaGetLastError();
+}
+
 template <int N, int TX>
 cudaError_t kspace_tma_n(const PassGeom& g, const cplx* W, cplx* Wout, cplx* S, const DevKProgram& P, const FreqTabs& ft,
                          const cplx* tw, cudaStream_t s) {
@@ -249,6 +263,15 @@ cudaError_t launch_pass_tma(const PassGeom& g, const PassIO& io, const cplx* tw,
 cudaError_t launch_fused_real_tma(const PassGeom& g, cplx* W, const DevDerived& D, double inv_n, unsigned long long step,
                                   const cplx* tw, cudaStream_t s) {
     if (!enabled("GOPF_TMA_REAL") || g.B != 1 || g.N < min_n()) return cudaErrorNotSupported;
+    const bool host_fast = (D.kind == DK_MONOMIAL && D.n_factors == 1 && D.ipower[0] >= 0 && D.ipower[0] <= 15) ||
+                           (D.kind == DK_RPN && D.poly_deg >= 0);
+    if (g.real_pairs && (g.A % 2) == 0 && host_fast && env_flag("GOPF_REAL_PAIRS", 1) != 0) {
+        switch (g.N) {
+            case 512: return real_pair_tma_n<512>(g, W, D, inv_n, tw, s);
+            case 1024: return real_pair_tma_n<1024>(g, W, D, inv_n, tw, s);
+            default: break;
+        }
+    }
     switch (g.N) {
         case 512: return real_tma_n<512>(g, W, D, inv_n, step, tw, s);
         case 1024: return real_tma_n<1024>(g, W, D, inv_n, step, tw, s);

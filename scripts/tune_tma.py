@@ -26,10 +26,12 @@ VARIANTS = [("register kernels", {"GOPF_TMA": "0", "GOPF_BLOCKED": "0"}),
             ("tma pass+real, register kspace, row-major", {"GOPF_TMA": "1", "GOPF_BLOCKED": "0", "GOPF_TMA_KSPACE": "0"}),
             ("tma all, row-major", {"GOPF_TMA": "1", "GOPF_BLOCKED": "0"}),
             ("tma all, blocked s=7, spectrum prefetch at compute start", {"GOPF_TMA": "1", "GOPF_BLOCKED": "1", "GOPF_TMA_SPF": "1"}),
-            ("tma all, blocked s=7, no spectrum prefetch", {"GOPF_TMA": "1", "GOPF_BLOCKED": "1", "GOPF_TMA_SPF": "2"})]
+            ("tma all, blocked s=7, no spectrum prefetch", {"GOPF_TMA": "1", "GOPF_BLOCKED": "1", "GOPF_TMA_SPF": "2"}),
+            ("final, complex-carrying real-space kernel", {"GOPF_REAL_PAIRS": "0"}),
+            ("final, paired real lines", {"GOPF_REAL_PAIRS": "1"})]
 if os.environ.get("TUNE_VARIANTS"):
     VARIANTS = [v for v in VARIANTS if any(w in v[0] for w in os.environ["TUNE_VARIANTS"].split(";"))]
-KEYS = ("GOPF_TMA", "GOPF_TMA_L2", "GOPF_TMA_PASS", "GOPF_TMA_REAL", "GOPF_TMA_KSPACE", "GOPF_BLOCKED", "GOPF_BLOCK_LOG", "GOPF_TMA_SPF")
+KEYS = ("GOPF_TMA", "GOPF_TMA_L2", "GOPF_TMA_PASS", "GOPF_TMA_REAL", "GOPF_TMA_KSPACE", "GOPF_BLOCKED", "GOPF_BLOCK_LOG", "GOPF_TMA_SPF", "GOPF_REAL_PAIRS")
 for G in grids:
     n = G ** 3
     os.environ["GOPF_TMA_MIN_N"] = str(min(G, 1024))

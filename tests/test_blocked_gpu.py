@@ -16,7 +16,8 @@ from oracle import pf as opf
 
 pytestmark = pytest.mark.gpu
 
-KEYS = ("GOPF_BLOCKED", "GOPF_BLOCK_LOG", "GOPF_TMA", "GOPF_TMA_MIN_N", "GOPF_TMA_KSPACE", "GOPF_TMA_PASS", "GOPF_TMA_REAL")
+KEYS = ("GOPF_BLOCKED", "GOPF_BLOCK_LOG", "GOPF_TMA", "GOPF_TMA_MIN_N", "GOPF_TMA_KSPACE", "GOPF_TMA_PASS", "GOPF_TMA_REAL",
+        "GOPF_REAL_PAIRS")
 
 
 @pytest.fixture()
@@ -88,6 +89,7 @@ def test_register_kernels_blocked_bitwise_and_vs_oracle(env, dims, log):
 def test_copy_engine_kernels_blocked_bitwise_512(env, kspace):
     dims, steps = [512, 512, 512], 3
     env["GOPF_TMA_MIN_N"] = "512"
+    env["GOPF_REAL_PAIRS"] = "0"  # the paired real-space kernel equals the others to rounding only (test_tma_gpu.py)
     env["GOPF_TMA"] = "0"
     env["GOPF_BLOCKED"] = "0"
     ref = _ch(dims, steps)

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture()
 def tma_env():
-    keys = ("GOPF_TMA", "GOPF_TMA_MIN_N", "GOPF_TMA_L2", "GOPF_TMA_PASS", "GOPF_TMA_REAL", "GOPF_TMA_KSPACE")
+    keys = ("GOPF_TMA", "GOPF_TMA_MIN_N", "GOPF_TMA_L2", "GOPF_TMA_PASS", "GOPF_TMA_REAL", "GOPF_TMA_KSPACE", "GOPF_REAL_PAIRS")
     saved = {k: os.environ.get(k) for k in keys}
     yield os.environ
     for k, v in saved.items():
@@ -88,7 +88,9 @@ _FUSED_CASES = [(which, dims, min_n, steps)
 @pytest.mark.parametrize("which,dims,min_n,steps", _FUSED_CASES,
                          ids=[f"{w}-{'x'.join(map(str, d))}-{n}-{k}" for w, d, n, k in _FUSED_CASES])
 def test_fused_step_bitwise(tma_env, dims, min_n, steps, which):
-    """Cahn-Hilliard through the fused kernels with the copy-engine variants switched on one at a time."""
+    """Cahn-Hilliard through the fused kernels with the copy-engine variants switched on one at a time (the real
+    field's two-lines-per-transform variant off: it is not bitwise, see test_real_pairs_*)."""
+    tma_env["GOPF_REAL_PAIRS"] = "0"
     tma_env["GOPF_TMA_MIN_N"] = str(min_n)
     tma_env["GOPF_TMA"] = "0"
     ref = _ch(dims, steps)
@@ -167,6 +169,7 @@ def _virtual_sharded(n, world, steps):
 def test_split_row_maps_virtual_ranks_bitwise_and_vs_single_gpu(tma_env, world):
     n, steps = 512, 3
     tma_env["GOPF_TMA_MIN_N"] = "512"
+    tma_env["GOPF_REAL_PAIRS"] = "0"
     tma_env["GOPF_TMA"] = "0"
     ref = _virtual_sharded(n, world, steps)
     tma_env["GOPF_TMA"] = "1"
@@ -176,3 +179,63 @@ def test_split_row_maps_virtual_ranks_bitwise_and_vs_single_gpu(tma_env, world):
     assert np.array_equal(got, ref)
     single = _ch([n, n, n], steps)
     assert np.linalg.norm(got - single) / np.linalg.norm(single) <= 1e-13
+    # the sharded phases with the paired real-space kernel (the slabs are real): equal to rounding
+    tma_env["GOPF_REAL_PAIRS"] = "1"
+    paired = _virtual_sharded(n, world, steps)
+    assert not np.array_equal(paired, got), "the paired kernel did not run in the sharded phases"
+    assert np.linalg.norm(paired - got) / np.linalg.norm(got) <= 1e-13
+
+
+# ---- real fields: two lines per complex transform in the real-space kernel (k_fused_real_pair_tma) -------------------
+def _ch_init(dims, steps, init):
+    n = int(np.prod(dims))
+    m = gpf.NewModel()
+    f = gpf.NewField("conc", n, init.copy())
+    m.AddScalar(gpf.NewScalar("gamma", synthetic.CAHN_HILLIARD_GAMMA))
+    m.AddScalar(gpf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
+    m.AddField(f)
+    m.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
+    s = gpf.NewSolver(m, dims, synthetic.CAHN_HILLIARD_DT)
+    assert s.IsFused
+    s.Upload()
+    s.StepDevice(steps)
+    s.Download()
+    out = f.Data.copy()
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("dims,min_n,steps", [([1024, 1024], 1024, 20), ([512, 512], 512, 20), ([512, 512, 512], 512, 3),
+                                              ([256, 1024], 1024, 8)],
+                         ids=lambda v: "x".join(map(str, v)) if isinstance(v, list) else str(v))
+def test_real_pairs_equal_the_complex_carrying_kernel_to_rounding(tma_env, dims, min_n, steps):
+    """A real field through the paired real-space kernel against the same run with every line carried as complex data
+    (GOPF_REAL_PAIRS=0): the imaginary residue of a line (1e-17 relative) lands in its partner instead of being carried
+    along, nothing else differs.  pf/euler.go:16-47; tolerance of the P-GPU vs 1-GPU comparisons (1e-13)."""
+    n = int(np.prod(dims))
+    init = synthetic.cahn_hilliard_initial(n, 0)
+    assert not init.imag.any()
+    tma_env["GOPF_TMA"] = "1"
+    tma_env["GOPF_TMA_MIN_N"] = str(min_n)
+    tma_env["GOPF_REAL_PAIRS"] = "0"
+    ref = _ch_init(dims, steps, init)
+    tma_env["GOPF_REAL_PAIRS"] = "1"
+    got = _ch_init(dims, steps, init)
+    assert not np.array_equal(got, ref), "the paired kernel did not run"
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-13
+    assert np.max(np.abs(got.imag)) <= 1e-13 * np.max(np.abs(got.real))
+
+
+def test_real_pairs_are_not_used_for_a_complex_field(tma_env):
+    """A field with an imaginary part keeps the complex-carrying kernel: bitwise the GOPF_REAL_PAIRS=0 result."""
+    dims = [1024, 1024]
+    n = int(np.prod(dims))
+    init = synthetic.cahn_hilliard_initial(n, 0)
+    init = init + 1j * 0.01 * np.roll(init.real, 17)
+    tma_env["GOPF_TMA"] = "1"
+    tma_env["GOPF_TMA_MIN_N"] = "1024"
+    tma_env["GOPF_REAL_PAIRS"] = "0"
+    ref = _ch_init(dims, 6, init)
+    tma_env["GOPF_REAL_PAIRS"] = "1"
+    got = _ch_init(dims, 6, init)
+    assert np.array_equal(got, ref)
