@@ -113,3 +113,44 @@ def test_sharded_matches_single_gpu_at_benchmark_scale(tmp_path, world, n, split
     got = np.concatenate([np.load(tmp_path / f"slab{r}.npy") for r in range(world)])
     ref = _single_gpu(n, sum(split))
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-13
+
+
+def _pipelined_world1(rank, world, port, n, steps, out_dir):
+    """One rank, but the real-space side pipelined in 8 plane chunks with the peer-storing pass on a second stream
+    (what P > 1 runs): copy-engine kernels on plane chunks under a grid cap, incl. the paired real-space kernel."""
+    import torch.distributed as tdist
+    from gopf_b200 import dist as gdist
+    from gopf_b200 import pf as gpf
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["GOPF_TMA_MIN_N"] = str(n)
+    torch.cuda.set_device(0)
+    tdist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        cells = n ** 3
+        model = gpf.NewModel()
+        f = gpf.NewField("conc", cells, synthetic.cahn_hilliard_initial(cells, 0))
+        model.AddScalar(gpf.NewScalar("gamma", synthetic.CAHN_HILLIARD_GAMMA))
+        model.AddScalar(gpf.NewScalar("m1", synthetic.CAHN_HILLIARD_M1))
+        model.AddField(f)
+        model.AddEquation(synthetic.CAHN_HILLIARD_EQUATION)
+        s = gdist.ShardedSolver(model, n, synthetic.CAHN_HILLIARD_DT, device=0, exchange="peer")
+        s.Upload()
+        with torch.cuda.stream(s.stream):
+            s.a_valid = gdist.run_steps_peer(s.phases, s.barrier, s.S, s.A, steps, s.a_valid, s.slab, 8, 48)
+        s.Download()
+        torch.cuda.synchronize()
+        np.save(os.path.join(out_dir, "slab0.npy"), f.Data)
+    finally:
+        tdist.destroy_process_group()
+
+
+def test_pipelined_plane_chunks_with_copy_engine_kernels_match_single_gpu(tmp_path):
+    """The chunked, two-stream real-space side of the sharded step at 512-cell lines with the copy-engine kernels
+    switched on for them (GOPF_TMA_MIN_N=512): against the single-GPU fused step, <= 1e-13."""
+    import torch.multiprocessing as mp
+    n, steps = 512, 3
+    mp.spawn(_pipelined_world1, args=(1, _free_port(), n, steps, str(tmp_path)), nprocs=1, join=True)
+    got = np.load(tmp_path / "slab0.npy")
+    ref = _single_gpu(n, steps)
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-13
