@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256)
     k_ie_rhs(const __grid_constant__ DevKProgram P, SpectraPtrs sp, SpectraPtrs out, FreqGeom fg, long long n) {
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
         double f[3] = {0.0, 0.0, 0.0};
-        ref_freq(fg, idx, f);
+        ref_freq_fast(fg, idx, n <= 0x7fffffffLL, f);  // 32-bit index arithmetic when the grid allows (same IEEE divides)
         const KPoint kp = make_kpoint(f[0], f[1], f[2]);
         auto get = [&](int b) -> cplx { return sp.s[b][idx]; };
         for (int i = 0; i < P.n_fields; ++i) {
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256)
                   FreqGeom fg, long long n) {
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
         double f[3] = {0.0, 0.0, 0.0};
-        ref_freq(fg, idx, f);
+        ref_freq_fast(fg, idx, n <= 0x7fffffffLL, f);  // 32-bit index arithmetic when the grid allows (same IEEE divides)
         const KPoint kp = make_kpoint(f[0], f[1], f[2]);
         auto get = [&](int b) -> cplx { return sp.s[b][idx]; };
         for (int i = 0; i < P.n_fields; ++i) {
@@ -214,9 +214,16 @@ void Solver::ie_residual(const double* x, double* out) {
         rp.s[i] = ie_rhs_prev_[i];
         res.s[i] = ie_res_[i];
     }
-    k_ie_residual<<<ie_grid(n), 256, 0, s>>>(prog_, S_, orig, rp, res, plan_->freq_geom(), n);
+    {
+        // algorithmic bytes: every spectrum read once, origFields and rhsPrev read, the residual written
+        int n_read = 0;
+        for (int b = 0; b < GOPF_MAX_SPECTRA; ++b)
+            if (S_.s[b]) n_read++;
+        const int id = tick("ie_residual_kernel", 16.0 * (double)n * (n_read + 3 * F));
+        k_ie_residual<<<ie_grid(n), 256, 0, s>>>(prog_, S_, orig, rp, res, plan_->freq_geom(), n);
+        tock(id);
+    }
     GOPF_CUDA(cudaGetLastError());
-    launches_++;
     for (int i = 0; i < F; ++i) {
         inverse_to_real(ie_res_[i], ie_res_[i]);  // IFFT and /N in place
         k_cplx_to_real<<<ie_grid(n), 256, 0, s>>>(ie_res_[i], out + (size_t)i * n, n);

@@ -65,11 +65,11 @@ def run(args):
     cells = n ** 3 // world
     exchange = getattr(args, "exchange", "peer")
     nchunks = getattr(args, "chunks", 8)
-    # SMs given to the NVLink-bound peer-storing pass while it overlaps the next chunk.  Measured on the 1024^3 step:
-    # P = 8: 48 best (32: 7.62, 48: 6.70, 64: 6.93, 96: 7.06 ms at 4 chunks; profiles/r1b_tuning_notes.md);
-    # P = 2: 48: 20.73, 64: 20.15, 80: 21.62, 96: 25.09 ms (the pass also moves its own half through HBM);
-    # P = 4 interpolated.
-    comm_ctas = getattr(args, "comm_ctas", 0) or {2: 64, 4: 56}.get(world, 48)
+    # SMs given to the NVLink-bound peer-storing pass while it overlaps the next chunk, measured on the 1024^3 step with
+    # this round's kernels (profiles/r2_tuning_notes.md):  P = 2: 48: 20.73, 64: 20.15, 80: 21.62, 96: 25.09 ms (the
+    # pass also moves its own half through HBM);  P = 8: 48: 6.59, 64: 6.42, 76: 6.36 ms (round 1, slower compute
+    # side: 48 best);  P = 4 not swept: 64.
+    comm_ctas = getattr(args, "comm_ctas", 0) or {2: 64, 4: 64, 8: 76}.get(world, 48)
     # the same sharded CUDA path at 256^3 against the oracle, before anything is timed
     parity = None if getattr(args, "no_parity", False) else B.parity_sharded(world, rank, local, exchange, nchunks, comm_ctas)
     model = gpf.NewModel()
