@@ -328,8 +328,8 @@ int gopf_solver_is_fused(gopf_solver* s, int* fused);
 int gopf_solver_force_generic(gopf_solver* s, int on);
 /* Run-time specialisation of registered functions (Model.RegisterFunction, pf/model.go:400-412):
  * the expression is compiled with NVRTC into a straight-line sm_100a kernel at first use instead
- * of being interpreted per cell.  Off unless GOPF_JIT=1 is in the environment when the solver is
- * created; gopf_solver_set_jit overrides that.  A function that fails to compile keeps the
+ * of being interpreted per cell.  On by default since round 2 (GOPF_JIT=0 in the environment when the solver is
+ * created switches it off); gopf_solver_set_jit overrides that.  A function that fails to compile keeps the
  * interpreter kernel (both are device paths); gopf_solver_jit_log tells why. */
 int gopf_solver_set_jit(gopf_solver* s, int on);
 /* With the specialisation on, also compile each registered function into the load of the first
