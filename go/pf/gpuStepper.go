@@ -43,19 +43,45 @@ import "C"
 import (
 	"fmt"
 	"os"
+	"sync"
 	"unsafe"
 )
 
 // GPUStepper is a TimeStepper backed by gopf_solver
 type GPUStepper struct {
-	model  *C.gopf_model
-	solver *C.gopf_solver
-	Dt     float64
+	model   *C.gopf_model
+	solver  *C.gopf_solver
+	Dt      float64
+	sources []uintptr // handles of this stepper's TimeDepSource closures in gpuSourceFuncs
 }
 
-// TimeDepSource closures of the model's point sources (pf/sourceTerm.go:11); the C library calls
-// them back on the host once per right-hand-side evaluation through gopfSourceTrampoline.
-var gpuSourceFuncs []TimeDepSource
+// TimeDepSource closures of the models' point sources (pf/sourceTerm.go:11); the C library calls
+// them back on the host once per right-hand-side evaluation through gopfSourceTrampoline with the
+// handle it was given at registration.  Handles belong to the stepper that registered them and are
+// released by its Close; the table is guarded because steppers may live on different goroutines.
+var (
+	gpuSourceMu    sync.Mutex
+	gpuSourceFuncs = map[uintptr]TimeDepSource{}
+	gpuSourceNext  uintptr
+)
+
+func gpuRegisterSource(f TimeDepSource) uintptr {
+	gpuSourceMu.Lock()
+	defer gpuSourceMu.Unlock()
+	gpuSourceNext++
+	gpuSourceFuncs[gpuSourceNext] = f
+	return gpuSourceNext
+}
+
+// GPUNoiseFuncs names the RegisterFunction entries that are WhiteNoise.Generate closures
+// (pf/noise.go:20-23): a Go closure cannot run on the device, so NewGPUStepper registers the device
+// generator of the same distribution for them (gopf_model_register_white_noise).  Set it before
+// NewGPUStepper, e.g. pf.GPUNoiseFuncs = map[string]*pf.WhiteNoise{"NOISE": &noise}; GPUNoiseSeed
+// seeds the counter-based stream (the reference's math/rand stream is unpinned).
+var (
+	GPUNoiseFuncs map[string]*WhiteNoise
+	GPUNoiseSeed  uint64
+)
 
 // GPUKSpaceNoise asks NewGPUStepper to draw the spectrum of plain explicit WhiteNoise terms at the
 // k-point (gopf_model_set_kspace_noise) instead of transforming a real-space noise field every step.
@@ -64,7 +90,10 @@ var GPUKSpaceNoise = false
 
 //export gopfSourceTrampoline
 func gopfSourceTrampoline(t C.double, user unsafe.Pointer) C.double {
-	return C.double(gpuSourceFuncs[int(uintptr(user))-1](float64(t)))
+	gpuSourceMu.Lock()
+	f := gpuSourceFuncs[uintptr(user)]
+	gpuSourceMu.Unlock()
+	return C.double(f(float64(t)))
 }
 
 func gpuCheck(status C.int) {
@@ -104,6 +133,11 @@ func NewGPUStepper(m *Model, domainSize []int, dt float64, scheme string, exprs 
 		gpuCheck(C.gopf_model_register_function(st.model, cn, ce))
 		C.free(unsafe.Pointer(cn))
 		C.free(unsafe.Pointer(ce))
+	}
+	for name, noise := range GPUNoiseFuncs { // RegisterFunction(name, noise.Generate), pf/noise.go:20-23
+		cn := cstr(name)
+		gpuCheck(C.gopf_model_register_white_noise(st.model, cn, C.double(noise.Strength), C.uint64_t(GPUNoiseSeed)))
+		C.free(unsafe.Pointer(cn))
 	}
 	register := func(name string, t interface{}) {
 		cn := cstr(name)
@@ -199,9 +233,10 @@ func NewGPUStepper(m *Model, domainSize []int, dt float64, scheme string, exprs 
 			for k, x := range srcs[i].Pos {
 				pos[k] = C.double(x)
 			}
-			gpuSourceFuncs = append(gpuSourceFuncs, srcs[i].f)
+			h := gpuRegisterSource(srcs[i].f)
+			st.sources = append(st.sources, h)
 			gpuCheck(C.gopf_model_add_source(st.model, C.int(eqNo), &pos[0], C.int(len(pos)),
-				C.gopf_source_trampoline_ptr(), C.gopf_index_as_ptr(C.uintptr_t(len(gpuSourceFuncs)))))
+				C.gopf_source_trampoline_ptr(), C.gopf_index_as_ptr(C.uintptr_t(h))))
 		}
 	}
 	dims := make([]C.int, len(domainSize))
@@ -363,10 +398,9 @@ func (st *GPUStepper) ChargeCurrent(name string, dim int, n int) [][]float64 {
 	return res
 }
 
-// GetTime returns the current time (pf.TimeStepper)
 // SetJit switches the run-time specialisation on or off: registered functions and the k-space
 // update are then compiled for this model by NVRTC at the next step instead of being interpreted.
-// Default: the GOPF_JIT environment variable.
+// Default: on (GOPF_JIT=0 in the environment switches it off).
 func (st *GPUStepper) SetJit(on bool) {
 	v := C.int(0)
 	if on {
@@ -382,6 +416,7 @@ func (st *GPUStepper) JitKernels() int {
 	return int(n)
 }
 
+// GetTime returns the current time (pf.TimeStepper)
 func (st *GPUStepper) GetTime() float64 {
 	var t C.double
 	gpuCheck(C.gopf_solver_get_time(st.solver, &t))
@@ -392,4 +427,10 @@ func (st *GPUStepper) GetTime() float64 {
 func (st *GPUStepper) Close() {
 	C.gopf_solver_destroy(st.solver)
 	C.gopf_model_destroy(st.model)
+	gpuSourceMu.Lock()
+	for _, h := range st.sources {
+		delete(gpuSourceFuncs, h)
+	}
+	gpuSourceMu.Unlock()
+	st.sources = nil
 }
