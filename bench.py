@@ -563,7 +563,7 @@ def run_single_gpu(args):
         # 256^3.  One step = one non-linear solve = many right-hand-side evaluations, so the contract fraction of
         # the Euler step does not apply: the record is the time per step and the launches behind it.
         try:
-            r = measure_workload("ch_sqgrad", WORKLOADS["ch_sqgrad"]["default_grid"], dev, 1, 2, stepper="implicit_euler")
+            r = measure_workload("ch_sqgrad", WORKLOADS["ch_sqgrad"]["default_grid"], dev, 3, 2, stepper="implicit_euler")
             r["workload"] += " (stepper: ImplicitEuler, DefaultNonLinSolver settings)"
             r["roofline"]["step_model"]["note"] = "fraction of the Euler step's contract; not meaningful for a Newton-Krylov solve"
             recs.append(r)
