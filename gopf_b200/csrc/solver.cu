@@ -1242,9 +1242,10 @@ void Solver::euler_step_fused() {
     }
     {
         PassGeom g2 = plan_->geom(2);
-        // real field + real fast-form program (real polynomial multipliers, no noise): the real-space kernel may
-        // carry two lines per complex transform (tma_kernels.cuh)
-        g2.real_pairs = (field_real_ && fused_prog_.fast == 1 && !has_knoise_) ? 1 : 0;
+        // real field + a fast-form program -- real polynomial multipliers (1) or a real tabulated factor with an
+        // optional Hermitian noise spectrum (2): the spectrum stays Hermitian, so the real-space kernel may carry two
+        // lines per complex transform (tma_kernels.cuh)
+        g2.real_pairs = (field_real_ && (fused_prog_.fast == 1 || fused_prog_.fast == 2)) ? 1 : 0;
         const int id = tick("fused_real", 32.0 * n);
         cudaError_t e = launch_fused_real(g2, 0, W_, nullptr, m_->derived[fused_derived_].dev, 1.0 / n,
                                           (unsigned long long)steps_taken_, plan_->twiddle(2), s);

@@ -262,6 +262,9 @@ cudaError_t launch_pass_tma(const PassGeom& g, const PassIO& io, const cplx* tw,
 
 cudaError_t launch_fused_real_tma(const PassGeom& g, cplx* W, const DevDerived& D, double inv_n, unsigned long long step,
                                   const cplx* tw, cudaStream_t s) {
+    // From GOPF_TMA_MIN_N (1024) on.  At 512-cell lines the paired kernel alone beats the register kernel (512^3:
+    // 0.89 -> 0.71 ms) but the step does not gain (6.29 -> 6.26 ms, cfg 5): between register kernels with 64-KB tiles
+    // it is the only launch with a 221-KB carve-out, and the two reconfigurations per step cost what it saves.
     if (!enabled("GOPF_TMA_REAL") || g.B != 1 || g.N < min_n()) return cudaErrorNotSupported;
     const bool host_fast = (D.kind == DK_MONOMIAL && D.n_factors == 1 && D.ipower[0] >= 0 && D.ipower[0] <= 15) ||
                            (D.kind == DK_RPN && D.poly_deg >= 0);

@@ -239,3 +239,30 @@ def test_real_pairs_are_not_used_for_a_complex_field(tma_env):
     tma_env["GOPF_REAL_PAIRS"] = "1"
     got = _ch_init(dims, 6, init)
     assert np.array_equal(got, ref)
+
+
+def _pfc(dims, steps):
+    from gopf_b200 import workloads
+    m, f, solver = workloads.build_pfc(gpf, gpf, dims, noise="device", kspace_noise=gpf.HasKSpaceNoise())
+    assert solver.IsFused and solver.FusedForm()[0] == 2
+    solver.Upload()
+    solver.StepDevice(steps)
+    solver.Download()
+    out = f.Data.copy()
+    solver.close()
+    return out
+
+
+@pytest.mark.parametrize("dims", [[512, 512], [1024, 1024]], ids=lambda d: "x".join(map(str, d)))
+def test_real_pairs_with_the_tabulated_form_and_kspace_noise(tma_env, dims):
+    """cfg 5's model (pair correlation + ideal mixture + Vandeven filter + white noise drawn in k-space) keeps a real
+    field real -- real tabulated factor, Hermitian noise spectrum -- so its real-space kernel pairs lines too:
+    equal to the complex-carrying run to rounding."""
+    tma_env["GOPF_TMA_MIN_N"] = str(dims[-1])
+    tma_env["GOPF_REAL_PAIRS"] = "0"
+    ref = _pfc(dims, 10)
+    tma_env["GOPF_REAL_PAIRS"] = "1"
+    gpfutil.TmaLaunchCount(reset=True)
+    got = _pfc(dims, 10)
+    assert gpfutil.TmaLaunchCount() > 0, "the paired kernel did not run"
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-13
